@@ -1,0 +1,119 @@
+/*
+ * tsvgp.h — C ABI of libtsvgp.so: the B200 (sm_100a) implementation of t-SVGP's dual-parameterised natural-gradient
+ * site update and its two read-only companions.
+ *
+ * The reference (AaltoML/t-SVGP) is pure Python on GPflow/TensorFlow and has NO FFI of its own; the boundary this
+ * library replaces is the method surface of `t_SVGP` (reference src/models/tsvgp.py).  Each entry point below cites the
+ * reference code it stands in for.  The Python mirror of that surface (t-svgp_b200/model.py) binds these symbols with
+ * ctypes and hands tensors over as DLPack capsules (tsvgp_dlpack_view) — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every array is float64, C-contiguous (row-major); num_latent_gps L = 1 in this round
+ *   - every `const double*` / `double*` argument may be a HOST pointer (pageable or pinned) or a DEVICE pointer on the
+ *     context's GPU; the library detects which (cudaPointerGetAttributes) and copies as needed
+ *   - return value: 0 = ok, < 0 = error code below; tsvgp_last_error() gives the message.  Calls on one context are
+ *     not re-entrant (one host thread per context); every call returns after its outputs are visible to the host
+ *   - the library owns no caller memory; inputs are borrowed for the duration of the call (set_data copies a host
+ *     minibatch to the device, or aliases a device one until the next set_data)
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with TSVGP_ERR_CUDA
+ */
+#ifndef TSVGP_H
+#define TSVGP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSVGP_ABI_VERSION 1
+
+enum {
+    TSVGP_OK = 0,
+    TSVGP_ERR_INVALID = -1,           /* bad argument / shape (reference: tf.debugging.assert_shapes, util.py:368-372)  */
+    TSVGP_ERR_CUDA = -2,              /* CUDA runtime failure, or no device                                              */
+    TSVGP_ERR_NOT_POSITIVE_DEFINITE = -3, /* a Cholesky failed (reference: TF InvalidArgumentError from tf.linalg.cholesky);
+                                             tsvgp_last_info() = 1-based failing pivot, LAPACK style                     */
+    TSVGP_ERR_NONPOSITIVE_VARIANCE = -4,  /* some predictive variance <= 0 (reference: tf.debugging.assert_positive,
+                                             tsvgp.py:113)                                                               */
+    TSVGP_ERR_COMM = -5,              /* NCCL failure                                                                    */
+    TSVGP_ERR_STATE = -6              /* called before the kernel / inducing points / data it needs were set             */
+};
+
+enum { TSVGP_KERNEL_SE = 0, TSVGP_KERNEL_MATERN52 = 1 };                       /* gpflow.kernels.{SquaredExponential,Matern52} */
+enum { TSVGP_LIK_GAUSSIAN = 0, TSVGP_LIK_BERNOULLI_PROBIT = 1, TSVGP_LIK_STUDENT_T = 2 }; /* gpflow.likelihoods.*        */
+
+typedef struct tsvgp_ctx tsvgp_ctx;   /* opaque: owns one CUDA stream, device buffers, optional NCCL communicator */
+
+/* ---- lifetime ------------------------------------------------------------------------------------------------- */
+int tsvgp_abi_version(void);
+int tsvgp_create(tsvgp_ctx** out, int device_id);          /* replaces t_SVGP.__init__ (tsvgp.py:122-157) device side    */
+void tsvgp_destroy(tsvgp_ctx* ctx);
+const char* tsvgp_last_error(const tsvgp_ctx* ctx);        /* ctx may be NULL: message of the last failed tsvgp_create    */
+int tsvgp_last_info(const tsvgp_ctx* ctx);                 /* failing pivot of the last TSVGP_ERR_NOT_POSITIVE_DEFINITE   */
+int tsvgp_set_option(tsvgp_ctx* ctx, const char* name, double value);   /* "chunk" (points per on-chip Kuf slab), "profile" */
+
+/* ---- model objects read by the path (tsvgp.py:209,268-269; GPflow kernel / likelihood / inducing attributes) ------ */
+/* lengthscales: HOST pointer, n_ls = 1 (isotropic) or D (ARD)                                                          */
+int tsvgp_set_kernel(tsvgp_ctx* ctx, int kind, double variance, const double* lengthscales, int n_ls);
+/* Gaussian: p0 = variance.  StudentT: p0 = scale, p1 = df.  Bernoulli: inv_probit link with GPflow's 1e-3 jitter.
+ * n_gh Gauss-Hermite points (<= 64; GPflow default 20); gh_x/gh_w (HOST, numpy.polynomial.hermite.hermgauss order)
+ * may be NULL, in which case the library generates them.                                                               */
+int tsvgp_set_likelihood(tsvgp_ctx* ctx, int kind, double p0, double p1, int n_gh, const double* gh_x, const double* gh_w);
+/* Z [M, D] inducing inputs (inducing_variable.Z); mean_Z [M] = mean_function(Z) or NULL for the Zero mean function     */
+int tsvgp_set_inducing(tsvgp_ctx* ctx, const double* Z, int M, int D, const double* mean_Z);
+
+/* ---- DenseSites state (src/sites.py:43-80): lambda_1 [M], lambda_2_sqrt [M, M] lower triangular -------------------- */
+/* NULL lambda_1 / lambda_2_sqrt = the reference defaults 0 and -1e-10 * I (tsvgp.py:174-180). Upper triangle ignored.  */
+int tsvgp_set_sites(tsvgp_ctx* ctx, const double* lambda_1, const double* lambda_2_sqrt);
+int tsvgp_get_sites(tsvgp_ctx* ctx, double* lambda_1, double* lambda_2_sqrt);     /* either may be NULL                  */
+int tsvgp_get_lambda_2(tsvgp_ctx* ctx, double* lambda_2);                          /* L2 L2^T (tsvgp.py:197-200)          */
+
+/* ---- data: this rank's rows of the minibatch ------------------------------------------------------------------------ */
+/* X [N, D], Y [N] (= [N,1]), mean_X [N] = mean_function(X) or NULL. Host data is copied; device data is aliased.        */
+int tsvgp_set_data(tsvgp_ctx* ctx, const double* X, const double* Y, int64_t N, int D, const double* mean_X);
+
+/* ---- the hot path ----------------------------------------------------------------------------------------------------- */
+/* t_SVGP.natgrad_step (tsvgp.py:234-304) on the resident data and sites.  scale = num_data / minibatch_size or 1
+ * (tsvgp.py:286-291) with minibatch_size summed over ranks.  elbo_before (may be NULL) receives the ELBO of the
+ * pre-update state on the same minibatch (a by-product of the same pass).                                              */
+int tsvgp_natgrad_step(tsvgp_ctx* ctx, double lr, double jitter, double scale, double* elbo_before);
+/* base_SVGP.elbo (tsvgp.py:79-95) on the resident data                                                                 */
+int tsvgp_elbo(tsvgp_ctx* ctx, double scale, double* out);
+/* base_SVGP.predict_f, full_cov = False (tsvgp.py:97-114): mean_out, var_out [N]                                        */
+int tsvgp_predict_f(tsvgp_ctx* ctx, const double* Xnew, int64_t N, int D, const double* mean_X, double* mean_out, double* var_out);
+/* t_SVGP.get_mean_chol_cov_inducing_posterior (tsvgp.py:202-212): m [M], chol_S [M, M]                                  */
+int tsvgp_posterior(tsvgp_ctx* ctx, double* m, double* chol_S);
+
+/* ---- multi-GPU: one context per rank, rows of the minibatch sharded over ranks, one all-reduce of the statistics ---- */
+int tsvgp_comm_unique_id(void* id_out_128_bytes);                                   /* ncclGetUniqueId                     */
+int tsvgp_comm_init(tsvgp_ctx* ctx, int world_size, int rank, const void* id_128_bytes);
+int tsvgp_comm_size(const tsvgp_ctx* ctx);
+
+/* ---- measurement ------------------------------------------------------------------------------------------------------ */
+/* CUDA-event durations (ms) of the last natgrad_step, on the context's stream.  out[0..n):
+ *  0 total, 1 prepare (posterior factors), 2 streaming pass, 3 all-reduce, 4 dense update,
+ *  with option "profile"=1 also 5 Kuf tiles, 6 variance product, 7 point statistics, 8 weighted SYRK, 9 Kuf*g,
+ *  10 number of slabs, 11 kernels launched                                                                              */
+int tsvgp_get_timings(tsvgp_ctx* ctx, double* out, int n);
+int tsvgp_sync(tsvgp_ctx* ctx);
+void* tsvgp_pinned_alloc(size_t bytes);                                             /* cudaHostAlloc, for staging buffers  */
+void tsvgp_pinned_free(void* p);
+
+/* ---- DLPack hand-over ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    void* data;          /* dl_tensor.data + byte_offset                       */
+    int64_t shape[3];    /* unused trailing dims = 1                           */
+    int ndim;
+    int device_type;     /* 1 = kDLCPU, 2 = kDLCUDA, 3 = kDLCUDAHost, 13 = kDLCUDAManaged */
+    int device_id;
+} tsvgp_view;
+/* Validates a `DLManagedTensor*` (float64, <= 3-D, compact row-major) taken from a "dltensor" capsule and describes it.
+ * The capsule is only borrowed: the library neither renames it nor calls its deleter.                                   */
+int tsvgp_dlpack_view(const void* dl_managed_tensor, tsvgp_view* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSVGP_H */

@@ -1,0 +1,39 @@
+// Shared device helpers for the t-SVGP sm_100a kernels: FP64 tensor-core MMA (DMMA), cp.async staging.
+// FP64 has no tcgen05/TMEM path on Blackwell; the FP64 tensor instruction is mma.sync m8n8k4 (SASS DMMA.8x8x4),
+// measured at 37.1 TFLOP/s on B200 (profiles/fp64_peak_r01.txt), equal to and sharing a pipe with DFMA.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define TSVGP_TILE 128  // all matrix dimensions inside the library are padded to a multiple of this
+
+namespace tsvgp {
+
+// kernels launched by this host thread (reported by tsvgp_get_timings; the bench's gpu_launches)
+extern thread_local long g_launches;
+inline int count_launch() { ++g_launches; return (int)cudaGetLastError(); }
+
+// D(8x8) += A(8x4,row) * B(4x8,col).  lane = 4*g + t :  a = A[g][t],  b = B[t][g],  c0,c1 = C[g][2t], C[g][2t+1]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace tsvgp

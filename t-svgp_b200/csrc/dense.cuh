@@ -1,0 +1,19 @@
+// Blocked dense M x M factorisations built on the DMMA GEMM engine and the diagonal-block kernels.
+// All matrices row-major, n a multiple of 128, explicit zeros in the unused triangle on output.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace tsvgp {
+
+// In-place lower Cholesky A = L L^T (reads the lower triangle of A; upper triangle zeroed on return).
+// dinv: workspace [n/128][128*128], receives the inverses of the diagonal blocks of L.
+// info: device int, set to (failing pivot index + 1) if A is not positive definite (left untouched otherwise).
+// Restates tf.linalg.cholesky as called at reference src/models/tsvgp.py:270,300 and src/util.py:382.
+int chol_lower(double* A, long ld, int n, double* dinv, int* info, cudaStream_t s);
+
+// Linv = L^-1 for lower-triangular L.  dinv must hold the inverses of L's diagonal blocks (from chol_lower, or
+// diag_trtri_launch).  tmp: workspace [n/2][ld].  Turns tf.linalg.triangular_solve / cholesky_solve
+// (reference tsvgp.py:271, util.py:386) into tensor-core products.
+int trtri_lower(const double* L, long ld, int n, const double* dinv, double* Linv, double* tmp, cudaStream_t s);
+
+}  // namespace tsvgp

@@ -1,0 +1,248 @@
+// FP64 DMMA GEMM engine (see gemm.cuh).  sm_100a only.
+#include "gemm.cuh"
+#include "common.cuh"
+
+namespace tsvgp {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, NTHREADS = 256;
+constexpr int KC_LD = BK + 4;    // [128][20] : rows 160 B apart -> the 4 rows of a half-warp fragment read hit distinct banks
+constexpr int MC_LD = BM + 4;    // [16][132]
+constexpr int KC_ELEMS = BM * KC_LD;
+constexpr int MC_ELEMS = BK * MC_LD;
+
+template <bool A_KC, bool B_KC, bool SCALE>
+struct Smem {
+    static constexpr int A_ELEMS = A_KC ? KC_ELEMS : MC_ELEMS;
+    static constexpr int B_ELEMS = B_KC ? KC_ELEMS : MC_ELEMS;
+    static constexpr int STAGE = A_ELEMS + B_ELEMS + (SCALE ? BK : 0);
+    static constexpr int BYTES = STAGE * STAGES * 8;
+};
+
+template <bool KC>
+__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, long ld, int row0, int k0, int tid) {
+    if (KC) {
+        // 128 rows x 16 k  = 1024 16-byte chunks
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int idx = tid + c * NTHREADS;
+            int r = idx >> 3, cc = (idx & 7) * 2;
+            cp_async16(s + r * KC_LD + cc, g + (long)(row0 + r) * ld + k0 + cc);
+        }
+    } else {
+        // 16 k-rows x 128
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int idx = tid + c * NTHREADS;
+            int r = idx >> 6, cc = (idx & 63) * 2;
+            cp_async16(s + r * MC_LD + cc, g + (long)(k0 + r) * ld + row0 + cc);
+        }
+    }
+}
+
+template <bool A_KC, bool B_KC, bool SCALE, int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(GemmP p) {
+    using S = Smem<A_KC, B_KC, SCALE>;
+    extern __shared__ __align__(16) double smem[];
+
+    const int tj = blockIdx.x, ti = blockIdx.y;
+    if (p.lower_out && tj > ti) return;
+    const int bz = blockIdx.z / p.ksplit, ks = blockIdx.z % p.ksplit;
+    const double* Ag = p.A + (long)bz * p.sA;
+    const double* Bg = p.B + (long)bz * p.sB;
+
+    int kb = 0, ke = p.k;
+    if (p.a_tri == 1) ke = min(ke, (ti + 1) * BM);
+    if (p.a_tri == 2) kb = max(kb, ti * BM);
+    if (p.b_tri == 1) ke = min(ke, (tj + 1) * BN);
+    if (p.b_tri == 2) kb = max(kb, tj * BN);
+    if (p.ksplit > 1) {
+        int nkt = max(ke - kb, 0) / BK;
+        int per = (nkt + p.ksplit - 1) / p.ksplit;
+        kb += ks * per * BK;
+        ke = min(ke, kb + per * BK);
+    }
+    const int KT = max(ke - kb, 0) / BK;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    auto issue = [&](int kt) {
+        if (kt < KT) {
+            double* sa = smem + (kt % STAGES) * S::STAGE;
+            double* sb = sa + S::A_ELEMS;
+            const int k0 = kb + kt * BK;
+            load_tile<A_KC>(sa, Ag, p.lda, ti * BM, k0, tid);
+            load_tile<B_KC>(sb, Bg, p.ldb, tj * BN, k0, tid);
+            if (SCALE && tid < BK / 2) cp_async16(sb + S::B_ELEMS + tid * 2, p.kscale + k0 + tid * 2);
+        }
+        cp_async_commit();
+    };
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue(s);
+
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        issue(kt + STAGES - 1);
+        const double* sa = smem + (kt % STAGES) * S::STAGE;
+        const double* sb = sa + S::A_ELEMS;
+        const double* ssc = sb + S::B_ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                a[i] = A_KC ? sa[(wm + 8 * i + g) * KC_LD + kk + t] : sa[(kk + t) * MC_LD + wm + 8 * i + g];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                b[j] = B_KC ? sb[(wn + 8 * j + g) * KC_LD + kk + t] : sb[(kk + t) * MC_LD + wn + 8 * j + g];
+            if (SCALE) {
+                const double h = ssc[kk + t];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] *= h;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();   // every global read of this CTA is complete: C may alias A (in-place panel solves)
+
+    if (EPI == EPI_STORE) {
+        const bool split = p.ksplit > 1;
+        double* Cg = split ? p.part + (long)ks * p.part_stride + (long)bz * p.sC : p.C + (long)bz * p.sC;
+        const double alpha = p.alpha, beta = split ? 0.0 : p.beta;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long row = ti * BM + wm + 8 * i + g;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = tj * BN + wn + 8 * j + 2 * t;
+                double2* ptr = reinterpret_cast<double2*>(Cg + row * p.ldc + col);
+                double2 o;
+                o.x = alpha * acc[i][j][0];
+                o.y = alpha * acc[i][j][1];
+                if (beta != 0.0) {
+                    const double2 old = *ptr;
+                    o.x += beta * old.x;
+                    o.y += beta * old.y;
+                }
+                *ptr = o;
+            }
+        }
+    } else {
+        // column sums of squares over this tile's 128 rows -> norm_out[ti][col]
+        double cs[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cs[j][0] = 0.0; cs[j][1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                cs[j][0] = fma(acc[i][j][0], acc[i][j][0], cs[j][0]);
+                cs[j][1] = fma(acc[i][j][1], acc[i][j][1], cs[j][1]);
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double v = cs[j][e];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                cs[j][e] = v;
+            }
+        }
+        double* red = smem;   // [2][128]; pipeline buffers are idle now
+        if (g == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                red[(warp & 1) * BN + wn + 8 * j + 2 * t] = cs[j][0];
+                red[(warp & 1) * BN + wn + 8 * j + 2 * t + 1] = cs[j][1];
+            }
+        }
+        __syncthreads();
+        if (tid < BN) p.norm_out[(long)bz * p.sC + (long)ti * p.ldn + tj * BN + tid] = red[tid] + red[BN + tid];
+    }
+}
+
+__global__ void splitk_reduce_kernel(GemmP p) {
+    const int tj = blockIdx.x, ti = blockIdx.y;
+    if (p.lower_out && tj > ti) return;
+    // 256 threads, each handles a 64-element strip of the 128x128 tile
+    for (int e = threadIdx.x; e < BM * BN / 2; e += blockDim.x) {
+        const int r = e / (BN / 2), c = (e % (BN / 2)) * 2;
+        const long off = (long)(ti * BM + r) * p.ldc + tj * BN + c;
+        double2 s = make_double2(0.0, 0.0);
+        for (int k = 0; k < p.ksplit; ++k) {
+            const double2 v = *reinterpret_cast<const double2*>(p.part + (long)k * p.part_stride + off);
+            s.x += v.x; s.y += v.y;
+        }
+        double2* ptr = reinterpret_cast<double2*>(p.C + off);
+        if (p.beta != 0.0) {
+            const double2 old = *ptr;
+            s.x += p.beta * old.x; s.y += p.beta * old.y;
+        }
+        *ptr = s;
+    }
+}
+
+template <bool A_KC, bool B_KC, bool SCALE, int EPI>
+int launch_inst(const GemmP& p, cudaStream_t stream) {
+    dim3 grid(p.n / BN, p.m / BM, p.batch * p.ksplit);
+    gemm_kernel<A_KC, B_KC, SCALE, EPI><<<grid, NTHREADS, Smem<A_KC, B_KC, SCALE>::BYTES, stream>>>(p);
+    return count_launch();
+}
+
+template <bool A_KC, bool B_KC, bool SCALE, int EPI>
+int init_inst() {
+    return (int)cudaFuncSetAttribute(gemm_kernel<A_KC, B_KC, SCALE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Smem<A_KC, B_KC, SCALE>::BYTES);
+}
+
+}  // namespace
+
+int gemm_init() {
+    int e = 0;
+    e |= init_inst<true, true, false, EPI_STORE>();
+    e |= init_inst<true, true, true, EPI_STORE>();
+    e |= init_inst<false, false, false, EPI_STORE>();
+    e |= init_inst<false, false, false, EPI_COLNORM>();
+    e |= init_inst<true, false, false, EPI_STORE>();
+    return e;
+}
+
+int gemm_launch(const GemmP& p, cudaStream_t stream) {
+    if (p.m % BM || p.n % BN || p.k % BK || p.m <= 0 || p.n <= 0) return -1;
+    const bool scale = p.kscale != nullptr;
+    if (p.a_kc && p.b_kc) {
+        if (p.epilogue != EPI_STORE) return -1;
+        return scale ? launch_inst<true, true, true, EPI_STORE>(p, stream) : launch_inst<true, true, false, EPI_STORE>(p, stream);
+    }
+    if (scale) return -1;
+    if (!p.a_kc && !p.b_kc) {
+        if (p.epilogue == EPI_COLNORM) return p.ksplit == 1 ? launch_inst<false, false, false, EPI_COLNORM>(p, stream) : -1;
+        return launch_inst<false, false, false, EPI_STORE>(p, stream);
+    }
+    if (p.a_kc && !p.b_kc) {
+        if (p.epilogue != EPI_STORE) return -1;
+        return launch_inst<true, false, false, EPI_STORE>(p, stream);
+    }
+    return -1;
+}
+
+int splitk_reduce_launch(const GemmP& p, cudaStream_t stream) {
+    dim3 grid(p.n / BN, p.m / BM, 1);
+    splitk_reduce_kernel<<<grid, 256, 0, stream>>>(p);
+    return count_launch();
+}
+
+}  // namespace tsvgp

@@ -1,0 +1,43 @@
+// FP64 DMMA GEMM engine: one tiled mainloop (128x128 CTA tile, 8 warps of 64x32, BK=16, 4-stage cp.async pipeline)
+// reused by the streaming statistics pass (weighted SYRK, triangular variance product) and by every dense M x M
+// operation of the natural-gradient step (reference math: src/models/tsvgp.py:234-304, src/util.py:349-391).
+//
+//   C[m x n] = alpha * sum_k A(i,k) * [kscale(k)] * B(k,j) + beta * C          (row-major C, all dims multiples of 128)
+//
+// Operand storage:  a_kc = 1 : A stored [m][k] (k contiguous) ;  a_kc = 0 : A stored [k][m]
+//                   b_kc = 1 : B stored [n][k]                ;  b_kc = 0 : B stored [k][n]
+// Triangular structure lets a tile skip k-blocks that are identically zero (operands carry explicit zeros there):
+//   a_tri = 1 : A(i,k) != 0 only for k <= i     a_tri = 2 : only for k >= i      (same for b_tri with j)
+// lower_out = 1 : only tiles with tile_i >= tile_j are computed (symmetric results).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace tsvgp {
+
+enum { EPI_STORE = 0, EPI_COLNORM = 1 };
+
+struct GemmP {
+    const double* A = nullptr; long lda = 0; int a_kc = 1;
+    const double* B = nullptr; long ldb = 0; int b_kc = 1;
+    double* C = nullptr; long ldc = 0;
+    int m = 0, n = 0, k = 0;
+    double alpha = 1.0, beta = 0.0;
+    int lower_out = 0;
+    int a_tri = 0, b_tri = 0;
+    const double* kscale = nullptr;   // optional [k] weights on the contraction index (the h_n of the weighted SYRK)
+    int epilogue = EPI_STORE;
+    double* norm_out = nullptr; long ldn = 0;   // EPI_COLNORM: norm_out[tile_i * ldn + j] = sum_{i in tile} C(i,j)^2
+    int ksplit = 1; double* part = nullptr; long part_stride = 0;   // split-K partial slabs [ksplit][m*ldc]; caller reduces
+    int batch = 1; long sA = 0, sB = 0, sC = 0;
+};
+
+// Launch on `stream`. Returns cudaError_t as int (0 = ok), -1 for an unsupported combination.
+int gemm_launch(const GemmP& p, cudaStream_t stream);
+
+// C = beta*C + sum_s part[s]  over the tiles gemm_launch wrote (lower tiles only if lower_out)
+int splitk_reduce_launch(const GemmP& p, cudaStream_t stream);
+
+// one-time: opt in to large dynamic shared memory for every instantiation
+int gemm_init();
+
+}  // namespace tsvgp

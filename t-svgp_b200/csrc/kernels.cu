@@ -1,0 +1,581 @@
+// Non-GEMM kernels of the t-SVGP natural-gradient path (see kernels.cuh).  sm_100a.
+#include "kernels.cuh"
+#include "common.cuh"
+#include <math.h>
+
+namespace tsvgp {
+
+// =====================================================================================================================
+// Covariance tiles.  Restates GPflow 2.2.1 stationaries.py / utilities/ops.py::square_distance:
+//   Xs = X / lengthscales ;  r2 = |xs|^2 + |zs|^2 - 2 xs.zs  (expansion form, not clipped for SE)
+//   SE: variance * exp(-r2/2) ;  Matern52: r = sqrt(max(r2,1e-36)), variance (1 + sqrt5 r + 5/3 r^2) exp(-sqrt5 r)
+// called by the reference at src/models/tsvgp.py:209,268,269 and inside gpflow.conditionals.conditional (:103).
+// =====================================================================================================================
+__global__ void scale_points_kernel(const double* __restrict__ X, long n, int D, const double* __restrict__ ls,
+                                    double* __restrict__ XsT, long ldx, double* __restrict__ x2, long n_pad) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    double s = 0.0;
+    if (i < n) {
+        for (int d = 0; d < D; ++d) {
+            const double v = X[i * D + d] / ls[d];
+            XsT[(long)d * ldx + i] = v;
+            s = fma(v, v, s);
+        }
+    } else {
+        for (int d = 0; d < D; ++d) XsT[(long)d * ldx + i] = 0.0;
+    }
+    x2[i] = s;
+}
+
+int scale_points_launch(const double* X, long n, int D, const double* ls, double* XsT, long ldx, double* x2, long n_pad,
+                        cudaStream_t s) {
+    if (n_pad <= 0) return 0;
+    scale_points_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, s>>>(X, n, D, ls, XsT, ldx, x2, n_pad);
+    return count_launch();
+}
+
+__global__ void unpack_rows_kernel(const double* __restrict__ ZsT, long ldz, int Mp, int D, double* __restrict__ Zs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Mp) return;
+    for (int d = 0; d < D; ++d) Zs[(long)i * D + d] = ZsT[(long)d * ldz + i];
+}
+int unpack_rows_launch(const double* ZsT, long ldz, int Mp, int D, double* Zs, cudaStream_t s) {
+    unpack_rows_kernel<<<(Mp + 255) / 256, 256, 0, s>>>(ZsT, ldz, Mp, D, Zs);
+    return count_launch();
+}
+
+template <int KIND>
+__device__ __forceinline__ double cov_from_r2(double r2, double variance) {
+    if (KIND == KERN_SE) {
+        return variance * exp(-0.5 * r2);
+    } else {
+        const double r = sqrt(fmax(r2, 1e-36));
+        const double sqrt5 = 2.23606797749978969641;
+        return variance * (1.0 + sqrt5 * r + (5.0 / 3.0) * (r * r)) * exp(-sqrt5 * r);
+    }
+}
+
+constexpr int KUF_DC = 16;   // feature chunk staged in shared memory
+constexpr int KUF_ROWS = 64; // inducing rows per CTA (2 groups of 32)
+
+template <int KIND>
+__global__ void __launch_bounds__(256) kuf_kernel(double variance, const double* __restrict__ XsT, long ldx,
+                                                  const double* __restrict__ x2, long n0, long n_valid,
+                                                  const double* __restrict__ Zs, const double* __restrict__ z2, int M, int D,
+                                                  const double* __restrict__ alpha, double* __restrict__ K, long ldk,
+                                                  double* __restrict__ mu_part, long ldmu, int pad_identity) {
+    __shared__ double sx[KUF_DC][128];
+    __shared__ __align__(16) double sz[KUF_ROWS][KUF_DC];
+    __shared__ double smu[128];
+    const int tid = threadIdx.x, nn = tid & 127, ig = tid >> 7;
+    const long c0 = (long)blockIdx.x * 128;          // chunk-local column of this tile
+    const long n = n0 + c0 + nn;                     // global point index
+    const int ibase = blockIdx.y * KUF_ROWS;
+
+    double dot[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) dot[r] = 0.0;
+
+    for (int dc = 0; dc < D; dc += KUF_DC) {
+        const int dlen = min(KUF_DC, D - dc);
+        __syncthreads();
+        for (int e = tid; e < KUF_DC * 128; e += 256) {
+            const int d = e >> 7, c = e & 127;
+            sx[d][c] = d < dlen ? XsT[(long)(dc + d) * ldx + n0 + c0 + c] : 0.0;
+        }
+        for (int e = tid; e < KUF_ROWS * KUF_DC; e += 256) {
+            const int r = e / KUF_DC, d = e % KUF_DC;
+            sz[r][d] = d < dlen ? Zs[(long)(ibase + r) * D + dc + d] : 0.0;
+        }
+        __syncthreads();
+        const int dl8 = (dlen + 7) & ~7;
+        for (int d8 = 0; d8 < dl8; d8 += 8) {
+            double x[8];
+#pragma unroll
+            for (int d = 0; d < 8; ++d) x[d] = sx[d8 + d][nn];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const double2* zp = reinterpret_cast<const double2*>(&sz[ig * 32 + r][d8]);
+                double acc = dot[r];
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const double2 zz = zp[d];
+                    acc = fma(x[2 * d], zz.x, acc);
+                    acc = fma(x[2 * d + 1], zz.y, acc);
+                }
+                dot[r] = acc;
+            }
+        }
+    }
+
+    const double xn2 = x2[n];
+    const bool col_ok = n < n_valid;
+    double mu = 0.0;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        const int i = ibase + ig * 32 + r;
+        double k;
+        if (i < M && col_ok) {
+            const double r2 = -2.0 * dot[r] + (xn2 + z2[i]);
+            k = cov_from_r2<KIND>(r2, variance);
+        } else {
+            k = (pad_identity && (long)i == n) ? 1.0 : 0.0;
+        }
+        K[(long)i * ldk + c0 + nn] = k;
+        if (alpha) mu = fma(alpha[i], k, mu);
+    }
+    if (alpha) {
+        if (ig == 1) smu[nn] = mu;
+        __syncthreads();
+        if (ig == 0) mu_part[(long)blockIdx.y * ldmu + c0 + nn] = mu + smu[nn];
+    }
+}
+
+int kuf_launch(int kind, double variance, const double* XsT, long ldx, const double* x2, long n0, long n_valid, int ncols,
+               const double* Zs, const double* z2, int M, int Mp, int D, const double* alpha, double* K, long ldk,
+               double* mu_part, long ldmu, int pad_identity, cudaStream_t s) {
+    dim3 grid(ncols / 128, Mp / KUF_ROWS);
+    if (kind == KERN_SE)
+        kuf_kernel<KERN_SE><<<grid, 256, 0, s>>>(variance, XsT, ldx, x2, n0, n_valid, Zs, z2, M, D, alpha, K, ldk, mu_part, ldmu, pad_identity);
+    else if (kind == KERN_MATERN52)
+        kuf_kernel<KERN_MATERN52><<<grid, 256, 0, s>>>(variance, XsT, ldx, x2, n0, n_valid, Zs, z2, M, D, alpha, K, ldk, mu_part, ldmu, pad_identity);
+    else
+        return -1;
+    return count_launch();
+}
+
+// =====================================================================================================================
+// Per-point q(f) marginals -> likelihood expectations and their gradients.
+// Restates gpflow.likelihoods (Gaussian closed form; ScalarLikelihood 20-point Gauss-Hermite for Bernoulli-probit and
+// StudentT) as called at reference src/models/tsvgp.py:88 and :256-259, with the gradients of the quadrature sum written
+// analytically instead of tf.GradientTape, and the clip of :262-263 (g_var <= -1e-8).
+// =====================================================================================================================
+
+template <int LIK>
+__device__ __forceinline__ void logp_and_grad(double f, double y, const LikSpec& lk, double& lp, double& dlp) {
+    if (LIK == LIK_BERNOULLI) {
+        // inv_probit with GPflow's 1e-3 jitter; logp = log(where(y == 1, p, 1 - p))
+        const double p = 0.5 * (1.0 + erf(f * 0.70710678118654752440)) * (1.0 - 2e-3) + 1e-3;
+        const double dp = (1.0 - 2e-3) * exp(-0.5 * f * f) * 0.39894228040143267794;
+        if (y == 1.0) { lp = log(p); dlp = dp / p; }
+        else { lp = log(1.0 - p); dlp = -dp / (1.0 - p); }
+    } else {
+        // StudentT: c0 - (df+1)/2 * log(1 + ((y-f)/scale)^2 / df)
+        const double r = y - f;
+        const double q = r / lk.p0;
+        lp = lk.c0 - 0.5 * (lk.p1 + 1.0) * log(1.0 + (1.0 / lk.p1) * (q * q));
+        dlp = (lk.p1 + 1.0) * r / (lk.p1 * lk.p0 * lk.p0 + r * r);
+    }
+}
+
+template <int LIK>
+__global__ void __launch_bounds__(256) point_stats_kernel(LikSpec lk, PointArgs a, GHTable gh) {
+    __shared__ double sred[8];
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    double ve = 0.0;
+    if (c < a.ncols) {
+        const bool valid = c < a.n_valid;
+        double mu = 0.0, q = 0.0;
+        for (int p = 0; p < a.n_mu_part; ++p) mu += a.mu_part[(long)p * a.ldmu + c];
+        for (int p = 0; p < a.n_q_part; ++p) q += a.q_part[(long)p * a.ldq + c];
+        const double mean = mu + (a.mean_off ? a.mean_off[c] : 0.0);
+        const double var = a.kdiag - q;
+        if (valid && !(var > 0.0)) atomicOr(a.flags, 1);
+        if (valid && a.mean_out) { a.mean_out[c] = mean; a.var_out[c] = var; }
+        double gm = 0.0, gv = 0.0;
+        if (valid && a.y) {
+            const double y = a.y[c];
+            if (LIK == LIK_GAUSSIAN) {
+                const double s2 = lk.p0, r = y - mean;
+                ve = -0.5 * 1.83787706640934548356 - 0.5 * log(s2) - 0.5 * (r * r + var) / s2;
+                gm = r / s2;
+                gv = -0.5 / s2;
+            } else {
+                const double sd = sqrt(var);
+                double gs = 0.0;
+                for (int k = 0; k < lk.n_gh; ++k) {
+                    const double f = mean + sd * gh.z[k];
+                    double lp, dlp;
+                    logp_and_grad<LIK>(f, y, lk, lp, dlp);
+                    const double wd = gh.w[k] * dlp;
+                    ve = fma(gh.w[k], lp, ve);
+                    gm += wd;
+                    gs = fma(wd, gh.z[k], gs);
+                }
+                gv = gs / (2.0 * sd);
+            }
+            gv = fmin(gv, -1e-8);
+        }
+        if (a.g) { a.g[c] = valid ? gm : 0.0; a.h[c] = valid ? gv : 0.0; }
+        if (!valid) ve = 0.0;
+    }
+    if (a.ve_blocks) {
+        ve = warp_sum(ve);
+        if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = ve;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < 8; ++w) s += sred[w];
+            a.ve_blocks[blockIdx.x] = s;
+        }
+    }
+}
+
+int point_stats_launch(const LikSpec& lik, const PointArgs& a, const GHTable& g_gh, cudaStream_t s) {
+    const int grid = (a.ncols + 255) / 256;
+    switch (lik.kind) {
+        case LIK_GAUSSIAN: point_stats_kernel<LIK_GAUSSIAN><<<grid, 256, 0, s>>>(lik, a, g_gh); break;
+        case LIK_BERNOULLI: point_stats_kernel<LIK_BERNOULLI><<<grid, 256, 0, s>>>(lik, a, g_gh); break;
+        case LIK_STUDENT_T: point_stats_kernel<LIK_STUDENT_T><<<grid, 256, 0, s>>>(lik, a, g_gh); break;
+        default: return -1;
+    }
+    return count_launch();
+}
+
+// =====================================================================================================================
+// M-vector products
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) gemv_n_kernel(const double* __restrict__ A, long lda, int m, long n,
+                                                     const double* __restrict__ x, double alpha, double beta,
+                                                     double* __restrict__ y) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= m) return;
+    const double* a = A + (long)row * lda;
+    double s0 = 0.0, s1 = 0.0;
+    long j = lane * 2;
+    for (; j + 1 < n; j += 64) {
+        const double2 av = *reinterpret_cast<const double2*>(a + j);
+        const double2 xv = *reinterpret_cast<const double2*>(x + j);
+        s0 = fma(av.x, xv.x, s0);
+        s1 = fma(av.y, xv.y, s1);
+    }
+    if (j < n) s0 = fma(a[j], x[j], s0);
+    const double s = warp_sum(s0 + s1);
+    if (lane == 0) y[row] = alpha * s + (beta != 0.0 ? beta * y[row] : 0.0);
+}
+
+int gemv_n_launch(const double* A, long lda, int m, long n, const double* x, double alpha, double beta, double* y, cudaStream_t s) {
+    gemv_n_kernel<<<(m + 7) / 8, 256, 0, s>>>(A, lda, m, n, x, alpha, beta, y);
+    return count_launch();
+}
+
+__global__ void __launch_bounds__(128) gemv_t_part_kernel(const double* __restrict__ A, long lda, int m, int n,
+                                                          const double* __restrict__ x, double* __restrict__ work) {
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    const int i0 = blockIdx.y * 64;
+    if (j >= n) return;
+    double s = 0.0;
+    const int i1 = min(i0 + 64, m);
+    for (int i = i0; i < i1; ++i) s = fma(A[(long)i * lda + j], x[i], s);
+    work[(long)blockIdx.y * n + j] = s;
+}
+__global__ void gemv_t_sum_kernel(const double* __restrict__ work, int nchunk, int n, double* __restrict__ y) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunk; ++c) s += work[(long)c * n + j];
+    y[j] = s;
+}
+
+int gemv_t_launch(const double* A, long lda, int m, int n, const double* x, double* y, double* work, cudaStream_t s) {
+    const int nchunk = (m + 63) / 64;
+    dim3 grid((n + 127) / 128, nchunk);
+    gemv_t_part_kernel<<<grid, 128, 0, s>>>(A, lda, m, n, x, work);
+    gemv_t_sum_kernel<<<(n + 255) / 256, 256, 0, s>>>(work, nchunk, n, y);
+    return count_launch();
+}
+
+// =====================================================================================================================
+// Diagonal 128x128 blocks: Cholesky (tf.linalg.cholesky at reference tsvgp.py:270,300 and util.py:377,382,388)
+// and triangular inverse (used to turn tf.linalg.triangular_solve / cholesky_solve into tensor-core products).
+// =====================================================================================================================
+constexpr int DB = 128, DB_LD = 129;
+
+// S holds lower-triangular L (row-major, ld 129). Computes X = L^-1: X[i][c] (c < i) is left in S[c][i] (upper triangle),
+// the diagonal of X in dinv[].  256 threads: lane pairs split each column's dot products.
+__device__ void tri_inverse_in_smem(double* S, double* dinv) {
+    const int tid = threadIdx.x;
+    if (tid < DB) dinv[tid] = 1.0 / S[tid * DB_LD + tid];
+    __syncthreads();
+    const int c = (tid >> 5) * 16 + ((tid & 31) >> 1), half = tid & 1;
+    for (int i = 1; i < DB; ++i) {
+        double s = 0.0;
+        if (c < i) {
+            const double* Li = S + i * DB_LD;
+            const double* Xc = S + c * DB_LD;
+            int j = c + half;
+            if (j == c) { s = Li[c] * dinv[c]; j += 2; }
+            for (; j < i; j += 2) s = fma(Li[j], Xc[j], s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (c < i && half == 0) S[c * DB_LD + i] = -s * dinv[i];
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+__device__ void store_inverse(const double* S, const double* dinv, double* Dinv) {
+    for (int e = threadIdx.x; e < DB * DB; e += blockDim.x) {
+        const int r = e >> 7, c = e & 127;
+        Dinv[e] = c < r ? S[c * DB_LD + r] : (c == r ? dinv[r] : 0.0);
+    }
+}
+
+__global__ void __launch_bounds__(256) diag_potrf_inv_kernel(double* A, long lda, double* Dinv, int blk, int* info) {
+    extern __shared__ double S[];   // [128][129]
+    __shared__ double dinv[DB];
+    __shared__ int fail;
+    const int tid = threadIdx.x;
+    if (tid == 0) fail = 0;
+    for (int e = tid; e < DB * DB; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        S[r * DB_LD + c] = c <= r ? A[(long)r * lda + c] : 0.0;
+    }
+    __syncthreads();
+    const int ti = tid & 15, tj = tid >> 4;
+    for (int k = 0; k < DB; ++k) {
+        const double akk = S[k * DB_LD + k];
+        if (!(akk > 0.0)) {   // uniform across the block (same shared value after the barrier)
+            if (tid == 0) fail = k + 1;
+            break;
+        }
+        const double d = sqrt(akk), inv = 1.0 / d;
+        __syncthreads();   // everyone has read akk before it is overwritten
+        if (tid == k) S[k * DB_LD + k] = d;
+        if (tid > k && tid < DB) S[tid * DB_LD + k] *= inv;
+        __syncthreads();
+        int i = k + 1 + ((ti - (k + 1)) & 15);
+        const int jfirst = k + 1 + ((tj - (k + 1)) & 15);
+        for (; i < DB; i += 16) {
+            const double lik = S[i * DB_LD + k];
+            for (int j = jfirst; j <= i; j += 16) S[i * DB_LD + j] = fma(-lik, S[j * DB_LD + k], S[i * DB_LD + j]);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (fail) {
+        if (tid == 0) atomicCAS(info, 0, blk * DB + fail);
+        return;
+    }
+    for (int e = tid; e < DB * DB; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        A[(long)r * lda + c] = c <= r ? S[r * DB_LD + c] : 0.0;
+    }
+    __syncthreads();
+    tri_inverse_in_smem(S, dinv);
+    store_inverse(S, dinv, Dinv);
+}
+
+__global__ void __launch_bounds__(256) diag_trtri_kernel(const double* L, long lda, double* Dinv) {
+    extern __shared__ double S[];
+    __shared__ double dinv[DB];
+    const double* A = L + (long)blockIdx.x * DB * lda + (long)blockIdx.x * DB;
+    for (int e = threadIdx.x; e < DB * DB; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        S[r * DB_LD + c] = c <= r ? A[(long)r * lda + c] : 0.0;
+    }
+    __syncthreads();
+    tri_inverse_in_smem(S, dinv);
+    store_inverse(S, dinv, Dinv + (long)blockIdx.x * DB * DB);
+}
+
+static bool g_diag_attr_set = false;
+static int diag_attr() {
+    if (g_diag_attr_set) return 0;
+    int e = (int)cudaFuncSetAttribute(diag_potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB * DB_LD * 8);
+    e |= (int)cudaFuncSetAttribute(diag_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB * DB_LD * 8);
+    if (e == 0) g_diag_attr_set = true;
+    return e;
+}
+
+int diag_potrf_inv_launch(double* A, long lda, double* Dinv, int blk_index, int* info, cudaStream_t s) {
+    if (int e = diag_attr()) return e;
+    diag_potrf_inv_kernel<<<1, 256, DB * DB_LD * 8, s>>>(A, lda, Dinv, blk_index, info);
+    return count_launch();
+}
+int diag_trtri_launch(const double* L, long lda, double* Dinv, int nblk, cudaStream_t s) {
+    if (int e = diag_attr()) return e;
+    diag_trtri_kernel<<<nblk, 256, DB * DB_LD * 8, s>>>(L, lda, Dinv);
+    return count_launch();
+}
+
+// =====================================================================================================================
+// Elementwise M x M utilities
+// =====================================================================================================================
+#define EW_GRID(n) dim3(((n) + 31) / 32, ((n) + 7) / 8), dim3(32, 8)
+#define EW_IJ const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y; if (i >= n || j >= n) return;
+
+__global__ void add_diag_kernel(double* A, long lda, int n, double v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[(long)i * lda + i] += v;
+}
+int add_diag_launch(double* A, long lda, int n, double v, cudaStream_t s) {
+    add_diag_kernel<<<(n + 255) / 256, 256, 0, s>>>(A, lda, n, v);
+    return count_launch();
+}
+__global__ void copy_add_diag_kernel(const double* A, double* B, long ld, int n, double v) {
+    EW_IJ;
+    B[(long)i * ld + j] = A[(long)i * ld + j] + (i == j ? v : 0.0);
+}
+int copy_add_diag_launch(const double* A, double* B, long ld, int n, double v, cudaStream_t s) {
+    copy_add_diag_kernel<<<EW_GRID(n), 0, s>>>(A, B, ld, n, v);
+    return count_launch();
+}
+__global__ void mirror_lower_kernel(double* A, long lda, int n) {
+    __shared__ double tile[32][33];
+    // block (bx, by) with by >= bx : read lower tile (by, bx), write transposed into (bx, by)
+    const int bx = blockIdx.x, by = blockIdx.y;
+    if (bx > by) return;
+    for (int r = threadIdx.y; r < 32; r += 8) tile[r][threadIdx.x] = A[(long)(by * 32 + r) * lda + bx * 32 + threadIdx.x];
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = bx * 32 + r, j = by * 32 + threadIdx.x;   // upper element (i, j), i <= j region
+        if (j > i) A[(long)i * lda + j] = tile[threadIdx.x][r];
+    }
+}
+int mirror_lower_launch(double* A, long lda, int n, cudaStream_t s) {
+    mirror_lower_kernel<<<dim3(n / 32, n / 32), dim3(32, 8), 0, s>>>(A, lda, n);
+    return count_launch();
+}
+__global__ void flip_sym_kernel(const double* W, double* Wf, long ld, int n) {
+    EW_IJ;
+    if (j > i) { Wf[(long)i * ld + j] = 0.0; return; }
+    const int a = n - 1 - i, b = n - 1 - j;   // a <= b : take the lower element W[b][a]
+    Wf[(long)i * ld + j] = W[(long)b * ld + a];
+}
+int flip_sym_launch(const double* W, double* Wf, long ld, int n, cudaStream_t s) {
+    flip_sym_kernel<<<EW_GRID(n), 0, s>>>(W, Wf, ld, n);
+    return count_launch();
+}
+__global__ void antitranspose_kernel(const double* Linv, double* V, long ld, int n) {
+    EW_IJ;
+    V[(long)i * ld + j] = j <= i ? Linv[(long)(n - 1 - j) * ld + (n - 1 - i)] : 0.0;
+}
+int antitranspose_launch(const double* Linv, double* V, long ld, int n, cudaStream_t s) {
+    antitranspose_kernel<<<EW_GRID(n), 0, s>>>(Linv, V, ld, n);
+    return count_launch();
+}
+__global__ void zero_upper_kernel(double* A, long lda, int n) {
+    EW_IJ;
+    if (j > i) A[(long)i * lda + j] = 0.0;
+}
+int zero_upper_launch(double* A, long lda, int n, cudaStream_t s) {
+    zero_upper_kernel<<<EW_GRID(n), 0, s>>>(A, lda, n);
+    return count_launch();
+}
+__global__ void finalize_sites_kernel(const double* P, double* L2, long ld, int M, int n) {
+    EW_IJ;
+    L2[(long)i * ld + j] = (j <= i && i < M) ? -P[(long)i * ld + j] : 0.0;
+}
+int finalize_sites_launch(const double* P, double* L2, long ld, int M, int Mp, cudaStream_t s) {
+    const int n = Mp;
+    finalize_sites_kernel<<<EW_GRID(n), 0, s>>>(P, L2, ld, M, Mp);
+    return count_launch();
+}
+__global__ void place_block_kernel(const double* src, long lds, double* dst, long ldd, int rows, int cols) {
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (i < rows && j < cols) dst[(long)i * ldd + j] = src[(long)i * lds + j];
+}
+int place_block_launch(const double* src, long lds, double* dst, long ldd, int rows, int cols, cudaStream_t s) {
+    place_block_kernel<<<dim3((cols + 31) / 32, (rows + 7) / 8), dim3(32, 8), 0, s>>>(src, lds, dst, ldd, rows, cols);
+    return count_launch();
+}
+__global__ void copy_lower_kernel(const double* src, long lds, int M, double* dst, long ldd, int n) {
+    EW_IJ;
+    dst[(long)i * ldd + j] = (i < M && j <= i) ? src[(long)i * lds + j] : 0.0;
+}
+int copy_lower_launch(const double* src, long lds, int M, double* dst, long ldd, int Mp, cudaStream_t s) {
+    const int n = Mp;
+    copy_lower_kernel<<<EW_GRID(n), 0, s>>>(src, lds, M, dst, ldd, Mp);
+    return count_launch();
+}
+
+// deterministic block reductions: fixed grid of 128 partial blocks, then one finishing block ------------------------
+constexpr int RED_BLOCKS = 128;
+__device__ __forceinline__ double block_sum_256(double v, double* sred) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < 8; ++w) s += sred[w];
+    __syncthreads();
+    return s;   // valid on thread 0
+}
+__global__ void __launch_bounds__(256) frob_part_kernel(const double* A, long lda, int n, double* part) {
+    __shared__ double sred[8];
+    double s = 0.0;
+    const long total = (long)n * n;
+    for (long e = (long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long)RED_BLOCKS * 256) {
+        const double v = A[(e / n) * lda + (e % n)];
+        s = fma(v, v, s);
+    }
+    s = block_sum_256(s, sred);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) frob_logdiag_finish_kernel(const double* A, long lda, int n, const double* part, double* out) {
+    __shared__ double sred[8];
+    double s = threadIdx.x < RED_BLOCKS ? part[threadIdx.x] : 0.0;
+    s = block_sum_256(s, sred);
+    if (threadIdx.x == 0) out[0] = s;
+    double l = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) l += log(A[(long)i * lda + i]);
+    l = block_sum_256(l, sred);
+    if (threadIdx.x == 0) out[1] = l;
+}
+static double* g_red_part[16] = {nullptr};
+static double* red_scratch() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) return nullptr;
+    if (!g_red_part[dev]) cudaMalloc(&g_red_part[dev], RED_BLOCKS * sizeof(double));
+    return g_red_part[dev];
+}
+int frob_logdiag_launch(const double* A, long lda, int n, double* out, cudaStream_t s) {
+    double* part = red_scratch();
+    if (!part) return -1;
+    frob_part_kernel<<<RED_BLOCKS, 256, 0, s>>>(A, lda, n, part);
+    frob_logdiag_finish_kernel<<<1, 256, 0, s>>>(A, lda, n, part, out);
+    return count_launch();
+}
+__global__ void __launch_bounds__(256) dot_kernel(const double* x, const double* y, int n, double* out) {
+    __shared__ double sred[8];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s = fma(x[i], y[i], s);
+    s = block_sum_256(s, sred);
+    if (threadIdx.x == 0) out[0] = s;
+}
+int dot_launch(const double* x, const double* y, int n, double* out, cudaStream_t s) {
+    dot_kernel<<<1, 256, 0, s>>>(x, y, n, out);
+    return count_launch();
+}
+__global__ void __launch_bounds__(256) sum_kernel(const double* x, long n, double* out) {
+    __shared__ double sred[8];
+    double s = 0.0;
+    for (long i = threadIdx.x; i < n; i += 256) s += x[i];
+    s = block_sum_256(s, sred);
+    if (threadIdx.x == 0) out[0] = s;
+}
+int sum_launch(const double* x, long n, double* out, cudaStream_t s) {
+    sum_kernel<<<1, 256, 0, s>>>(x, n, out);
+    return count_launch();
+}
+__global__ void update_lambda1_kernel(double* l1, const double* G1, const double* G2mZ, int n, double lr, double scale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) l1[i] = (1.0 - lr) * l1[i] + lr * scale * (G1[i] - 2.0 * G2mZ[i]);
+}
+int update_lambda1_launch(double* l1, const double* G1, const double* G2mZ, int n, double lr, double scale, cudaStream_t s) {
+    update_lambda1_kernel<<<(n + 255) / 256, 256, 0, s>>>(l1, G1, G2mZ, n, lr, scale);
+    return count_launch();
+}
+__global__ void vsub_kernel(const double* a, const double* b, double* y, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = a[i] - b[i];
+}
+int vsub_launch(const double* a, const double* b, double* y, int n, cudaStream_t s) {
+    vsub_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, y, n);
+    return count_launch();
+}
+
+}  // namespace tsvgp

@@ -1,0 +1,81 @@
+// Non-GEMM kernels of the t-SVGP path: covariance tiles, per-point likelihood statistics, M-vector products,
+// diagonal-block factorisation, and small elementwise M x M utilities.  Launchers return cudaError_t as int.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace tsvgp {
+
+enum { KERN_SE = 0, KERN_MATERN52 = 1 };
+enum { LIK_GAUSSIAN = 0, LIK_BERNOULLI = 1, LIK_STUDENT_T = 2 };
+constexpr int MAX_GH = 64;
+
+struct LikSpec {
+    int kind = LIK_GAUSSIAN;
+    double p0 = 1.0;   // Gaussian: variance ; StudentT: scale
+    double p1 = 3.0;   // StudentT: df
+    double c0 = 0.0;   // StudentT: log-density constant
+    int n_gh = 20;
+};
+
+// Xs^T[d][n] = X[n][d] / ls[d]  (feature-major, leading dim ldx >= n_pad, columns n >= n zeroed) ; x2[n] = sum_d Xs^2
+int scale_points_launch(const double* X, long n, int D, const double* ls, double* XsT, long ldx, double* x2, long n_pad,
+                        cudaStream_t s);
+
+// K[i][c] = k(z_i, x_{n0+c}) for i < Mp, c < ncols (multiple of 128).  Rows i >= M and columns n0+c >= n_valid are zero,
+// or the identity (K[i][c] = (i == n0+c)) when pad_identity.  If alpha != null also writes
+// mu_part[i/64][c] = sum_{i in 64-row group} alpha[i] K[i][c].
+int kuf_launch(int kind, double variance, const double* XsT, long ldx, const double* x2, long n0, long n_valid, int ncols,
+               const double* ZsT_rows /*Zs [Mp][D]*/, const double* z2, int M, int Mp, int D, const double* alpha, double* K,
+               long ldk, double* mu_part, long ldmu, int pad_identity, cudaStream_t s);
+
+struct PointArgs {
+    const double* mu_part; int n_mu_part; long ldmu;   // partial means   [n_mu_part][ldmu]
+    const double* q_part; int n_q_part; long ldq;      // partial |T^T k|^2 [n_q_part][ldq]
+    const double* y;            // [ncols] (chunk-local pointer) or null (predict)
+    const double* mean_off;     // [ncols] mean_function(X) or null
+    double kdiag;               // k(x,x) = kernel variance
+    long n_valid;               // chunk-local number of real points (<= ncols)
+    int ncols;
+    double* g; double* h;       // out: d ve/d mean, clipped d ve/d var  (zero for padding columns), may be null
+    double* mean_out; double* var_out;   // out (predict), may be null; written only for c < n_valid
+    double* ve_blocks;          // out: per-block sum of ve   [gridDim.x]
+    int* flags;                 // flags[0] |= 1 if any var <= 0
+};
+struct GHTable { double z[MAX_GH]; double w[MAX_GH]; };   // nodes sqrt(2) x_k and weights w_k / sqrt(pi), passed by value
+int point_stats_launch(const LikSpec& lik, const PointArgs& a, const GHTable& gh, cudaStream_t s);
+
+// y[i] = alpha * sum_j A[i][j] x[j] + beta * y[i]      (row-major A [m][n], lda)
+int gemv_n_launch(const double* A, long lda, int m, long n, const double* x, double alpha, double beta, double* y, cudaStream_t s);
+// y[j] = sum_i A[i][j] x[i]   (uses work [nchunk][n]); deterministic two-stage
+int gemv_t_launch(const double* A, long lda, int m, int n, const double* x, double* y, double* work, cudaStream_t s);
+
+// Zs[i][d] = ZsT[d][i]  (row-major copy of the scaled inducing inputs, [Mp][D])
+int unpack_rows_launch(const double* ZsT, long ldz, int Mp, int D, double* Zs, cudaStream_t s);
+
+// --- diagonal blocks --------------------------------------------------------------------------------------------
+// In-place lower Cholesky of the 128x128 block at A (lda) and its inverse into Dinv (ld 128, dense lower).
+// info[0] = first failing global pivot index + 1 (blk_index*128 + k + 1), left untouched on success.
+int diag_potrf_inv_launch(double* A, long lda, double* Dinv, int blk_index, int* info, cudaStream_t s);
+// Dinv[b] = inverse of the lower-triangular 128x128 diagonal block b of L, b < nblk (batched)
+int diag_trtri_launch(const double* L, long lda, double* Dinv, int nblk, cudaStream_t s);
+
+// --- elementwise M x M utilities ---------------------------------------------------------------------------------
+int add_diag_launch(double* A, long lda, int n, double v, cudaStream_t s);
+int copy_add_diag_launch(const double* A, double* B, long ld, int n, double v, cudaStream_t s);           // B = A + v I
+int mirror_lower_launch(double* A, long lda, int n, cudaStream_t s);                                       // A[j][i] = A[i][j], i > j
+int flip_sym_launch(const double* W, double* Wf, long ld, int n, cudaStream_t s);                          // Wf[i][j] = W_sym[n-1-i][n-1-j], lower
+int antitranspose_launch(const double* Linv, double* V, long ld, int n, cudaStream_t s);                   // V[i][j] = Linv[n-1-j][n-1-i] (lower), upper zero
+int zero_upper_launch(double* A, long lda, int n, cudaStream_t s);
+int finalize_sites_launch(const double* P, double* L2, long ld, int M, int Mp, cudaStream_t s);            // L2 = -tril(P) on [0,M)^2, 0 elsewhere
+int place_block_launch(const double* src, long lds, double* dst, long ldd, int rows, int cols, cudaStream_t s);  // dst[0:rows,0:cols] = src
+int copy_lower_launch(const double* src, long lds, int M, double* dst, long ldd, int Mp, cudaStream_t s);  // dst = [[tril(src),0],[0,0]]
+// scalars: out[0] = sum_ij A^2 ; out[1] = sum_i log(diag A) ; single block, deterministic
+int frob_logdiag_launch(const double* A, long lda, int n, double* out, cudaStream_t s);
+int dot_launch(const double* x, const double* y, int n, double* out, cudaStream_t s);
+int sum_launch(const double* x, long n, double* out, cudaStream_t s);
+// lambda_1 <- (1-lr) lambda_1 + lr*scale*(G1 - 2 G2mZ)
+int update_lambda1_launch(double* l1, const double* G1, const double* G2mZ, int n, double lr, double scale, cudaStream_t s);
+// y = a - b
+int vsub_launch(const double* a, const double* b, double* y, int n, cudaStream_t s);
+
+}  // namespace tsvgp
