@@ -28,6 +28,11 @@ extern "C" {
 #endif
 
 #define TSVGP_ABI_VERSION 1
+#if defined(__GNUC__)
+#define TSVGP_API __attribute__((visibility("default")))
+#else
+#define TSVGP_API
+#endif
 
 enum {
     TSVGP_OK = 0,
@@ -47,59 +52,64 @@ enum { TSVGP_LIK_GAUSSIAN = 0, TSVGP_LIK_BERNOULLI_PROBIT = 1, TSVGP_LIK_STUDENT
 typedef struct tsvgp_ctx tsvgp_ctx;   /* opaque: owns one CUDA stream, device buffers, optional NCCL communicator */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------- */
-int tsvgp_abi_version(void);
-int tsvgp_create(tsvgp_ctx** out, int device_id);          /* replaces t_SVGP.__init__ (tsvgp.py:122-157) device side    */
-void tsvgp_destroy(tsvgp_ctx* ctx);
-const char* tsvgp_last_error(const tsvgp_ctx* ctx);        /* ctx may be NULL: message of the last failed tsvgp_create    */
-int tsvgp_last_info(const tsvgp_ctx* ctx);                 /* failing pivot of the last TSVGP_ERR_NOT_POSITIVE_DEFINITE   */
-int tsvgp_set_option(tsvgp_ctx* ctx, const char* name, double value);   /* "chunk" (points per on-chip Kuf slab), "profile" */
+TSVGP_API int tsvgp_abi_version(void);
+TSVGP_API int tsvgp_create(tsvgp_ctx** out, int device_id);          /* replaces t_SVGP.__init__ (tsvgp.py:122-157) device side    */
+TSVGP_API void tsvgp_destroy(tsvgp_ctx* ctx);
+TSVGP_API const char* tsvgp_last_error(const tsvgp_ctx* ctx);        /* ctx may be NULL: message of the last failed tsvgp_create    */
+TSVGP_API int tsvgp_last_info(const tsvgp_ctx* ctx);                 /* failing pivot of the last TSVGP_ERR_NOT_POSITIVE_DEFINITE   */
+TSVGP_API int tsvgp_set_option(tsvgp_ctx* ctx, const char* name, double value);   /* see below */
+
+/* options: "chunk" (points per Kuf slab; 0 = automatic, ~32 MB slabs that stay in L2), "streams" (1|2 ping-pong streams),
+ * "cache_factors" (1 = keep chol(Kuu+jitter I) and the posterior factors while kernel, Z and sites are unchanged),
+ * "invalidate" (any value: drop every cached factor now)                                                              */
 
 /* ---- model objects read by the path (tsvgp.py:209,268-269; GPflow kernel / likelihood / inducing attributes) ------ */
 /* lengthscales: HOST pointer, n_ls = 1 (isotropic) or D (ARD)                                                          */
-int tsvgp_set_kernel(tsvgp_ctx* ctx, int kind, double variance, const double* lengthscales, int n_ls);
+TSVGP_API int tsvgp_set_kernel(tsvgp_ctx* ctx, int kind, double variance, const double* lengthscales, int n_ls);
 /* Gaussian: p0 = variance.  StudentT: p0 = scale, p1 = df.  Bernoulli: inv_probit link with GPflow's 1e-3 jitter.
  * n_gh Gauss-Hermite points (<= 64; GPflow default 20); gh_x/gh_w (HOST, numpy.polynomial.hermite.hermgauss order)
  * may be NULL, in which case the library generates them.                                                               */
-int tsvgp_set_likelihood(tsvgp_ctx* ctx, int kind, double p0, double p1, int n_gh, const double* gh_x, const double* gh_w);
+TSVGP_API int tsvgp_set_likelihood(tsvgp_ctx* ctx, int kind, double p0, double p1, int n_gh, const double* gh_x, const double* gh_w);
 /* Z [M, D] inducing inputs (inducing_variable.Z); mean_Z [M] = mean_function(Z) or NULL for the Zero mean function     */
-int tsvgp_set_inducing(tsvgp_ctx* ctx, const double* Z, int M, int D, const double* mean_Z);
+TSVGP_API int tsvgp_set_inducing(tsvgp_ctx* ctx, const double* Z, int M, int D, const double* mean_Z);
 
 /* ---- DenseSites state (src/sites.py:43-80): lambda_1 [M], lambda_2_sqrt [M, M] lower triangular -------------------- */
 /* NULL lambda_1 / lambda_2_sqrt = the reference defaults 0 and -1e-10 * I (tsvgp.py:174-180). Upper triangle ignored.  */
-int tsvgp_set_sites(tsvgp_ctx* ctx, const double* lambda_1, const double* lambda_2_sqrt);
-int tsvgp_get_sites(tsvgp_ctx* ctx, double* lambda_1, double* lambda_2_sqrt);     /* either may be NULL                  */
-int tsvgp_get_lambda_2(tsvgp_ctx* ctx, double* lambda_2);                          /* L2 L2^T (tsvgp.py:197-200)          */
+TSVGP_API int tsvgp_set_sites(tsvgp_ctx* ctx, const double* lambda_1, const double* lambda_2_sqrt);
+TSVGP_API int tsvgp_get_sites(tsvgp_ctx* ctx, double* lambda_1, double* lambda_2_sqrt);     /* either may be NULL                  */
+TSVGP_API int tsvgp_get_lambda_2(tsvgp_ctx* ctx, double* lambda_2);                          /* L2 L2^T (tsvgp.py:197-200)          */
 
 /* ---- data: this rank's rows of the minibatch ------------------------------------------------------------------------ */
 /* X [N, D], Y [N] (= [N,1]), mean_X [N] = mean_function(X) or NULL. Host data is copied; device data is aliased.        */
-int tsvgp_set_data(tsvgp_ctx* ctx, const double* X, const double* Y, int64_t N, int D, const double* mean_X);
+TSVGP_API int tsvgp_set_data(tsvgp_ctx* ctx, const double* X, const double* Y, int64_t N, int D, const double* mean_X);
 
 /* ---- the hot path ----------------------------------------------------------------------------------------------------- */
 /* t_SVGP.natgrad_step (tsvgp.py:234-304) on the resident data and sites.  scale = num_data / minibatch_size or 1
  * (tsvgp.py:286-291) with minibatch_size summed over ranks.  elbo_before (may be NULL) receives the ELBO of the
  * pre-update state on the same minibatch (a by-product of the same pass).                                              */
-int tsvgp_natgrad_step(tsvgp_ctx* ctx, double lr, double jitter, double scale, double* elbo_before);
+TSVGP_API int tsvgp_natgrad_step(tsvgp_ctx* ctx, double lr, double jitter, double scale, double* elbo_before);
 /* base_SVGP.elbo (tsvgp.py:79-95) on the resident data                                                                 */
-int tsvgp_elbo(tsvgp_ctx* ctx, double scale, double* out);
+TSVGP_API int tsvgp_elbo(tsvgp_ctx* ctx, double scale, double* out);
+/* base_SVGP.prior_kl (tsvgp.py:65-70): KL[q(u) || p(u)] of the current sites                                            */
+TSVGP_API int tsvgp_prior_kl(tsvgp_ctx* ctx, double* out);
 /* base_SVGP.predict_f, full_cov = False (tsvgp.py:97-114): mean_out, var_out [N]                                        */
-int tsvgp_predict_f(tsvgp_ctx* ctx, const double* Xnew, int64_t N, int D, const double* mean_X, double* mean_out, double* var_out);
+TSVGP_API int tsvgp_predict_f(tsvgp_ctx* ctx, const double* Xnew, int64_t N, int D, const double* mean_X, double* mean_out, double* var_out);
 /* t_SVGP.get_mean_chol_cov_inducing_posterior (tsvgp.py:202-212): m [M], chol_S [M, M]                                  */
-int tsvgp_posterior(tsvgp_ctx* ctx, double* m, double* chol_S);
+TSVGP_API int tsvgp_posterior(tsvgp_ctx* ctx, double* m, double* chol_S);
 
 /* ---- multi-GPU: one context per rank, rows of the minibatch sharded over ranks, one all-reduce of the statistics ---- */
-int tsvgp_comm_unique_id(void* id_out_128_bytes);                                   /* ncclGetUniqueId                     */
-int tsvgp_comm_init(tsvgp_ctx* ctx, int world_size, int rank, const void* id_128_bytes);
-int tsvgp_comm_size(const tsvgp_ctx* ctx);
+TSVGP_API int tsvgp_comm_unique_id(void* id_out_128_bytes);                                   /* ncclGetUniqueId                     */
+TSVGP_API int tsvgp_comm_init(tsvgp_ctx* ctx, int world_size, int rank, const void* id_128_bytes);
+TSVGP_API int tsvgp_comm_size(const tsvgp_ctx* ctx);
 
 /* ---- measurement ------------------------------------------------------------------------------------------------------ */
 /* CUDA-event durations (ms) of the last natgrad_step, on the context's stream.  out[0..n):
- *  0 total, 1 prepare (posterior factors), 2 streaming pass, 3 all-reduce, 4 dense update,
- *  with option "profile"=1 also 5 Kuf tiles, 6 variance product, 7 point statistics, 8 weighted SYRK, 9 Kuf*g,
- *  10 number of slabs, 11 kernels launched                                                                              */
-int tsvgp_get_timings(tsvgp_ctx* ctx, double* out, int n);
-int tsvgp_sync(tsvgp_ctx* ctx);
-void* tsvgp_pinned_alloc(size_t bytes);                                             /* cudaHostAlloc, for staging buffers  */
-void tsvgp_pinned_free(void* p);
+ *  0 total, 1 prepare (posterior factors), 2 streaming pass, 3 all-reduce, 4 dense update, 5 number of slabs,
+ *  6 kernels launched by the step                                                                                       */
+TSVGP_API int tsvgp_get_timings(tsvgp_ctx* ctx, double* out, int n);
+TSVGP_API int tsvgp_sync(tsvgp_ctx* ctx);
+TSVGP_API void* tsvgp_pinned_alloc(size_t bytes);                                             /* cudaHostAlloc, for staging buffers  */
+TSVGP_API void tsvgp_pinned_free(void* p);
 
 /* ---- DLPack hand-over ---------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -111,7 +121,7 @@ typedef struct {
 } tsvgp_view;
 /* Validates a `DLManagedTensor*` (float64, <= 3-D, compact row-major) taken from a "dltensor" capsule and describes it.
  * The capsule is only borrowed: the library neither renames it nor calls its deleter.                                   */
-int tsvgp_dlpack_view(const void* dl_managed_tensor, tsvgp_view* out);
+TSVGP_API int tsvgp_dlpack_view(const void* dl_managed_tensor, tsvgp_view* out);
 
 #ifdef __cplusplus
 }

@@ -283,6 +283,7 @@ int gemv_t_launch(const double* A, long lda, int m, int n, const double* x, doub
     dim3 grid((n + 127) / 128, nchunk);
     gemv_t_part_kernel<<<grid, 128, 0, s>>>(A, lda, m, n, x, work);
     gemv_t_sum_kernel<<<(n + 255) / 256, 256, 0, s>>>(work, nchunk, n, y);
+    ++g_launches;
     return count_launch();
 }
 
@@ -464,13 +465,14 @@ int zero_upper_launch(double* A, long lda, int n, cudaStream_t s) {
     zero_upper_kernel<<<EW_GRID(n), 0, s>>>(A, lda, n);
     return count_launch();
 }
-__global__ void finalize_sites_kernel(const double* P, double* L2, long ld, int M, int n) {
+__global__ void finalize_sites_kernel(const double* P, double* L2, long ld, int M, int n, const double* bad, const int* info) {
     EW_IJ;
+    if ((bad && bad[0] != 0.0) || (info && (info[0] | info[1] | info[2] | info[3]))) return;   // failed step: the sites stay as they were
     L2[(long)i * ld + j] = (j <= i && i < M) ? -P[(long)i * ld + j] : 0.0;
 }
-int finalize_sites_launch(const double* P, double* L2, long ld, int M, int Mp, cudaStream_t s) {
+int finalize_sites_launch(const double* P, double* L2, long ld, int M, int Mp, const double* bad, const int* info, cudaStream_t s) {
     const int n = Mp;
-    finalize_sites_kernel<<<EW_GRID(n), 0, s>>>(P, L2, ld, M, Mp);
+    finalize_sites_kernel<<<EW_GRID(n), 0, s>>>(P, L2, ld, M, Mp, bad, info);
     return count_launch();
 }
 __global__ void place_block_kernel(const double* src, long lds, double* dst, long ldd, int rows, int cols) {
@@ -537,6 +539,7 @@ int frob_logdiag_launch(const double* A, long lda, int n, double* out, cudaStrea
     if (!part) return -1;
     frob_part_kernel<<<RED_BLOCKS, 256, 0, s>>>(A, lda, n, part);
     frob_logdiag_finish_kernel<<<1, 256, 0, s>>>(A, lda, n, part, out);
+    ++g_launches;
     return count_launch();
 }
 __global__ void __launch_bounds__(256) dot_kernel(const double* x, const double* y, int n, double* out) {
@@ -561,12 +564,15 @@ int sum_launch(const double* x, long n, double* out, cudaStream_t s) {
     sum_kernel<<<1, 256, 0, s>>>(x, n, out);
     return count_launch();
 }
-__global__ void update_lambda1_kernel(double* l1, const double* G1, const double* G2mZ, int n, double lr, double scale) {
+__global__ void update_lambda1_kernel(double* l1, const double* G1, const double* G2mZ, int n, double lr, double scale,
+                                      const double* bad, const int* info) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((bad && bad[0] != 0.0) || (info && (info[0] | info[1] | info[2] | info[3]))) return;
     if (i < n) l1[i] = (1.0 - lr) * l1[i] + lr * scale * (G1[i] - 2.0 * G2mZ[i]);
 }
-int update_lambda1_launch(double* l1, const double* G1, const double* G2mZ, int n, double lr, double scale, cudaStream_t s) {
-    update_lambda1_kernel<<<(n + 255) / 256, 256, 0, s>>>(l1, G1, G2mZ, n, lr, scale);
+int update_lambda1_launch(double* l1, const double* G1, const double* G2mZ, int n, double lr, double scale, const double* bad,
+                          const int* info, cudaStream_t s) {
+    update_lambda1_kernel<<<(n + 255) / 256, 256, 0, s>>>(l1, G1, G2mZ, n, lr, scale, bad, info);
     return count_launch();
 }
 __global__ void vsub_kernel(const double* a, const double* b, double* y, int n) {
@@ -575,6 +581,87 @@ __global__ void vsub_kernel(const double* a, const double* b, double* y, int n) 
 }
 int vsub_launch(const double* a, const double* b, double* y, int n, cudaStream_t s) {
     vsub_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, y, n);
+    return count_launch();
+}
+
+
+// out[0] = sum_ij A[i][j] * B[i][j] over the n x n leading block (deterministic two-stage)
+__global__ void __launch_bounds__(256) matdot_part_kernel(const double* A, const double* B, long ld, int n, double* part) {
+    __shared__ double sred[8];
+    double s = 0.0;
+    const long total = (long)n * n;
+    for (long e = (long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long)RED_BLOCKS * 256) {
+        const long o = (e / n) * ld + (e % n);
+        s = fma(A[o], B[o], s);
+    }
+    s = block_sum_256(s, sred);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) sum_parts_kernel(const double* part, double* out) {
+    __shared__ double sred[8];
+    double s = threadIdx.x < RED_BLOCKS ? part[threadIdx.x] : 0.0;
+    s = block_sum_256(s, sred);
+    if (threadIdx.x == 0) out[0] = s;
+}
+int matdot_launch(const double* A, const double* B, long ld, int n, double* out, cudaStream_t s) {
+    double* part = red_scratch();
+    if (!part) return -1;
+    matdot_part_kernel<<<RED_BLOCKS, 256, 0, s>>>(A, B, ld, n, part);
+    sum_parts_kernel<<<1, 256, 0, s>>>(part, out);
+    ++g_launches;
+    return count_launch();
+}
+__global__ void __launch_bounds__(256) logdiag_kernel(const double* A, long lda, int n, double* out) {
+    __shared__ double sred[8];
+    double l = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) l += log(A[(long)i * lda + i]);
+    l = block_sum_256(l, sred);
+    if (threadIdx.x == 0) out[0] = l;
+}
+int logdiag_launch(const double* A, long lda, int n, double* out, cudaStream_t s) {
+    logdiag_kernel<<<1, 256, 0, s>>>(A, lda, n, out);
+    return count_launch();
+}
+// P = coef * G on [0,M)^2 plus jitter on its diagonal; identity on the padding block [M,n)
+__global__ void init_update_kernel(const double* G, double* P, long ld, int M, int n, double coef, double jitter) {
+    EW_IJ;
+    double v;
+    if (i < M && j < M) v = coef * G[(long)i * ld + j] + (i == j ? jitter : 0.0);
+    else v = i == j ? 1.0 : 0.0;
+    P[(long)i * ld + j] = v;
+}
+int init_update_launch(const double* G, double* P, long ld, int M, int Mp, double coef, double jitter, cudaStream_t s) {
+    const int n = Mp;
+    init_update_kernel<<<EW_GRID(n), 0, s>>>(G, P, ld, M, Mp, coef, jitter);
+    return count_launch();
+}
+__global__ void set_scaled_identity_kernel(double* A, long ld, int M, int n, double v, double vpad) {
+    EW_IJ;
+    A[(long)i * ld + j] = i == j ? (i < M ? v : vpad) : 0.0;
+}
+int set_scaled_identity_launch(double* A, long ld, int M, int Mp, double v, double vpad, cudaStream_t s) {
+    const int n = Mp;
+    set_scaled_identity_kernel<<<EW_GRID(n), 0, s>>>(A, ld, M, Mp, v, vpad);
+    return count_launch();
+}
+__global__ void vadd_inplace_kernel(double* dst, const double* src, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+int vadd_inplace_launch(double* dst, const double* src, long n, cudaStream_t s) {
+    vadd_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, src, n);
+    return count_launch();
+}
+// stats tail: out[0] = sum of ve partials, out[1] = flags[0] as a double
+__global__ void __launch_bounds__(256) stats_tail_kernel(const double* ve_blocks, long nblocks, const int* flags, double* out) {
+    __shared__ double sred[8];
+    double s = 0.0;
+    for (long i = threadIdx.x; i < nblocks; i += 256) s += ve_blocks[i];
+    s = block_sum_256(s, sred);
+    if (threadIdx.x == 0) { out[0] = s; out[1] = flags[0] ? 1.0 : 0.0; }
+}
+int stats_tail_launch(const double* ve_blocks, long nblocks, const int* flags, double* out, cudaStream_t s) {
+    stats_tail_kernel<<<1, 256, 0, s>>>(ve_blocks, nblocks, flags, out);
     return count_launch();
 }
 

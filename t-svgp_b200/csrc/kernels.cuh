@@ -66,7 +66,8 @@ int mirror_lower_launch(double* A, long lda, int n, cudaStream_t s);            
 int flip_sym_launch(const double* W, double* Wf, long ld, int n, cudaStream_t s);                          // Wf[i][j] = W_sym[n-1-i][n-1-j], lower
 int antitranspose_launch(const double* Linv, double* V, long ld, int n, cudaStream_t s);                   // V[i][j] = Linv[n-1-j][n-1-i] (lower), upper zero
 int zero_upper_launch(double* A, long lda, int n, cudaStream_t s);
-int finalize_sites_launch(const double* P, double* L2, long ld, int M, int Mp, cudaStream_t s);            // L2 = -tril(P) on [0,M)^2, 0 elsewhere
+// L2 = -tril(P) on [0,M)^2, 0 elsewhere — skipped on the device when *bad != 0 or any of info[0..3] != 0 (failed step keeps old sites)
+int finalize_sites_launch(const double* P, double* L2, long ld, int M, int Mp, const double* bad, const int* info, cudaStream_t s);
 int place_block_launch(const double* src, long lds, double* dst, long ldd, int rows, int cols, cudaStream_t s);  // dst[0:rows,0:cols] = src
 int copy_lower_launch(const double* src, long lds, int M, double* dst, long ldd, int Mp, cudaStream_t s);  // dst = [[tril(src),0],[0,0]]
 // scalars: out[0] = sum_ij A^2 ; out[1] = sum_i log(diag A) ; single block, deterministic
@@ -74,8 +75,17 @@ int frob_logdiag_launch(const double* A, long lda, int n, double* out, cudaStrea
 int dot_launch(const double* x, const double* y, int n, double* out, cudaStream_t s);
 int sum_launch(const double* x, long n, double* out, cudaStream_t s);
 // lambda_1 <- (1-lr) lambda_1 + lr*scale*(G1 - 2 G2mZ)
-int update_lambda1_launch(double* l1, const double* G1, const double* G2mZ, int n, double lr, double scale, cudaStream_t s);
+int update_lambda1_launch(double* l1, const double* G1, const double* G2mZ, int n, double lr, double scale, const double* bad,
+                          const int* info, cudaStream_t s);
 // y = a - b
 int vsub_launch(const double* a, const double* b, double* y, int n, cudaStream_t s);
+
+int matdot_launch(const double* A, const double* B, long ld, int n, double* out, cudaStream_t s);   // sum_ij A_ij B_ij
+int logdiag_launch(const double* A, long lda, int n, double* out, cudaStream_t s);                  // sum_i log A_ii
+// P = coef*G + jitter*I on [0,M)^2, identity on the padding block
+int init_update_launch(const double* G, double* P, long ld, int M, int Mp, double coef, double jitter, cudaStream_t s);
+int set_scaled_identity_launch(double* A, long ld, int M, int Mp, double v, double vpad, cudaStream_t s);
+int vadd_inplace_launch(double* dst, const double* src, long n, cudaStream_t s);
+int stats_tail_launch(const double* ve_blocks, long nblocks, const int* flags, double* out, cudaStream_t s);
 
 }  // namespace tsvgp

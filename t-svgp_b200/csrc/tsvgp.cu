@@ -1,0 +1,986 @@
+// libtsvgp.so — C ABI (include/tsvgp.h) and step orchestration of the t-SVGP natural-gradient path on one B200.
+//
+// What one natgrad_step does on the device (reference: src/models/tsvgp.py:234-304, src/util.py:349-391; algebra in
+// DESIGN.md):
+//   prepare : K = k(Z,Z), K6 = K + 1e-6 I; W = I + L2^T K6 L2; reverse Cholesky W = Uw Uw^T; T = L2 Uw^-T (lower);
+//             alpha = lambda_1 - T T^T K6 lambda_1 (= K6^-1 m_q); mZ = K alpha                      [M x M work]
+//   stream  : per slab of `chunk` points, on two alternating streams:
+//               Kuf slab + partial means  ->  |T^T k_n|^2 by a triangular DMMA product with a column-norm epilogue
+//               -> per-point likelihood statistics (g_n, h_n, ve_n)  ->  B += Kuf diag(h) Kfu (DMMA SYRK), b += Kuf g
+//   reduce  : one all-reduce (NCCL) of [B | b | sum ve | flag] when the minibatch is sharded over ranks
+//   update  : G2 = K9^-1 B K9^-1, G1 = K9^-1 b, lambda_1, P = (1-lr) L2 L2^T - 2 lr s G2 + jitter I, L2 = -chol(P)
+// There is no CPU path: every entry point that computes needs a CUDA device.
+#include "../../include/tsvgp.h"
+#include "common.cuh"
+#include "dense.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+#include "nccl_dyn.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+namespace tsvgp {
+thread_local long g_launches = 0;
+}
+using namespace tsvgp;
+
+namespace {
+
+thread_local std::string g_create_error;
+constexpr double GPFLOW_DEFAULT_JITTER = 1e-6;   // gpflow.config.default_jitter() (GPflow 2.2.1), tsvgp.py:209-211
+
+inline long round_up(long v, long m) { return (v + m - 1) / m * m; }
+
+struct Pool {
+    std::vector<void*> ptrs;
+    cudaError_t last = cudaSuccess;
+    double* get(size_t n_doubles) {
+        void* p = nullptr;
+        last = cudaMalloc(&p, (n_doubles ? n_doubles : 1) * sizeof(double));
+        if (last != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        return (double*)p;
+    }
+    void release() {
+        for (void* p : ptrs) cudaFree(p);
+        ptrs.clear();
+    }
+};
+
+enum { MODE_STATS = 0, MODE_ELBO = 1, MODE_PREDICT = 2 };
+enum { INFO_W = 0, INFO_K9 = 1, INFO_P = 2, INFO_S = 3, N_INFO = 4 };
+enum { EV_T0 = 0, EV_PREP, EV_STREAM, EV_REDUCE, EV_DENSE, N_EV };
+// device scalars
+enum { SC_LOGDIAG_W = 0, SC_M_ALPHA, SC_TR_QK, N_SCAL = 8 };
+
+}  // namespace
+
+struct tsvgp_ctx {
+    int dev = 0;
+    cudaStream_t s_main = nullptr, s_pp[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev[N_EV] = {};
+    std::string err;
+    int last_info = 0;
+
+    // options
+    long chunk_opt = 0;        // 0 = automatic
+    int n_streams = 2;
+    int cache_factors = 1;     // keep chol(K9) and the posterior factors between calls while their inputs are unchanged
+
+    // kernel / likelihood
+    int kern_kind = -1;
+    double kern_var = 1.0;
+    std::vector<double> ls_host;
+    LikSpec lik;
+    GHTable gh;
+    bool lik_set = false;
+
+    // inducing points and M x M state
+    int M = 0, Mp = 0, D = 0;
+    Pool pm;
+    double *Zraw = nullptr, *ZsT = nullptr, *Zs = nullptr, *z2 = nullptr, *ls_dev = nullptr, *meanZ_off = nullptr;
+    bool has_meanZ = false;
+    double *K = nullptr, *K6 = nullptr, *L2 = nullptr, *lam1 = nullptr;
+    double *Wm = nullptr, *Wf = nullptr, *V = nullptr, *T = nullptr, *X1 = nullptr, *X2 = nullptr, *C9 = nullptr, *C9inv = nullptr;
+    double *G2 = nullptr, *P = nullptr, *tmp = nullptr, *dinv = nullptr;
+    double *stats[2] = {nullptr, nullptr};   // [B (Mp*Mp) | b (Mp) | tail (4)] per ping-pong stream
+    double *alpha = nullptr, *mZ = nullptr, *mq = nullptr, *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *gwork = nullptr;
+    double *scal = nullptr;
+    int* info = nullptr;    // [N_INFO]
+    int* flags = nullptr;   // [2]
+    bool sites_set = false, kuu_valid = false, post_valid = false, kl_valid = false, k9_valid = false;
+    double k9_jitter = 0.0;
+    double kl_host = 0.0;
+
+    // data (this rank's rows)
+    Pool pd;
+    long N = 0, n_pad = 0;
+    int dataD = 0;
+    const double *X = nullptr, *Y = nullptr, *meanX = nullptr;
+    double *Xown = nullptr, *Yown = nullptr, *meanXown = nullptr;
+    long cap_x = 0, cap_n = 0;
+    double *XsT = nullptr, *x2 = nullptr;
+    long cap_xs = 0;
+    bool xs_valid = false;
+
+    // slab workspace
+    Pool pc;
+    long chunk = 0;
+    int chunk_Mp = 0;
+    double *slab[2] = {}, *mu_part[2] = {}, *q_part[2] = {}, *gbuf[2] = {}, *hbuf[2] = {};
+    double* ve_blocks = nullptr;
+    long ve_cap = 0;
+
+    // multi-GPU
+    NcclComm comm = nullptr;
+    int world = 1, rank = 0;
+
+    double timings[16] = {};
+};
+
+namespace {
+
+#define FAIL(code, ...)                                   \
+    do {                                                  \
+        char b_[512];                                     \
+        snprintf(b_, sizeof b_, __VA_ARGS__);             \
+        c->err = b_;                                      \
+        return (code);                                    \
+    } while (0)
+#define CU(x)                                                                                            \
+    do {                                                                                                 \
+        cudaError_t e_ = (x);                                                                            \
+        if (e_ != cudaSuccess) FAIL(TSVGP_ERR_CUDA, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define LA(x)                                                                                                      \
+    do {                                                                                                           \
+        int e_ = (x);                                                                                              \
+        if (e_ > 0) FAIL(TSVGP_ERR_CUDA, "%s: %s (%s:%d)", #x, cudaGetErrorString((cudaError_t)e_), __FILE__, __LINE__); \
+        if (e_ < 0) FAIL(TSVGP_ERR_INVALID, "%s: unsupported launch configuration (%s:%d)", #x, __FILE__, __LINE__); \
+    } while (0)
+#define OK(x)                    \
+    do {                         \
+        int r_ = (x);            \
+        if (r_ != TSVGP_OK) return r_; \
+    } while (0)
+#define NEED(p)                                                               \
+    do {                                                                      \
+        if (!(p)) FAIL(TSVGP_ERR_CUDA, "device allocation failed (%s:%d)", __FILE__, __LINE__); \
+    } while (0)
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---- M-dependent state ----------------------------------------------------------------------------------------------
+int alloc_m_state(tsvgp_ctx* c, int M, int D) {
+    c->pm.release();
+    c->M = M; c->D = D; c->Mp = (int)round_up(M, TSVGP_TILE);
+    const size_t mm = (size_t)c->Mp * c->Mp, mp = c->Mp;
+    Pool& p = c->pm;
+    NEED(c->Zraw = p.get((size_t)M * D)); NEED(c->ZsT = p.get((size_t)D * mp)); NEED(c->Zs = p.get(mp * D));
+    NEED(c->z2 = p.get(mp)); NEED(c->ls_dev = p.get(D)); NEED(c->meanZ_off = p.get(mp));
+    NEED(c->K = p.get(mm)); NEED(c->K6 = p.get(mm)); NEED(c->L2 = p.get(mm)); NEED(c->lam1 = p.get(mp));
+    NEED(c->Wm = p.get(mm)); NEED(c->Wf = p.get(mm)); NEED(c->V = p.get(mm)); NEED(c->T = p.get(mm));
+    NEED(c->X1 = p.get(mm)); NEED(c->X2 = p.get(mm)); NEED(c->C9 = p.get(mm)); NEED(c->C9inv = p.get(mm));
+    NEED(c->G2 = p.get(mm)); NEED(c->P = p.get(mm)); NEED(c->tmp = p.get(mm / 2 + mp)); NEED(c->dinv = p.get((size_t)(c->Mp / 128) * 128 * 128));
+    for (int s = 0; s < 2; ++s) NEED(c->stats[s] = p.get(mm + mp + 4));
+    NEED(c->alpha = p.get(mp)); NEED(c->mZ = p.get(mp)); NEED(c->mq = p.get(mp)); NEED(c->v1 = p.get(mp)); NEED(c->v2 = p.get(mp));
+    NEED(c->v3 = p.get(mp)); NEED(c->gwork = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal = p.get(N_SCAL));
+    NEED(c->info = (int*)p.get(N_INFO)); NEED(c->flags = (int*)p.get(2));
+    c->sites_set = c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = false;
+    c->chunk = 0;   // slab workspace depends on Mp
+    return TSVGP_OK;
+}
+
+int default_sites(tsvgp_ctx* c) {   // tsvgp.py:174-180 : lambda_1 = 0, lambda_2_sqrt = -1e-10 I
+    CU(cudaMemsetAsync(c->lam1, 0, sizeof(double) * c->Mp, c->s_main));
+    LA(set_scaled_identity_launch(c->L2, c->Mp, c->M, c->Mp, -1e-10, 0.0, c->s_main));
+    c->sites_set = true;
+    c->post_valid = c->kl_valid = false;
+    return TSVGP_OK;
+}
+
+int upload_lengthscales(tsvgp_ctx* c) {
+    if (c->kern_kind < 0) FAIL(TSVGP_ERR_STATE, "kernel not set (tsvgp_set_kernel)");
+    if (c->D <= 0) FAIL(TSVGP_ERR_STATE, "inducing points not set (tsvgp_set_inducing)");
+    if (c->ls_host.size() != 1 && (int)c->ls_host.size() != c->D)
+        FAIL(TSVGP_ERR_INVALID, "lengthscales has %zu entries, expected 1 or D=%d", c->ls_host.size(), c->D);
+    std::vector<double> ls(c->D);
+    for (int d = 0; d < c->D; ++d) ls[d] = c->ls_host.size() == 1 ? c->ls_host[0] : c->ls_host[d];
+    CU(cudaMemcpyAsync(c->ls_dev, ls.data(), sizeof(double) * c->D, cudaMemcpyHostToDevice, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));   // `ls` is a stack temporary
+    return TSVGP_OK;
+}
+
+// K = k(Z,Z) (identity on the padding block), K6 = K + default_jitter I            tsvgp.py:209-211, :268
+int ensure_kuu(tsvgp_ctx* c) {
+    if (c->kuu_valid) return TSVGP_OK;
+    if (c->M <= 0) FAIL(TSVGP_ERR_STATE, "inducing points not set (tsvgp_set_inducing)");
+    OK(upload_lengthscales(c));
+    cudaStream_t s = c->s_main;
+    LA(scale_points_launch(c->Zraw, c->M, c->D, c->ls_dev, c->ZsT, c->Mp, c->z2, c->Mp, s));
+    LA(unpack_rows_launch(c->ZsT, c->Mp, c->Mp, c->D, c->Zs, s));
+    LA(kuf_launch(c->kern_kind, c->kern_var, c->ZsT, c->Mp, c->z2, 0, c->M, c->Mp, c->Zs, c->z2, c->M, c->Mp, c->D, nullptr,
+                  c->K, c->Mp, nullptr, 0, 1, s));
+    LA(copy_add_diag_launch(c->K, c->K6, c->Mp, c->Mp, GPFLOW_DEFAULT_JITTER, s));
+    c->kuu_valid = true;
+    c->post_valid = c->kl_valid = c->k9_valid = false;
+    return TSVGP_OK;
+}
+
+// Posterior factors of q(u) from the dense sites (replaces posterior_from_dense_site, util.py:349-391, and the
+// conditional's use of it, tsvgp.py:102-112): T, alpha, mZ, log det W.
+int ensure_posterior(tsvgp_ctx* c) {
+    OK(ensure_kuu(c));
+    if (c->post_valid && c->cache_factors) return TSVGP_OK;
+    if (!c->sites_set) OK(default_sites(c));
+    cudaStream_t s = c->s_main;
+    const int n = c->Mp;
+    const long ld = c->Mp;
+    {   // X1 = K6 L2
+        GemmP p;
+        p.A = c->K6; p.lda = ld; p.a_kc = 1;
+        p.B = c->L2; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
+        p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
+        LA(gemm_launch(p, s));
+    }
+    LA(set_scaled_identity_launch(c->Wm, ld, n, n, 1.0, 1.0, s));
+    {   // W = I + L2^T X1 (lower tiles)
+        GemmP p;
+        p.A = c->L2; p.lda = ld; p.a_kc = 0; p.a_tri = 2;
+        p.B = c->X1; p.ldb = ld; p.b_kc = 0;
+        p.C = c->Wm; p.ldc = ld; p.m = p.n = p.k = n;
+        p.beta = 1.0; p.lower_out = 1;
+        LA(gemm_launch(p, s));
+    }
+    // reverse Cholesky W = Uw Uw^T through the index flip J W J = Lr Lr^T
+    LA(flip_sym_launch(c->Wm, c->Wf, ld, n, s));
+    LA(chol_lower(c->Wf, ld, n, c->dinv, c->info + INFO_W, s));
+    LA(logdiag_launch(c->Wf, ld, n, c->scal + SC_LOGDIAG_W, s));
+    LA(trtri_lower(c->Wf, ld, n, c->dinv, c->X2, c->tmp, s));
+    LA(antitranspose_launch(c->X2, c->V, ld, n, s));   // V = Uw^-T (lower)
+    CU(cudaMemsetAsync(c->T, 0, sizeof(double) * (size_t)n * ld, s));
+    {   // T = L2 V  (lower x lower)
+        GemmP p;
+        p.A = c->L2; p.lda = ld; p.a_kc = 1; p.a_tri = 1;
+        p.B = c->V; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
+        p.C = c->T; p.ldc = ld; p.m = p.n = p.k = n;
+        p.lower_out = 1;
+        LA(gemm_launch(p, s));
+    }
+    // alpha = lambda_1 - T T^T K6 lambda_1
+    LA(gemv_n_launch(c->K6, ld, n, n, c->lam1, 1.0, 0.0, c->v1, s));
+    LA(gemv_t_launch(c->T, ld, n, n, c->v1, c->v2, c->gwork, s));
+    LA(gemv_n_launch(c->T, ld, n, n, c->v2, 1.0, 0.0, c->v3, s));
+    LA(vsub_launch(c->lam1, c->v3, c->alpha, n, s));
+    // m_q = K6 alpha ; mZ = K alpha (+ mean_function(Z))   — predict_f(Z) of tsvgp.py:249-254 uses the un-jittered K
+    LA(gemv_n_launch(c->K6, ld, n, n, c->alpha, 1.0, 0.0, c->mq, s));
+    LA(gemv_n_launch(c->K, ld, n, n, c->alpha, 1.0, 0.0, c->mZ, s));
+    if (c->has_meanZ) LA(vadd_inplace_launch(c->mZ, c->meanZ_off, c->M, s));
+    c->post_valid = true;
+    c->kl_valid = false;
+    return TSVGP_OK;
+}
+
+// KL[q(u) || p(u)] = 1/2 ( m^T alpha - tr(Q K6) + log det W )   (gauss_kl with K6; tsvgp.py:65-70). Scalars stay on the
+// device until the caller's final synchronisation.
+int ensure_kl_terms(tsvgp_ctx* c) {
+    if (c->kl_valid && c->cache_factors) return TSVGP_OK;
+    cudaStream_t s = c->s_main;
+    const int n = c->Mp;
+    const long ld = c->Mp;
+    {   // X1 = K6 T
+        GemmP p;
+        p.A = c->K6; p.lda = ld; p.a_kc = 1;
+        p.B = c->T; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
+        p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
+        LA(gemm_launch(p, s));
+    }
+    LA(matdot_launch(c->T, c->X1, ld, n, c->scal + SC_TR_QK, s));
+    LA(dot_launch(c->mq, c->alpha, n, c->scal + SC_M_ALPHA, s));
+    c->kl_valid = true;
+    return TSVGP_OK;
+}
+
+double kl_from_scalars(const double* sc) { return 0.5 * (sc[SC_M_ALPHA] - sc[SC_TR_QK] + 2.0 * sc[SC_LOGDIAG_W]); }
+
+// ---- data ----------------------------------------------------------------------------------------------------------
+int ensure_xs(tsvgp_ctx* c) {
+    if (c->xs_valid) return TSVGP_OK;
+    if (!c->X) FAIL(TSVGP_ERR_STATE, "no data resident (tsvgp_set_data)");
+    OK(ensure_kuu(c));
+    if (c->dataD != c->D) FAIL(TSVGP_ERR_INVALID, "X has D=%d but the inducing points have D=%d", c->dataD, c->D);
+    LA(scale_points_launch(c->X, c->N, c->D, c->ls_dev, c->XsT, c->n_pad, c->x2, c->n_pad, c->s_main));
+    c->xs_valid = true;
+    return TSVGP_OK;
+}
+
+long pick_chunk(const tsvgp_ctx* c) {
+    long nc = c->chunk_opt;
+    if (nc <= 0) {   // one slab = Mp * nc * 8 B ~ 32 MB, so both ping-pong slabs stay inside the 126 MB L2
+        nc = (32l << 20) / (8l * c->Mp);
+        if (nc > 8192) nc = 8192;
+    }
+    nc = nc / 128 * 128;
+    if (nc < 128) nc = 128;
+    return nc;
+}
+
+int ensure_slabs(tsvgp_ctx* c, long n_points) {
+    const long nc = pick_chunk(c);
+    const long nchunks = (n_points + nc - 1) / nc;
+    const long ve_need = (nchunks + 1) * ((nc + 255) / 256);
+    if (c->chunk == nc && c->chunk_Mp == c->Mp && c->ve_cap >= ve_need) return TSVGP_OK;
+    c->pc.release();
+    Pool& p = c->pc;
+    for (int s = 0; s < 2; ++s) {
+        NEED(c->slab[s] = p.get((size_t)c->Mp * nc));
+        NEED(c->mu_part[s] = p.get((size_t)(c->Mp / 64) * nc));
+        NEED(c->q_part[s] = p.get((size_t)(c->Mp / 128) * nc));
+        NEED(c->gbuf[s] = p.get(nc));
+        NEED(c->hbuf[s] = p.get(nc));
+    }
+    NEED(c->ve_blocks = p.get(ve_need));
+    c->ve_cap = ve_need;
+    c->chunk = nc;
+    c->chunk_Mp = c->Mp;
+    return TSVGP_OK;
+}
+
+// The streaming pass over `N` points whose scaled, feature-major coordinates are XsT/x2.
+int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, long N, const double* y, const double* mean_off,
+                int mode, double* mean_out, double* var_out) {
+    OK(ensure_slabs(c, N));
+    const long nc = c->chunk;
+    const int Mp = c->Mp;
+    const int nstr = c->n_streams == 1 ? 1 : 2;
+    const long vstride = (nc + 255) / 256;
+    const long nchunks = (N + nc - 1) / nc;
+    cudaStream_t sm = c->s_main;
+
+    CU(cudaMemsetAsync(c->flags, 0, 2 * sizeof(int), sm));
+    CU(cudaMemsetAsync(c->ve_blocks, 0, sizeof(double) * (size_t)(nchunks * vstride), sm));
+    if (mode == MODE_STATS)
+        for (int s = 0; s < nstr; ++s) CU(cudaMemsetAsync(c->stats[s], 0, sizeof(double) * ((size_t)Mp * Mp + Mp + 4), sm));
+    CU(cudaEventRecord(c->ev_fork, sm));
+    for (int s = 0; s < nstr; ++s) CU(cudaStreamWaitEvent(c->s_pp[s], c->ev_fork, 0));
+
+    for (long ci = 0; ci < nchunks; ++ci) {
+        const int b = (int)(ci % nstr);
+        cudaStream_t s = c->s_pp[b];
+        const long n0 = ci * nc;
+        const long nvalid = N - n0 < nc ? N - n0 : nc;
+        const int ncols = (int)round_up(nvalid, 128);
+        // (a) covariance slab K[Mp x ncols] and the partial means sum_i alpha_i K[i][n]
+        LA(kuf_launch(c->kern_kind, c->kern_var, XsT, ldx, x2, n0, N, ncols, c->Zs, c->z2, c->M, Mp, c->D, c->alpha, c->slab[b],
+                      nc, c->mu_part[b], nc, 0, s));
+        {   // (b) |T^T k_n|^2 : upper-triangular T^T times the slab, reduced to column norms in the epilogue
+            GemmP p;
+            p.A = c->T; p.lda = Mp; p.a_kc = 0; p.a_tri = 2;
+            p.B = c->slab[b]; p.ldb = nc; p.b_kc = 0;
+            p.m = Mp; p.n = ncols; p.k = Mp;
+            p.epilogue = EPI_COLNORM; p.norm_out = c->q_part[b]; p.ldn = nc;
+            LA(gemm_launch(p, s));
+        }
+        {   // (c) marginals -> likelihood expectations and gradients
+            PointArgs a;
+            a.mu_part = c->mu_part[b]; a.n_mu_part = Mp / 64; a.ldmu = nc;
+            a.q_part = c->q_part[b]; a.n_q_part = Mp / 128; a.ldq = nc;
+            a.y = y ? y + n0 : nullptr;
+            a.mean_off = mean_off ? mean_off + n0 : nullptr;
+            a.kdiag = c->kern_var;
+            a.n_valid = nvalid; a.ncols = ncols;
+            a.g = mode == MODE_STATS ? c->gbuf[b] : nullptr; a.h = mode == MODE_STATS ? c->hbuf[b] : nullptr;
+            a.mean_out = mean_out ? mean_out + n0 : nullptr; a.var_out = var_out ? var_out + n0 : nullptr;
+            a.ve_blocks = c->ve_blocks + ci * vstride;
+            a.flags = c->flags;
+            LA(point_stats_launch(c->lik, a, c->gh, s));
+        }
+        if (mode == MODE_STATS) {
+            {   // (d) B += K diag(h) K^T, lower tiles
+                GemmP p;
+                p.A = c->slab[b]; p.lda = nc; p.a_kc = 1;
+                p.B = c->slab[b]; p.ldb = nc; p.b_kc = 1;
+                p.C = c->stats[b]; p.ldc = Mp; p.m = p.n = Mp; p.k = ncols;
+                p.beta = 1.0; p.lower_out = 1; p.kscale = c->hbuf[b];
+                LA(gemm_launch(p, s));
+            }
+            // (e) b += K g
+            LA(gemv_n_launch(c->slab[b], nc, Mp, ncols, c->gbuf[b], 1.0, 1.0, c->stats[b] + (size_t)Mp * Mp, s));
+        }
+    }
+    for (int s = 0; s < nstr; ++s) {
+        CU(cudaEventRecord(c->ev_join[s], c->s_pp[s]));
+        CU(cudaStreamWaitEvent(sm, c->ev_join[s], 0));
+    }
+    const size_t mm = (size_t)Mp * Mp;
+    if (mode == MODE_STATS && nstr == 2) LA(vadd_inplace_launch(c->stats[0], c->stats[1], (long)(mm + Mp), sm));
+    LA(stats_tail_launch(c->ve_blocks, nchunks * vstride, c->flags, c->stats[0] + mm + Mp, sm));
+    return TSVGP_OK;
+}
+
+int all_reduce(tsvgp_ctx* c, double* buf, size_t count) {
+    if (c->world <= 1) return TSVGP_OK;
+    NcclApi& api = nccl_api();
+    int r = api.AllReduce(buf, buf, count, NCCL_FLOAT64, NCCL_SUM, c->comm, c->s_main);
+    if (r != 0) FAIL(TSVGP_ERR_COMM, "ncclAllReduce: %s", api.GetErrorString ? api.GetErrorString(r) : "error");
+    return TSVGP_OK;
+}
+
+// K9 = K + jitter I = C9 C9^T and C9^-1 (tsvgp.py:268-271), kept while kernel, Z and jitter are unchanged
+int ensure_k9(tsvgp_ctx* c, double jitter) {
+    if (c->k9_valid && c->k9_jitter == jitter && c->cache_factors) return TSVGP_OK;
+    cudaStream_t s = c->s_main;
+    LA(copy_add_diag_launch(c->K, c->C9, c->Mp, c->Mp, jitter, s));
+    LA(chol_lower(c->C9, c->Mp, c->Mp, c->dinv, c->info + INFO_K9, s));
+    LA(trtri_lower(c->C9, c->Mp, c->Mp, c->dinv, c->C9inv, c->tmp, s));
+    c->k9_valid = true;
+    c->k9_jitter = jitter;
+    return TSVGP_OK;
+}
+
+// tsvgp.py:268-303 after the statistics are complete in stats[0]
+int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale) {
+    cudaStream_t s = c->s_main;
+    const int n = c->Mp;
+    const long ld = c->Mp;
+    const size_t mm = (size_t)n * n;
+    double* B = c->stats[0];
+    double* bvec = c->stats[0] + mm;
+    const double* bad = c->stats[0] + mm + n + 1;
+    OK(ensure_k9(c, jitter));
+    LA(mirror_lower_launch(B, ld, n, s));
+    {   // X1 = C9^-1 B
+        GemmP p;
+        p.A = c->C9inv; p.lda = ld; p.a_kc = 1; p.a_tri = 1;
+        p.B = B; p.ldb = ld; p.b_kc = 0;
+        p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
+        LA(gemm_launch(p, s));
+    }
+    {   // X2 = X1 C9^-T  (symmetric; lower tiles then mirrored)
+        GemmP p;
+        p.A = c->X1; p.lda = ld; p.a_kc = 1;
+        p.B = c->C9inv; p.ldb = ld; p.b_kc = 1; p.b_tri = 1;
+        p.C = c->X2; p.ldc = ld; p.m = p.n = p.k = n;
+        p.lower_out = 1;
+        LA(gemm_launch(p, s));
+    }
+    LA(mirror_lower_launch(c->X2, ld, n, s));
+    {   // X1 = C9^-T X2
+        GemmP p;
+        p.A = c->C9inv; p.lda = ld; p.a_kc = 0; p.a_tri = 2;
+        p.B = c->X2; p.ldb = ld; p.b_kc = 0;
+        p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
+        LA(gemm_launch(p, s));
+    }
+    {   // G2 = X1 C9^-1  (symmetric)
+        GemmP p;
+        p.A = c->X1; p.lda = ld; p.a_kc = 1;
+        p.B = c->C9inv; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
+        p.C = c->G2; p.ldc = ld; p.m = p.n = p.k = n;
+        p.lower_out = 1;
+        LA(gemm_launch(p, s));
+    }
+    LA(mirror_lower_launch(c->G2, ld, n, s));
+    // G1 = C9^-T C9^-1 b ; G2 mZ
+    LA(gemv_n_launch(c->C9inv, ld, n, n, bvec, 1.0, 0.0, c->v1, s));
+    LA(gemv_t_launch(c->C9inv, ld, n, n, c->v1, c->v2, c->gwork, s));
+    LA(gemv_n_launch(c->G2, ld, n, n, c->mZ, 1.0, 0.0, c->v3, s));
+    // P = (1-lr) L2 L2^T - 2 lr scale G2 + jitter I                                     tsvgp.py:293-300
+    LA(init_update_launch(c->G2, c->P, ld, c->M, n, -2.0 * lr * scale, jitter, s));
+    if (lr != 1.0) {
+        GemmP p;
+        p.A = c->L2; p.lda = ld; p.a_kc = 1; p.a_tri = 1;
+        p.B = c->L2; p.ldb = ld; p.b_kc = 1; p.b_tri = 1;
+        p.C = c->P; p.ldc = ld; p.m = p.n = p.k = n;
+        p.alpha = 1.0 - lr; p.beta = 1.0; p.lower_out = 1;
+        LA(gemm_launch(p, s));
+    }
+    LA(chol_lower(c->P, ld, n, c->dinv, c->info + INFO_P, s));
+    // commit (skipped on the device if any variance was non-positive or a factorisation failed)
+    LA(update_lambda1_launch(c->lam1, c->v2, c->v3, c->M, lr, scale, bad, c->info, s));
+    LA(finalize_sites_launch(c->P, c->L2, ld, c->M, n, bad, c->info, s));
+    return TSVGP_OK;
+}
+
+int check_info(tsvgp_ctx* c, const int* info_h) {
+    static const char* what[N_INFO] = {"I + L2^T K6 L2 (posterior)", "Kuu + jitter I", "-2 lambda_2 + jitter I (site update)", "S_q"};
+    for (int i = 0; i < N_INFO; ++i)
+        if (info_h[i]) {
+            c->last_info = info_h[i];
+            if (i == INFO_K9) c->k9_valid = false;
+            c->post_valid = c->kl_valid = false;
+            FAIL(TSVGP_ERR_NOT_POSITIVE_DEFINITE, "Cholesky of %s failed at pivot %d", what[i], info_h[i]);
+        }
+    return TSVGP_OK;
+}
+
+void gauss_hermite(int n, double* x, double* w) {   // numpy.polynomial.hermite.hermgauss(n): ascending nodes, weights
+    const double PIM4 = 0.7511255444649425;
+    const int m = (n + 1) / 2;
+    double z = 0;
+    for (int i = 0; i < m; ++i) {
+        if (i == 0) z = sqrt(2.0 * n + 1.0) - 1.85575 * pow(2.0 * n + 1.0, -0.16667);
+        else if (i == 1) z -= 1.14 * pow((double)n, 0.426) / z;
+        else if (i == 2) z = 1.86 * z - 0.86 * x[n - 1];
+        else if (i == 3) z = 1.91 * z - 0.91 * x[n - 2];
+        else z = 2.0 * z - x[n - 1 - (i - 2)];
+        double pp = 1;
+        for (int its = 0; its < 100; ++its) {
+            double p1 = PIM4, p2 = 0.0;
+            for (int j = 0; j < n; ++j) {
+                const double p3 = p2;
+                p2 = p1;
+                p1 = z * sqrt(2.0 / (j + 1)) * p2 - sqrt((double)j / (j + 1)) * p3;
+            }
+            pp = sqrt(2.0 * n) * p2;
+            const double z1 = z;
+            z = z1 - p1 / pp;
+            if (fabs(z - z1) <= 1e-15 * (1.0 + fabs(z))) break;
+        }
+        x[n - 1 - i] = z;
+        x[i] = -z;
+        w[i] = w[n - 1 - i] = 2.0 / (pp * pp);
+    }
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+extern "C" {
+
+int tsvgp_abi_version(void) { return TSVGP_ABI_VERSION; }
+
+int tsvgp_create(tsvgp_ctx** out, int device_id) {
+    if (!out) return TSVGP_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " — libtsvgp has no CPU fallback";
+        cudaGetLastError();
+        return TSVGP_ERR_CUDA;
+    }
+    if (device_id < 0 || device_id >= ndev) {
+        g_create_error = "device_id out of range";
+        return TSVGP_ERR_INVALID;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device_id);
+    if (prop.major != 10) {
+        g_create_error = std::string("device is ") + prop.name + " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                         "); libtsvgp is built for sm_100a only";
+        return TSVGP_ERR_CUDA;
+    }
+    tsvgp_ctx* c = new tsvgp_ctx();
+    c->dev = device_id;
+    bool ok = cudaSetDevice(device_id) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking) == cudaSuccess;
+    for (int s = 0; s < 2 && ok; ++s) {
+        ok = ok && cudaStreamCreateWithFlags(&c->s_pp[s], cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&c->ev_join[s], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < N_EV && ok; ++i) ok = ok && cudaEventCreate(&c->ev[i]) == cudaSuccess;
+    ok = ok && gemm_init() == 0;
+    if (!ok) {
+        g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete c;
+        return TSVGP_ERR_CUDA;
+    }
+    *out = c;
+    return TSVGP_OK;
+}
+
+void tsvgp_destroy(tsvgp_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->dev);
+    cudaDeviceSynchronize();
+    if (c->comm) nccl_api().CommDestroy(c->comm);
+    c->pm.release(); c->pd.release(); c->pc.release();
+    for (int s = 0; s < 2; ++s) {
+        if (c->s_pp[s]) cudaStreamDestroy(c->s_pp[s]);
+        if (c->ev_join[s]) cudaEventDestroy(c->ev_join[s]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int i = 0; i < N_EV; ++i)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->s_main) cudaStreamDestroy(c->s_main);
+    delete c;
+}
+
+const char* tsvgp_last_error(const tsvgp_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+int tsvgp_last_info(const tsvgp_ctx* c) { return c ? c->last_info : 0; }
+
+int tsvgp_set_option(tsvgp_ctx* c, const char* name, double value) {
+    if (!c || !name) return TSVGP_ERR_INVALID;
+    if (!strcmp(name, "chunk")) { c->chunk_opt = (long)value; return TSVGP_OK; }
+    if (!strcmp(name, "streams")) { c->n_streams = value >= 2 ? 2 : 1; return TSVGP_OK; }
+    if (!strcmp(name, "cache_factors")) { c->cache_factors = value != 0.0; return TSVGP_OK; }
+    if (!strcmp(name, "invalidate")) { c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = false; return TSVGP_OK; }
+    FAIL(TSVGP_ERR_INVALID, "unknown option '%s'", name);
+}
+
+int tsvgp_set_kernel(tsvgp_ctx* c, int kind, double variance, const double* lengthscales, int n_ls) {
+    if (!c) return TSVGP_ERR_INVALID;
+    if (kind != TSVGP_KERNEL_SE && kind != TSVGP_KERNEL_MATERN52) FAIL(TSVGP_ERR_INVALID, "unknown kernel kind %d", kind);
+    if (!lengthscales || n_ls < 1 || !(variance > 0.0)) FAIL(TSVGP_ERR_INVALID, "kernel needs variance > 0 and >= 1 lengthscale");
+    for (int i = 0; i < n_ls; ++i)
+        if (!(lengthscales[i] > 0.0)) FAIL(TSVGP_ERR_INVALID, "lengthscales must be positive");
+    c->kern_kind = kind; c->kern_var = variance;
+    c->ls_host.assign(lengthscales, lengthscales + n_ls);
+    c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = false;
+    c->xs_valid = false;
+    return TSVGP_OK;
+}
+
+int tsvgp_set_likelihood(tsvgp_ctx* c, int kind, double p0, double p1, int n_gh, const double* gh_x, const double* gh_w) {
+    if (!c) return TSVGP_ERR_INVALID;
+    if (kind < TSVGP_LIK_GAUSSIAN || kind > TSVGP_LIK_STUDENT_T) FAIL(TSVGP_ERR_INVALID, "unknown likelihood kind %d", kind);
+    if (kind != TSVGP_LIK_BERNOULLI_PROBIT && !(p0 > 0.0)) FAIL(TSVGP_ERR_INVALID, "likelihood variance / scale must be positive");
+    if (kind == TSVGP_LIK_STUDENT_T && !(p1 > 0.0)) FAIL(TSVGP_ERR_INVALID, "Student-t df must be positive");
+    if (kind != TSVGP_LIK_GAUSSIAN && (n_gh < 1 || n_gh > MAX_GH)) FAIL(TSVGP_ERR_INVALID, "n_gh must be in [1, %d]", MAX_GH);
+    c->lik.kind = kind; c->lik.p0 = p0; c->lik.p1 = p1; c->lik.n_gh = kind == TSVGP_LIK_GAUSSIAN ? 0 : n_gh;
+    if (kind == TSVGP_LIK_STUDENT_T)   // gpflow.logdensities.student_t constant
+        c->lik.c0 = lgamma((p1 + 1.0) * 0.5) - lgamma(p1 * 0.5) - 0.5 * (log(p0 * p0) + log(p1) + log(M_PI));
+    if (kind != TSVGP_LIK_GAUSSIAN) {
+        double x[MAX_GH], w[MAX_GH];
+        if (gh_x && gh_w) { memcpy(x, gh_x, sizeof(double) * n_gh); memcpy(w, gh_w, sizeof(double) * n_gh); }
+        else gauss_hermite(n_gh, x, w);
+        for (int k = 0; k < n_gh; ++k) {   // gpflow.quadrature.gauss_hermite: nodes sqrt(2) x_k, weights w_k / sqrt(pi)
+            c->gh.z[k] = x[k] * sqrt(2.0);
+            c->gh.w[k] = w[k] / sqrt(M_PI);
+        }
+    }
+    c->lik_set = true;
+    return TSVGP_OK;
+}
+
+int tsvgp_set_inducing(tsvgp_ctx* c, const double* Z, int M, int D, const double* mean_Z) {
+    if (!c) return TSVGP_ERR_INVALID;
+    if (!Z || M < 1 || D < 1) FAIL(TSVGP_ERR_INVALID, "Z must be [M >= 1, D >= 1]");
+    CU(cudaSetDevice(c->dev));
+    if (M != c->M || D != c->D) {
+        CU(cudaStreamSynchronize(c->s_main));
+        OK(alloc_m_state(c, M, D));
+    }
+    CU(cudaMemcpyAsync(c->Zraw, Z, sizeof(double) * (size_t)M * D, cudaMemcpyDefault, c->s_main));
+    c->has_meanZ = mean_Z != nullptr;
+    if (mean_Z) {
+        CU(cudaMemsetAsync(c->meanZ_off, 0, sizeof(double) * c->Mp, c->s_main));
+        CU(cudaMemcpyAsync(c->meanZ_off, mean_Z, sizeof(double) * M, cudaMemcpyDefault, c->s_main));
+    }
+    CU(cudaStreamSynchronize(c->s_main));
+    c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = false;
+    return TSVGP_OK;
+}
+
+int tsvgp_set_sites(tsvgp_ctx* c, const double* lambda_1, const double* lambda_2_sqrt) {
+    if (!c) return TSVGP_ERR_INVALID;
+    if (c->M <= 0) FAIL(TSVGP_ERR_STATE, "inducing points not set (tsvgp_set_inducing)");
+    CU(cudaSetDevice(c->dev));
+    cudaStream_t s = c->s_main;
+    if (!c->sites_set || (!lambda_1 && !lambda_2_sqrt)) OK(default_sites(c));
+    if (lambda_1) {
+        CU(cudaMemsetAsync(c->lam1, 0, sizeof(double) * c->Mp, s));
+        CU(cudaMemcpyAsync(c->lam1, lambda_1, sizeof(double) * c->M, cudaMemcpyDefault, s));
+    }
+    if (lambda_2_sqrt) {
+        CU(cudaMemsetAsync(c->L2, 0, sizeof(double) * (size_t)c->Mp * c->Mp, s));
+        CU(cudaMemcpy2DAsync(c->L2, sizeof(double) * c->Mp, lambda_2_sqrt, sizeof(double) * c->M, sizeof(double) * c->M, c->M,
+                             cudaMemcpyDefault, s));
+        LA(zero_upper_launch(c->L2, c->Mp, c->Mp, s));   // sites.py:63 — the triangular() transform keeps the lower triangle
+    }
+    CU(cudaStreamSynchronize(s));
+    c->sites_set = true;
+    c->post_valid = c->kl_valid = false;
+    return TSVGP_OK;
+}
+
+int tsvgp_get_sites(tsvgp_ctx* c, double* lambda_1, double* lambda_2_sqrt) {
+    if (!c) return TSVGP_ERR_INVALID;
+    if (c->M <= 0) FAIL(TSVGP_ERR_STATE, "inducing points not set (tsvgp_set_inducing)");
+    CU(cudaSetDevice(c->dev));
+    if (!c->sites_set) OK(default_sites(c));
+    cudaStream_t s = c->s_main;
+    if (lambda_1) CU(cudaMemcpyAsync(lambda_1, c->lam1, sizeof(double) * c->M, cudaMemcpyDefault, s));
+    if (lambda_2_sqrt)
+        CU(cudaMemcpy2DAsync(lambda_2_sqrt, sizeof(double) * c->M, c->L2, sizeof(double) * c->Mp, sizeof(double) * c->M, c->M,
+                             cudaMemcpyDefault, s));
+    CU(cudaStreamSynchronize(s));
+    return TSVGP_OK;
+}
+
+int tsvgp_get_lambda_2(tsvgp_ctx* c, double* lambda_2) {
+    if (!c || !lambda_2) return TSVGP_ERR_INVALID;
+    if (c->M <= 0) FAIL(TSVGP_ERR_STATE, "inducing points not set (tsvgp_set_inducing)");
+    CU(cudaSetDevice(c->dev));
+    if (!c->sites_set) OK(default_sites(c));
+    cudaStream_t s = c->s_main;
+    const int n = c->Mp;
+    GemmP p;   // L2 L2^T (tsvgp.py:197-200), lower tiles then mirrored
+    p.A = c->L2; p.lda = n; p.a_kc = 1; p.a_tri = 1;
+    p.B = c->L2; p.ldb = n; p.b_kc = 1; p.b_tri = 1;
+    p.C = c->X2; p.ldc = n; p.m = p.n = p.k = n; p.lower_out = 1;
+    LA(gemm_launch(p, s));
+    LA(mirror_lower_launch(c->X2, n, n, s));
+    CU(cudaMemcpy2DAsync(lambda_2, sizeof(double) * c->M, c->X2, sizeof(double) * n, sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
+    CU(cudaStreamSynchronize(s));
+    return TSVGP_OK;
+}
+
+int tsvgp_set_data(tsvgp_ctx* c, const double* X, const double* Y, int64_t N, int D, const double* mean_X) {
+    if (!c) return TSVGP_ERR_INVALID;
+    if (!X || !Y || N < 1) FAIL(TSVGP_ERR_INVALID, "X [N >= 1, D] and Y [N] are required");
+    if (c->D > 0 && D != c->D) FAIL(TSVGP_ERR_INVALID, "X has D=%d but the inducing points have D=%d", D, c->D);
+    CU(cudaSetDevice(c->dev));
+    cudaStream_t s = c->s_main;
+    const long npad = round_up(N, 128);
+    if (npad > c->cap_n || (long)N * D > c->cap_x) {   // (re)allocate the owned staging and scaled-coordinate buffers
+        CU(cudaStreamSynchronize(s));
+        c->pd.release();
+        c->cap_n = npad; c->cap_x = (long)N * D;
+        NEED(c->Xown = c->pd.get((size_t)N * D)); NEED(c->Yown = c->pd.get(npad)); NEED(c->meanXown = c->pd.get(npad));
+        NEED(c->XsT = c->pd.get((size_t)D * npad)); NEED(c->x2 = c->pd.get(npad));
+    }
+    if (is_device_ptr(X)) c->X = X;
+    else { CU(cudaMemcpyAsync(c->Xown, X, sizeof(double) * (size_t)N * D, cudaMemcpyHostToDevice, s)); c->X = c->Xown; }
+    if (is_device_ptr(Y)) c->Y = Y;
+    else { CU(cudaMemcpyAsync(c->Yown, Y, sizeof(double) * N, cudaMemcpyHostToDevice, s)); c->Y = c->Yown; }
+    if (!mean_X) c->meanX = nullptr;
+    else if (is_device_ptr(mean_X)) c->meanX = mean_X;
+    else { CU(cudaMemcpyAsync(c->meanXown, mean_X, sizeof(double) * N, cudaMemcpyHostToDevice, s)); c->meanX = c->meanXown; }
+    c->N = N; c->n_pad = npad;
+    c->dataD = D;
+    c->xs_valid = false;
+    return TSVGP_OK;
+}
+
+static int require_model(tsvgp_ctx* c, bool need_data) {
+    if (c->kern_kind < 0) FAIL(TSVGP_ERR_STATE, "kernel not set (tsvgp_set_kernel)");
+    if (!c->lik_set) FAIL(TSVGP_ERR_STATE, "likelihood not set (tsvgp_set_likelihood)");
+    if (c->M <= 0) FAIL(TSVGP_ERR_STATE, "inducing points not set (tsvgp_set_inducing)");
+    if (need_data && !c->X) FAIL(TSVGP_ERR_STATE, "no data resident (tsvgp_set_data)");
+    return TSVGP_OK;
+}
+
+int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, double* elbo_before) {
+    if (!c) return TSVGP_ERR_INVALID;
+    OK(require_model(c, true));
+    CU(cudaSetDevice(c->dev));
+    cudaStream_t s = c->s_main;
+    const long launches0 = g_launches;
+    const size_t mm = (size_t)c->Mp * c->Mp;
+    CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
+    CU(cudaEventRecord(c->ev[EV_T0], s));
+    OK(ensure_xs(c));
+    OK(ensure_posterior(c));
+    if (elbo_before) OK(ensure_kl_terms(c));
+    CU(cudaEventRecord(c->ev[EV_PREP], s));
+    OK(stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_STATS, nullptr, nullptr));
+    CU(cudaEventRecord(c->ev[EV_STREAM], s));
+    OK(all_reduce(c, c->stats[0], mm + c->Mp + 4));
+    CU(cudaEventRecord(c->ev[EV_REDUCE], s));
+    OK(dense_update(c, lr, jitter, scale));
+    CU(cudaEventRecord(c->ev[EV_DENSE], s));
+
+    double tail[4], sc[N_SCAL];
+    int info_h[N_INFO];
+    CU(cudaMemcpyAsync(tail, c->stats[0] + mm + c->Mp, sizeof tail, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(sc, c->scal, sizeof sc, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(info_h, c->info, sizeof info_h, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    // the step consumed the posterior factors of the old sites
+    c->post_valid = c->kl_valid = false;
+    float ms = 0;
+    for (int i = 0; i < 4; ++i) { cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]); c->timings[1 + i] = ms; }
+    cudaEventElapsedTime(&ms, c->ev[EV_T0], c->ev[EV_DENSE]);
+    c->timings[0] = ms;
+    c->timings[5] = (double)((c->N + c->chunk - 1) / c->chunk);
+    c->timings[6] = (double)(g_launches - launches0);
+    OK(check_info(c, info_h));
+    if (tail[1] != 0.0) {
+        c->post_valid = c->kl_valid = false;
+        FAIL(TSVGP_ERR_NONPOSITIVE_VARIANCE, "predict_f: non-positive predictive variance (sites unchanged)");
+    }
+    if (elbo_before) *elbo_before = scale * tail[0] - kl_from_scalars(sc);
+    return TSVGP_OK;
+}
+
+int tsvgp_elbo(tsvgp_ctx* c, double scale, double* out) {
+    if (!c || !out) return TSVGP_ERR_INVALID;
+    OK(require_model(c, true));
+    CU(cudaSetDevice(c->dev));
+    cudaStream_t s = c->s_main;
+    const size_t mm = (size_t)c->Mp * c->Mp;
+    CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
+    OK(ensure_xs(c));
+    OK(ensure_posterior(c));
+    OK(ensure_kl_terms(c));
+    OK(stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_ELBO, nullptr, nullptr));
+    OK(all_reduce(c, c->stats[0] + mm + c->Mp, 4));
+    double tail[4], sc[N_SCAL];
+    int info_h[N_INFO];
+    CU(cudaMemcpyAsync(tail, c->stats[0] + mm + c->Mp, sizeof tail, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(sc, c->scal, sizeof sc, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(info_h, c->info, sizeof info_h, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    OK(check_info(c, info_h));
+    if (tail[1] != 0.0) FAIL(TSVGP_ERR_NONPOSITIVE_VARIANCE, "predict_f: non-positive predictive variance");
+    *out = scale * tail[0] - kl_from_scalars(sc);
+    return TSVGP_OK;
+}
+
+int tsvgp_prior_kl(tsvgp_ctx* c, double* out) {
+    if (!c || !out) return TSVGP_ERR_INVALID;
+    OK(require_model(c, false));
+    CU(cudaSetDevice(c->dev));
+    cudaStream_t s = c->s_main;
+    CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
+    OK(ensure_posterior(c));
+    OK(ensure_kl_terms(c));
+    double sc[N_SCAL];
+    int info_h[N_INFO];
+    CU(cudaMemcpyAsync(sc, c->scal, sizeof sc, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(info_h, c->info, sizeof info_h, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    OK(check_info(c, info_h));
+    *out = kl_from_scalars(sc);
+    return TSVGP_OK;
+}
+
+int tsvgp_predict_f(tsvgp_ctx* c, const double* Xnew, int64_t N, int D, const double* mean_X, double* mean_out, double* var_out) {
+    if (!c) return TSVGP_ERR_INVALID;
+    if (!Xnew || !mean_out || !var_out || N < 1) FAIL(TSVGP_ERR_INVALID, "Xnew [N >= 1, D], mean_out [N], var_out [N] are required");
+    OK(require_model(c, false));
+    if (D != c->D) FAIL(TSVGP_ERR_INVALID, "Xnew has D=%d but the inducing points have D=%d", D, c->D);
+    CU(cudaSetDevice(c->dev));
+    cudaStream_t s = c->s_main;
+    CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
+    OK(ensure_posterior(c));
+    const long npad = round_up(N, 128);
+    Pool tp;
+    struct Rel { Pool& p; cudaStream_t s; ~Rel() { cudaStreamSynchronize(s); p.release(); } } rel{tp, s};
+    double *xd = nullptr, *xsT, *x2, *md, *vd, *moff = nullptr;
+    const double* xsrc = Xnew;
+    if (!is_device_ptr(Xnew)) {
+        NEED(xd = tp.get((size_t)N * D));
+        CU(cudaMemcpyAsync(xd, Xnew, sizeof(double) * (size_t)N * D, cudaMemcpyHostToDevice, s));
+        xsrc = xd;
+    }
+    NEED(xsT = tp.get((size_t)D * npad)); NEED(x2 = tp.get(npad)); NEED(md = tp.get(npad)); NEED(vd = tp.get(npad));
+    if (mean_X) {
+        NEED(moff = tp.get(npad));
+        CU(cudaMemcpyAsync(moff, mean_X, sizeof(double) * N, cudaMemcpyDefault, s));
+    }
+    LA(scale_points_launch(xsrc, N, D, c->ls_dev, xsT, npad, x2, npad, s));
+    OK(stream_pass(c, xsT, npad, x2, N, nullptr, moff, MODE_PREDICT, md, vd));
+    double tail[4];
+    int info_h[N_INFO];
+    const size_t mm = (size_t)c->Mp * c->Mp;
+    CU(cudaMemcpyAsync(tail, c->stats[0] + mm + c->Mp, sizeof tail, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(info_h, c->info, sizeof info_h, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(mean_out, md, sizeof(double) * N, cudaMemcpyDefault, s));
+    CU(cudaMemcpyAsync(var_out, vd, sizeof(double) * N, cudaMemcpyDefault, s));
+    CU(cudaStreamSynchronize(s));
+    OK(check_info(c, info_h));
+    if (tail[1] != 0.0) FAIL(TSVGP_ERR_NONPOSITIVE_VARIANCE, "predict_f: non-positive predictive variance");
+    return TSVGP_OK;
+}
+
+int tsvgp_posterior(tsvgp_ctx* c, double* m, double* chol_S) {
+    if (!c) return TSVGP_ERR_INVALID;
+    OK(require_model(c, false));
+    CU(cudaSetDevice(c->dev));
+    cudaStream_t s = c->s_main;
+    const int n = c->Mp;
+    CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
+    OK(ensure_posterior(c));
+    if (m) CU(cudaMemcpyAsync(m, c->mq, sizeof(double) * c->M, cudaMemcpyDefault, s));
+    if (chol_S) {   // S = K6 - (K6 T)(K6 T)^T   (util.py:387-388)
+        GemmP p;
+        p.A = c->K6; p.lda = n; p.a_kc = 1;
+        p.B = c->T; p.ldb = n; p.b_kc = 0; p.b_tri = 2;
+        p.C = c->X1; p.ldc = n; p.m = p.n = p.k = n;
+        LA(gemm_launch(p, s));
+        c->kl_valid = false;   // X1 is shared with the KL terms
+        CU(cudaMemcpyAsync(c->X2, c->K6, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, s));
+        GemmP q;
+        q.A = c->X1; q.lda = n; q.a_kc = 1;
+        q.B = c->X1; q.ldb = n; q.b_kc = 1;
+        q.C = c->X2; q.ldc = n; q.m = q.n = q.k = n;
+        q.alpha = -1.0; q.beta = 1.0; q.lower_out = 1;
+        LA(gemm_launch(q, s));
+        LA(chol_lower(c->X2, n, n, c->dinv, c->info + INFO_S, s));
+        CU(cudaMemcpy2DAsync(chol_S, sizeof(double) * c->M, c->X2, sizeof(double) * n, sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
+    }
+    int info_h[N_INFO];
+    CU(cudaMemcpyAsync(info_h, c->info, sizeof info_h, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return check_info(c, info_h);
+}
+
+int tsvgp_comm_unique_id(void* id_out_128_bytes) {
+    NcclApi& api = nccl_api();
+    if (!api.ok() || !id_out_128_bytes) return TSVGP_ERR_COMM;
+    NcclUniqueId id;
+    if (api.GetUniqueId(&id) != 0) return TSVGP_ERR_COMM;
+    memcpy(id_out_128_bytes, &id, sizeof id);
+    return TSVGP_OK;
+}
+
+int tsvgp_comm_init(tsvgp_ctx* c, int world_size, int rank, const void* id_128_bytes) {
+    if (!c) return TSVGP_ERR_INVALID;
+    if (world_size < 1 || rank < 0 || rank >= world_size || !id_128_bytes) FAIL(TSVGP_ERR_INVALID, "bad world_size / rank / id");
+    NcclApi& api = nccl_api();
+    if (!api.ok()) FAIL(TSVGP_ERR_COMM, "libnccl.so.2 could not be loaded: %s", dlerror());
+    CU(cudaSetDevice(c->dev));
+    NcclUniqueId id;
+    memcpy(&id, id_128_bytes, sizeof id);
+    int r = api.CommInitRank(&c->comm, world_size, id, rank);
+    if (r != 0) FAIL(TSVGP_ERR_COMM, "ncclCommInitRank: %s", api.GetErrorString ? api.GetErrorString(r) : "error");
+    c->world = world_size; c->rank = rank;
+    return TSVGP_OK;
+}
+
+int tsvgp_comm_size(const tsvgp_ctx* c) { return c ? c->world : 0; }
+
+int tsvgp_get_timings(tsvgp_ctx* c, double* out, int n) {
+    if (!c || !out) return TSVGP_ERR_INVALID;
+    for (int i = 0; i < n; ++i) out[i] = i < 16 ? c->timings[i] : 0.0;
+    return TSVGP_OK;
+}
+
+int tsvgp_sync(tsvgp_ctx* c) {
+    if (!c) return TSVGP_ERR_INVALID;
+    CU(cudaSetDevice(c->dev));
+    CU(cudaStreamSynchronize(c->s_main));
+    return TSVGP_OK;
+}
+
+void* tsvgp_pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void tsvgp_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
+// --- DLPack (dlpack.h v0.8 layout) -------------------------------------------------------------------------------
+typedef struct { int32_t device_type; int32_t device_id; } DLDevice_;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } DLDataType_;
+typedef struct {
+    void* data; DLDevice_ device; int32_t ndim; DLDataType_ dtype; int64_t* shape; int64_t* strides; uint64_t byte_offset;
+} DLTensor_;
+
+int tsvgp_dlpack_view(const void* dl_managed_tensor, tsvgp_view* out) {
+    if (!dl_managed_tensor || !out) return TSVGP_ERR_INVALID;
+    const DLTensor_* t = (const DLTensor_*)dl_managed_tensor;   // DLManagedTensor begins with its DLTensor
+    if (t->dtype.code != 2 /* kDLFloat */ || t->dtype.bits != 64 || t->dtype.lanes != 1) return TSVGP_ERR_INVALID;
+    if (t->ndim < 1 || t->ndim > 3) return TSVGP_ERR_INVALID;
+    int64_t expect = 1;
+    for (int i = t->ndim - 1; i >= 0; --i) {   // compact row-major (strides may be NULL)
+        if (t->strides && t->shape[i] > 1 && t->strides[i] != expect) return TSVGP_ERR_INVALID;
+        expect *= t->shape[i];
+    }
+    out->data = (char*)t->data + t->byte_offset;
+    out->ndim = t->ndim;
+    for (int i = 0; i < 3; ++i) out->shape[i] = i < t->ndim ? t->shape[i] : 1;
+    out->device_type = t->device.device_type;
+    out->device_id = t->device.device_id;
+    return TSVGP_OK;
+}
+
+}  // extern "C"

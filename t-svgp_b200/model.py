@@ -1,0 +1,326 @@
+"""
+Host-side mirror of the reference's `t_SVGP` (reference src/models/tsvgp.py:117-304) for the one hot path this package
+implements: `natgrad_step`, `elbo`, `predict_f` over `DenseSites (lambda_1, lambda_2_sqrt)`.
+
+The GPflow kernel, likelihood and inducing-variable objects are used unchanged: only the attributes the reference path
+reads are touched (duck-typed; `.numpy()` is honoured):
+    kernel      SquaredExponential / RBF / Matern52 : .variance, .lengthscales (scalar, [D] or [1, D])
+    likelihood  Gaussian (.variance) | Bernoulli (inv_probit link) | StudentT (.scale, .df)   [+ .num_gauss_hermite_points]
+    inducing    InducingPoints (.Z) or an ndarray [M, D]
+    mean_function  None / Zero, or a callable evaluated on the host
+All arithmetic runs in libtsvgp.so on the GPU (float64); tensors cross through DLPack + ctypes.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import as_tensor
+
+DEFAULT_N_GH = 20  # gpflow.likelihoods.ScalarLikelihood default (GPflow 2.2.1)
+
+
+def _value(p):
+    if hasattr(p, "numpy"):
+        p = p.numpy()
+    return np.asarray(p, dtype=np.float64)
+
+
+def _kernel_spec(kernel):
+    name = type(kernel).__name__
+    if name in ("SquaredExponential", "RBF"):
+        kind = _lib.KERNEL_SE
+    elif name == "Matern52":
+        kind = _lib.KERNEL_MATERN52
+    else:
+        raise NotImplementedError(f"kernel {name}: the B200 path implements SquaredExponential and Matern52")
+    active = getattr(kernel, "active_dims", None)
+    if active is not None and not (isinstance(active, slice) and active == slice(None, None, None)):
+        raise NotImplementedError("active_dims other than all dimensions")
+    ls = np.atleast_1d(_value(kernel.lengthscales)).reshape(-1)
+    return kind, float(_value(kernel.variance)), ls
+
+
+def _likelihood_spec(lik):
+    name = type(lik).__name__
+    n_gh = int(getattr(lik, "num_gauss_hermite_points", DEFAULT_N_GH))
+    if name == "Gaussian":
+        return _lib.LIK_GAUSSIAN, float(_value(lik.variance)), 0.0, 0
+    if name == "Bernoulli":
+        link = getattr(lik, "invlink", None)
+        if link is not None and getattr(link, "__name__", "inv_probit") != "inv_probit":
+            raise NotImplementedError("Bernoulli: only the inv_probit link is implemented")
+        return _lib.LIK_BERNOULLI_PROBIT, 0.0, 0.0, n_gh
+    if name == "StudentT":
+        return _lib.LIK_STUDENT_T, float(_value(lik.scale)), float(_value(lik.df)), n_gh
+    raise NotImplementedError(f"likelihood {name}: the B200 path implements Gaussian, Bernoulli (probit) and StudentT")
+
+
+class DenseSites:
+    """reference src/sites.py:43-80 — a view of the device-resident sites of one model."""
+
+    def __init__(self, model):
+        self._model = model
+
+    @property
+    def lambda_1(self):
+        return self._model.lambda_1
+
+    @property
+    def lambda_2_sqrt(self):
+        return self._model.lambda_2_sqrt
+
+    @property
+    def lambda_2(self):
+        return self._model.lambda_2
+
+
+class t_SVGP:
+    """Drop-in for the reference `t_SVGP` on the natgrad / elbo / predict_f path (num_latent_gps = 1)."""
+
+    def __init__(self, kernel, likelihood, inducing_variable, *, mean_function=None, num_latent_gps=1, lambda_1=None,
+                 lambda_2_sqrt=None, num_data=None, force=False, device=0):
+        self._lib = _lib.load()
+        self.kernel = kernel
+        self.likelihood = likelihood
+        self.inducing_variable = inducing_variable
+        self.mean_function = mean_function
+        self.num_data = num_data
+        self.whiten = False
+        self.force = force
+        self.name = "t_svgp"
+        if lambda_2_sqrt is not None:
+            lambda_2_sqrt = np.asarray(lambda_2_sqrt, dtype=np.float64)
+            assert lambda_2_sqrt.ndim == 3  # tsvgp.py:182
+            num_latent_gps = lambda_2_sqrt.shape[0]
+        if num_latent_gps != 1:
+            raise NotImplementedError("num_latent_gps > 1 (SURVEY §8f item 3) is not built yet")
+        self.num_latent_gps = 1
+        ctx = C.c_void_p()
+        rc = self._lib.tsvgp_create(C.byref(ctx), int(device))
+        if rc != _lib.OK:
+            msg = self._lib.tsvgp_last_error(None)
+            raise _lib.TsvgpError(rc, msg.decode() if msg else "tsvgp_create failed")
+        self._ctx = ctx
+        self.world_size, self.rank = 1, 0
+        self._kernel_key = self._lik_key = self._z_key = None
+        self._resident = None  # (N_local, keepalive) of the data set by set_data
+        self._sync_objects()
+        if lambda_1 is not None or lambda_2_sqrt is not None:
+            self.assign_sites(lambda_1, None if lambda_2_sqrt is None else lambda_2_sqrt[0])
+
+    # ---- lifetime ------------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.tsvgp_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        _lib.raise_for(self._lib, self._ctx, rc)
+
+    def set_option(self, name, value):
+        self._check(self._lib.tsvgp_set_option(self._ctx, name.encode(), float(value)))
+
+    # ---- model objects -> device (re-read on every call: GPflow parameters are mutable) ---------------------------
+    def _Z(self):
+        iv = self.inducing_variable
+        return _value(iv.Z if hasattr(iv, "Z") else iv)
+
+    def _mean_fn(self, X):
+        mf = self.mean_function
+        if mf is None or type(mf).__name__ == "Zero":
+            return None
+        return np.ascontiguousarray(_value(mf(X)).reshape(X.shape[0], -1)[:, 0])
+
+    def _sync_objects(self):
+        kind, var, ls = _kernel_spec(self.kernel)
+        key = (kind, var, ls.tobytes())
+        if key != self._kernel_key:
+            self._check(self._lib.tsvgp_set_kernel(self._ctx, kind, var, ls.ctypes.data_as(_lib._dp), ls.size))
+            self._kernel_key = key
+        lk = _likelihood_spec(self.likelihood)
+        if lk != self._lik_key:
+            gx = gw = None
+            if lk[3] > 0:
+                x, w = np.polynomial.hermite.hermgauss(lk[3])
+                gx, gw = x.ctypes.data_as(_lib._dp), w.ctypes.data_as(_lib._dp)
+            self._check(self._lib.tsvgp_set_likelihood(self._ctx, lk[0], lk[1], lk[2], lk[3], gx, gw))
+            self._lik_key = lk
+        Z = np.ascontiguousarray(self._Z())
+        if Z.ndim != 2:
+            raise _lib.InvalidArgumentError(_lib.ERR_INVALID, "inducing inputs must be [M, D]")
+        mz = self._mean_fn(Z)
+        zkey = (Z.shape, Z.tobytes(), None if mz is None else mz.tobytes())
+        if zkey != self._z_key:
+            self._check(self._lib.tsvgp_set_inducing(self._ctx, Z.ctypes.data, Z.shape[0], Z.shape[1], None if mz is None else mz.ctypes.data))
+            self._z_key = zkey
+        self._M, self._D = Z.shape
+
+    @property
+    def num_inducing(self):
+        return self._M
+
+    # ---- DenseSites state (sites.py:43-80; tsvgp.py:187-200) --------------------------------------------------------
+    @property
+    def sites(self):
+        return DenseSites(self)
+
+    @property
+    def lambda_1(self):
+        out = np.empty((self._M, 1))
+        self._check(self._lib.tsvgp_get_sites(self._ctx, out.ctypes.data, None))
+        return out
+
+    @property
+    def lambda_2_sqrt(self):
+        out = np.empty((1, self._M, self._M))
+        self._check(self._lib.tsvgp_get_sites(self._ctx, None, out.ctypes.data))
+        return out
+
+    @property
+    def lambda_2(self):
+        out = np.empty((1, self._M, self._M))
+        self._check(self._lib.tsvgp_get_lambda_2(self._ctx, out.ctypes.data))
+        return out
+
+    def assign_sites(self, lambda_1=None, lambda_2_sqrt=None):
+        """`lambda_1.assign(...)` / `lambda_2_sqrt.assign(...)` of the reference (tsvgp.py:302-303)."""
+        l1 = l2 = None
+        if lambda_1 is not None:
+            l1 = np.ascontiguousarray(np.asarray(lambda_1, dtype=np.float64).reshape(-1))
+            if l1.size != self._M:
+                raise _lib.InvalidArgumentError(_lib.ERR_INVALID, f"lambda_1 must have {self._M} entries")
+        if lambda_2_sqrt is not None:
+            l2 = np.ascontiguousarray(np.asarray(lambda_2_sqrt, dtype=np.float64).reshape(-1, self._M, self._M)[0])
+        self._check(self._lib.tsvgp_set_sites(self._ctx, None if l1 is None else l1.ctypes.data, None if l2 is None else l2.ctypes.data))
+
+    def get_mean_chol_cov_inducing_posterior(self):
+        """tsvgp.py:202-212 -> (m_q [M, 1], chol_S [1, M, M])."""
+        self._sync_objects()
+        m = np.empty((self._M, 1))
+        cs = np.empty((1, self._M, self._M))
+        self._check(self._lib.tsvgp_posterior(self._ctx, m.ctypes.data, cs.ctypes.data))
+        return m, cs
+
+    # ---- data -----------------------------------------------------------------------------------------------------
+    def set_data(self, data):
+        """Make (X [N, D], Y [N, 1]) — this rank's rows of the minibatch — resident on the GPU.  Host arrays are copied
+        (H2D); device tensors (DLPack) are aliased and must stay alive and unchanged until the next set_data."""
+        X, Y = data
+        tx, ty = as_tensor(X, "X"), as_tensor(Y, "Y")
+        if len(tx.shape) != 2:
+            raise _lib.InvalidArgumentError(_lib.ERR_INVALID, "X must be [N, D]")
+        N, D = tx.shape
+        ny = int(np.prod(ty.shape))
+        if ny != N:
+            raise _lib.InvalidArgumentError(_lib.ERR_INVALID, f"Y must be [N, 1] with N = {N} (num_latent_gps = 1), got {ty.shape}")
+        mean_x = None
+        if self._mean_fn(np.zeros((1, D))) is not None:
+            if tx.on_device:
+                raise NotImplementedError("a non-zero mean_function needs host-resident X")
+            mean_x = self._mean_fn(np.asarray(X, dtype=np.float64))
+        self._check(self._lib.tsvgp_set_data(self._ctx, tx.ptr, ty.ptr, N, D, None if mean_x is None else mean_x.ctypes.data))
+        self._resident = (N, (tx, ty, mean_x))
+        return N
+
+    def _scale(self, n_local, global_minibatch_size):
+        n = n_local if global_minibatch_size is None else int(global_minibatch_size)
+        if global_minibatch_size is None and self.world_size > 1:
+            raise ValueError("sharded over ranks: pass global_minibatch_size (rows summed over all ranks)")
+        return float(self.num_data) / float(n) if self.num_data is not None else 1.0  # tsvgp.py:89-94, 286-291
+
+    def _ingest(self, data):
+        if data is not None:
+            return self.set_data(data)
+        if self._resident is None:
+            raise _lib.TsvgpError(_lib.ERR_STATE, "no data: pass data=(X, Y) or call set_data first")
+        return self._resident[0]
+
+    # ---- the path ---------------------------------------------------------------------------------------------------
+    def natgrad_step(self, data=None, lr=0.1, jitter=1e-9, *, global_minibatch_size=None, return_elbo=False):
+        """tsvgp.py:234-304.  Mutates lambda_1 / lambda_2_sqrt (on the device).  `data=None` reuses the resident data."""
+        self._sync_objects()
+        n = self._ingest(data)
+        out = C.c_double()
+        self._check(self._lib.tsvgp_natgrad_step(self._ctx, float(lr), float(jitter), self._scale(n, global_minibatch_size),
+                                                 C.byref(out) if return_elbo else None))
+        return out.value if return_elbo else None
+
+    def elbo(self, data=None, *, global_minibatch_size=None):
+        """tsvgp.py:79-95."""
+        self._sync_objects()
+        n = self._ingest(data)
+        out = C.c_double()
+        self._check(self._lib.tsvgp_elbo(self._ctx, self._scale(n, global_minibatch_size), C.byref(out)))
+        return out.value
+
+    def maximum_log_likelihood_objective(self, data=None):  # tsvgp.py:72-77
+        return self.elbo(data)
+
+    def training_loss(self, data=None):
+        return -self.elbo(data)
+
+    def prior_kl(self):
+        """tsvgp.py:65-70."""
+        self._sync_objects()
+        out = C.c_double()
+        self._check(self._lib.tsvgp_prior_kl(self._ctx, C.byref(out)))
+        return out.value
+
+    def predict_f(self, Xnew, full_cov=False, full_output_cov=False):
+        """tsvgp.py:97-114 -> (mean [N, 1], var [N, 1]); raises if any variance is <= 0 (:113)."""
+        if full_cov or full_output_cov:
+            raise NotImplementedError("full_cov / full_output_cov: never exercised on this path by the reference")
+        self._sync_objects()
+        tx = as_tensor(Xnew, "Xnew")
+        if len(tx.shape) != 2:
+            raise _lib.InvalidArgumentError(_lib.ERR_INVALID, "Xnew must be [N, D]")
+        N, D = tx.shape
+        mean_x = None
+        if self._mean_fn(np.zeros((1, D))) is not None:
+            mean_x = self._mean_fn(np.asarray(Xnew, dtype=np.float64))
+        mean, var = np.empty((N, 1)), np.empty((N, 1))
+        self._check(self._lib.tsvgp_predict_f(self._ctx, tx.ptr, N, D, None if mean_x is None else mean_x.ctypes.data,
+                                              mean.ctypes.data, var.ctypes.data))
+        return mean, var
+
+    # ---- multi-GPU: one model (context) per rank ------------------------------------------------------------------------
+    def init_comm(self, world_size, rank, unique_id: bytes):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.tsvgp_comm_init(self._ctx, int(world_size), int(rank), buf))
+        self.world_size, self.rank = int(world_size), int(rank)
+
+    def timings(self):
+        """CUDA-event milliseconds of the last natgrad_step (see tsvgp_get_timings)."""
+        buf = (C.c_double * 8)()
+        self._check(self._lib.tsvgp_get_timings(self._ctx, buf, 8))
+        keys = ["total", "prepare", "stream", "allreduce", "dense", "slabs", "launches"]
+        return {k: buf[i] for i, k in enumerate(keys)}
+
+    def sync(self):
+        self._check(self._lib.tsvgp_sync(self._ctx))
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId — call on rank 0 and send the 128 bytes to the other ranks."""
+    lib = _lib.load()
+    buf = C.create_string_buffer(128)
+    rc = lib.tsvgp_comm_unique_id(buf)
+    if rc != _lib.OK:
+        raise _lib.TsvgpError(rc, "NCCL is not available")
+    return buf.raw
+
+
+def shard_rows(n_rows, world_size, rank):
+    """Contiguous, near-equal row ranges of the minibatch: rank r owns rows [lo, hi)."""
+    base, rem = divmod(int(n_rows), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

@@ -1,0 +1,44 @@
+"""
+Attribute-only stand-ins for the GPflow objects the path reads (GPflow 2.2.1 is not installable in this image).  They
+carry NO arithmetic: class names and attribute names are GPflow's, so `t_SVGP` treats them exactly like the real objects.
+"""
+import numpy as np
+
+
+class SquaredExponential:
+    def __init__(self, variance=1.0, lengthscales=1.0):
+        self.variance = float(variance)
+        self.lengthscales = np.asarray(lengthscales, dtype=np.float64)
+
+
+RBF = SquaredExponential
+
+
+class Matern52:
+    def __init__(self, variance=1.0, lengthscales=1.0):
+        self.variance = float(variance)
+        self.lengthscales = np.asarray(lengthscales, dtype=np.float64)
+
+
+class Gaussian:
+    def __init__(self, variance=1.0):
+        self.variance = float(variance)
+
+
+class Bernoulli:
+    pass
+
+
+class StudentT:
+    def __init__(self, scale=1.0, df=3.0):
+        self.scale = float(scale)
+        self.df = float(df)
+
+
+class InducingPoints:
+    def __init__(self, Z):
+        self.Z = np.array(Z, dtype=np.float64)
+
+    @property
+    def num_inducing(self):
+        return self.Z.shape[0]

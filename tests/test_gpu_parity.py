@@ -1,0 +1,198 @@
+"""
+GPU parity: the CUDA path (through the C-ABI, via the Python mirror of t_SVGP) against the NumPy oracle on the same
+seeded inputs.  Tolerance (BASELINE.json north_star): relative error <= 1e-9 on lambda_1, lambda_2, ELBO and the
+predictive moments — norm-wise, max|a-b| / max|b| (element-wise relative error on near-zero lambda_2 entries
+is meaningless).
+"""
+import numpy as np
+import pytest
+
+from oracle import tsvgp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def _objects(cfg):
+    import tsvgp_b200.synth as synth
+    return synth.build_objects(cfg, orc)
+
+
+def run_pair(cfg, n_rows, M, steps=2, num_data=None, lr=None, Xtest_rows=257, mean_function=None, ard=None, options=None):
+    import tsvgp_b200 as tb
+    import tsvgp_b200.synth as synth
+
+    X, Y, Z = synth.make_minibatch(cfg, n_rows=n_rows, M=M)
+    kernel, lik = _objects(cfg)
+    if ard is not None:
+        kernel.lengthscales = orc._param(ard)
+    lr = cfg["lr"] if lr is None else lr
+    ref = orc.OracleTSVGP(kernel, lik, orc.InducingPoints(Z.copy()), num_data=num_data, mean_function=mean_function)
+    dev = tb.t_SVGP(kernel, lik, orc.InducingPoints(Z.copy()), num_data=num_data, mean_function=mean_function)
+    for k, v in (options or {}).items():
+        dev.set_option(k, v)
+    rng = np.random.default_rng(7)
+    Xt = X[rng.permutation(X.shape[0])[:Xtest_rows]] + 0.05 * rng.standard_normal((min(Xtest_rows, X.shape[0]), X.shape[1]))
+    errs = {}
+    for s in range(steps):
+        e_ref = ref.elbo((X, Y))
+        e_dev_by = dev.natgrad_step((X, Y), lr=lr, return_elbo=True)
+        ref.natgrad_step((X, Y), lr=lr)
+        errs[f"elbo_before_step{s}"] = abs(e_dev_by - e_ref) / abs(e_ref)
+        errs[f"lambda_1_step{s}"] = relerr(dev.lambda_1, ref.lambda_1)
+        errs[f"lambda_2_step{s}"] = relerr(dev.lambda_2, ref.lambda_2)
+    errs["elbo"] = abs(dev.elbo((X, Y)) - ref.elbo((X, Y))) / abs(ref.elbo((X, Y)))
+    mu_d, var_d = dev.predict_f(Xt)
+    mu_r, var_r = ref.predict_f(Xt)
+    errs["mean"] = relerr(mu_d, mu_r)
+    errs["var"] = relerr(var_d, var_r)
+    errs["prior_kl"] = abs(dev.prior_kl() - ref.prior_kl()) / max(abs(ref.prior_kl()), 1e-300)
+    m_d, cs_d = dev.get_mean_chol_cov_inducing_posterior()
+    m_r, cs_r = ref.get_mean_chol_cov_inducing_posterior()
+    errs["m_q"] = relerr(m_d, m_r)
+    errs["S_q"] = relerr(cs_d[0] @ cs_d[0].T, cs_r[0] @ cs_r[0].T)
+    l2s = dev.lambda_2_sqrt
+    assert np.all(np.diagonal(l2s[0]) < 0) and np.allclose(np.triu(l2s[0], 1), 0.0)  # tsvgp.py:300 : -chol(...)
+    dev.close()
+    return errs
+
+
+def check(errs, tol=TOL):
+    bad = {k: v for k, v in errs.items() if not (v <= tol)}
+    assert not bad, "relative errors above %.0e: %s\nall: %s" % (tol, bad, errs)
+
+
+def test_cfg1_gaussian_se_1d_full():
+    import tsvgp_b200.synth as synth
+    cfg = synth.describe("cfg1")
+    check(run_pair(cfg, n_rows=10_000, M=50, steps=2))   # the reference's own CPU-runnable case at its full size
+
+
+def test_cfg2_bernoulli_gh20():
+    import tsvgp_b200.synth as synth
+    cfg = synth.describe("cfg2")
+    check(run_pair(cfg, n_rows=10_000, M=500, steps=2, num_data=100_000))   # full minibatch size of configs[1]
+
+
+def test_cfg3_matern52_reduced():
+    import tsvgp_b200.synth as synth
+    cfg = synth.describe("cfg3")
+    check(run_pair(cfg, n_rows=6000, M=640, steps=2, num_data=60_000))
+
+
+def test_cfg4_se_reduced():
+    import tsvgp_b200.synth as synth
+    cfg = synth.describe("cfg4")
+    check(run_pair(cfg, n_rows=5000, M=768, steps=2))
+
+
+def test_cfg5_student_t_reduced():
+    import tsvgp_b200.synth as synth
+    cfg = synth.describe("cfg5")
+    check(run_pair(cfg, n_rows=5000, M=512, steps=2, num_data=125_000))
+
+
+@pytest.mark.parametrize("n_rows,M", [(1, 1), (3, 2), (127, 128), (129, 129), (1000, 257), (2049, 100)])
+def test_ragged_shapes(n_rows, M):
+    # rows / inducing counts that are not multiples of the 128-wide tiles, down to a single point
+    import tsvgp_b200.synth as synth
+    cfg = synth.describe("cfg2", ls=2.0)
+    check(run_pair(cfg, n_rows=n_rows, M=M, steps=2, Xtest_rows=min(n_rows, 50)))
+
+
+def test_multi_slab_and_single_stream():
+    # several slabs per pass (ping-pong accumulators) and the single-stream schedule give the same numbers
+    import tsvgp_b200.synth as synth
+    cfg = synth.describe("cfg3")
+    check(run_pair(cfg, n_rows=3000, M=256, steps=2, options={"chunk": 256}))
+    check(run_pair(cfg, n_rows=3000, M=256, steps=2, options={"chunk": 384, "streams": 1}))
+
+
+def test_lr_one_and_ard_and_mean_function():
+    import tsvgp_b200.synth as synth
+    cfg = synth.describe("cfg5")
+    ard = np.linspace(2.0, 4.0, cfg["D"])
+    check(run_pair(cfg, n_rows=1500, M=200, steps=3, lr=1.0, ard=ard, mean_function=lambda X: 0.3 + 0.1 * X[:, :1]))
+
+
+def test_minibatch_scaling_identity():
+    # reference tests/models/test_tsvgp.py:148-165 : num_data = 8 with one point == the point replicated 8 times
+    import tsvgp_b200 as tb
+    rng = np.random.RandomState(123)
+    X = rng.rand(8, 1) * 2 - 1
+    Y = np.sin(3 * X) + 0.2 * rng.randn(8, 1)
+    k, lik = orc.SquaredExponential(lengthscales=0.5, variance=2.25), orc.Gaussian(variance=0.3)
+    m = tb.t_SVGP(k, lik, orc.InducingPoints(X.copy()))
+    for _ in range(5):
+        m.natgrad_step((X, Y), lr=0.9)
+    e2 = m.elbo((X[0].repeat(8)[:, None], Y[0].repeat(8)[:, None]))
+    m.num_data = 8
+    e1 = m.elbo((X[0][:, None], Y[0][:, None]))
+    assert abs(e1 - e2) <= 1e-10 * abs(e2)
+    m.close()
+
+
+def test_gaussian_fixed_point_is_gp_regression():
+    # reference tests/models/test_tsvgp.py:106-120 (decimal=4): Z = X, lr -> optimum == exact GP regression
+    import tsvgp_b200 as tb
+    rng = np.random.RandomState(123)
+    X = rng.rand(8, 1) * 2 - 1
+    Y = np.sin(X * 3 * 3.14) + 0.3 * np.cos(X * 9 * 3.14) + 0.5 * np.sin(X * 7 * 3.14) + 0.2 * rng.randn(8, 1)
+    k, lik = orc.SquaredExponential(lengthscales=2.0, variance=2.25), orc.Gaussian(variance=0.3)
+    m = tb.t_SVGP(k, lik, orc.InducingPoints(X.copy()))
+    for _ in range(10):
+        m.natgrad_step((X, Y), lr=0.9)
+    np.testing.assert_almost_equal(m.elbo((X, Y)), orc.gpr_log_marginal_likelihood(k, X, Y, 0.3), decimal=4)
+    mu, var = m.predict_f(X + 1.0)
+    mu_g, var_g = orc.gpr_predict_f(k, X, Y, 0.3, X + 1.0)
+    np.testing.assert_array_almost_equal(mu, mu_g, decimal=4)
+    np.testing.assert_array_almost_equal(var, var_g, decimal=4)
+    e0 = m.elbo((X, Y))
+    m.natgrad_step((X, Y), lr=0.9)   # :134-145 unchanged at the optimum
+    np.testing.assert_almost_equal(e0, m.elbo((X, Y)), decimal=4)
+    m.close()
+
+
+def test_errors_leave_sites_unchanged():
+    import tsvgp_b200 as tb
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((200, 2))
+    Y = rng.standard_normal((200, 1))
+    Z = np.concatenate([X[:10], X[:1]])   # duplicated inducing point: Kuu + 0*I is singular
+    m = tb.t_SVGP(orc.SquaredExponential(lengthscales=1.0), orc.Gaussian(variance=0.1), Z)
+    m.natgrad_step((X, Y), lr=0.5)         # fine with the default jitter
+    l1, l2 = m.lambda_1, m.lambda_2_sqrt
+    with pytest.raises(tb.InvalidArgumentError) as ei:
+        m.natgrad_step((X, Y), lr=0.5, jitter=0.0)
+    assert isinstance(ei.value, tb.NotPositiveDefiniteError) and ei.value.pivot == 11
+    np.testing.assert_array_equal(m.lambda_1, l1)
+    np.testing.assert_array_equal(m.lambda_2_sqrt, l2)
+    with pytest.raises(tb.InvalidArgumentError):
+        m.predict_f(np.zeros((3, 5)))     # wrong D
+    m.natgrad_step((X, Y), lr=0.5)         # the context is still usable
+    m.close()
+
+
+def test_device_resident_dlpack_inputs():
+    # tensors already on the GPU are aliased through DLPack (torch is only the producer here, not part of the product)
+    torch = pytest.importorskip("torch")
+    import tsvgp_b200 as tb
+    import tsvgp_b200.synth as synth
+    cfg = synth.describe("cfg3")
+    X, Y, Z = synth.make_minibatch(cfg, n_rows=2000, M=128)
+    kernel, lik = _objects(cfg)
+    a = tb.t_SVGP(kernel, lik, Z.copy())
+    b = tb.t_SVGP(kernel, lik, Z.copy())
+    Xd, Yd = torch.from_numpy(X).cuda(), torch.from_numpy(Y).cuda()
+    a.natgrad_step((X, Y), lr=0.5)
+    b.set_data((Xd, Yd))
+    b.natgrad_step(lr=0.5)
+    np.testing.assert_array_equal(a.lambda_1, b.lambda_1)
+    np.testing.assert_array_equal(a.lambda_2_sqrt, b.lambda_2_sqrt)
+    a.close(); b.close()

@@ -1,0 +1,10 @@
+"""Import shim: the package directory is `t-svgp_b200/` (not a valid module name); `import tsvgp_b200` loads it."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "t-svgp_b200")
+_spec = importlib.util.spec_from_file_location("tsvgp_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["tsvgp_b200"] = _mod
+_spec.loader.exec_module(_mod)
