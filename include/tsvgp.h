@@ -61,7 +61,10 @@ TSVGP_API int tsvgp_set_option(tsvgp_ctx* ctx, const char* name, double value); 
 
 /* options: "chunk" (points per Kuf slab; 0 = automatic, ~32 MB slabs that stay in L2), "streams" (1|2 ping-pong streams),
  * "cache_factors" (1 = keep chol(Kuu+jitter I) and the posterior factors while kernel, Z and sites are unchanged),
- * "invalidate" (any value: drop every cached factor now)                                                              */
+ * "invalidate" (any value: drop every cached factor now),
+ * "route" (0 = automatic, 1 = fused: B = Kuf diag(h) Kfu then K9^-1 B K9^-1 — 2 M^2 flops per point, rounding ~ eps cond(Kuu)^2;
+ *          2 = whitened: C9^-1 Kuf first, as the reference's order A = K9^-1 Kuf — 3 M^2 flops per point, rounding ~ eps cond),
+ * "route_cond_max" (automatic: fused while the power-iteration estimate of cond(Kuu + jitter I) is below this; default 2e4) */
 
 /* ---- model objects read by the path (tsvgp.py:209,268-269; GPflow kernel / likelihood / inducing attributes) ------ */
 /* lengthscales: HOST pointer, n_ls = 1 (isotropic) or D (ARD)                                                          */
@@ -105,7 +108,7 @@ TSVGP_API int tsvgp_comm_size(const tsvgp_ctx* ctx);
 /* ---- measurement ------------------------------------------------------------------------------------------------------ */
 /* CUDA-event durations (ms) of the last natgrad_step, on the context's stream.  out[0..n):
  *  0 total, 1 prepare (posterior factors), 2 streaming pass, 3 all-reduce, 4 dense update, 5 number of slabs,
- *  6 kernels launched by the step                                                                                       */
+ *  6 kernels launched by the step, 7 route used (1 fused, 2 whitened), 8 estimated cond(Kuu + jitter I) (0 if not probed) */
 TSVGP_API int tsvgp_get_timings(tsvgp_ctx* ctx, double* out, int n);
 TSVGP_API int tsvgp_sync(tsvgp_ctx* ctx);
 TSVGP_API void* tsvgp_pinned_alloc(size_t bytes);                                             /* cudaHostAlloc, for staging buffers  */

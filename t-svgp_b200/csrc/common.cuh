@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #define TSVGP_TILE 128  // all matrix dimensions inside the library are padded to a multiple of this
 
@@ -11,7 +12,19 @@ namespace tsvgp {
 
 // kernels launched by this host thread (reported by tsvgp_get_timings; the bench's gpu_launches)
 extern thread_local long g_launches;
-inline int count_launch() { ++g_launches; return (int)cudaGetLastError(); }
+extern int g_debug_sync;   // TSVGP_DEBUG_SYNC=1 : synchronise after every launch so a faulting kernel is reported at its call site
+inline int count_launch_at(const char* where) {
+    ++g_launches;
+    if (g_debug_sync) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            fprintf(stderr, "[tsvgp] launch #%ld in %s: %s\n", g_launches, where, cudaGetErrorString(e));
+            return (int)e;
+        }
+    }
+    return (int)cudaGetLastError();
+}
+#define count_launch() count_launch_at(__func__)
 
 // D(8x8) += A(8x4,row) * B(4x8,col).  lane = 4*g + t :  a = A[g][t],  b = B[t][g],  c0,c1 = C[g][2t], C[g][2t+1]
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {

@@ -652,6 +652,15 @@ int vadd_inplace_launch(double* dst, const double* src, long n, cudaStream_t s) 
     vadd_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, src, n);
     return count_launch();
 }
+// v[i] = 1 + 0.5 sin(1.7 i) for i < M, 0 on the padding: deterministic start vector of the conditioning probe
+__global__ void probe_vector_kernel(double* v, int M, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i < M ? 1.0 + 0.5 * sin(1.7 * (double)i) : 0.0;
+}
+int probe_vector_launch(double* v, int M, int Mp, cudaStream_t s) {
+    probe_vector_kernel<<<(Mp + 255) / 256, 256, 0, s>>>(v, M, Mp);
+    return count_launch();
+}
 // stats tail: out[0] = sum of ve partials, out[1] = flags[0] as a double
 __global__ void __launch_bounds__(256) stats_tail_kernel(const double* ve_blocks, long nblocks, const int* flags, double* out) {
     __shared__ double sred[8];

@@ -85,6 +85,7 @@ int logdiag_launch(const double* A, long lda, int n, double* out, cudaStream_t s
 // P = coef*G + jitter*I on [0,M)^2, identity on the padding block
 int init_update_launch(const double* G, double* P, long ld, int M, int Mp, double coef, double jitter, cudaStream_t s);
 int set_scaled_identity_launch(double* A, long ld, int M, int Mp, double v, double vpad, cudaStream_t s);
+int probe_vector_launch(double* v, int M, int Mp, cudaStream_t s);
 int vadd_inplace_launch(double* dst, const double* src, long n, cudaStream_t s);
 int stats_tail_launch(const double* ve_blocks, long nblocks, const int* flags, double* out, cudaStream_t s);
 

@@ -19,12 +19,14 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
 
 namespace tsvgp {
 thread_local long g_launches = 0;
+int g_debug_sync = 0;
 }
 using namespace tsvgp;
 
@@ -55,7 +57,8 @@ enum { MODE_STATS = 0, MODE_ELBO = 1, MODE_PREDICT = 2 };
 enum { INFO_W = 0, INFO_K9 = 1, INFO_P = 2, INFO_S = 3, N_INFO = 4 };
 enum { EV_T0 = 0, EV_PREP, EV_STREAM, EV_REDUCE, EV_DENSE, N_EV };
 // device scalars
-enum { SC_LOGDIAG_W = 0, SC_M_ALPHA, SC_TR_QK, N_SCAL = 8 };
+enum { SC_LOGDIAG_W = 0, SC_M_ALPHA, SC_TR_QK, SC_PK0, SC_PK1, SC_PI0, SC_PI1, N_SCAL = 8 };
+enum { ROUTE_AUTO = 0, ROUTE_FUSED = 1, ROUTE_WHITENED = 2 };
 
 }  // namespace
 
@@ -70,6 +73,10 @@ struct tsvgp_ctx {
     long chunk_opt = 0;        // 0 = automatic
     int n_streams = 2;
     int cache_factors = 1;     // keep chol(K9) and the posterior factors between calls while their inputs are unchanged
+    int route_opt = ROUTE_AUTO;     // statistics route: fused (B = Kuf H Kfu, then K9^-1 B K9^-1) or whitened (C9^-1 Kuf first)
+    double route_cond_max = 2e4;    // auto: fused while the estimated cond(Kuu + jitter I) is below this
+    int route = ROUTE_FUSED;        // route of the current / last step
+    double cond_est = 0.0;
 
     // kernel / likelihood
     int kern_kind = -1;
@@ -111,6 +118,8 @@ struct tsvgp_ctx {
     Pool pc;
     long chunk = 0;
     int chunk_Mp = 0;
+    int chunk_route = 0;
+    double *wslab[2] = {};
     double *slab[2] = {}, *mu_part[2] = {}, *q_part[2] = {}, *gbuf[2] = {}, *hbuf[2] = {};
     double* ve_blocks = nullptr;
     long ve_cap = 0;
@@ -172,7 +181,8 @@ int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     NEED(c->K = p.get(mm)); NEED(c->K6 = p.get(mm)); NEED(c->L2 = p.get(mm)); NEED(c->lam1 = p.get(mp));
     NEED(c->Wm = p.get(mm)); NEED(c->Wf = p.get(mm)); NEED(c->V = p.get(mm)); NEED(c->T = p.get(mm));
     NEED(c->X1 = p.get(mm)); NEED(c->X2 = p.get(mm)); NEED(c->C9 = p.get(mm)); NEED(c->C9inv = p.get(mm));
-    NEED(c->G2 = p.get(mm)); NEED(c->P = p.get(mm)); NEED(c->tmp = p.get(mm / 2 + mp)); NEED(c->dinv = p.get((size_t)(c->Mp / 128) * 128 * 128));
+    NEED(c->G2 = p.get(mm)); NEED(c->P = p.get(mm)); NEED(c->tmp = p.get((size_t)((c->Mp / 128 + 1) / 2) * 128 * mp));   // trtri_lower: ceil(nblk/2) block rows
+    NEED(c->dinv = p.get((size_t)(c->Mp / 128) * 128 * 128));
     for (int s = 0; s < 2; ++s) NEED(c->stats[s] = p.get(mm + mp + 4));
     NEED(c->alpha = p.get(mp)); NEED(c->mZ = p.get(mp)); NEED(c->mq = p.get(mp)); NEED(c->v1 = p.get(mp)); NEED(c->v2 = p.get(mp));
     NEED(c->v3 = p.get(mp)); NEED(c->gwork = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal = p.get(N_SCAL));
@@ -309,6 +319,7 @@ long pick_chunk(const tsvgp_ctx* c) {
     long nc = c->chunk_opt;
     if (nc <= 0) {   // one slab = Mp * nc * 8 B ~ 32 MB, so both ping-pong slabs stay inside the 126 MB L2
         nc = (32l << 20) / (8l * c->Mp);
+        if (c->route == ROUTE_WHITENED) nc /= 2;   // a second (whitened) slab per stream shares the L2
         if (nc > 8192) nc = 8192;
     }
     nc = nc / 128 * 128;
@@ -320,11 +331,15 @@ int ensure_slabs(tsvgp_ctx* c, long n_points) {
     const long nc = pick_chunk(c);
     const long nchunks = (n_points + nc - 1) / nc;
     const long ve_need = (nchunks + 1) * ((nc + 255) / 256);
-    if (c->chunk == nc && c->chunk_Mp == c->Mp && c->ve_cap >= ve_need) return TSVGP_OK;
+    const bool need_w = c->route == ROUTE_WHITENED;
+    if (c->chunk == nc && c->chunk_Mp == c->Mp && c->ve_cap >= ve_need && (!need_w || c->wslab[0])) return TSVGP_OK;
+    CU(cudaStreamSynchronize(c->s_main));
     c->pc.release();
+    c->wslab[0] = c->wslab[1] = nullptr;
     Pool& p = c->pc;
     for (int s = 0; s < 2; ++s) {
         NEED(c->slab[s] = p.get((size_t)c->Mp * nc));
+        if (need_w) NEED(c->wslab[s] = p.get((size_t)c->Mp * nc));
         NEED(c->mu_part[s] = p.get((size_t)(c->Mp / 64) * nc));
         NEED(c->q_part[s] = p.get((size_t)(c->Mp / 128) * nc));
         NEED(c->gbuf[s] = p.get(nc));
@@ -387,16 +402,25 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
             LA(point_stats_launch(c->lik, a, c->gh, s));
         }
         if (mode == MODE_STATS) {
+            const double* stat_slab = c->slab[b];
+            if (c->route == ROUTE_WHITENED) {   // (c') whitened slab  C9^-1 K  (reference order: A = K9^-1 Kuf first, tsvgp.py:271)
+                GemmP p;
+                p.A = c->C9inv; p.lda = Mp; p.a_kc = 1; p.a_tri = 1;
+                p.B = c->slab[b]; p.ldb = nc; p.b_kc = 0;
+                p.C = c->wslab[b]; p.ldc = nc; p.m = Mp; p.n = ncols; p.k = Mp;
+                LA(gemm_launch(p, s));
+                stat_slab = c->wslab[b];
+            }
             {   // (d) B += K diag(h) K^T, lower tiles
                 GemmP p;
-                p.A = c->slab[b]; p.lda = nc; p.a_kc = 1;
-                p.B = c->slab[b]; p.ldb = nc; p.b_kc = 1;
+                p.A = stat_slab; p.lda = nc; p.a_kc = 1;
+                p.B = stat_slab; p.ldb = nc; p.b_kc = 1;
                 p.C = c->stats[b]; p.ldc = Mp; p.m = p.n = Mp; p.k = ncols;
                 p.beta = 1.0; p.lower_out = 1; p.kscale = c->hbuf[b];
                 LA(gemm_launch(p, s));
             }
             // (e) b += K g
-            LA(gemv_n_launch(c->slab[b], nc, Mp, ncols, c->gbuf[b], 1.0, 1.0, c->stats[b] + (size_t)Mp * Mp, s));
+            LA(gemv_n_launch(stat_slab, nc, Mp, ncols, c->gbuf[b], 1.0, 1.0, c->stats[b] + (size_t)Mp * Mp, s));
         }
     }
     for (int s = 0; s < nstr; ++s) {
@@ -426,6 +450,40 @@ int ensure_k9(tsvgp_ctx* c, double jitter) {
     LA(trtri_lower(c->C9, c->Mp, c->Mp, c->dinv, c->C9inv, c->tmp, s));
     c->k9_valid = true;
     c->k9_jitter = jitter;
+    c->cond_est = 0.0;
+    if (c->route_opt == ROUTE_AUTO) {
+        // conditioning probe: 8 power iterations each on K and on K9^-1 = C9^-T C9^-1; Rayleigh ratios of the last two
+        // iterates give lambda_max(K) and 1/lambda_min(K9) (both from below)
+        const int n = c->Mp;
+        double *a = c->v1, *b = c->v2;
+        LA(probe_vector_launch(a, c->M, n, s));
+        for (int it = 0; it < 8; ++it) {
+            if (it == 7) LA(dot_launch(a, a, c->M, c->scal + SC_PK0, s));
+            LA(gemv_n_launch(c->K, n, c->M, c->M, a, 1.0, 0.0, b, s));
+            double* t = a; a = b; b = t;
+        }
+        LA(dot_launch(a, a, c->M, c->scal + SC_PK1, s));
+        LA(probe_vector_launch(a, c->M, n, s));
+        for (int it = 0; it < 8; ++it) {
+            if (it == 7) LA(dot_launch(a, a, n, c->scal + SC_PI0, s));
+            LA(gemv_n_launch(c->C9inv, n, n, n, a, 1.0, 0.0, b, s));
+            LA(gemv_t_launch(c->C9inv, n, n, n, b, a, c->gwork, s));
+        }
+        LA(dot_launch(a, a, n, c->scal + SC_PI1, s));
+        double sc[N_SCAL];
+        CU(cudaMemcpyAsync(sc, c->scal, sizeof sc, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        const double lmax = sqrt(sc[SC_PK1] / sc[SC_PK0]) + jitter, inv_lmin = sqrt(sc[SC_PI1] / sc[SC_PI0]);
+        c->cond_est = lmax * inv_lmin;
+        if (!(c->cond_est == c->cond_est)) c->cond_est = INFINITY;   // failed factorisation: the step will report it
+    }
+    return TSVGP_OK;
+}
+
+int choose_route(tsvgp_ctx* c, double jitter) {
+    OK(ensure_k9(c, jitter));
+    if (c->route_opt == ROUTE_AUTO) c->route = c->cond_est <= c->route_cond_max ? ROUTE_FUSED : ROUTE_WHITENED;
+    else c->route = c->route_opt;
     return TSVGP_OK;
 }
 
@@ -438,28 +496,32 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale) {
     double* B = c->stats[0];
     double* bvec = c->stats[0] + mm;
     const double* bad = c->stats[0] + mm + n + 1;
-    OK(ensure_k9(c, jitter));
     LA(mirror_lower_launch(B, ld, n, s));
-    {   // X1 = C9^-1 B
-        GemmP p;
-        p.A = c->C9inv; p.lda = ld; p.a_kc = 1; p.a_tri = 1;
-        p.B = B; p.ldb = ld; p.b_kc = 0;
-        p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
-        LA(gemm_launch(p, s));
+    if (c->route == ROUTE_FUSED) {
+        {   // X1 = C9^-1 B
+            GemmP p;
+            p.A = c->C9inv; p.lda = ld; p.a_kc = 1; p.a_tri = 1;
+            p.B = B; p.ldb = ld; p.b_kc = 0;
+            p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
+            LA(gemm_launch(p, s));
+        }
+        {   // X2 = X1 C9^-T  (symmetric; lower tiles then mirrored)
+            GemmP p;
+            p.A = c->X1; p.lda = ld; p.a_kc = 1;
+            p.B = c->C9inv; p.ldb = ld; p.b_kc = 1; p.b_tri = 1;
+            p.C = c->X2; p.ldc = ld; p.m = p.n = p.k = n;
+            p.lower_out = 1;
+            LA(gemm_launch(p, s));
+        }
+        LA(mirror_lower_launch(c->X2, ld, n, s));
+        LA(gemv_n_launch(c->C9inv, ld, n, n, bvec, 1.0, 0.0, c->v1, s));   // v1 = C9^-1 b
     }
-    {   // X2 = X1 C9^-T  (symmetric; lower tiles then mirrored)
-        GemmP p;
-        p.A = c->X1; p.lda = ld; p.a_kc = 1;
-        p.B = c->C9inv; p.ldb = ld; p.b_kc = 1; p.b_tri = 1;
-        p.C = c->X2; p.ldc = ld; p.m = p.n = p.k = n;
-        p.lower_out = 1;
-        LA(gemm_launch(p, s));
-    }
-    LA(mirror_lower_launch(c->X2, ld, n, s));
-    {   // X1 = C9^-T X2
+    const double* Bw = c->route == ROUTE_FUSED ? c->X2 : B;      // C9^-1 (Kuf H Kfu) C9^-T, symmetric
+    const double* bw = c->route == ROUTE_FUSED ? c->v1 : bvec;   // C9^-1 Kuf g
+    {   // X1 = C9^-T Bw
         GemmP p;
         p.A = c->C9inv; p.lda = ld; p.a_kc = 0; p.a_tri = 2;
-        p.B = c->X2; p.ldb = ld; p.b_kc = 0;
+        p.B = Bw; p.ldb = ld; p.b_kc = 0;
         p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
         LA(gemm_launch(p, s));
     }
@@ -472,9 +534,8 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale) {
         LA(gemm_launch(p, s));
     }
     LA(mirror_lower_launch(c->G2, ld, n, s));
-    // G1 = C9^-T C9^-1 b ; G2 mZ
-    LA(gemv_n_launch(c->C9inv, ld, n, n, bvec, 1.0, 0.0, c->v1, s));
-    LA(gemv_t_launch(c->C9inv, ld, n, n, c->v1, c->v2, c->gwork, s));
+    // G1 = C9^-T bw ; G2 mZ
+    LA(gemv_t_launch(c->C9inv, ld, n, n, bw, c->v2, c->gwork, s));
     LA(gemv_n_launch(c->G2, ld, n, n, c->mZ, 1.0, 0.0, c->v3, s));
     // P = (1-lr) L2 L2^T - 2 lr scale G2 + jitter I                                     tsvgp.py:293-300
     LA(init_update_launch(c->G2, c->P, ld, c->M, n, -2.0 * lr * scale, jitter, s));
@@ -565,6 +626,7 @@ int tsvgp_create(tsvgp_ctx** out, int device_id) {
                          "); libtsvgp is built for sm_100a only";
         return TSVGP_ERR_CUDA;
     }
+    if (const char* dbg = getenv("TSVGP_DEBUG_SYNC")) g_debug_sync = atoi(dbg);
     tsvgp_ctx* c = new tsvgp_ctx();
     c->dev = device_id;
     bool ok = cudaSetDevice(device_id) == cudaSuccess;
@@ -609,6 +671,8 @@ int tsvgp_set_option(tsvgp_ctx* c, const char* name, double value) {
     if (!c || !name) return TSVGP_ERR_INVALID;
     if (!strcmp(name, "chunk")) { c->chunk_opt = (long)value; return TSVGP_OK; }
     if (!strcmp(name, "streams")) { c->n_streams = value >= 2 ? 2 : 1; return TSVGP_OK; }
+    if (!strcmp(name, "route")) { c->route_opt = (int)value; c->k9_valid = false; return TSVGP_OK; }
+    if (!strcmp(name, "route_cond_max")) { c->route_cond_max = value; return TSVGP_OK; }
     if (!strcmp(name, "cache_factors")) { c->cache_factors = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "invalidate")) { c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = false; return TSVGP_OK; }
     FAIL(TSVGP_ERR_INVALID, "unknown option '%s'", name);
@@ -769,6 +833,7 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
     OK(ensure_xs(c));
     OK(ensure_posterior(c));
     if (elbo_before) OK(ensure_kl_terms(c));
+    OK(choose_route(c, jitter));
     CU(cudaEventRecord(c->ev[EV_PREP], s));
     OK(stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_STATS, nullptr, nullptr));
     CU(cudaEventRecord(c->ev[EV_STREAM], s));
@@ -791,6 +856,8 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
     c->timings[0] = ms;
     c->timings[5] = (double)((c->N + c->chunk - 1) / c->chunk);
     c->timings[6] = (double)(g_launches - launches0);
+    c->timings[7] = (double)c->route;
+    c->timings[8] = c->cond_est;
     OK(check_info(c, info_h));
     if (tail[1] != 0.0) {
         c->post_valid = c->kl_valid = false;

@@ -300,9 +300,9 @@ class t_SVGP:
 
     def timings(self):
         """CUDA-event milliseconds of the last natgrad_step (see tsvgp_get_timings)."""
-        buf = (C.c_double * 8)()
-        self._check(self._lib.tsvgp_get_timings(self._ctx, buf, 8))
-        keys = ["total", "prepare", "stream", "allreduce", "dense", "slabs", "launches"]
+        buf = (C.c_double * 9)()
+        self._check(self._lib.tsvgp_get_timings(self._ctx, buf, 9))
+        keys = ["total", "prepare", "stream", "allreduce", "dense", "slabs", "launches", "route", "cond_est"]
         return {k: buf[i] for i, k in enumerate(keys)}
 
     def sync(self):
