@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""
+bench.py — natgrad_step datapoints/s of the B200 t-SVGP path (BASELINE.json metric), one JSON line on rank 0.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg3] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one `t_SVGP.natgrad_step` (posterior factors + streaming statistics pass + all-reduce + dense site update) over
+one minibatch of the named config, sharded by rows over the N ranks (strong scaling: the minibatch is fixed).
+  value : minibatch rows / step time with the minibatch resident in HBM when the clock starts (4 distinct minibatches rotate)
+  e2e   : the same through the public API with HOST (pinned) buffers: H2D of the rank's rows every step, and the pre-step
+          ELBO and lambda_1 read back, inside the timed region
+  roofline     : the DMMA weighted-SYRK kernel, timed live with CUDA events (single-stream profiled pass after the timed region)
+  cpu_baseline : the NumPy/SciPy restatement of the reference (oracle/) on the host cores, bounded sample, extrapolated in N
+`--impl reference` times that CPU restatement alone (TensorFlow/GPflow are not installable in this image).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FP64_PEAK_TFLOPS = 37.1   # measured on this pool: tools/fp64_peak (DMMA m8n8k4 issue rate), profiles/fp64_peak_r01.txt
+N_RESIDENT_MINIBATCHES = 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="cfg3")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--minibatch", type=int, default=None, help="override the config's minibatch rows (debugging)")
+    ap.add_argument("--M", type=int, default=None, help="override the number of inducing points (debugging)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--keep-cache", action="store_true", help="do not invalidate the kernel-matrix factors every step")
+    return ap.parse_args()
+
+
+# ---- clocks -------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out, _ = self.p.communicate()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- CPU baseline (oracle = NumPy restatement of the reference) -------------------------------------------------------
+def cpu_reference_step_time(cfg, M, n_rows, repeats=1):
+    """Seconds of one reference-order natgrad_step (oracle) on `n_rows` rows with the full M, from non-trivial sites."""
+    import tsvgp_b200.synth as synth
+    from oracle import tsvgp_oracle as orc
+    X, Y, Z = synth.make_minibatch(cfg, n_rows=n_rows, M=M)
+    kernel, lik = synth.build_objects(cfg, orc)
+    m = orc.OracleTSVGP(kernel, lik, orc.InducingPoints(Z), num_data=cfg["N"])
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        m.natgrad_step((X, Y), lr=cfg["lr"])
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(cfg, M, Nb, n_small, n_large):
+    """t(N) = a + b N fitted on two row counts (dense M x M part + streaming part), extrapolated to the full minibatch."""
+    cpu_reference_step_time(cfg, M, 64)            # warm OpenBLAS threads / page in
+    t_small = cpu_reference_step_time(cfg, M, n_small)
+    t_large = cpu_reference_step_time(cfg, M, n_large)
+    b = max((t_large - t_small) / (n_large - n_small), 1e-12)
+    a = max(t_small - b * n_small, 0.0)
+    t_full = a + b * Nb
+    return {"value": Nb / t_full, "unit": "datapoints/s", "cores": cpu_threads(), "kind": "port",
+            "sample": f"oracle (NumPy/SciPy restatement of the reference, not TensorFlow) natgrad_step at {n_small} and {n_large} rows, "
+                      f"M={M} full; t(N)=a+bN extrapolated to the {Nb}-row minibatch (a={a:.3f}s dense, b={b * 1e6:.3f}us/row)",
+            "host_cpus": os.cpu_count(), "t_full_step_s": t_full}
+
+
+def sample_sizes(M):
+    # bounded: ~10-30 s of CPU work in total (8 N M^2 streaming + 37 M^3 dense flops at a few hundred GFLOP/s)
+    budget = 2.5e12
+    n_large = int(min(65536, max(2048, budget / (8.0 * M * M))))
+    n_large = max(256, n_large // 256 * 256)
+    return max(128, n_large // 4), n_large
+
+
+# ---- the reference arm -----------------------------------------------------------------------------------------------
+def run_reference(args, cfg, M, Nb):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_small, n_large = sample_sizes(M)
+    a_dense = None
+    times = []
+    cpu_reference_step_time(cfg, M, 64)
+    t_small = cpu_reference_step_time(cfg, M, n_small)
+    for i in range(args.warmup + args.steps):
+        t = cpu_reference_step_time(cfg, M, n_large)
+        if i >= args.warmup:
+            times.append(t)
+    t_large = float(np.mean(times))
+    b = max((t_large - t_small) / (n_large - n_small), 1e-12)
+    a_dense = max(t_small - b * n_small, 0.0)
+    t_full = a_dense + b * Nb
+    value = Nb / t_full
+    line = {
+        "impl": "reference", "metric": "natgrad_step datapoints/sec", "value": value, "unit": "datapoints/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(cfg, M, Nb, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "datapoints/s", "cores": cpu_threads(), "kind": "port",
+                         "sample": f"each step = oracle natgrad_step on {n_large} rows (M={M} full); dense part from a {n_small}-row step; "
+                                   f"t(N)=a+bN extrapolated to {Nb} rows (a={a_dense:.3f}s, b={b * 1e6:.3f}us/row); NumPy/SciPy restatement, "
+                                   "TensorFlow/GPflow not installable here", "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "datapoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, M, Nb, n_gpus):
+    return {"workload": f"{cfg['name']}: {cfg['lik']} likelihood, synthetic D={cfg['D']}, N={cfg['N']}, M={M}, {cfg['kernel']} kernel, "
+                        f"minibatch {Nb} sharded by rows over {n_gpus} GPU(s), lr={cfg['lr']}",
+            "M": M, "D": cfg["D"], "minibatch": Nb, "num_data": cfg["N"], "kernel": cfg["kernel"], "likelihood": cfg["lik"],
+            "parallelism": f"rows/{n_gpus} + 1 allreduce, dense phase replicated",
+            "l2": f"inputs larger than L2: {N_RESIDENT_MINIBATCHES} distinct resident minibatches rotate; the Kuf slabs are L2-resident by design"}
+
+
+# ---- our arm -------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    import tsvgp_b200.synth as synth
+    cfg = synth.describe(args.config)
+    M = args.M or cfg["M"]
+    Nb = args.minibatch or cfg["Nb"]
+    if args.impl == "reference":
+        return run_reference(args, cfg, M, Nb)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist   # plumbing only: rendezvous, barrier, max over ranks (gloo; no tensors on the GPU)
+        dist.init_process_group("gloo")
+
+    import tsvgp_b200 as tb
+    from tsvgp_b200 import standins as st
+
+    kernel, lik = synth.build_objects(cfg, st)
+    lo, hi = tb.shard_rows(Nb, world, rank)
+    n_local = hi - lo
+    # synthetic minibatches (same seeds on every rank; each rank keeps its rows)
+    mbs_host = []
+    Z = None
+    for i in range(N_RESIDENT_MINIBATCHES):
+        X, Y, Zi = synth.make_minibatch(cfg, n_rows=Nb, M=M, seed_offset=100 * i)
+        if Z is None:
+            Z = Zi
+        mbs_host.append((np.ascontiguousarray(X[lo:hi]), np.ascontiguousarray(Y[lo:hi])))
+        del X, Y
+
+    model = tb.t_SVGP(kernel, lik, Z, num_data=cfg["N"], device=local_rank)
+    if world > 1:
+        import torch
+        if rank == 0:
+            uid = tb.comm_unique_id()
+            t = torch.tensor(list(uid), dtype=torch.uint8)
+        else:
+            t = torch.zeros(128, dtype=torch.uint8)
+        dist.broadcast(t, 0)
+        model.init_comm(world, rank, bytes(t.tolist()))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    mbs_dev = [(model.device_array(X), model.device_array(Y)) for X, Y in mbs_host]
+    invalidate = not args.keep_cache
+
+    def step_resident(i):
+        if invalidate:
+            model.set_option("invalidate", 1)   # kernel matrices and their factors are rebuilt every step, as the reference does
+        model.set_data(mbs_dev[i % N_RESIDENT_MINIBATCHES])
+        model.natgrad_step(lr=cfg["lr"], global_minibatch_size=Nb)
+
+    # ---------- value: device-resident inputs ----------
+    for i in range(args.warmup):
+        step_resident(i)
+    model.sync(); barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches = 0
+    phase = {"prepare": 0.0, "stream": 0.0, "allreduce": 0.0, "dense": 0.0}
+    model.timer_start()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_resident(args.warmup + i)
+        tm = model.timings()
+        launches += int(tm["launches"])
+        for k in phase:
+            phase[k] += tm[k] / args.steps
+    ms_dev = model.timer_stop()
+    wall = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = max_over_ranks(ms_dev)
+    ms_per_step = ms_total / args.steps
+    value = Nb / (ms_per_step * 1e-3)
+    route = model.timings()
+
+    # ---------- e2e: host (pinned) buffers through the public API, H2D + result read-back every step ----------
+    e2e = None
+    if not args.no_e2e:
+        pinned = []
+        for X, Y in mbs_host:
+            px, py = tb.pinned_empty(X.shape), tb.pinned_empty(Y.shape)
+            px[...] = X; py[...] = Y
+            pinned.append((px, py))
+
+        def step_e2e(i):
+            if invalidate:
+                model.set_option("invalidate", 1)
+            e = model.natgrad_step(pinned[i % N_RESIDENT_MINIBATCHES], lr=cfg["lr"], global_minibatch_size=Nb, return_elbo=True)
+            l1 = model.lambda_1
+            return e, l1
+
+        for i in range(min(args.warmup, 2)):
+            step_e2e(i)
+        model.sync(); barrier()
+        model.timer_start()
+        for i in range(args.steps):
+            step_e2e(i)
+        ms_e2e = max_over_ranks(model.timer_stop()) / args.steps
+        barrier()
+        e2e = {"value": Nb / (ms_e2e * 1e-3), "unit": "datapoints/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(n_local * (cfg["D"] + 1) * 8), "d2h_bytes_per_step": int(8 + 8 * M),
+               "api": "t_SVGP.natgrad_step((X_host, Y_host), return_elbo=True) + .lambda_1, per rank on its rows"}
+
+    # ---------- roofline: per-kernel CUDA-event timing, single stream ----------
+    model.set_option("profile", 1)
+    step_resident(0); step_resident(1)
+    kp = model.kernel_profile()
+    model.set_option("profile", 0)
+    Mp = (M + 127) // 128 * 128
+    syrk_ms, syrk_n = kp["syrk"]
+    var_ms, var_n = kp["variance_gemm"]
+    rows_per_launch = n_local / max(syrk_n, 1)
+    syrk_flops = float(M) * M * rows_per_launch   # algorithmic: lower triangle of k k^T, 2 flops per entry = M^2 per point
+    syrk_t = syrk_ms * 1e-3 / max(syrk_n, 1)
+    achieved = syrk_flops / syrk_t / 1e12
+    traffic = None
+    summ = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(summ):
+        try:
+            traffic = json.load(open(summ)).get(args.config, {}).get("syrk_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "kernel": "gemm_kernel<kc,kc,scale> (weighted SYRK B += K diag(h) K^T, DMMA m8n8k4)",
+                "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
+                "traffic": traffic,
+                "peak_source": "measured FP64 DMMA issue rate on this pool (tools/fp64_peak -> profiles/fp64_peak_r01.txt); "
+                               "MEASURED_PEAKS.json carries no FP64 figure and the profiling guide states no FP64 fallback",
+                "flops_per_launch": syrk_flops, "avg_launch_ms": syrk_t * 1e3, "launches_profiled": syrk_n}
+    var_t = var_ms * 1e-3 / max(var_n, 1)
+    q = lik_q(cfg)
+    f_pt = synth.flops_per_point(M, cfg["D"], q)
+    step_flops = Nb * f_pt + synth.dense_flops(M)
+    kernels = {k: {"ms_total": v[0], "launches": v[1]} for k, v in kp.items()}
+    kernels["variance_gemm"]["achieved_tflops"] = float(M) * M * rows_per_launch / var_t / 1e12 if var_t > 0 else None
+    extra = {
+        "step_fp64_frac": step_flops / (ms_per_step * 1e-3) / (world * FP64_PEAK_TFLOPS * 1e12),
+        "step_algorithmic_flops": step_flops, "flops_per_point": f_pt,
+        "hbm_stream_frac": Nb * 8 * (cfg["D"] + 1) / max(phase["stream"] * 1e-3, 1e-9) / (world * 6554.2e9),
+        "phase_ms": phase, "kernels": kernels, "route": int(route["route"]), "cond_est": route["cond_est"],
+        "wall_ms_per_step": wall * 1e3 / args.steps,
+    }
+
+    line = {
+        "metric": "natgrad_step datapoints/sec", "value": value, "unit": "datapoints/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(cfg, M, Nb, world), "clocks": clocks, "e2e": e2e,
+        "gpu_launches": launches, "roofline": roofline, "detail": extra,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_small, n_large = sample_sizes(M)
+        line["cpu_baseline"] = cpu_baseline(cfg, M, Nb, n_small, n_large)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    model.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def lik_q(cfg):
+    return 0 if cfg["lik"] == "Gaussian" else 20
+
+
+if __name__ == "__main__":
+    main()

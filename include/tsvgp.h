@@ -111,6 +111,18 @@ TSVGP_API int tsvgp_comm_size(const tsvgp_ctx* ctx);
  *  6 kernels launched by the step, 7 route used (1 fused, 2 whitened), 8 estimated cond(Kuu + jitter I) (0 if not probed) */
 TSVGP_API int tsvgp_get_timings(tsvgp_ctx* ctx, double* out, int n);
 TSVGP_API int tsvgp_sync(tsvgp_ctx* ctx);
+/* With option "profile" = 1 the streaming pass runs on one stream and brackets every kernel with CUDA events.  After a
+ * natgrad_step, out[2*k] = summed duration (ms) and out[2*k+1] = launch count of kernel class k:
+ *  0 Kuf slab, 1 variance product (triangular DMMA GEMM + column norms), 2 point statistics, 3 whitening GEMM,
+ *  4 weighted SYRK (DMMA), 5 Kuf g                                                                                      */
+TSVGP_API int tsvgp_get_kernel_profile(tsvgp_ctx* ctx, double* out, int n);
+/* CUDA-event stopwatch on the context's stream (every call's work, host<->device copies included, is ordered on it)   */
+TSVGP_API int tsvgp_timer_start(tsvgp_ctx* ctx);
+TSVGP_API int tsvgp_timer_stop(tsvgp_ctx* ctx, double* ms);      /* records, synchronises, returns the elapsed time      */
+/* device staging without a tensor library: plain cudaMalloc / cudaFree / cudaMemcpy(Default) on the context's device   */
+TSVGP_API void* tsvgp_device_alloc(tsvgp_ctx* ctx, size_t bytes);
+TSVGP_API void tsvgp_device_free(tsvgp_ctx* ctx, void* p);
+TSVGP_API int tsvgp_memcpy(tsvgp_ctx* ctx, void* dst, const void* src, size_t bytes);
 TSVGP_API void* tsvgp_pinned_alloc(size_t bytes);                                             /* cudaHostAlloc, for staging buffers  */
 TSVGP_API void tsvgp_pinned_free(void* p);
 

@@ -69,6 +69,12 @@ _SIGNATURES = {
     "tsvgp_comm_size": (C.c_int, [C.c_void_p]),
     "tsvgp_get_timings": (C.c_int, [C.c_void_p, _dp, C.c_int]),
     "tsvgp_sync": (C.c_int, [C.c_void_p]),
+    "tsvgp_get_kernel_profile": (C.c_int, [C.c_void_p, _dp, C.c_int]),
+    "tsvgp_timer_start": (C.c_int, [C.c_void_p]),
+    "tsvgp_timer_stop": (C.c_int, [C.c_void_p, _dp]),
+    "tsvgp_device_alloc": (C.c_void_p, [C.c_void_p, C.c_size_t]),
+    "tsvgp_device_free": (None, [C.c_void_p, C.c_void_p]),
+    "tsvgp_memcpy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "tsvgp_pinned_alloc": (C.c_void_p, [C.c_size_t]),
     "tsvgp_pinned_free": (None, [C.c_void_p]),
     "tsvgp_dlpack_view": (C.c_int, [C.c_void_p, C.POINTER(View)]),
@@ -130,10 +136,62 @@ class Tensor:
         self.ptr, self.shape, self.on_device, self.device_id, self._keep = ptr, tuple(shape), on_device, device_id, keep
 
 
+class DeviceArray:
+    """A float64 row-major array in GPU memory owned by this object (cudaMalloc through the C-ABI; no tensor library)."""
+
+    def __init__(self, model, host_array):
+        a = np.ascontiguousarray(host_array, dtype=np.float64)
+        self._model, self.shape, self.nbytes = model, a.shape, a.nbytes
+        self.ptr = model._lib.tsvgp_device_alloc(model._ctx, a.nbytes)
+        if not self.ptr:
+            raise TsvgpError(ERR_CUDA, f"cudaMalloc of {a.nbytes} bytes failed")
+        raise_for(model._lib, model._ctx, model._lib.tsvgp_memcpy(model._ctx, self.ptr, a.ctypes.data, a.nbytes))
+
+    def numpy(self):
+        out = np.empty(self.shape)
+        raise_for(self._model._lib, self._model._ctx, self._model._lib.tsvgp_memcpy(self._model._ctx, out.ctypes.data, self.ptr, self.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr and getattr(self._model, "_ctx", None):
+            self._model._lib.tsvgp_device_free(self._model._ctx, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape):
+    """A float64 NumPy array over page-locked host memory (cudaHostAlloc), for full-speed host->device copies."""
+    lib = load()
+    n = int(np.prod(shape))
+    ptr = lib.tsvgp_pinned_alloc(max(n, 1) * 8)
+    if not ptr:
+        raise TsvgpError(ERR_CUDA, "cudaHostAlloc failed")
+    buf = (C.c_double * max(n, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
+    _PINNED[arr.ctypes.data] = ptr   # freed at interpreter exit by the driver; explicit pinned_free for long runs
+    return arr
+
+
+_PINNED = {}
+
+
+def pinned_free(arr):
+    ptr = _PINNED.pop(arr.ctypes.data, None)
+    if ptr:
+        load().tsvgp_pinned_free(ptr)
+
+
 def as_tensor(obj, name="tensor"):
     """numpy arrays / anything with __dlpack__ (cupy, torch, jax ...) -> Tensor.  Host data is made float64-contiguous;
     device data must already be float64 and compact (the C side validates the DLTensor)."""
     lib = load()
+    if isinstance(obj, DeviceArray):
+        return Tensor(obj.ptr, obj.shape, True, 0, obj)
     if not hasattr(obj, "__dlpack__") or isinstance(obj, (list, tuple)):
         obj = np.ascontiguousarray(obj, dtype=np.float64)
     if isinstance(obj, np.ndarray):

@@ -129,6 +129,10 @@ struct tsvgp_ctx {
     int world = 1, rank = 0;
 
     double timings[16] = {};
+    int profile = 0;
+    std::vector<cudaEvent_t> pev;   // profile-mode event pool
+    double kprof[12] = {};
+    cudaEvent_t ev_sw[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -358,7 +362,18 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
     OK(ensure_slabs(c, N));
     const long nc = c->chunk;
     const int Mp = c->Mp;
-    const int nstr = c->n_streams == 1 ? 1 : 2;
+    const int nstr = (c->n_streams == 1 || c->profile) ? 1 : 2;
+    const bool prof = c->profile && mode == MODE_STATS;
+    size_t pev_used = 0;
+    auto mark = [&](cudaStream_t st) -> int {   // profile mode: one event between consecutive kernels
+        if (!prof) return 0;
+        if (pev_used == c->pev.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return 1;
+            c->pev.push_back(e);
+        }
+        return cudaEventRecord(c->pev[pev_used++], st) != cudaSuccess;
+    };
     const long vstride = (nc + 255) / 256;
     const long nchunks = (N + nc - 1) / nc;
     cudaStream_t sm = c->s_main;
@@ -376,9 +391,11 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
         const long n0 = ci * nc;
         const long nvalid = N - n0 < nc ? N - n0 : nc;
         const int ncols = (int)round_up(nvalid, 128);
+        if (mark(s)) FAIL(TSVGP_ERR_CUDA, "profile event");
         // (a) covariance slab K[Mp x ncols] and the partial means sum_i alpha_i K[i][n]
         LA(kuf_launch(c->kern_kind, c->kern_var, XsT, ldx, x2, n0, N, ncols, c->Zs, c->z2, c->M, Mp, c->D, c->alpha, c->slab[b],
                       nc, c->mu_part[b], nc, 0, s));
+        mark(s);
         {   // (b) |T^T k_n|^2 : upper-triangular T^T times the slab, reduced to column norms in the epilogue
             GemmP p;
             p.A = c->T; p.lda = Mp; p.a_kc = 0; p.a_tri = 2;
@@ -387,6 +404,7 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
             p.epilogue = EPI_COLNORM; p.norm_out = c->q_part[b]; p.ldn = nc;
             LA(gemm_launch(p, s));
         }
+        mark(s);
         {   // (c) marginals -> likelihood expectations and gradients
             PointArgs a;
             a.mu_part = c->mu_part[b]; a.n_mu_part = Mp / 64; a.ldmu = nc;
@@ -401,6 +419,7 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
             a.flags = c->flags;
             LA(point_stats_launch(c->lik, a, c->gh, s));
         }
+        mark(s);
         if (mode == MODE_STATS) {
             const double* stat_slab = c->slab[b];
             if (c->route == ROUTE_WHITENED) {   // (c') whitened slab  C9^-1 K  (reference order: A = K9^-1 Kuf first, tsvgp.py:271)
@@ -411,6 +430,7 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
                 LA(gemm_launch(p, s));
                 stat_slab = c->wslab[b];
             }
+            mark(s);
             {   // (d) B += K diag(h) K^T, lower tiles
                 GemmP p;
                 p.A = stat_slab; p.lda = nc; p.a_kc = 1;
@@ -419,9 +439,23 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
                 p.beta = 1.0; p.lower_out = 1; p.kscale = c->hbuf[b];
                 LA(gemm_launch(p, s));
             }
+            mark(s);
             // (e) b += K g
             LA(gemv_n_launch(stat_slab, nc, Mp, ncols, c->gbuf[b], 1.0, 1.0, c->stats[b] + (size_t)Mp * Mp, s));
+            mark(s);
         }
+    }
+    if (prof) {   // 7 events per slab: [start, kuf, var, point, whiten, syrk, gemv]
+        CU(cudaStreamSynchronize(c->s_pp[0]));
+        for (int k = 0; k < 12; ++k) c->kprof[k] = 0.0;
+        for (size_t e = 0; e + 6 < pev_used; e += 7)
+            for (int k = 0; k < 6; ++k) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, c->pev[e + k], c->pev[e + k + 1]);
+                if (k == 3 && c->route != ROUTE_WHITENED) continue;
+                c->kprof[2 * k] += ms;
+                c->kprof[2 * k + 1] += 1.0;
+            }
     }
     for (int s = 0; s < nstr; ++s) {
         CU(cudaEventRecord(c->ev_join[s], c->s_pp[s]));
@@ -658,6 +692,9 @@ void tsvgp_destroy(tsvgp_ctx* c) {
         if (c->ev_join[s]) cudaEventDestroy(c->ev_join[s]);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i)
+        if (c->ev_sw[i]) cudaEventDestroy(c->ev_sw[i]);
     for (int i = 0; i < N_EV; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->s_main) cudaStreamDestroy(c->s_main);
@@ -673,6 +710,7 @@ int tsvgp_set_option(tsvgp_ctx* c, const char* name, double value) {
     if (!strcmp(name, "streams")) { c->n_streams = value >= 2 ? 2 : 1; return TSVGP_OK; }
     if (!strcmp(name, "route")) { c->route_opt = (int)value; c->k9_valid = false; return TSVGP_OK; }
     if (!strcmp(name, "route_cond_max")) { c->route_cond_max = value; return TSVGP_OK; }
+    if (!strcmp(name, "profile")) { c->profile = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "cache_factors")) { c->cache_factors = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "invalidate")) { c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = false; return TSVGP_OK; }
     FAIL(TSVGP_ERR_INVALID, "unknown option '%s'", name);
@@ -1008,6 +1046,51 @@ int tsvgp_comm_size(const tsvgp_ctx* c) { return c ? c->world : 0; }
 int tsvgp_get_timings(tsvgp_ctx* c, double* out, int n) {
     if (!c || !out) return TSVGP_ERR_INVALID;
     for (int i = 0; i < n; ++i) out[i] = i < 16 ? c->timings[i] : 0.0;
+    return TSVGP_OK;
+}
+
+int tsvgp_get_kernel_profile(tsvgp_ctx* c, double* out, int n) {
+    if (!c || !out) return TSVGP_ERR_INVALID;
+    for (int i = 0; i < n; ++i) out[i] = i < 12 ? c->kprof[i] : 0.0;
+    return TSVGP_OK;
+}
+
+int tsvgp_timer_start(tsvgp_ctx* c) {
+    if (!c) return TSVGP_ERR_INVALID;
+    CU(cudaSetDevice(c->dev));
+    for (int i = 0; i < 2; ++i)
+        if (!c->ev_sw[i]) CU(cudaEventCreate(&c->ev_sw[i]));
+    CU(cudaEventRecord(c->ev_sw[0], c->s_main));
+    return TSVGP_OK;
+}
+
+int tsvgp_timer_stop(tsvgp_ctx* c, double* ms) {
+    if (!c || !ms || !c->ev_sw[1]) return TSVGP_ERR_INVALID;
+    CU(cudaSetDevice(c->dev));
+    CU(cudaEventRecord(c->ev_sw[1], c->s_main));
+    CU(cudaEventSynchronize(c->ev_sw[1]));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, c->ev_sw[0], c->ev_sw[1]));
+    *ms = f;
+    return TSVGP_OK;
+}
+
+void* tsvgp_device_alloc(tsvgp_ctx* c, size_t bytes) {
+    if (!c || cudaSetDevice(c->dev) != cudaSuccess) return nullptr;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void tsvgp_device_free(tsvgp_ctx* c, void* p) {
+    if (c && p && cudaSetDevice(c->dev) == cudaSuccess) cudaFree(p);
+}
+
+int tsvgp_memcpy(tsvgp_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c || !dst || !src) return TSVGP_ERR_INVALID;
+    CU(cudaSetDevice(c->dev));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));
     return TSVGP_OK;
 }
 

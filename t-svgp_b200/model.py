@@ -305,6 +305,25 @@ class t_SVGP:
         keys = ["total", "prepare", "stream", "allreduce", "dense", "slabs", "launches", "route", "cond_est"]
         return {k: buf[i] for i, k in enumerate(keys)}
 
+    def kernel_profile(self):
+        """Per-kernel-class CUDA-event totals of the last natgrad_step run with option profile=1: {class: (ms, launches)}."""
+        buf = (C.c_double * 12)()
+        self._check(self._lib.tsvgp_get_kernel_profile(self._ctx, buf, 12))
+        names = ["kuf", "variance_gemm", "point_stats", "whiten_gemm", "syrk", "kuf_g"]
+        return {k: (buf[2 * i], int(buf[2 * i + 1])) for i, k in enumerate(names)}
+
+    def timer_start(self):
+        self._check(self._lib.tsvgp_timer_start(self._ctx))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(self._lib.tsvgp_timer_stop(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def device_array(self, host_array):
+        """Upload a host array into GPU memory owned by the returned handle (usable as X / Y in set_data)."""
+        return _lib.DeviceArray(self, host_array)
+
     def sync(self):
         self._check(self._lib.tsvgp_sync(self._ctx))
 
