@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--keep-cache", action="store_true", help="do not invalidate the kernel-matrix factors every step")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (tsvgp_set_option), repeatable")
     return ap.parse_args()
 
 
@@ -211,6 +212,9 @@ def main():
         del X, Y
 
     model = tb.t_SVGP(kernel, lik, Z, num_data=cfg["N"], device=local_rank)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        model.set_option(k, float(v))
     if world > 1:
         import torch
         if rank == 0:

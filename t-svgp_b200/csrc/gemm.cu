@@ -1,6 +1,8 @@
 // FP64 DMMA GEMM engine (see gemm.cuh).  sm_100a only.
 #include "gemm.cuh"
 #include "common.cuh"
+#include <math.h>
+#include <stdlib.h>
 
 namespace tsvgp {
 
@@ -41,6 +43,65 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
     }
 }
 
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue(const GemmP& p, double (&acc)[8][4][2], double* smem, int ti, int tj, int bz, int ks,
+                                              int tid, int warp, int g, int t, int wm, int wn) {
+    if (EPI == EPI_STORE) {
+        const bool split = p.ksplit > 1;
+        double* Cg = split ? p.part + (long)ks * p.part_stride + (long)bz * p.sC
+                           : ((p.C2 != nullptr && ks == 1) ? p.C2 : p.C) + (long)bz * p.sC;
+        const double alpha = p.alpha, beta = split ? 0.0 : p.beta;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long row = ti * BM + wm + 8 * i + g;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = tj * BN + wn + 8 * j + 2 * t;
+                double2* ptr = reinterpret_cast<double2*>(Cg + row * p.ldc + col);
+                double2 o;
+                o.x = alpha * acc[i][j][0];
+                o.y = alpha * acc[i][j][1];
+                if (beta != 0.0) {
+                    const double2 old = *ptr;
+                    o.x += beta * old.x;
+                    o.y += beta * old.y;
+                }
+                *ptr = o;
+            }
+        }
+    } else {
+        // column sums of squares over this tile's 128 rows -> norm_out[ti][col]
+        double cs[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cs[j][0] = 0.0; cs[j][1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                cs[j][0] = fma(acc[i][j][0], acc[i][j][0], cs[j][0]);
+                cs[j][1] = fma(acc[i][j][1], acc[i][j][1], cs[j][1]);
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double v = cs[j][e];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                cs[j][e] = v;
+            }
+        }
+        double* red = smem;   // [2][128]; pipeline buffers are idle now
+        if (g == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                red[(warp & 1) * BN + wn + 8 * j + 2 * t] = cs[j][0];
+                red[(warp & 1) * BN + wn + 8 * j + 2 * t + 1] = cs[j][1];
+            }
+        }
+        __syncthreads();
+        if (tid < BN) p.norm_out[(long)bz * p.sC + (long)ti * p.ldn + tj * BN + tid] = red[tid] + red[BN + tid];
+    }
+}
+
 template <bool A_KC, bool B_KC, bool SCALE, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(GemmP p) {
     using S = Smem<A_KC, B_KC, SCALE>;
@@ -48,7 +109,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(GemmP p) {
 
     const int tj = blockIdx.x, ti = blockIdx.y;
     if (p.lower_out && tj > ti) return;
-    const int bz = blockIdx.z / p.ksplit, ks = blockIdx.z % p.ksplit;
+    const int zdiv = p.C2 != nullptr ? 2 : p.ksplit;
+    const int bz = blockIdx.z / zdiv, ks = blockIdx.z % zdiv;
     const double* Ag = p.A + (long)bz * p.sA;
     const double* Bg = p.B + (long)bz * p.sB;
 
@@ -63,6 +125,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(GemmP p) {
         kb += ks * per * BK;
         ke = min(ke, kb + per * BK);
     }
+    const bool piece2 = p.C2 != nullptr && ks == 1;
+    if (p.C2 != nullptr) { if (piece2) kb = max(kb, p.ksp); else ke = min(ke, p.ksp); }
     const int KT = max(ke - kb, 0) / BK;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -119,59 +183,111 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(GemmP p) {
     cp_async_wait<0>();
     __syncthreads();   // every global read of this CTA is complete: C may alias A (in-place panel solves)
 
-    if (EPI == EPI_STORE) {
-        const bool split = p.ksplit > 1;
-        double* Cg = split ? p.part + (long)ks * p.part_stride + (long)bz * p.sC : p.C + (long)bz * p.sC;
-        const double alpha = p.alpha, beta = split ? 0.0 : p.beta;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const long row = ti * BM + wm + 8 * i + g;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int col = tj * BN + wn + 8 * j + 2 * t;
-                double2* ptr = reinterpret_cast<double2*>(Cg + row * p.ldc + col);
-                double2 o;
-                o.x = alpha * acc[i][j][0];
-                o.y = alpha * acc[i][j][1];
-                if (beta != 0.0) {
-                    const double2 old = *ptr;
-                    o.x += beta * old.x;
-                    o.y += beta * old.y;
-                }
-                *ptr = o;
-            }
-        }
-    } else {
-        // column sums of squares over this tile's 128 rows -> norm_out[ti][col]
-        double cs[4][2];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            cs[j][0] = 0.0; cs[j][1] = 0.0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                cs[j][0] = fma(acc[i][j][0], acc[i][j][0], cs[j][0]);
-                cs[j][1] = fma(acc[i][j][1], acc[i][j][1], cs[j][1]);
-            }
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                double v = cs[j][e];
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 8);
-                v += __shfl_xor_sync(0xffffffffu, v, 16);
-                cs[j][e] = v;
-            }
-        }
-        double* red = smem;   // [2][128]; pipeline buffers are idle now
-        if (g == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                red[(warp & 1) * BN + wn + 8 * j + 2 * t] = cs[j][0];
-                red[(warp & 1) * BN + wn + 8 * j + 2 * t + 1] = cs[j][1];
-            }
-        }
-        __syncthreads();
-        if (tid < BN) p.norm_out[(long)bz * p.sC + (long)ti * p.ldn + tj * BN + tid] = red[tid] + red[BN + tid];
+    gemm_epilogue<EPI>(p, acc, smem, ti, tj, bz, ks, tid, warp, g, t, wm, wn);
+}
+
+// ---- decoupled pipeline ---------------------------------------------------------------------------------------------
+// Same tiling, but stage hand-over goes through mbarriers instead of a CTA-wide barrier per k-tile: every thread's
+// cp.async group arrives on full[stage] when it lands; a warp that has consumed a stage arrives on empty[stage]; a stage is
+// refilled two tiles after it was consumed, so warps may drift up to two k-tiles apart and the DMMA pipe of an SM
+// sub-partition is not drained at every tile boundary (ncu r01: 84 % DMMA-pipe active with the barrier version).
+constexpr int PSTAGES = 5;
+
+template <bool A_KC, bool B_KC, bool SCALE, int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
+    using S = Smem<A_KC, B_KC, SCALE>;
+    extern __shared__ __align__(16) double smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGE * PSTAGES);
+    uint64_t* empty = full + PSTAGES;
+
+    const int tj = blockIdx.x, ti = blockIdx.y;
+    if (p.lower_out && tj > ti) return;
+    const int zdiv = p.C2 != nullptr ? 2 : p.ksplit;
+    const int bz = blockIdx.z / zdiv, ks = blockIdx.z % zdiv;
+    const double* Ag = p.A + (long)bz * p.sA;
+    const double* Bg = p.B + (long)bz * p.sB;
+
+    int kb = 0, ke = p.k;
+    if (p.a_tri == 1) ke = min(ke, (ti + 1) * BM);
+    if (p.a_tri == 2) kb = max(kb, ti * BM);
+    if (p.b_tri == 1) ke = min(ke, (tj + 1) * BN);
+    if (p.b_tri == 2) kb = max(kb, tj * BN);
+    if (p.ksplit > 1) {
+        int nkt = max(ke - kb, 0) / BK;
+        int per = (nkt + p.ksplit - 1) / p.ksplit;
+        kb += ks * per * BK;
+        ke = min(ke, kb + per * BK);
     }
+    const bool piece2 = p.C2 != nullptr && ks == 1;
+    if (p.C2 != nullptr) { if (piece2) kb = max(kb, p.ksp); else ke = min(ke, p.ksp); }
+    const int KT = max(ke - kb, 0) / BK;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < PSTAGES; ++s) { mbar_init(&full[s], NTHREADS); mbar_init(&empty[s], NTHREADS / 32); }
+    }
+    __syncthreads();
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    int ps = 0, pround = 0, L = 0;          // producer cursor: tile L goes to stage ps, the pround-th use of that stage
+    auto produce = [&]() {
+        if (L < KT) {
+            if (pround > 0) mbar_wait(&empty[ps], (pround - 1) & 1);
+            double* sa = smem + ps * S::STAGE;
+            double* sb = sa + S::A_ELEMS;
+            const int k0 = kb + L * BK;
+            load_tile<A_KC>(sa, Ag, p.lda, ti * BM, k0, tid);
+            load_tile<B_KC>(sb, Bg, p.ldb, tj * BN, k0, tid);
+            if (SCALE && tid < BK / 2) cp_async16(sb + S::B_ELEMS + tid * 2, p.kscale + k0 + tid * 2);
+            cp_async_mbar_arrive(&full[ps]);
+        }
+        ++L;
+        if (++ps == PSTAGES) { ps = 0; ++pround; }
+    };
+#pragma unroll
+    for (int s = 0; s < PSTAGES - 2; ++s) produce();
+
+    int cs = 0, cph = 0;
+    for (int kt = 0; kt < KT; ++kt) {
+        produce();
+        mbar_wait(&full[cs], cph);
+        const double* sa = smem + cs * S::STAGE;
+        const double* sb = sa + S::A_ELEMS;
+        const double* ssc = sb + S::B_ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                a[i] = A_KC ? sa[(wm + 8 * i + g) * KC_LD + kk + t] : sa[(kk + t) * MC_LD + wm + 8 * i + g];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                b[j] = B_KC ? sb[(wn + 8 * j + g) * KC_LD + kk + t] : sb[(kk + t) * MC_LD + wn + 8 * j + g];
+            if (SCALE) {
+                const double h = ssc[kk + t];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] *= h;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[cs]);
+        if (++cs == PSTAGES) { cs = 0; cph ^= 1; }
+    }
+    __syncthreads();   // every global read of this CTA has landed and every warp is out of the pipeline buffers
+
+    gemm_epilogue<EPI>(p, acc, smem, ti, tj, bz, ks, tid, warp, g, t, wm, wn);
 }
 
 __global__ void splitk_reduce_kernel(GemmP p) {
@@ -195,22 +311,34 @@ __global__ void splitk_reduce_kernel(GemmP p) {
     }
 }
 
+int g_variant = 1;   // 1 = mbarrier-decoupled pipeline (default), 0 = CTA-barrier pipeline (TSVGP_GEMM_VARIANT=0, for A/B timing)
+
+template <bool A_KC, bool B_KC, bool SCALE>
+constexpr int mb_bytes() { return Smem<A_KC, B_KC, SCALE>::STAGE * PSTAGES * 8 + 2 * PSTAGES * 8; }
+
 template <bool A_KC, bool B_KC, bool SCALE, int EPI>
 int launch_inst(const GemmP& p, cudaStream_t stream) {
-    dim3 grid(p.n / BN, p.m / BM, p.batch * p.ksplit);
-    gemm_kernel<A_KC, B_KC, SCALE, EPI><<<grid, NTHREADS, Smem<A_KC, B_KC, SCALE>::BYTES, stream>>>(p);
+    dim3 grid(p.n / BN, p.m / BM, p.batch * (p.C2 ? 2 : p.ksplit));
+    if (g_variant == 1)
+        gemm_kernel_mb<A_KC, B_KC, SCALE, EPI><<<grid, NTHREADS, mb_bytes<A_KC, B_KC, SCALE>(), stream>>>(p);
+    else
+        gemm_kernel<A_KC, B_KC, SCALE, EPI><<<grid, NTHREADS, Smem<A_KC, B_KC, SCALE>::BYTES, stream>>>(p);
     return count_launch();
 }
 
 template <bool A_KC, bool B_KC, bool SCALE, int EPI>
 int init_inst() {
-    return (int)cudaFuncSetAttribute(gemm_kernel<A_KC, B_KC, SCALE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Smem<A_KC, B_KC, SCALE>::BYTES);
+    int e = (int)cudaFuncSetAttribute(gemm_kernel<A_KC, B_KC, SCALE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Smem<A_KC, B_KC, SCALE>::BYTES);
+    e |= (int)cudaFuncSetAttribute(gemm_kernel_mb<A_KC, B_KC, SCALE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   mb_bytes<A_KC, B_KC, SCALE>());
+    return e;
 }
 
 }  // namespace
 
 int gemm_init() {
+    if (const char* v = getenv("TSVGP_GEMM_VARIANT")) g_variant = atoi(v);
     int e = 0;
     e |= init_inst<true, true, false, EPI_STORE>();
     e |= init_inst<true, true, true, EPI_STORE>();
@@ -220,7 +348,23 @@ int gemm_init() {
     return e;
 }
 
+int balanced_ksplit(int tiles, int k) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const double waves = (double)tiles / sms;
+    const double f = waves / ceil(waves);
+    int ksp = (int)(f * k / BK + 0.5) * BK;
+    if (ksp < BK || k - ksp < 4 * BK) return k;   // nothing (worth) splitting off
+    return ksp;
+}
+
 int gemm_launch(const GemmP& p, cudaStream_t stream) {
+    if (p.C2 && (p.ksplit != 1 || p.epilogue != EPI_STORE || p.ksp % BK || p.ksp <= 0 || p.ksp >= p.k)) return -1;
     if (p.m % BM || p.n % BN || p.k % BK || p.m <= 0 || p.n <= 0) return -1;
     const bool scale = p.kscale != nullptr;
     if (p.a_kc && p.b_kc) {

@@ -29,6 +29,10 @@ struct GemmP {
     double* norm_out = nullptr; long ldn = 0;   // EPI_COLNORM: norm_out[tile_i * ldn + j] = sum_{i in tile} C(i,j)^2
     int ksplit = 1; double* part = nullptr; long part_stride = 0;   // split-K partial slabs [ksplit][m*ldc]; caller reduces
     int batch = 1; long sA = 0, sB = 0, sC = 0;
+    // Two-piece k split for load balance (no atomics): CTAs with blockIdx.z == 0 contract k in [0, ksp) into C, CTAs with
+    // blockIdx.z == 1 contract [ksp, k) into C2 (same layout, same beta).  The z = 0 pieces are dispatched first; with
+    // ksp / k = (T / P) / ceil(T / P) for T output tiles on P SMs, greedy in-order dispatch fills every SM equally.
+    int ksp = 0; double* C2 = nullptr;
 };
 
 // Launch on `stream`. Returns cudaError_t as int (0 = ok), -1 for an unsupported combination.
@@ -36,6 +40,9 @@ int gemm_launch(const GemmP& p, cudaStream_t stream);
 
 // C = beta*C + sum_s part[s]  over the tiles gemm_launch wrote (lower tiles only if lower_out)
 int splitk_reduce_launch(const GemmP& p, cudaStream_t stream);
+
+// k split point for `tiles` equal output tiles of contraction length k on this device's SMs (multiple of 16; k = no split)
+int balanced_ksplit(int tiles, int k);
 
 // one-time: opt in to large dynamic shared memory for every instantiation
 int gemm_init();

@@ -72,6 +72,7 @@ struct tsvgp_ctx {
     // options
     long chunk_opt = 0;        // 0 = automatic
     int n_streams = 2;
+    int balance = 1;           // split the SYRK's contraction in two pieces so that every SM gets equal work
     int cache_factors = 1;     // keep chol(K9) and the posterior factors between calls while their inputs are unchanged
     int route_opt = ROUTE_AUTO;     // statistics route: fused (B = Kuf H Kfu, then K9^-1 B K9^-1) or whitened (C9^-1 Kuf first)
     double route_cond_max = 2e4;    // auto: fused while the estimated cond(Kuu + jitter I) is below this
@@ -95,6 +96,7 @@ struct tsvgp_ctx {
     double *Wm = nullptr, *Wf = nullptr, *V = nullptr, *T = nullptr, *X1 = nullptr, *X2 = nullptr, *C9 = nullptr, *C9inv = nullptr;
     double *G2 = nullptr, *P = nullptr, *tmp = nullptr, *dinv = nullptr;
     double *stats[2] = {nullptr, nullptr};   // [B (Mp*Mp) | b (Mp) | tail (4)] per ping-pong stream
+    double *stats2[2] = {nullptr, nullptr};  // second B accumulator per stream: the split-off k piece of the balanced SYRK
     double *alpha = nullptr, *mZ = nullptr, *mq = nullptr, *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *gwork = nullptr;
     double *scal = nullptr;
     int* info = nullptr;    // [N_INFO]
@@ -187,7 +189,7 @@ int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     NEED(c->X1 = p.get(mm)); NEED(c->X2 = p.get(mm)); NEED(c->C9 = p.get(mm)); NEED(c->C9inv = p.get(mm));
     NEED(c->G2 = p.get(mm)); NEED(c->P = p.get(mm)); NEED(c->tmp = p.get((size_t)((c->Mp / 128 + 1) / 2) * 128 * mp));   // trtri_lower: ceil(nblk/2) block rows
     NEED(c->dinv = p.get((size_t)(c->Mp / 128) * 128 * 128));
-    for (int s = 0; s < 2; ++s) NEED(c->stats[s] = p.get(mm + mp + 4));
+    for (int s = 0; s < 2; ++s) { NEED(c->stats[s] = p.get(mm + mp + 4)); NEED(c->stats2[s] = p.get(mm)); }
     NEED(c->alpha = p.get(mp)); NEED(c->mZ = p.get(mp)); NEED(c->mq = p.get(mp)); NEED(c->v1 = p.get(mp)); NEED(c->v2 = p.get(mp));
     NEED(c->v3 = p.get(mp)); NEED(c->gwork = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal = p.get(N_SCAL));
     NEED(c->info = (int*)p.get(N_INFO)); NEED(c->flags = (int*)p.get(2));
@@ -321,11 +323,9 @@ int ensure_xs(tsvgp_ctx* c) {
 
 long pick_chunk(const tsvgp_ctx* c) {
     long nc = c->chunk_opt;
-    if (nc <= 0) {   // one slab = Mp * nc * 8 B ~ 32 MB, so both ping-pong slabs stay inside the 126 MB L2
-        nc = (32l << 20) / (8l * c->Mp);
-        if (c->route == ROUTE_WHITENED) nc /= 2;   // a second (whitened) slab per stream shares the L2
-        if (nc > 8192) nc = 8192;
-    }
+    if (nc <= 0) nc = 8192;   // measured on B200 (profiles/): the more tiles per launch the better the SMs stay filled; slabs
+                              // beyond the L2 cost little because both DMMA products re-read them M/128 times from L2/HBM at
+                              // far below the bandwidth roof
     nc = nc / 128 * 128;
     if (nc < 128) nc = 128;
     return nc;
@@ -381,7 +381,10 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
     CU(cudaMemsetAsync(c->flags, 0, 2 * sizeof(int), sm));
     CU(cudaMemsetAsync(c->ve_blocks, 0, sizeof(double) * (size_t)(nchunks * vstride), sm));
     if (mode == MODE_STATS)
-        for (int s = 0; s < nstr; ++s) CU(cudaMemsetAsync(c->stats[s], 0, sizeof(double) * ((size_t)Mp * Mp + Mp + 4), sm));
+        for (int s = 0; s < nstr; ++s) {
+            CU(cudaMemsetAsync(c->stats[s], 0, sizeof(double) * ((size_t)Mp * Mp + Mp + 4), sm));
+            CU(cudaMemsetAsync(c->stats2[s], 0, sizeof(double) * (size_t)Mp * Mp, sm));
+        }
     CU(cudaEventRecord(c->ev_fork, sm));
     for (int s = 0; s < nstr; ++s) CU(cudaStreamWaitEvent(c->s_pp[s], c->ev_fork, 0));
 
@@ -437,6 +440,9 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
                 p.B = stat_slab; p.ldb = nc; p.b_kc = 1;
                 p.C = c->stats[b]; p.ldc = Mp; p.m = p.n = Mp; p.k = ncols;
                 p.beta = 1.0; p.lower_out = 1; p.kscale = c->hbuf[b];
+                const int nt = Mp / 128;
+                const int ksp = c->balance ? balanced_ksplit(nt * (nt + 1) / 2, ncols) : ncols;
+                if (ksp < ncols) { p.ksp = ksp; p.C2 = c->stats2[b]; }
                 LA(gemm_launch(p, s));
             }
             mark(s);
@@ -462,7 +468,10 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
         CU(cudaStreamWaitEvent(sm, c->ev_join[s], 0));
     }
     const size_t mm = (size_t)Mp * Mp;
-    if (mode == MODE_STATS && nstr == 2) LA(vadd_inplace_launch(c->stats[0], c->stats[1], (long)(mm + Mp), sm));
+    if (mode == MODE_STATS) {
+        if (nstr == 2) LA(vadd_inplace_launch(c->stats[0], c->stats[1], (long)(mm + Mp), sm));
+        for (int s = 0; s < nstr && c->balance; ++s) LA(vadd_inplace_launch(c->stats[0], c->stats2[s], (long)mm, sm));
+    }
     LA(stats_tail_launch(c->ve_blocks, nchunks * vstride, c->flags, c->stats[0] + mm + Mp, sm));
     return TSVGP_OK;
 }
@@ -710,6 +719,7 @@ int tsvgp_set_option(tsvgp_ctx* c, const char* name, double value) {
     if (!strcmp(name, "streams")) { c->n_streams = value >= 2 ? 2 : 1; return TSVGP_OK; }
     if (!strcmp(name, "route")) { c->route_opt = (int)value; c->k9_valid = false; return TSVGP_OK; }
     if (!strcmp(name, "route_cond_max")) { c->route_cond_max = value; return TSVGP_OK; }
+    if (!strcmp(name, "balance")) { c->balance = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "profile")) { c->profile = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "cache_factors")) { c->cache_factors = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "invalidate")) { c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = false; return TSVGP_OK; }
