@@ -49,6 +49,27 @@ def kl(K6, T, alpha, Uw):
     return 0.5 * (float(m[:, 0] @ alpha[:, 0]) - trQK + logdetW)
 
 
+def local_statistics(Kuf, g, h):
+    """What one rank accumulates over its rows (fused route): B = Kuf diag(h) Kfu, b = Kuf g.  Summed over ranks by the
+    one all-reduce of the step."""
+    return (Kuf * h) @ Kuf.T, Kuf @ g
+
+
+def update_from_statistics(K, B, b, alpha, lambda_1, L2, lr, scale, jitter=1e-9):
+    """The replicated dense phase after the all-reduce."""
+    M = K.shape[0]
+    C9 = sla.cholesky(K + jitter * np.eye(M), lower=True)
+    C9inv = sla.solve_triangular(C9, np.eye(M), lower=True)
+    K9inv = C9inv.T @ C9inv
+    G2 = K9inv @ B @ K9inv
+    G1 = K9inv @ b
+    mZ = K @ alpha[:, 0]
+    g0 = G1 - 2.0 * G2 @ mZ
+    l1 = (1 - lr) * lambda_1[:, 0] + lr * scale * g0
+    P = (1 - lr) * (L2 @ L2.T) + lr * scale * (-2.0 * G2) + jitter * np.eye(M)
+    return l1[:, None], -sla.cholesky(P, lower=True)
+
+
 def natgrad(K, Kuf, g, h, alpha, lambda_1, L2, lr, scale, jitter=1e-9, whiten=False):
     M = K.shape[0]
     K9 = K + jitter * np.eye(M)

@@ -1,0 +1,123 @@
+"""
+CPU-side checks of the boundary: libtsvgp.so loads, exports every entry point include/tsvgp.h declares, the ctypes table
+matches the header, the library refuses to compute without a GPU (no CPU fallback), the DLPack view validates tensors, and
+the host logic (object duck-typing, sharding, synthetic configs) behaves.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "tsvgp.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"TSVGP_API\s+[\w\s\*]+?\b(tsvgp_\w+)\s*\(", src)))
+
+
+def have_gpu():
+    try:
+        return subprocess.run(["nvidia-smi", "-L"], capture_output=True, timeout=20).returncode == 0
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    import tsvgp_b200
+    lib = tsvgp_b200.load()
+    names = declared_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/tsvgp.h but not exported by libtsvgp.so"
+    assert sorted(tsvgp_b200.exported_names()) == names, "ctypes signature table and header disagree"
+    assert lib.tsvgp_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import tsvgp_b200
+    from oracle import tsvgp_oracle as orc
+    if have_gpu():
+        pytest.skip("a GPU is present")
+    with pytest.raises(tsvgp_b200.TsvgpError) as ei:
+        tsvgp_b200.t_SVGP(orc.SquaredExponential(), orc.Gaussian(), np.zeros((3, 1)))
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+
+
+def test_product_never_imports_the_oracle_or_torch():
+    pkg = os.path.join(ROOT, "t-svgp_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("the oracle module", ""), fn
+            assert not re.search(r"^\s*(import|from)\s+torch", src, re.M), fn
+
+
+def test_dlpack_view_validates():
+    import tsvgp_b200
+    from tsvgp_b200 import _lib
+    lib = tsvgp_b200.load()
+    a = np.arange(12, dtype=np.float64).reshape(3, 4)
+    t = _lib.as_tensor(a)
+    assert t.ptr == a.ctypes.data and t.shape == (3, 4) and not t.on_device
+    # non-contiguous / wrong dtype host arrays are copied into float64 row-major by the host side
+    t2 = _lib.as_tensor(a.T)
+    assert t2.shape == (4, 3)
+    t3 = _lib.as_tensor(a.astype(np.float32))
+    assert t3.shape == (3, 4)
+    # the C side rejects a float32 DLPack tensor and a strided one
+    for bad in (a.astype(np.float32), a[:, ::2]):
+        cap = bad.__dlpack__()
+        ptr = _lib._PyCapsule_GetPointer(cap, b"dltensor")
+        assert lib.tsvgp_dlpack_view(ptr, C.byref(_lib.View())) == _lib.ERR_INVALID
+    ro = a.copy(); ro.flags.writeable = False
+    assert _lib.as_tensor(ro).ptr == ro.ctypes.data
+
+
+def test_duck_typing_of_gpflow_objects():
+    from tsvgp_b200 import model, standins as st, _lib
+    kind, var, ls = model._kernel_spec(st.Matern52(variance=1.5, lengthscales=[[1.0, 2.0]]))   # [1, D] as uci_regression.py:42-44
+    assert (kind, var, ls.tolist()) == (_lib.KERNEL_MATERN52, 1.5, [1.0, 2.0])
+    assert model._kernel_spec(st.RBF(2.0, 0.5))[0] == _lib.KERNEL_SE
+
+    class Param(float):   # gpflow.Parameter answers .numpy()
+        def numpy(self):
+            return float(self)
+
+    k = st.SquaredExponential()
+    k.variance, k.lengthscales = Param(2.25), Param(2.0)
+    assert model._kernel_spec(k)[1:] == (2.25, np.array([2.0]))
+    assert model._likelihood_spec(st.Gaussian(0.3)) == (_lib.LIK_GAUSSIAN, 0.3, 0.0, 0)
+    assert model._likelihood_spec(st.Bernoulli()) == (_lib.LIK_BERNOULLI_PROBIT, 0.0, 0.0, 20)
+    assert model._likelihood_spec(st.StudentT(0.4, 3.0)) == (_lib.LIK_STUDENT_T, 0.4, 3.0, 20)
+
+    class Poisson:
+        pass
+
+    with pytest.raises(NotImplementedError):
+        model._likelihood_spec(Poisson())
+
+
+def test_shard_rows_partitions():
+    from tsvgp_b200 import shard_rows
+    for n in (1, 7, 8, 1000, 1_000_001):
+        for w in (1, 2, 3, 8):
+            spans = [shard_rows(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_synthetic_configs_have_the_survey_shapes():
+    import tsvgp_b200.synth as synth
+    for name, (M, D) in {"cfg1": (50, 1), "cfg2": (500, 8), "cfg3": (2048, 16), "cfg4": (8192, 8), "cfg5": (4096, 32)}.items():
+        cfg = synth.describe(name)
+        assert (cfg["M"], cfg["D"]) == (M, D)
+        X, Y, Z = synth.make_minibatch(cfg, n_rows=300, M=40)
+        assert X.shape == (300, D) and Y.shape == (300, 1) and Z.shape == (40, D)
+    assert synth.flops_per_point(2048, 16) == 2 * 2048 ** 2 + 2048 * 38 + 4 * 2048

@@ -1,0 +1,80 @@
+"""
+GPU, >= 2 devices: the minibatch sharded by rows over two ranks (one context per GPU, one NCCL all-reduce of the statistics)
+gives the single-GPU result.  Skipped on a one-GPU box; `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`.
+"""
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_gpus():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30)
+        return len([l for l in out.stdout.splitlines() if l.startswith("GPU ")])
+    except Exception:
+        return 0
+
+
+def _case():
+    import tsvgp_b200.synth as synth
+    from tsvgp_b200 import standins as st
+    cfg = synth.describe("cfg5")
+    X, Y, Z = synth.make_minibatch(cfg, n_rows=5001, M=300)
+    kernel, lik = synth.build_objects(cfg, st)
+    return cfg, X, Y, Z, kernel, lik
+
+
+def _rank(rank, world, conn, out):
+    sys.path.insert(0, ROOT)
+    import tsvgp_b200 as tb
+    cfg, X, Y, Z, kernel, lik = _case()
+    m = tb.t_SVGP(kernel, lik, Z, num_data=50_010, device=rank)
+    if rank == 0:
+        uid = tb.comm_unique_id()
+        for c in conn:
+            c.send(uid)
+    else:
+        uid = conn.recv()
+    m.init_comm(world, rank, uid)
+    lo, hi = tb.shard_rows(X.shape[0], world, rank)
+    elbos = []
+    for _ in range(2):
+        elbos.append(m.natgrad_step((X[lo:hi], Y[lo:hi]), lr=cfg["lr"], global_minibatch_size=X.shape[0], return_elbo=True))
+    elbos.append(m.elbo((X[lo:hi], Y[lo:hi]), global_minibatch_size=X.shape[0]))
+    mu, var = m.predict_f(X[:50])
+    out.put((rank, m.lambda_1, m.lambda_2, elbos, mu, var))
+    m.close()
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs >= 2 GPUs")
+def test_two_gpu_sharded_step_matches_single_gpu():
+    import tsvgp_b200 as tb
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    a, b = ctx.Pipe()
+    procs = [ctx.Process(target=_rank, args=(0, 2, [a], out)), ctx.Process(target=_rank, args=(1, 2, b, out))]
+    for p in procs:
+        p.start()
+    res = sorted([out.get(timeout=300) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    cfg, X, Y, Z, kernel, lik = _case()
+    single = tb.t_SVGP(kernel, lik, Z, num_data=50_010)
+    e = [single.natgrad_step((X, Y), lr=cfg["lr"], return_elbo=True) for _ in range(2)] + [None]
+    e[2] = single.elbo((X, Y))
+    mu, var = single.predict_f(X[:50])
+    rel = lambda x, y: float(np.max(np.abs(np.asarray(x) - np.asarray(y))) / np.max(np.abs(y)))  # noqa: E731
+    for rank, l1, l2, elbos, mu_r, var_r in res:
+        assert rel(l1, single.lambda_1) < 1e-11 and rel(l2, single.lambda_2) < 1e-11     # summation order only
+        assert rel(elbos, e) < 1e-11 and rel(mu_r, mu) < 1e-11 and rel(var_r, var) < 1e-11
+    np.testing.assert_array_equal(res[0][1], res[1][1])   # replicated dense phase: both ranks hold identical sites
+    np.testing.assert_array_equal(res[0][2], res[1][2])
+    single.close()
