@@ -53,27 +53,31 @@ int chol_lower(double* A, long ld, int n, double* dinv, int* info, cudaStream_t 
     return zero_upper_launch(A, ld, n, s);
 }
 
-static int trtri_rec(const double* L, long ld, int lo, int hi, double* Linv, double* tmp, cudaStream_t s) {
-    if (hi - lo <= 1) return 0;
-    const int mid = (lo + hi) / 2;
-    TRY(trtri_rec(L, ld, lo, mid, Linv, tmp, s));
-    TRY(trtri_rec(L, ld, mid, hi, Linv, tmp, s));
-    const int mrows = (hi - mid) * NB, ncols = (mid - lo) * NB;
-    {   // tmp = C * Ainv,  C = L[mid:hi, lo:mid],  Ainv = Linv[lo:mid, lo:mid] (lower: B(k,j) != 0 only for k >= j)
+// Bottom-up triangular inverse.  At level h (blocks) every node [lo, lo + 2h) combines its finished halves:
+//   Linv[right, left] = -Linv[right, right] * L[right, left] * Linv[left, left]
+// All full nodes of a level have the same shape and a constant stride, so they go out as ONE batched launch per product
+// (2 launches per level instead of 2 per node); a ragged last node (n not a power of two) is launched on its own.
+static int trtri_level(const double* L, long ld, int lo, int hl, int hr, int batch, long stride, double* Linv, double* tmp,
+                       long tmp_stride, cudaStream_t s) {
+    const int mid = lo + hl;
+    const int mrows = hr * NB, ncols = hl * NB;
+    {   // tmp = C * Ainv,  C = L[right, left],  Ainv = Linv[left, left] (lower: B(k,j) != 0 only for k >= j)
         GemmP p;
         p.A = L + (long)mid * NB * ld + (long)lo * NB; p.lda = ld; p.a_kc = 1;
         p.B = Linv + (long)lo * NB * ld + (long)lo * NB; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
         p.C = tmp; p.ldc = ld;
         p.m = mrows; p.n = ncols; p.k = ncols;
+        p.batch = batch; p.sA = stride; p.sB = stride; p.sC = tmp_stride;
         TRY(gemm_launch(p, s));
     }
-    {   // Linv[mid:hi, lo:mid] = -Binv * tmp,  Binv = Linv[mid:hi, mid:hi] (lower: A(i,k) != 0 only for k <= i)
+    {   // Linv[right, left] = -Binv * tmp,  Binv = Linv[right, right] (lower: A(i,k) != 0 only for k <= i)
         GemmP p;
         p.A = Linv + (long)mid * NB * ld + (long)mid * NB; p.lda = ld; p.a_kc = 1; p.a_tri = 1;
         p.B = tmp; p.ldb = ld; p.b_kc = 0;
         p.C = Linv + (long)mid * NB * ld + (long)lo * NB; p.ldc = ld;
         p.m = mrows; p.n = ncols; p.k = mrows;
         p.alpha = -1.0;
+        p.batch = batch; p.sA = stride; p.sB = tmp_stride; p.sC = stride;
         TRY(gemm_launch(p, s));
     }
     return 0;
@@ -84,7 +88,15 @@ int trtri_lower(const double* L, long ld, int n, const double* dinv, double* Lin
     if (cudaMemsetAsync(Linv, 0, sizeof(double) * (size_t)n * ld, s) != cudaSuccess) return (int)cudaGetLastError();
     for (int b = 0; b < nblk; ++b)
         TRY(place_block_launch(dinv + (long)b * NB * NB, NB, Linv + (long)b * NB * ld + (long)b * NB, ld, NB, NB, s));
-    return trtri_rec(L, ld, 0, nblk, Linv, tmp, s);
+    for (int h = 1; h < nblk; h *= 2) {
+        const int full = nblk / (2 * h);                 // nodes with both halves of size h
+        const long stride = (long)2 * h * NB * (ld + 1);
+        const long tmp_stride = (long)h * NB * ld;       // node b's scratch: rows [b*h*NB, (b+1)*h*NB) of tmp
+        if (full > 0) TRY(trtri_level(L, ld, 0, h, h, full, stride, Linv, tmp, tmp_stride, s));
+        const int lo = full * 2 * h, rem = nblk - lo;    // ragged node: left half complete, right half shorter
+        if (rem > h) TRY(trtri_level(L, ld, lo, h, rem - h, 1, 0, Linv, tmp, 0, s));
+    }
+    return 0;
 }
 
 }  // namespace tsvgp

@@ -2,6 +2,9 @@
 #include "gemm.cuh"
 #include "common.cuh"
 #include <math.h>
+#include <map>
+#include <utility>
+#include <vector>
 #include <stdlib.h>
 
 namespace tsvgp {
@@ -348,6 +351,25 @@ int gemm_init() {
     return e;
 }
 
+// Greedy in-order dispatch of `tiles` big pieces (kt1 k-tiles each) then `tiles` small pieces (kt - kt1 each) onto `sms`
+// single-CTA SMs; every piece also pays `ovh` k-tiles of prologue / epilogue (pipeline fill, C tile read-modify-write).
+static double dispatch_makespan(int tiles, int sms, int kt1, int kt2, double ovh) {
+    std::vector<double> free_at(sms, 0.0);
+    auto run = [&](int count, double len) {
+        for (int i = 0; i < count; ++i) {
+            int best = 0;
+            for (int s = 1; s < sms; ++s)
+                if (free_at[s] < free_at[best]) best = s;
+            free_at[best] += len;
+        }
+    };
+    run(tiles, kt1 + ovh);
+    if (kt2 > 0) run(tiles, kt2 + ovh);
+    double m = 0.0;
+    for (double f : free_at) m = f > m ? f : m;
+    return m;
+}
+
 int balanced_ksplit(int tiles, int k) {
     static int sms = 0;
     if (!sms) {
@@ -356,11 +378,23 @@ int balanced_ksplit(int tiles, int k) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
-    const double waves = (double)tiles / sms;
-    const double f = waves / ceil(waves);
-    int ksp = (int)(f * k / BK + 0.5) * BK;
-    if (ksp < BK || k - ksp < 4 * BK) return k;   // nothing (worth) splitting off
-    return ksp;
+    static std::map<std::pair<int, int>, int> cache;   // one host thread per context; a race would only recompute
+    const auto key = std::make_pair(tiles, k);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    const int kt = k / BK;
+    const double ovh = 3.0;   // measured: a split-off piece costs about 3 k-tiles beyond its DMMA work (tools/gemm_bench)
+    int best = k;
+    double best_t = dispatch_makespan(tiles, sms, kt, 0, ovh);
+    const double waves = (double)tiles / sms, f0 = waves / ceil(waves);
+    for (int d = -6; d <= 14; ++d) {   // candidates around the ideal fraction, biased towards larger first pieces
+        const int kt1 = (int)(f0 * kt) + d * (kt >= 256 ? kt / 128 : 1);
+        if (kt1 < 1 || kt - kt1 < 4) continue;
+        const double t = dispatch_makespan(tiles, sms, kt1, kt - kt1, ovh);
+        if (t < best_t * 0.985) { best_t = t; best = kt1 * BK; }
+    }
+    cache[key] = best;
+    return best;
 }
 
 int gemm_launch(const GemmP& p, cudaStream_t stream) {

@@ -45,37 +45,74 @@ int unpack_rows_launch(const double* ZsT, long ldz, int Mp, int D, double* Zs, c
     return count_launch();
 }
 
+// ---- branch-free FP64 math for the covariance epilogue (the CUDA library calls carry slow-path branches and re-materialise
+// their constants per call site; here the constants live in registers across the whole tile) ---------------------------
+// exp(x) for x <= ~0 (clamped at -700): Cody-Waite reduction by ln2, degree-13 Taylor on |f| <= 0.347 (truncation 4e-18).
+__device__ __forceinline__ double exp_nonpos(double x) {
+    x = fmax(x, -700.0);
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);   // 1.5 * 2^52 : rint in the low mantissa bits
+    const int n = __double2loint(t);
+    const double fn = t - 6755399441055744.0;
+    double f = fma(fn, -6.93147180369123816490e-01, x);
+    f = fma(fn, -1.90821492927058770002e-10, f);
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, f, 2.08767569878681e-09);          // 1/12!
+    p = fma(p, f, 2.505210838544172e-08);         // 1/11!
+    p = fma(p, f, 2.755731922398589e-07);         // 1/10!
+    p = fma(p, f, 2.7557319223985893e-06);        // 1/9!
+    p = fma(p, f, 2.48015873015873e-05);          // 1/8!
+    p = fma(p, f, 1.984126984126984e-04);         // 1/7!
+    p = fma(p, f, 1.388888888888889e-03);         // 1/6!
+    p = fma(p, f, 8.333333333333333e-03);         // 1/5!
+    p = fma(p, f, 4.1666666666666664e-02);        // 1/4!
+    p = fma(p, f, 1.6666666666666666e-01);        // 1/3!
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    return p * __hiloint2double((n + 1023) << 20, 0);
+}
+// sqrt(m) for normal m > 0: hardware reciprocal-sqrt seed, two Newton steps, one residual correction
+__device__ __forceinline__ double sqrt_pos(double m) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(m));
+    const double hm = 0.5 * m;
+    y = y * fma(-hm * y, y, 1.5);
+    y = y * fma(-hm * y, y, 1.5);
+    double r = m * y;
+    const double e = fma(-r, r, m);
+    return fma(0.5 * y, e, r);
+}
+
 template <int KIND>
 __device__ __forceinline__ double cov_from_r2(double r2, double variance) {
     if (KIND == KERN_SE) {
-        return variance * exp(-0.5 * r2);
+        return variance * exp_nonpos(-0.5 * r2);
     } else {
-        const double r = sqrt(fmax(r2, 1e-36));
+        const double r = sqrt_pos(fmax(r2, 1e-36));
         const double sqrt5 = 2.23606797749978969641;
-        return variance * (1.0 + sqrt5 * r + (5.0 / 3.0) * (r * r)) * exp(-sqrt5 * r);
+        return variance * fma(5.0 / 3.0, r * r, fma(sqrt5, r, 1.0)) * exp_nonpos(-sqrt5 * r);
     }
 }
 
 constexpr int KUF_DC = 16;   // feature chunk staged in shared memory
-constexpr int KUF_ROWS = 64; // inducing rows per CTA (2 groups of 32)
+constexpr int KUF_ROWS = 64; // inducing rows per CTA: 4 thread groups of 16 rows; each thread owns 16 rows x 2 columns
 
 template <int KIND>
-__global__ void __launch_bounds__(256) kuf_kernel(double variance, const double* __restrict__ XsT, long ldx,
-                                                  const double* __restrict__ x2, long n0, long n_valid,
-                                                  const double* __restrict__ Zs, const double* __restrict__ z2, int M, int D,
-                                                  const double* __restrict__ alpha, double* __restrict__ K, long ldk,
-                                                  double* __restrict__ mu_part, long ldmu, int pad_identity) {
+__global__ void __launch_bounds__(256, 2) kuf_kernel(double variance, const double* __restrict__ XsT, long ldx,
+                                                     const double* __restrict__ x2, long n0, long n_valid,
+                                                     const double* __restrict__ Zs, const double* __restrict__ z2, int M, int D,
+                                                     const double* __restrict__ alpha, double* __restrict__ K, long ldk,
+                                                     double* __restrict__ mu_part, long ldmu, int pad_identity) {
     __shared__ double sx[KUF_DC][128];
     __shared__ __align__(16) double sz[KUF_ROWS][KUF_DC];
-    __shared__ double smu[128];
-    const int tid = threadIdx.x, nn = tid & 127, ig = tid >> 7;
-    const long c0 = (long)blockIdx.x * 128;          // chunk-local column of this tile
-    const long n = n0 + c0 + nn;                     // global point index
-    const int ibase = blockIdx.y * KUF_ROWS;
+    __shared__ double smu[4][128];
+    const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+    const long c0 = (long)blockIdx.x * 128;          // chunk-local first column of this tile
+    const int ibase = blockIdx.y * KUF_ROWS, rbase = ty * 16;
 
-    double dot[32];
+    double dot[16][2];
 #pragma unroll
-    for (int r = 0; r < 32; ++r) dot[r] = 0.0;
+    for (int r = 0; r < 16; ++r) { dot[r][0] = 0.0; dot[r][1] = 0.0; }
 
     for (int dc = 0; dc < D; dc += KUF_DC) {
         const int dlen = min(KUF_DC, D - dc);
@@ -89,46 +126,51 @@ __global__ void __launch_bounds__(256) kuf_kernel(double variance, const double*
             sz[r][d] = d < dlen ? Zs[(long)(ibase + r) * D + dc + d] : 0.0;
         }
         __syncthreads();
-        const int dl8 = (dlen + 7) & ~7;
-        for (int d8 = 0; d8 < dl8; d8 += 8) {
-            double x[8];
+        const int dl4 = (dlen + 3) & ~3;
+        for (int d4 = 0; d4 < dl4; d4 += 4) {
+            double xa[4], xb[4];
 #pragma unroll
-            for (int d = 0; d < 8; ++d) x[d] = sx[d8 + d][nn];
+            for (int d = 0; d < 4; ++d) { xa[d] = sx[d4 + d][tx]; xb[d] = sx[d4 + d][tx + 64]; }
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                const double2* zp = reinterpret_cast<const double2*>(&sz[ig * 32 + r][d8]);
-                double acc = dot[r];
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    const double2 zz = zp[d];
-                    acc = fma(x[2 * d], zz.x, acc);
-                    acc = fma(x[2 * d + 1], zz.y, acc);
-                }
-                dot[r] = acc;
+            for (int r = 0; r < 16; ++r) {
+                const double2* zp = reinterpret_cast<const double2*>(&sz[rbase + r][d4]);
+                const double2 z01 = zp[0], z23 = zp[1];
+                double a = dot[r][0], b = dot[r][1];
+                a = fma(xa[0], z01.x, a); b = fma(xb[0], z01.x, b);
+                a = fma(xa[1], z01.y, a); b = fma(xb[1], z01.y, b);
+                a = fma(xa[2], z23.x, a); b = fma(xb[2], z23.x, b);
+                a = fma(xa[3], z23.y, a); b = fma(xb[3], z23.y, b);
+                dot[r][0] = a; dot[r][1] = b;
             }
         }
     }
 
-    const double xn2 = x2[n];
-    const bool col_ok = n < n_valid;
-    double mu = 0.0;
+    const long na = n0 + c0 + tx, nb = na + 64;       // global point indices of this thread's two columns
+    const double xa2 = x2[na], xb2 = x2[nb];
+    const bool oka = na < n_valid, okb = nb < n_valid;
+    double mua = 0.0, mub = 0.0;
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
-        const int i = ibase + ig * 32 + r;
-        double k;
-        if (i < M && col_ok) {
-            const double r2 = -2.0 * dot[r] + (xn2 + z2[i]);
-            k = cov_from_r2<KIND>(r2, variance);
-        } else {
-            k = (pad_identity && (long)i == n) ? 1.0 : 0.0;
+    for (int r = 0; r < 16; ++r) {
+        const int i = ibase + rbase + r;
+        const double zi2 = z2[i];
+        double ka = cov_from_r2<KIND>(fma(-2.0, dot[r][0], xa2 + zi2), variance);
+        double kb = cov_from_r2<KIND>(fma(-2.0, dot[r][1], xb2 + zi2), variance);
+        const bool row_ok = i < M;
+        if (!(row_ok && oka)) ka = (pad_identity && (long)i == na) ? 1.0 : 0.0;
+        if (!(row_ok && okb)) kb = (pad_identity && (long)i == nb) ? 1.0 : 0.0;
+        K[(long)i * ldk + c0 + tx] = ka;
+        K[(long)i * ldk + c0 + tx + 64] = kb;
+        if (alpha) {
+            const double al = alpha[i];
+            mua = fma(al, ka, mua);
+            mub = fma(al, kb, mub);
         }
-        K[(long)i * ldk + c0 + nn] = k;
-        if (alpha) mu = fma(alpha[i], k, mu);
     }
     if (alpha) {
-        if (ig == 1) smu[nn] = mu;
+        smu[ty][tx] = mua;
+        smu[ty][tx + 64] = mub;
         __syncthreads();
-        if (ig == 0) mu_part[(long)blockIdx.y * ldmu + c0 + nn] = mu + smu[nn];
+        if (tid < 128) mu_part[(long)blockIdx.y * ldmu + c0 + tid] = (smu[0][tid] + smu[1][tid]) + (smu[2][tid] + smu[3][tid]);
     }
 }
 
@@ -293,70 +335,166 @@ int gemv_t_launch(const double* A, long lda, int m, int n, const double* x, doub
 // =====================================================================================================================
 constexpr int DB = 128, DB_LD = 129;
 
-// S holds lower-triangular L (row-major, ld 129). Computes X = L^-1: X[i][c] (c < i) is left in S[c][i] (upper triangle),
-// the diagonal of X in dinv[].  256 threads: lane pairs split each column's dot products.
-__device__ void tri_inverse_in_smem(double* S, double* dinv) {
-    const int tid = threadIdx.x;
-    if (tid < DB) dinv[tid] = 1.0 / S[tid * DB_LD + tid];
-    __syncthreads();
-    const int c = (tid >> 5) * 16 + ((tid & 31) >> 1), half = tid & 1;
-    for (int i = 1; i < DB; ++i) {
-        double s = 0.0;
-        if (c < i) {
-            const double* Li = S + i * DB_LD;
-            const double* Xc = S + c * DB_LD;
-            int j = c + half;
-            if (j == c) { s = Li[c] * dinv[c]; j += 2; }
-            for (; j < i; j += 2) s = fma(Li[j], Xc[j], s);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (c < i && half == 0) S[c * DB_LD + i] = -s * dinv[i];
-        __syncwarp();
-    }
-    __syncthreads();
-}
-
-__device__ void store_inverse(const double* S, const double* dinv, double* Dinv) {
-    for (int e = threadIdx.x; e < DB * DB; e += blockDim.x) {
-        const int r = e >> 7, c = e & 127;
-        Dinv[e] = c < r ? S[c * DB_LD + r] : (c == r ? dinv[r] : 0.0);
-    }
-}
-
-__global__ void __launch_bounds__(256) diag_potrf_inv_kernel(double* A, long lda, double* Dinv, int blk, int* info) {
-    extern __shared__ double S[];   // [128][129]
+// X = L^-1 for the lower-triangular 128x128 L in shared memory S (row-major, ld 129), written to Dinv (ld 128, dense, zeros
+// above the diagonal).  Same register tiling as the Cholesky below: thread (ti, tj) of a 16x16 grid owns X[16 ii + ti][16 jj + tj].
+// Right-looking elimination of L X = I: per pivot k the owners of row k scale it by 1 / L[k][k], publish it through a
+// double-buffered shared row (ONE barrier per pivot), and every thread updates its rows i > k with FMAs only
+// (X[i][c] -= L[i][k] X[k][c], c <= k).  The row-by-row dot-product form this replaces was latency-bound (160 us / block).
+__device__ void tri_inverse_regs(const double* S, double* Dinv) {
+    __shared__ double xrow[2][DB];
     __shared__ double dinv[DB];
-    __shared__ int fail;
-    const int tid = threadIdx.x;
-    if (tid == 0) fail = 0;
-    for (int e = tid; e < DB * DB; e += 256) {
-        const int r = e >> 7, c = e & 127;
-        S[r * DB_LD + c] = c <= r ? A[(long)r * lda + c] : 0.0;
-    }
+    const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
+    if (tid < DB) dinv[tid] = 1.0 / S[tid * DB_LD + tid];
+    double x[8][8];
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) x[ii][jj] = (16 * ii + ti == 16 * jj + tj) ? 1.0 : 0.0;
     __syncthreads();
-    const int ti = tid & 15, tj = tid >> 4;
-    for (int k = 0; k < DB; ++k) {
-        const double akk = S[k * DB_LD + k];
-        if (!(akk > 0.0)) {   // uniform across the block (same shared value after the barrier)
-            if (tid == 0) fail = k + 1;
-            break;
-        }
-        const double d = sqrt(akk), inv = 1.0 / d;
-        __syncthreads();   // everyone has read akk before it is overwritten
-        if (tid == k) S[k * DB_LD + k] = d;
-        if (tid > k && tid < DB) S[tid * DB_LD + k] *= inv;
-        __syncthreads();
-        int i = k + 1 + ((ti - (k + 1)) & 15);
-        const int jfirst = k + 1 + ((tj - (k + 1)) & 15);
-        for (; i < DB; i += 16) {
-            const double lik = S[i * DB_LD + k];
-            for (int j = jfirst; j <= i; j += 16) S[i * DB_LD + j] = fma(-lik, S[j * DB_LD + k], S[i * DB_LD + j]);
-        }
-        __syncthreads();
+    if (ti == 0) {   // publish row 0 : X[0][0] = 1 / L[0][0]
+        x[0][0] *= dinv[0];
+        if (tj == 0) xrow[0][0] = x[0][0];
     }
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+        for (int kk = 0; kk < 16; ++kk) {
+            const int k = kb * 16 + kk, buf = k & 1;
+            __syncthreads();
+            double l[8];
+#pragma unroll
+            for (int ii = kb; ii < 8; ++ii) {
+                const int i = 16 * ii + ti;
+                l[ii] = i > k ? S[i * DB_LD + k] : 0.0;
+            }
+#pragma unroll
+            for (int jj = 0; jj <= kb; ++jj) {
+                const int c = 16 * jj + tj;
+                const double xk = c <= k ? xrow[buf][c] : 0.0;
+#pragma unroll
+                for (int ii = kb; ii < 8; ++ii) x[ii][jj] = fma(-l[ii], xk, x[ii][jj]);
+            }
+            // finish and publish row k + 1 (owners: row residue (kk + 1) % 16 in block kb, or residue 0 in block kb + 1)
+            if (k + 1 < DB) {
+                const int nb = buf ^ 1;
+                const double dk = dinv[k + 1];
+                if (kk < 15) {
+                    if (ti == kk + 1) {
+#pragma unroll
+                        for (int jj = 0; jj <= kb; ++jj) {
+                            x[kb][jj] *= dk;
+                            xrow[nb][16 * jj + tj] = x[kb][jj];
+                        }
+                    }
+                } else if (kb < 7) {
+                    constexpr int KN = 7;
+                    if (ti == 0) {
+#pragma unroll
+                        for (int jj = 0; jj <= (kb + 1 < 8 ? kb + 1 : KN); ++jj) {
+                            x[kb + 1 < 8 ? kb + 1 : KN][jj] *= dk;
+                            xrow[nb][16 * jj + tj] = x[kb + 1 < 8 ? kb + 1 : KN][jj];
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int i = 16 * ii + ti, c = 16 * jj + tj;
+            Dinv[i * DB + c] = c <= i ? x[ii][jj] : 0.0;
+        }
+}
+
+// Right-looking Cholesky of one 128x128 block with the whole block in REGISTERS: thread (ti, tj) of a 16x16 grid owns the
+// 8x8 elements A[16 ii + ti][16 jj + tj].  Per pivot: the 16 owners of column k publish it (and the diagonal owner its
+// 1/sqrt) through a double-buffered shared column, ONE barrier, then every thread updates its registers with FMAs only.
+__global__ void __launch_bounds__(256) diag_potrf_inv_kernel(double* A, long lda, double* Dinv, int blk, int* info) {
+    extern __shared__ double S[];   // [128][129] : receives L, then the workspace of the triangular inverse
+    __shared__ double col[2][DB];
+    __shared__ double rsq[2];
+    const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
+    double a[8][8];
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int r = 16 * ii + ti, c = 16 * jj + tj;
+            a[ii][jj] = c <= r ? A[(long)r * lda + c] : 0.0;
+        }
+    for (int e = tid; e < DB * DB_LD; e += 256) S[e] = 0.0;
+    int failed = 0;
+    if (tj == 0) {   // publish column 0
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) col[0][16 * ii + ti] = a[ii][0];
+        if (ti == 0) rsq[0] = rsqrt(a[0][0]);
+    }
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+        for (int kk = 0; kk < 16; ++kk) {
+            const int k = kb * 16 + kk, buf = k & 1;
+            __syncthreads();
+            const double akk = col[buf][k];
+            if (!(akk > 0.0)) { failed = k + 1; goto finish; }   // uniform: every thread reads the same value
+            const double rs = rsq[buf];
+            double li[8], lj[8];
+#pragma unroll
+            for (int ii = kb; ii < 8; ++ii) {
+                const int r = 16 * ii + ti;
+                li[ii] = r > k ? col[buf][r] * rs : 0.0;
+            }
+#pragma unroll
+            for (int jj = kb; jj < 8; ++jj) {
+                const int c = 16 * jj + tj;
+                lj[jj] = c > k ? col[buf][c] * rs : 0.0;
+            }
+            if (tj == kk) {   // owners of column k store the finished column of L
+#pragma unroll
+                for (int ii = kb; ii < 8; ++ii) {
+                    const int r = 16 * ii + ti;
+                    if (r > k) S[r * DB_LD + k] = li[ii];
+                    else if (r == k) S[k * DB_LD + k] = akk * rs;
+                }
+            }
+            // the next pivot first: its 1/sqrt is the longest dependency of the next iteration
+            const int nb = buf ^ 1;
+            constexpr int KN = 7;
+            if (kk < 15) {
+                a[kb][kb] = fma(-li[kb], lj[kb], a[kb][kb]);
+                if (tj == kk + 1 && ti == kk + 1) rsq[nb] = rsqrt(a[kb][kb]);
+            } else if (kb < 7) {
+                a[kb + 1 < 8 ? kb + 1 : KN][kb + 1 < 8 ? kb + 1 : KN] =
+                    fma(-li[kb + 1 < 8 ? kb + 1 : KN], lj[kb + 1 < 8 ? kb + 1 : KN], a[kb + 1 < 8 ? kb + 1 : KN][kb + 1 < 8 ? kb + 1 : KN]);
+                if (tj == 0 && ti == 0) rsq[nb] = rsqrt(a[kb + 1 < 8 ? kb + 1 : KN][kb + 1 < 8 ? kb + 1 : KN]);
+            }
+#pragma unroll
+            for (int ii = kb; ii < 8; ++ii)
+#pragma unroll
+                for (int jj = kb; jj < 8; ++jj) {
+                    const bool done = kk < 15 ? (ii == kb && jj == kb) : (ii == kb + 1 && jj == kb + 1);   // already updated above
+                    if (!done) a[ii][jj] = fma(-li[ii], lj[jj], a[ii][jj]);
+                }
+            // publish column k + 1 from the updated registers (owner column residue (kk + 1) % 16, block kb or kb + 1)
+            if (k + 1 < DB) {
+                if (kk < 15) {
+                    if (tj == kk + 1) {
+#pragma unroll
+                        for (int ii = kb; ii < 8; ++ii) col[nb][16 * ii + ti] = a[ii][kb];
+                    }
+                } else if (kb < 7) {
+                    if (tj == 0) {
+#pragma unroll
+                        for (int ii = kb + 1; ii < 8; ++ii) col[nb][16 * ii + ti] = a[ii][kb + 1 < 8 ? kb + 1 : KN];
+                    }
+                }
+            }
+        }
+    }
+finish:
     __syncthreads();
-    if (fail) {
-        if (tid == 0) atomicCAS(info, 0, blk * DB + fail);
+    if (failed) {
+        if (tid == 0) atomicCAS(info, 0, blk * DB + failed);
         return;
     }
     for (int e = tid; e < DB * DB; e += 256) {
@@ -364,21 +502,18 @@ __global__ void __launch_bounds__(256) diag_potrf_inv_kernel(double* A, long lda
         A[(long)r * lda + c] = c <= r ? S[r * DB_LD + c] : 0.0;
     }
     __syncthreads();
-    tri_inverse_in_smem(S, dinv);
-    store_inverse(S, dinv, Dinv);
+    tri_inverse_regs(S, Dinv);
 }
 
 __global__ void __launch_bounds__(256) diag_trtri_kernel(const double* L, long lda, double* Dinv) {
     extern __shared__ double S[];
-    __shared__ double dinv[DB];
     const double* A = L + (long)blockIdx.x * DB * lda + (long)blockIdx.x * DB;
     for (int e = threadIdx.x; e < DB * DB; e += 256) {
         const int r = e >> 7, c = e & 127;
         S[r * DB_LD + c] = c <= r ? A[(long)r * lda + c] : 0.0;
     }
     __syncthreads();
-    tri_inverse_in_smem(S, dinv);
-    store_inverse(S, dinv, Dinv + (long)blockIdx.x * DB * DB);
+    tri_inverse_regs(S, Dinv + (long)blockIdx.x * DB * DB);
 }
 
 static bool g_diag_attr_set = false;
