@@ -113,46 +113,61 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
-def cpu_baseline(cfg, M, Nb, n_small, n_large):
-    """t(N) = a + b N fitted on two row counts (dense M x M part + streaming part), extrapolated to the full minibatch."""
-    cpu_reference_step_time(cfg, M, 64)            # warm OpenBLAS threads / page in
-    t_small = cpu_reference_step_time(cfg, M, n_small)
-    t_large = cpu_reference_step_time(cfg, M, n_large)
-    b = max((t_large - t_small) / (n_large - n_small), 1e-12)
+CPU_FLOP_BUDGET = 2.5e12   # ~10-30 s of host work at a few hundred GFLOP/s
+CPU_M_CAP = 4096           # above this the 37 M^3 dense part alone exceeds the budget: measure at the cap and scale
+
+
+def reference_flops(n, M):
+    return 8.0 * n * M * M + 37.0 * M ** 3   # what the reference's operation order executes
+
+
+def cpu_fit(cfg, M, Nb, budget=None):
+    """Reference-order step time on the host for the (Nb, M) workload from a bounded sample -> (seconds, description)."""
+    def timer(n, m):
+        return cpu_reference_step_time(cfg, m, n)
+    budget = budget or CPU_FLOP_BUDGET
+    if reference_flops(Nb, M) <= budget:
+        timer(min(Nb, 64), M)
+        t = min(timer(Nb, M), timer(Nb, M))
+        return t, f"the full {Nb}-row minibatch at M={M} (best of 2)"
+    Mc = min(M, CPU_M_CAP)
+    n_large = int(max(1024, (budget - 37.0 * Mc ** 3) / (8.0 * Mc * Mc) / 1.25)) // 256 * 256
+    n_large = int(min(max(n_large, 2048), 65536, Nb))
+    n_small = max(256, n_large // 4)
+    timer(64, Mc)                                  # warm the BLAS threads and the allocator
+    t_small, t_large = timer(n_small, Mc), timer(n_large, Mc)
+    b = max((t_large - t_small) / (n_large - n_small), 1e-9)
     a = max(t_small - b * n_small, 0.0)
-    t_full = a + b * Nb
+    note = f"t(N)=a+bN fitted at {n_small} and {n_large} rows, M={Mc} (a={a:.3f}s dense part, b={b * 1e6:.2f}us/row)"
+    if Mc != M:
+        a *= (M / Mc) ** 3
+        b *= (M / Mc) ** 2
+        note += (f", then scaled to M={M} by (M/{Mc})^3 for a and (M/{Mc})^2 for b because the 37 M^3 dense flops at M={M} alone "
+                 "exceed the sample budget")
+    return a + b * Nb, note + f", extrapolated to the {Nb}-row minibatch"
+
+
+def cpu_baseline(cfg, M, Nb):
+    t_full, note = cpu_fit(cfg, M, Nb)
     return {"value": Nb / t_full, "unit": "datapoints/s", "cores": cpu_threads(), "kind": "port",
-            "sample": f"oracle (NumPy/SciPy restatement of the reference, not TensorFlow) natgrad_step at {n_small} and {n_large} rows, "
-                      f"M={M} full; t(N)=a+bN extrapolated to the {Nb}-row minibatch (a={a:.3f}s dense, b={b * 1e6:.3f}us/row)",
+            "sample": "oracle (NumPy/SciPy restatement of the reference, not TensorFlow) natgrad_step: " + note,
             "host_cpus": os.cpu_count(), "t_full_step_s": t_full}
-
-
-def sample_sizes(M):
-    # bounded: ~10-30 s of CPU work in total (8 N M^2 streaming + 37 M^3 dense flops at a few hundred GFLOP/s)
-    budget = 2.5e12
-    n_large = int(min(65536, max(2048, budget / (8.0 * M * M))))
-    n_large = max(256, n_large // 256 * 256)
-    return max(128, n_large // 4), n_large
 
 
 # ---- the reference arm -----------------------------------------------------------------------------------------------
 def run_reference(args, cfg, M, Nb):
+    """The reference's CPU implementation of the path (oracle port: the reference itself needs GPflow/TensorFlow, which this
+    image cannot install).  Each step is one bounded sample (see cpu_fit); the value is the mean over the timed steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_small, n_large = sample_sizes(M)
-    a_dense = None
-    times = []
-    cpu_reference_step_time(cfg, M, 64)
-    t_small = cpu_reference_step_time(cfg, M, n_small)
-    for i in range(args.warmup + args.steps):
-        t = cpu_reference_step_time(cfg, M, n_large)
+    vals, note = [], ""
+    per_step_budget = max(CPU_FLOP_BUDGET * 6.0 / max(args.warmup + args.steps, 1), 1.2 * 37.0 * min(M, CPU_M_CAP) ** 3)
+    for i in range(args.warmup + args.steps):   # the whole run stays within a few minutes of host time
+        t_full, note = cpu_fit(cfg, M, Nb, budget=min(per_step_budget, CPU_FLOP_BUDGET))
         if i >= args.warmup:
-            times.append(t)
-    t_large = float(np.mean(times))
-    b = max((t_large - t_small) / (n_large - n_small), 1e-12)
-    a_dense = max(t_small - b * n_small, 0.0)
-    t_full = a_dense + b * Nb
+            vals.append(t_full)
+    t_full = float(np.mean(vals))
     value = Nb / t_full
     line = {
         "impl": "reference", "metric": "natgrad_step datapoints/sec", "value": value, "unit": "datapoints/s", "n_gpus": args.gpus,
@@ -160,9 +175,8 @@ def run_reference(args, cfg, M, Nb):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(cfg, M, Nb, args.gpus),
         "cpu_baseline": {"value": value, "unit": "datapoints/s", "cores": cpu_threads(), "kind": "port",
-                         "sample": f"each step = oracle natgrad_step on {n_large} rows (M={M} full); dense part from a {n_small}-row step; "
-                                   f"t(N)=a+bN extrapolated to {Nb} rows (a={a_dense:.3f}s, b={b * 1e6:.3f}us/row); NumPy/SciPy restatement, "
-                                   "TensorFlow/GPflow not installable here", "host_cpus": os.cpu_count()},
+                         "sample": "each step = oracle (NumPy/SciPy restatement; GPflow/TensorFlow not installable here) natgrad_step: " + note,
+                         "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": "datapoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -344,8 +358,7 @@ def main():
         "gpu_launches": launches, "roofline": roofline, "detail": extra,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_small, n_large = sample_sizes(M)
-        line["cpu_baseline"] = cpu_baseline(cfg, M, Nb, n_small, n_large)
+        line["cpu_baseline"] = cpu_baseline(cfg, M, Nb)
     if rank == 0:
         print(json.dumps(line), flush=True)
     model.close()
