@@ -64,8 +64,8 @@ enum { ROUTE_AUTO = 0, ROUTE_FUSED = 1, ROUTE_WHITENED = 2 };
 
 struct tsvgp_ctx {
     int dev = 0;
-    cudaStream_t s_main = nullptr, s_pp[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev[N_EV] = {};
+    cudaStream_t s_main = nullptr, s_pp[2] = {nullptr, nullptr}, s_side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev[N_EV] = {}, ev_kuu = nullptr, ev_side = nullptr;
     std::string err;
     int last_info = 0;
 
@@ -99,6 +99,8 @@ struct tsvgp_ctx {
     double *stats2[2] = {nullptr, nullptr};  // second B accumulator per stream: the split-off k piece of the balanced SYRK
     double *alpha = nullptr, *mZ = nullptr, *mq = nullptr, *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *gwork = nullptr;
     double *scal = nullptr;
+    double *tmp2 = nullptr, *dinv2 = nullptr, *pv1 = nullptr, *pv2 = nullptr, *gwork2 = nullptr, *scal2 = nullptr;   // side-stream workspace (K9 factor)
+    bool k9_pending = false;   // K9 work enqueued on the side stream, probe not read yet
     int* info = nullptr;    // [N_INFO]
     int* flags = nullptr;   // [2]
     bool sites_set = false, kuu_valid = false, post_valid = false, kl_valid = false, k9_valid = false;
@@ -125,6 +127,8 @@ struct tsvgp_ctx {
     double *slab[2] = {}, *mu_part[2] = {}, *q_part[2] = {}, *gbuf[2] = {}, *hbuf[2] = {};
     double* ve_blocks = nullptr;
     long ve_cap = 0;
+    double* kpart[2] = {};     // split-K partial tiles of the SYRK when M is so small that its tiles cannot fill the SMs
+    int ksplit = 1;
 
     // multi-GPU
     NcclComm comm = nullptr;
@@ -193,6 +197,8 @@ int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     NEED(c->alpha = p.get(mp)); NEED(c->mZ = p.get(mp)); NEED(c->mq = p.get(mp)); NEED(c->v1 = p.get(mp)); NEED(c->v2 = p.get(mp));
     NEED(c->v3 = p.get(mp)); NEED(c->gwork = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal = p.get(N_SCAL));
     NEED(c->info = (int*)p.get(N_INFO)); NEED(c->flags = (int*)p.get(2));
+    NEED(c->tmp2 = p.get((size_t)((c->Mp / 128 + 1) / 2) * 128 * mp)); NEED(c->dinv2 = p.get((size_t)(c->Mp / 128) * 128 * 128));
+    NEED(c->pv1 = p.get(mp)); NEED(c->pv2 = p.get(mp)); NEED(c->gwork2 = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal2 = p.get(N_SCAL));
     c->sites_set = c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = false;
     c->chunk = 0;   // slab workspace depends on Mp
     return TSVGP_OK;
@@ -349,6 +355,22 @@ int ensure_slabs(tsvgp_ctx* c, long n_points) {
         NEED(c->gbuf[s] = p.get(nc));
         NEED(c->hbuf[s] = p.get(nc));
     }
+    {   // few output tiles (small M): split the SYRK's contraction over the idle SMs, partials reduced by a second kernel
+        const int nt = c->Mp / 128, tiles = nt * (nt + 1) / 2;
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->dev);
+        c->ksplit = 1;
+        if (tiles * 2 <= sms) {
+            c->ksplit = sms / tiles;
+            const int max_split = (int)(nc / 256);     // at least 16 k-tiles per piece
+            if (c->ksplit > max_split) c->ksplit = max_split;
+            if (c->ksplit < 2) c->ksplit = 1;
+        }
+        for (int s = 0; s < 2; ++s) {
+            c->kpart[s] = nullptr;
+            if (c->ksplit > 1) NEED(c->kpart[s] = p.get((size_t)c->ksplit * c->Mp * c->Mp));
+        }
+    }
     NEED(c->ve_blocks = p.get(ve_need));
     c->ve_cap = ve_need;
     c->chunk = nc;
@@ -441,9 +463,16 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
                 p.C = c->stats[b]; p.ldc = Mp; p.m = p.n = Mp; p.k = ncols;
                 p.beta = 1.0; p.lower_out = 1; p.kscale = c->hbuf[b];
                 const int nt = Mp / 128;
-                const int ksp = c->balance ? balanced_ksplit(nt * (nt + 1) / 2, ncols) : ncols;
-                if (ksp < ncols) { p.ksp = ksp; p.C2 = c->stats2[b]; }
-                LA(gemm_launch(p, s));
+                const int ks_here = c->ksplit < ncols / 256 ? c->ksplit : ncols / 256;
+                if (ks_here > 1) {
+                    p.ksplit = ks_here; p.part = c->kpart[b]; p.part_stride = (long)Mp * Mp;
+                    LA(gemm_launch(p, s));
+                    LA(splitk_reduce_launch(p, s));
+                } else {
+                    const int ksp = c->balance ? balanced_ksplit(nt * (nt + 1) / 2, ncols) : ncols;
+                    if (ksp < ncols) { p.ksp = ksp; p.C2 = c->stats2[b]; }
+                    LA(gemm_launch(p, s));
+                }
             }
             mark(s);
             // (e) b += K g
@@ -484,47 +513,59 @@ int all_reduce(tsvgp_ctx* c, double* buf, size_t count) {
     return TSVGP_OK;
 }
 
-// K9 = K + jitter I = C9 C9^T and C9^-1 (tsvgp.py:268-271), kept while kernel, Z and jitter are unchanged
-int ensure_k9(tsvgp_ctx* c, double jitter) {
+// K9 = K + jitter I = C9 C9^T and C9^-1 (tsvgp.py:268-271), kept while kernel, Z and jitter are unchanged.  It depends on the
+// kernel matrix only, so it is factored on a SIDE stream (own workspace) while the main stream builds the posterior factors
+// from the sites; both chains are latency-bound, so running them side by side nearly halves the prepare phase.
+int start_k9(tsvgp_ctx* c, double jitter) {
     if (c->k9_valid && c->k9_jitter == jitter && c->cache_factors) return TSVGP_OK;
-    cudaStream_t s = c->s_main;
+    cudaStream_t s = c->s_side;
+    CU(cudaEventRecord(c->ev_kuu, c->s_main));
+    CU(cudaStreamWaitEvent(s, c->ev_kuu, 0));
     LA(copy_add_diag_launch(c->K, c->C9, c->Mp, c->Mp, jitter, s));
-    LA(chol_lower(c->C9, c->Mp, c->Mp, c->dinv, c->info + INFO_K9, s));
-    LA(trtri_lower(c->C9, c->Mp, c->Mp, c->dinv, c->C9inv, c->tmp, s));
+    LA(chol_lower(c->C9, c->Mp, c->Mp, c->dinv2, c->info + INFO_K9, s));
+    LA(trtri_lower(c->C9, c->Mp, c->Mp, c->dinv2, c->C9inv, c->tmp2, s));
     c->k9_valid = true;
     c->k9_jitter = jitter;
     c->cond_est = 0.0;
+    c->k9_pending = true;
     if (c->route_opt == ROUTE_AUTO) {
         // conditioning probe: 8 power iterations each on K and on K9^-1 = C9^-T C9^-1; Rayleigh ratios of the last two
         // iterates give lambda_max(K) and 1/lambda_min(K9) (both from below)
         const int n = c->Mp;
-        double *a = c->v1, *b = c->v2;
+        double *a = c->pv1, *b = c->pv2;
         LA(probe_vector_launch(a, c->M, n, s));
         for (int it = 0; it < 8; ++it) {
-            if (it == 7) LA(dot_launch(a, a, c->M, c->scal + SC_PK0, s));
+            if (it == 7) LA(dot_launch(a, a, c->M, c->scal2 + SC_PK0, s));
             LA(gemv_n_launch(c->K, n, c->M, c->M, a, 1.0, 0.0, b, s));
             double* t = a; a = b; b = t;
         }
-        LA(dot_launch(a, a, c->M, c->scal + SC_PK1, s));
+        LA(dot_launch(a, a, c->M, c->scal2 + SC_PK1, s));
         LA(probe_vector_launch(a, c->M, n, s));
         for (int it = 0; it < 8; ++it) {
-            if (it == 7) LA(dot_launch(a, a, n, c->scal + SC_PI0, s));
+            if (it == 7) LA(dot_launch(a, a, n, c->scal2 + SC_PI0, s));
             LA(gemv_n_launch(c->C9inv, n, n, n, a, 1.0, 0.0, b, s));
-            LA(gemv_t_launch(c->C9inv, n, n, n, b, a, c->gwork, s));
+            LA(gemv_t_launch(c->C9inv, n, n, n, b, a, c->gwork2, s));
         }
-        LA(dot_launch(a, a, n, c->scal + SC_PI1, s));
-        double sc[N_SCAL];
-        CU(cudaMemcpyAsync(sc, c->scal, sizeof sc, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-        const double lmax = sqrt(sc[SC_PK1] / sc[SC_PK0]) + jitter, inv_lmin = sqrt(sc[SC_PI1] / sc[SC_PI0]);
-        c->cond_est = lmax * inv_lmin;
-        if (!(c->cond_est == c->cond_est)) c->cond_est = INFINITY;   // failed factorisation: the step will report it
+        LA(dot_launch(a, a, n, c->scal2 + SC_PI1, s));
     }
+    CU(cudaEventRecord(c->ev_side, s));
     return TSVGP_OK;
 }
 
+// joins the side stream, reads the conditioning probe (if one ran) and fixes the statistics route of this step
 int choose_route(tsvgp_ctx* c, double jitter) {
-    OK(ensure_k9(c, jitter));
+    if (c->k9_pending) {
+        if (c->route_opt == ROUTE_AUTO) {
+            double sc[N_SCAL];
+            CU(cudaMemcpyAsync(sc, c->scal2, sizeof sc, cudaMemcpyDeviceToHost, c->s_side));
+            CU(cudaStreamSynchronize(c->s_side));
+            const double lmax = sqrt(sc[SC_PK1] / sc[SC_PK0]) + jitter, inv_lmin = sqrt(sc[SC_PI1] / sc[SC_PI0]);
+            c->cond_est = lmax * inv_lmin;
+            if (!(c->cond_est == c->cond_est)) c->cond_est = INFINITY;   // failed factorisation: the step will report it
+        }
+        CU(cudaStreamWaitEvent(c->s_main, c->ev_side, 0));
+        c->k9_pending = false;
+    }
     if (c->route_opt == ROUTE_AUTO) c->route = c->cond_est <= c->route_cond_max ? ROUTE_FUSED : ROUTE_WHITENED;
     else c->route = c->route_opt;
     return TSVGP_OK;
@@ -679,6 +720,9 @@ int tsvgp_create(tsvgp_ctx** out, int device_id) {
         ok = ok && cudaEventCreateWithFlags(&c->ev_join[s], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->s_side, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_kuu, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < N_EV && ok; ++i) ok = ok && cudaEventCreate(&c->ev[i]) == cudaSuccess;
     ok = ok && gemm_init() == 0;
     if (!ok) {
@@ -701,6 +745,9 @@ void tsvgp_destroy(tsvgp_ctx* c) {
         if (c->ev_join[s]) cudaEventDestroy(c->ev_join[s]);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_kuu) cudaEventDestroy(c->ev_kuu);
+    if (c->ev_side) cudaEventDestroy(c->ev_side);
+    if (c->s_side) cudaStreamDestroy(c->s_side);
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i)
         if (c->ev_sw[i]) cudaEventDestroy(c->ev_sw[i]);
@@ -766,7 +813,8 @@ int tsvgp_set_inducing(tsvgp_ctx* c, const double* Z, int M, int D, const double
     if (!Z || M < 1 || D < 1) FAIL(TSVGP_ERR_INVALID, "Z must be [M >= 1, D >= 1]");
     CU(cudaSetDevice(c->dev));
     if (M != c->M || D != c->D) {
-        CU(cudaStreamSynchronize(c->s_main));
+        CU(cudaDeviceSynchronize());
+        c->k9_pending = false;
         OK(alloc_m_state(c, M, D));
     }
     CU(cudaMemcpyAsync(c->Zraw, Z, sizeof(double) * (size_t)M * D, cudaMemcpyDefault, c->s_main));
@@ -879,6 +927,8 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
     CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
     CU(cudaEventRecord(c->ev[EV_T0], s));
     OK(ensure_xs(c));
+    OK(ensure_kuu(c));
+    OK(start_k9(c, jitter));
     OK(ensure_posterior(c));
     if (elbo_before) OK(ensure_kl_terms(c));
     OK(choose_route(c, jitter));
