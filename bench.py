@@ -205,6 +205,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    # stdout carries exactly ONE line (the JSON): keep NCCL's version banner (printed to stdout when the box exports
+    # NCCL_DEBUG=VERSION/INFO) out of it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("BENCH_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     if world > 1:
         import torch.distributed as dist   # plumbing only: rendezvous, barrier, max over ranks (gloo; no tensors on the GPU)
         dist.init_process_group("gloo")
@@ -237,7 +241,14 @@ def main():
         else:
             t = torch.zeros(128, dtype=torch.uint8)
         dist.broadcast(t, 0)
-        model.init_comm(world, rank, bytes(t.tolist()))
+        sys.stdout.flush()
+        saved = os.dup(1)              # NCCL may printf its version banner to stdout during ncclCommInitRank: send it to stderr
+        os.dup2(2, 1)
+        try:
+            model.init_comm(world, rank, bytes(t.tolist()))
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if dist is not None:
