@@ -407,88 +407,136 @@ __device__ void tri_inverse_regs(const double* S, double* Dinv) {
         }
 }
 
-// Right-looking Cholesky of one 128x128 block with the whole block in REGISTERS: thread (ti, tj) of a 16x16 grid owns the
-// 8x8 elements A[16 ii + ti][16 jj + tj].  Per pivot: the 16 owners of column k publish it (and the diagonal owner its
-// 1/sqrt) through a double-buffered shared column, ONE barrier, then every thread updates its registers with FMAs only.
+// Cholesky A = L L^T of one 128x128 block AND X = L^-1, fused, with both matrices in REGISTERS: thread (ti, tj) of a 16x16
+// grid owns A[16 ii + ti][16 jj + tj] and X[16 ii + ti][16 jj + tj] for jj <= ii.  One barrier per pivot k:
+//   * the 16 owners of column k + 1 (one half-warp) take the pivot's 1/sqrt by shuffle and publish the SCALED column, so no
+//     other thread multiplies or masks anything: everyone just loads l_i, l_j and issues FMAs;
+//   * the right-looking elimination of L X = I rides on the same loads one pivot behind: X[i][:] -= L[i][k-1] X[k-1][:].
+// (r01: separate barrier-per-pivot Cholesky 55 us + inverse 47 us per block, both issue-bound on redundant scaling.)
 __global__ void __launch_bounds__(256) diag_potrf_inv_kernel(double* A, long lda, double* Dinv, int blk, int* info) {
-    extern __shared__ double S[];   // [128][129] : receives L, then the workspace of the triangular inverse
-    __shared__ double col[2][DB];
+    extern __shared__ double S[];   // [128][129] : staging of L for the coalesced write-back
+    __shared__ double col[2][DB];   // scaled column k of L (zeros for rows <= k)
+    __shared__ double xrow[2][DB];  // finished row k of X
     __shared__ double rsq[2];
-    const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
-    double a[8][8];
+    __shared__ int sfail;
+    const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4, lane = tid & 31;
+    const unsigned hmask = 0xFFFFu << (lane & 16);
+    double a[8][8], x[8][8];
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii)
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
+        for (int jj = 0; jj <= ii; ++jj) {
             const int r = 16 * ii + ti, c = 16 * jj + tj;
             a[ii][jj] = c <= r ? A[(long)r * lda + c] : 0.0;
+            x[ii][jj] = r == c ? 1.0 : 0.0;
         }
     for (int e = tid; e < DB * DB_LD; e += 256) S[e] = 0.0;
-    int failed = 0;
-    if (tj == 0) {   // publish column 0
+    if (tid == 0) sfail = 0;
+    __syncthreads();
+    if (tj == 0) {   // publish the scaled column 0
+        const double piv = __shfl_sync(hmask, a[0][0], lane & 16);
+        const double rs = rsqrt(piv);
+        if (ti == 0) {
+            rsq[0] = rs;
+            if (!(piv > 0.0)) sfail = 1;
+            S[0] = piv * rs;
+        }
 #pragma unroll
-        for (int ii = 0; ii < 8; ++ii) col[0][16 * ii + ti] = a[ii][0];
-        if (ti == 0) rsq[0] = rsqrt(a[0][0]);
+        for (int ii = 0; ii < 8; ++ii) {
+            const int r = 16 * ii + ti;
+            const double l = r > 0 ? a[ii][0] * rs : 0.0;
+            col[0][r] = l;
+            if (r > 0) S[r * DB_LD] = l;
+        }
     }
+    double lprev[8];
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) lprev[ii] = 0.0;
+    int failed = 0;
 #pragma unroll
     for (int kb = 0; kb < 8; ++kb) {
         for (int kk = 0; kk < 16; ++kk) {
-            const int k = kb * 16 + kk, buf = k & 1;
+            const int k = kb * 16 + kk, buf = k & 1, nb = buf ^ 1;
             __syncthreads();
-            const double akk = col[buf][k];
-            if (!(akk > 0.0)) { failed = k + 1; goto finish; }   // uniform: every thread reads the same value
-            const double rs = rsq[buf];
-            double li[8], lj[8];
+            if (sfail) { failed = sfail; goto finish; }   // uniform
+            double li[8];
 #pragma unroll
-            for (int ii = kb; ii < 8; ++ii) {
-                const int r = 16 * ii + ti;
-                li[ii] = r > k ? col[buf][r] * rs : 0.0;
+            for (int ii = kb; ii < 8; ++ii) li[ii] = col[buf][16 * ii + ti];
+            // (1) inverse, one pivot behind: X[i][c] -= L[i][k-1] X[k-1][c]   (lprev is zero for rows <= k-1)
+            if (k > 0) {
+#pragma unroll
+                for (int jj = 0; jj <= kb; ++jj) {
+                    const int c = 16 * jj + tj;
+                    const double xr = c < k ? xrow[nb][c] : 0.0;
+#pragma unroll
+                    for (int ii = kb; ii < 8; ++ii) x[ii][jj] = fma(-lprev[ii], xr, x[ii][jj]);
+                }
+            }
+            // (2) row k of X is complete: scale by 1 / L[k][k] and publish
+            if (ti == kk) {
+                const double rs = rsq[buf];
+#pragma unroll
+                for (int jj = 0; jj <= kb; ++jj) {
+                    const int c = 16 * jj + tj;
+                    if (c <= k) {
+                        x[kb][jj] *= rs;
+                        xrow[buf][c] = x[kb][jj];
+                    }
+                }
+            }
+            // (3) Cholesky update with the scaled column k; the owners of column k + 1 go first and publish it
+            if (kk < 15) {
+                if (tj == kk + 1) {
+#pragma unroll
+                    for (int ii = kb; ii < 8; ++ii) a[ii][kb] = fma(-li[ii], col[buf][16 * kb + tj], a[ii][kb]);
+                    const double piv = __shfl_sync(hmask, a[kb][kb], (lane & 16) | tj);   // the lane with ti == tj
+                    const double rs = rsqrt(piv);
+                    if (ti == tj) {
+                        rsq[nb] = rs;
+                        if (!(piv > 0.0)) sfail = k + 2;
+                        S[(k + 1) * DB_LD + k + 1] = piv * rs;
+                    }
+#pragma unroll
+                    for (int ii = kb; ii < 8; ++ii) {
+                        const int r = 16 * ii + ti;
+                        const double l = r > k + 1 ? a[ii][kb] * rs : 0.0;
+                        col[nb][r] = l;
+                        if (r > k + 1) S[r * DB_LD + k + 1] = l;
+                    }
+                }
+            } else if (kb < 7) {
+                constexpr int KN = 7;
+                const int jn = kb + 1 < 8 ? kb + 1 : KN;   // (static) block of column k + 1
+                if (tj == 0) {
+#pragma unroll
+                    for (int ii = jn; ii < 8; ++ii) a[ii][jn] = fma(-li[ii], col[buf][16 * jn], a[ii][jn]);
+                    const double piv = __shfl_sync(hmask, a[jn][jn], lane & 16);           // the lane with ti == 0
+                    const double rs = rsqrt(piv);
+                    if (ti == 0) {
+                        rsq[nb] = rs;
+                        if (!(piv > 0.0)) sfail = k + 2;
+                        S[(k + 1) * DB_LD + k + 1] = piv * rs;
+                    }
+#pragma unroll
+                    for (int ii = jn; ii < 8; ++ii) {
+                        const int r = 16 * ii + ti;
+                        const double l = r > k + 1 ? a[ii][jn] * rs : 0.0;
+                        col[nb][r] = l;
+                        if (r > k + 1) S[r * DB_LD + k + 1] = l;
+                    }
+                }
             }
 #pragma unroll
             for (int jj = kb; jj < 8; ++jj) {
-                const int c = 16 * jj + tj;
-                lj[jj] = c > k ? col[buf][c] * rs : 0.0;
-            }
-            if (tj == kk) {   // owners of column k store the finished column of L
+                // the column published above was already updated by its owners: skip it there
+                const bool mine = kk < 15 ? (jj == kb && tj == kk + 1) : (jj == kb + 1 && tj == 0);
+                if (mine) continue;
+                const double lj = col[buf][16 * jj + tj];
 #pragma unroll
-                for (int ii = kb; ii < 8; ++ii) {
-                    const int r = 16 * ii + ti;
-                    if (r > k) S[r * DB_LD + k] = li[ii];
-                    else if (r == k) S[k * DB_LD + k] = akk * rs;
-                }
-            }
-            // the next pivot first: its 1/sqrt is the longest dependency of the next iteration
-            const int nb = buf ^ 1;
-            constexpr int KN = 7;
-            if (kk < 15) {
-                a[kb][kb] = fma(-li[kb], lj[kb], a[kb][kb]);
-                if (tj == kk + 1 && ti == kk + 1) rsq[nb] = rsqrt(a[kb][kb]);
-            } else if (kb < 7) {
-                a[kb + 1 < 8 ? kb + 1 : KN][kb + 1 < 8 ? kb + 1 : KN] =
-                    fma(-li[kb + 1 < 8 ? kb + 1 : KN], lj[kb + 1 < 8 ? kb + 1 : KN], a[kb + 1 < 8 ? kb + 1 : KN][kb + 1 < 8 ? kb + 1 : KN]);
-                if (tj == 0 && ti == 0) rsq[nb] = rsqrt(a[kb + 1 < 8 ? kb + 1 : KN][kb + 1 < 8 ? kb + 1 : KN]);
+                for (int ii = jj; ii < 8; ++ii) a[ii][jj] = fma(-li[ii], lj, a[ii][jj]);
             }
 #pragma unroll
-            for (int ii = kb; ii < 8; ++ii)
-#pragma unroll
-                for (int jj = kb; jj < 8; ++jj) {
-                    const bool done = kk < 15 ? (ii == kb && jj == kb) : (ii == kb + 1 && jj == kb + 1);   // already updated above
-                    if (!done) a[ii][jj] = fma(-li[ii], lj[jj], a[ii][jj]);
-                }
-            // publish column k + 1 from the updated registers (owner column residue (kk + 1) % 16, block kb or kb + 1)
-            if (k + 1 < DB) {
-                if (kk < 15) {
-                    if (tj == kk + 1) {
-#pragma unroll
-                        for (int ii = kb; ii < 8; ++ii) col[nb][16 * ii + ti] = a[ii][kb];
-                    }
-                } else if (kb < 7) {
-                    if (tj == 0) {
-#pragma unroll
-                        for (int ii = kb + 1; ii < 8; ++ii) col[nb][16 * ii + ti] = a[ii][kb + 1 < 8 ? kb + 1 : KN];
-                    }
-                }
-            }
+            for (int ii = kb; ii < 8; ++ii) lprev[ii] = li[ii];
         }
     }
 finish:
@@ -501,8 +549,13 @@ finish:
         const int r = e >> 7, c = e & 127;
         A[(long)r * lda + c] = c <= r ? S[r * DB_LD + c] : 0.0;
     }
-    __syncthreads();
-    tri_inverse_regs(S, Dinv);
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int i = 16 * ii + ti, c = 16 * jj + tj;
+            Dinv[i * DB + c] = (jj <= ii && c <= i) ? x[ii][jj < ii ? jj : ii] : 0.0;
+        }
 }
 
 __global__ void __launch_bounds__(256) diag_trtri_kernel(const double* L, long lda, double* Dinv) {
