@@ -78,7 +78,19 @@ class DenseSites:
 
 
 class t_SVGP:
-    """Drop-in for the reference `t_SVGP` on the natgrad / elbo / predict_f path (num_latent_gps = 1)."""
+    """Drop-in for the reference `t_SVGP` on the natgrad / elbo / predict_f path.
+
+    `num_latent_gps = L > 1` (shared kernel and inducing points, one site pair per latent, `Y [N, L]`; reference
+    tsvgp.py:276-281 and its Bernoulli fixture with L = 2, tests/models/test_tsvgp.py:45-88) is served by L independent
+    device contexts — the latents do not interact in the reference either: every quantity is computed per latent and
+    `variational_expectations` sums over the latent axis.  It is functional coverage, not yet a fused multi-latent pass."""
+
+    def __new__(cls, kernel, likelihood, inducing_variable, *, num_latent_gps=1, lambda_2_sqrt=None, **kw):
+        if lambda_2_sqrt is not None:
+            num_latent_gps = np.asarray(lambda_2_sqrt).shape[0]
+        if num_latent_gps > 1 and cls is t_SVGP:
+            return object.__new__(MultiLatent_t_SVGP)
+        return object.__new__(cls)
 
     def __init__(self, kernel, likelihood, inducing_variable, *, mean_function=None, num_latent_gps=1, lambda_1=None,
                  lambda_2_sqrt=None, num_data=None, force=False, device=0):
@@ -95,8 +107,7 @@ class t_SVGP:
             lambda_2_sqrt = np.asarray(lambda_2_sqrt, dtype=np.float64)
             assert lambda_2_sqrt.ndim == 3  # tsvgp.py:182
             num_latent_gps = lambda_2_sqrt.shape[0]
-        if num_latent_gps != 1:
-            raise NotImplementedError("num_latent_gps > 1 (SURVEY §8f item 3) is not built yet")
+        assert num_latent_gps == 1   # L > 1 is routed to MultiLatent_t_SVGP by __new__
         self.num_latent_gps = 1
         ctx = C.c_void_p()
         rc = self._lib.tsvgp_create(C.byref(ctx), int(device))
@@ -326,6 +337,95 @@ class t_SVGP:
 
     def sync(self):
         self._check(self._lib.tsvgp_sync(self._ctx))
+
+
+class MultiLatent_t_SVGP(t_SVGP):
+    """`t_SVGP(..., num_latent_gps=L)` for L > 1: L single-latent models side by side (see t_SVGP)."""
+
+    def __init__(self, kernel, likelihood, inducing_variable, *, mean_function=None, num_latent_gps=1, lambda_1=None,
+                 lambda_2_sqrt=None, num_data=None, force=False, device=0):
+        if lambda_2_sqrt is not None:
+            lambda_2_sqrt = np.asarray(lambda_2_sqrt, dtype=np.float64)
+            assert lambda_2_sqrt.ndim == 3  # tsvgp.py:182
+            num_latent_gps = lambda_2_sqrt.shape[0]
+        if mean_function is not None and type(mean_function).__name__ != "Zero":
+            raise NotImplementedError("mean_function with num_latent_gps > 1")
+        L = self.num_latent_gps = int(num_latent_gps)
+        self.kernel, self.likelihood, self.inducing_variable = kernel, likelihood, inducing_variable
+        self.mean_function, self.whiten, self.force, self.name = mean_function, False, force, "t_svgp"
+        l1 = None if lambda_1 is None else np.asarray(lambda_1, dtype=np.float64).reshape(-1, L)
+        self._parts = [t_SVGP(kernel, likelihood, inducing_variable, num_data=num_data, force=force, device=device,
+                              lambda_1=None if l1 is None else l1[:, l:l + 1],
+                              lambda_2_sqrt=None if lambda_2_sqrt is None else lambda_2_sqrt[l:l + 1]) for l in range(L)]
+        self._M = self._parts[0]._M
+        self.world_size, self.rank = 1, 0
+
+    num_data = property(lambda self: self._parts[0].num_data, lambda self, v: [setattr(p, "num_data", v) for p in self._parts] and None)
+
+    def close(self):
+        for p in getattr(self, "_parts", []):
+            p.close()
+
+    def set_option(self, name, value):
+        for p in self._parts:
+            p.set_option(name, value)
+
+    @property
+    def lambda_1(self):
+        return np.concatenate([p.lambda_1 for p in self._parts], axis=1)
+
+    @property
+    def lambda_2_sqrt(self):
+        return np.concatenate([p.lambda_2_sqrt for p in self._parts], axis=0)
+
+    @property
+    def lambda_2(self):
+        return np.concatenate([p.lambda_2 for p in self._parts], axis=0)
+
+    def assign_sites(self, lambda_1=None, lambda_2_sqrt=None):
+        for l, p in enumerate(self._parts):
+            p.assign_sites(None if lambda_1 is None else np.asarray(lambda_1)[:, l], None if lambda_2_sqrt is None else np.asarray(lambda_2_sqrt)[l])
+
+    def get_mean_chol_cov_inducing_posterior(self):
+        out = [p.get_mean_chol_cov_inducing_posterior() for p in self._parts]
+        return np.concatenate([o[0] for o in out], axis=1), np.concatenate([o[1] for o in out], axis=0)
+
+    def _split(self, data):
+        X, Y = data
+        Y = np.asarray(Y, dtype=np.float64)
+        if Y.ndim != 2 or Y.shape[1] != self.num_latent_gps:
+            raise _lib.InvalidArgumentError(_lib.ERR_INVALID, f"Y must be [N, {self.num_latent_gps}]")
+        return [(X, np.ascontiguousarray(Y[:, l:l + 1])) for l in range(self.num_latent_gps)]
+
+    def set_data(self, data):
+        return [p.set_data(d) for p, d in zip(self._parts, self._split(data))][0]
+
+    def natgrad_step(self, data=None, lr=0.1, jitter=1e-9, *, global_minibatch_size=None, return_elbo=False):
+        parts = self._split(data) if data is not None else [None] * self.num_latent_gps
+        e = [p.natgrad_step(d, lr, jitter, global_minibatch_size=global_minibatch_size, return_elbo=return_elbo)
+             for p, d in zip(self._parts, parts)]
+        return sum(e) if return_elbo else None
+
+    def elbo(self, data=None, *, global_minibatch_size=None):   # sum over latents of (scaled expectations - KL_l)
+        parts = self._split(data) if data is not None else [None] * self.num_latent_gps
+        return sum(p.elbo(d, global_minibatch_size=global_minibatch_size) for p, d in zip(self._parts, parts))
+
+    def prior_kl(self):
+        return sum(p.prior_kl() for p in self._parts)
+
+    def predict_f(self, Xnew, full_cov=False, full_output_cov=False):
+        out = [p.predict_f(Xnew, full_cov, full_output_cov) for p in self._parts]
+        return np.concatenate([o[0] for o in out], axis=1), np.concatenate([o[1] for o in out], axis=1)
+
+    def init_comm(self, world_size, rank, unique_id):
+        raise NotImplementedError("sharding with num_latent_gps > 1")
+
+    def timings(self):
+        return self._parts[-1].timings()
+
+    def sync(self):
+        for p in self._parts:
+            p.sync()
 
 
 def comm_unique_id() -> bytes:

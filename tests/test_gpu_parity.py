@@ -224,3 +224,55 @@ def test_device_resident_dlpack_inputs():
     np.testing.assert_array_equal(a.lambda_1, b.lambda_1)
     np.testing.assert_array_equal(a.lambda_2_sqrt, b.lambda_2_sqrt)
     a.close(); b.close()
+
+
+def test_two_latent_gps_match_the_reference_fixture():
+    # reference tests/models/test_tsvgp.py:45-88 runs its Bernoulli fixture with num_latent_gps in {1, 2}
+    import tsvgp_b200 as tb
+    rng = np.random.RandomState(123)
+    X = rng.rand(40, 1) * 2 - 1
+    F = np.stack([np.sin(3 * X[:, 0]), np.cos(4 * X[:, 0])], axis=1)
+    Y = (F + 0.2 * rng.randn(40, 2) > 0).astype(float)
+    kernel, lik = orc.SquaredExponential(lengthscales=0.15, variance=2.25), orc.Bernoulli()
+    Z = np.linspace(-1, 1, 12)[:, None]      # cond(Kuu) ~ 1e2: the 1e-9 gate is meaningful
+    ref = orc.OracleTSVGP(kernel, lik, orc.InducingPoints(Z.copy()), num_latent_gps=2)
+    dev = tb.t_SVGP(kernel, lik, Z.copy(), num_latent_gps=2)
+    assert dev.lambda_1.shape == (12, 2) and dev.lambda_2_sqrt.shape == (2, 12, 12)
+    for _ in range(3):
+        ref.natgrad_step((X, Y), lr=0.8)
+        dev.natgrad_step((X, Y), lr=0.8)
+    errs = {"lambda_1": relerr(dev.lambda_1, ref.lambda_1), "lambda_2": relerr(dev.lambda_2, ref.lambda_2),
+            "elbo": abs(dev.elbo((X, Y)) - ref.elbo((X, Y))) / abs(ref.elbo((X, Y)))}
+    mu_d, var_d = dev.predict_f(X + 0.1)
+    mu_r, var_r = ref.predict_f(X + 0.1)
+    errs["mean"], errs["var"] = relerr(mu_d, mu_r), relerr(var_d, var_r)
+    check(errs)
+    dev.close()
+
+
+@pytest.mark.parametrize("lengthscale", [1.0, 4.0, 8.0])
+def test_cuda_is_as_close_to_exact_arithmetic_as_the_oracle(lengthscale):
+    # the long-double arbiter (oracle/longdouble.py, reference operation order) is the truth; the float64 oracle sits
+    # eps * cond away from it; the CUDA path must not sit further away than a small multiple of that
+    import tsvgp_b200 as tb
+    from oracle import longdouble as ld
+    rng = np.random.RandomState(0)
+    N, M, D = 150, 24, 8
+    X, Z = rng.randn(N, D), rng.randn(M, D)
+    Y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.randn(N, 1)
+    kernel, lik = orc.SquaredExponential(variance=1.0, lengthscales=lengthscale), orc.Gaussian(variance=0.1)
+    ref = orc.OracleTSVGP(kernel, lik, orc.InducingPoints(Z))
+    ref.natgrad_step((X, Y), lr=0.7)
+    l1, L2 = ref.lambda_1.copy(), ref.lambda_2_sqrt.copy()
+    t1, tL2 = ld.natgrad_step_gaussian(X, Y, Z, 1.0, lengthscale, 0.1, l1[:, 0], L2[0], lr=0.7)
+    truth1, truth2 = np.asarray(t1, dtype=np.float64), np.asarray(tL2 @ tL2.T, dtype=np.float64)
+    ref.natgrad_step((X, Y), lr=0.7)
+    dev = tb.t_SVGP(kernel, lik, Z.copy(), lambda_1=l1, lambda_2_sqrt=L2)
+    dev.natgrad_step((X, Y), lr=0.7)
+    e_ref = max(relerr(ref.lambda_1[:, 0], truth1), relerr(ref.lambda_2[0], truth2))
+    e_dev = max(relerr(dev.lambda_1[:, 0], truth1), relerr(dev.lambda_2[0], truth2))
+    _record({"oracle_vs_longdouble": e_ref, "cuda_vs_longdouble": e_dev, "route": dev.timings()["route"], "cond_est": dev.timings()["cond_est"]})
+    # fused route (cond below route_cond_max): eps * cond^2, required to stay 10x under the 1e-9 contract;
+    # whitened route: the reference's own eps * cond
+    assert e_dev <= max(20.0 * e_ref + 1e-13, 1e-10), (e_dev, e_ref)
+    dev.close()
