@@ -420,7 +420,6 @@ __global__ void __launch_bounds__(256) diag_potrf_inv_kernel(double* A, long lda
     __shared__ double rsq[2];
     __shared__ int sfail;
     const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4, lane = tid & 31;
-    const unsigned hmask = 0xFFFFu << (lane & 16);
     double a[8][8], x[8][8];
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii)
@@ -433,8 +432,9 @@ __global__ void __launch_bounds__(256) diag_potrf_inv_kernel(double* A, long lda
     for (int e = tid; e < DB * DB_LD; e += 256) S[e] = 0.0;
     if (tid == 0) sfail = 0;
     __syncthreads();
+    const double piv0 = __shfl_sync(0xffffffffu, a[0][0], lane & 16);
     if (tj == 0) {   // publish the scaled column 0
-        const double piv = __shfl_sync(hmask, a[0][0], lane & 16);
+        const double piv = piv0;
         const double rs = rsqrt(piv);
         if (ti == 0) {
             rsq[0] = rs;
@@ -486,10 +486,15 @@ __global__ void __launch_bounds__(256) diag_potrf_inv_kernel(double* A, long lda
             }
             // (3) Cholesky update with the scaled column k; the owners of column k + 1 go first and publish it
             if (kk < 15) {
-                if (tj == kk + 1) {
+                const bool own = tj == kk + 1;
+                if (own) {
 #pragma unroll
                     for (int ii = kb; ii < 8; ++ii) a[ii][kb] = fma(-li[ii], col[buf][16 * kb + tj], a[ii][kb]);
-                    const double piv = __shfl_sync(hmask, a[kb][kb], (lane & 16) | tj);   // the lane with ti == tj
+                }
+                // full-warp shuffle (a run-time half-warp mask costs a MATCH.ANY / BRA.DIV slow path per pivot): every
+                // half-warp reads its lane with ti == kk + 1; only the owners' half-warp uses the value
+                const double piv = __shfl_sync(0xffffffffu, a[kb][kb], (lane & 16) | (kk + 1));
+                if (own) {
                     const double rs = rsqrt(piv);
                     if (ti == tj) {
                         rsq[nb] = rs;
@@ -507,10 +512,13 @@ __global__ void __launch_bounds__(256) diag_potrf_inv_kernel(double* A, long lda
             } else if (kb < 7) {
                 constexpr int KN = 7;
                 const int jn = kb + 1 < 8 ? kb + 1 : KN;   // (static) block of column k + 1
-                if (tj == 0) {
+                const bool own = tj == 0;
+                if (own) {
 #pragma unroll
                     for (int ii = jn; ii < 8; ++ii) a[ii][jn] = fma(-li[ii], col[buf][16 * jn], a[ii][jn]);
-                    const double piv = __shfl_sync(hmask, a[jn][jn], lane & 16);           // the lane with ti == 0
+                }
+                const double piv = __shfl_sync(0xffffffffu, a[jn][jn], lane & 16);         // the lane with ti == 0
+                if (own) {
                     const double rs = rsqrt(piv);
                     if (ti == 0) {
                         rsq[nb] = rs;
