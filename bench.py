@@ -323,6 +323,16 @@ def main():
                "h2d_bytes_per_step": int(n_local * (cfg["D"] + 1) * 8), "d2h_bytes_per_step": int(8 + 8 * M),
                "api": "t_SVGP.natgrad_step((X_host, Y_host), return_elbo=True) + .lambda_1, per rank on its rows"}
 
+    # ---------- M-step gradient pass (next-row feature; reported, not part of the metric) ----------
+    grad_ms = None
+    if world == 1 and cfg["D"] <= 63:
+        model.set_data(mbs_dev[0])
+        model.elbo_and_grad(global_minibatch_size=Nb)
+        model.timer_start()
+        for i in range(2):
+            model.elbo_and_grad(global_minibatch_size=Nb)
+        grad_ms = model.timer_stop() / 2
+
     # ---------- roofline: per-kernel CUDA-event timing, single stream ----------
     model.set_option("profile", 1)
     step_resident(0); step_resident(1)
@@ -360,6 +370,7 @@ def main():
         "hbm_stream_frac": Nb * 8 * (cfg["D"] + 1) / max(phase["stream"] * 1e-3, 1e-9) / (world * 6554.2e9),
         "phase_ms": phase, "kernels": kernels, "route": int(route["route"]), "cond_est": route["cond_est"],
         "wall_ms_per_step": wall * 1e3 / args.steps,
+        "elbo_and_grad_ms": grad_ms,
     }
 
     line = {

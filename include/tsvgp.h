@@ -95,6 +95,13 @@ TSVGP_API int tsvgp_natgrad_step(tsvgp_ctx* ctx, double lr, double jitter, doubl
 TSVGP_API int tsvgp_elbo(tsvgp_ctx* ctx, double scale, double* out);
 /* base_SVGP.prior_kl (tsvgp.py:65-70): KL[q(u) || p(u)] of the current sites                                            */
 TSVGP_API int tsvgp_prior_kl(tsvgp_ctx* ctx, double* out);
+/* M-step: ELBO of the resident minibatch and its gradient w.r.t. the kernel variance, the lengthscales (n_ls entries, as
+ * given to tsvgp_set_kernel), the inducing inputs Z [M, D] and the likelihood parameter (Gaussian: variance; StudentT:
+ * scale; Bernoulli: 0), with the sites held fixed — what the reference obtains by TensorFlow autodiff through `elbo`
+ * (tsvgp.py:79-95; callers docs/notebooks/mnist.py:161-163,188-189; pinned by tests/models/test_tsvgp.py:168-188).
+ * Gradients are w.r.t. the constrained (natural) parameter values; Zero mean function; D <= 63.                         */
+TSVGP_API int tsvgp_elbo_grad(tsvgp_ctx* ctx, double scale, double* elbo, double* d_variance, double* d_lengthscales,
+                              double* d_Z, double* d_lik);
 /* base_SVGP.predict_f, full_cov = False (tsvgp.py:97-114): mean_out, var_out [N]                                        */
 TSVGP_API int tsvgp_predict_f(tsvgp_ctx* ctx, const double* Xnew, int64_t N, int D, const double* mean_X, double* mean_out, double* var_out);
 /* t_SVGP.get_mean_chol_cov_inducing_posterior (tsvgp.py:202-212): m [M], chol_S [M, M]                                  */

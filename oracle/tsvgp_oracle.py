@@ -473,3 +473,83 @@ def gpr_predict_f(kernel, X, Y, noise_variance, Xnew):
     fvar = kernel.K_diag(Xnew) - np.sum(np.square(A), axis=0)
     fmean = A.T @ triangular_solve(Lm, Y)
     return fmean, fvar[:, None]
+
+
+# ----------------------------------------------------------------------------------------
+# M-step: gradients of the ELBO w.r.t. kernel variance, lengthscales, inducing inputs and
+# likelihood parameters with the sites held fixed.  The reference obtains them by TensorFlow
+# autodiff through `elbo` (tsvgp.py:79-95; callers docs/notebooks/mnist.py:161-163,188-189;
+# pinned by tests/models/test_tsvgp.py:168-188).  Here: the analytic derivative of the same
+# function (DESIGN.md "M-step gradients"), validated against central differences of
+# OracleTSVGP.elbo in tests/test_elbo_gradients_cpu.py.
+# ----------------------------------------------------------------------------------------
+def _kernel_dr2(kernel, r2):
+    """dK/d(r^2) of the stationary kernels (K as a function of the scaled squared distance)."""
+    var = float(kernel.variance)
+    if isinstance(kernel, SquaredExponential):
+        return -0.5 * var * np.exp(-0.5 * r2)
+    r = np.sqrt(np.maximum(r2, 1e-36))
+    sqrt5 = np.sqrt(5.0)
+    return -(5.0 / 6.0) * var * (1.0 + sqrt5 * r) * np.exp(-sqrt5 * r)
+
+
+def elbo_gradients(model, data):
+    """-> (elbo, dict(variance=, lengthscales=[D], Z=[M, D], likelihood=...)) for num_latent_gps = 1, Zero mean function.
+    `likelihood` is d/d(variance) for Gaussian, d/d(scale) for StudentT, None for Bernoulli."""
+    X, Y = (np.asarray(a, dtype=np.float64) for a in data)
+    kernel, lik = model.kernel, model.likelihood
+    Z = np.asarray(model.inducing_variable.Z)
+    M, D = Z.shape
+    N = X.shape[0]
+    ls = np.broadcast_to(np.asarray(kernel.lengthscales, dtype=np.float64).reshape(-1), (D,)).copy()
+    var = float(kernel.variance)
+    s = model.num_data / N if model.num_data is not None else 1.0
+    lam1, L2 = model.lambda_1[:, 0], model.lambda_2_sqrt[0]
+    Lam2 = L2 @ L2.T
+    K = kernel.K(Z)
+    K6 = K + DEFAULT_JITTER * np.eye(M)
+    Kuf_ = kernel.K(Z, X)
+    IK = np.eye(M) + Lam2 @ K6
+    alpha = np.linalg.solve(IK, lam1)                 # K6^-1 m_q
+    Q = np.linalg.solve(IK, Lam2)                     # (Lam2^-1 + K6)^-1, symmetric
+    Q = 0.5 * (Q + Q.T)
+    m = K6 @ alpha
+    mu = Kuf_.T @ alpha
+    v = var - np.sum(Kuf_ * (Q @ Kuf_), axis=0)
+    ve, g, h = lik.ve_and_grads(mu[:, None], v[:, None], Y)
+    g, h = g[:, 0], h[:, 0]
+    kl = 0.5 * (m @ alpha - np.trace(Q @ K6) + np.linalg.slogdet(IK)[1])
+    elbo = s * np.sum(ve) - kl
+    b = Kuf_ @ g
+    B = (Kuf_ * h) @ Kuf_.T
+    G_uf = s * (np.outer(alpha, g) - 2.0 * (Q @ Kuf_) * h)                       # dELBO/dKuf
+    sym = lambda A: 0.5 * (A + A.T)  # noqa: E731
+    G_K = s * (Q @ B @ Q - sym(np.outer(Q @ b, alpha))) - 0.5 * (np.outer(alpha, alpha) - 2.0 * sym(np.outer(Q @ m, alpha)) + Q @ K6 @ Q)
+    Zs, Xs = Z / ls, X / ls
+    r2_uf = square_distance(Zs, Xs)
+    r2_uu = square_distance(Zs, None)
+    E_uf = G_uf * _kernel_dr2(kernel, r2_uf)
+    E_uu = G_K * _kernel_dr2(kernel, r2_uu)
+    np.fill_diagonal(E_uu, 0.0)                       # r = 0 on the diagonal: no dependence on Z or the lengthscales
+    d_ls = np.empty(D)
+    d_Z = np.empty((M, D))
+    for d in range(D):
+        duf = Zs[:, d:d + 1] - Xs[None, :, d]
+        duu = Zs[:, d:d + 1] - Zs[None, :, d]
+        d_ls[d] = -(2.0 / ls[d]) * (np.sum(E_uf * duf * duf) + np.sum(E_uu * duu * duu))
+        d_Z[:, d] = (2.0 / ls[d]) * (np.sum(E_uf * duf, axis=1) + 2.0 * np.sum(E_uu * duu, axis=1))
+    d_var = (np.sum(G_uf * Kuf_) + np.sum(G_K * K)) / var + s * np.sum(h)
+    if isinstance(lik, Gaussian):
+        s2 = float(lik.variance)
+        d_lik = s * np.sum(-0.5 / s2 + 0.5 * (np.square(Y[:, 0] - mu) + v) / (s2 * s2))
+    elif isinstance(lik, StudentT):
+        z, w = gh_points_and_weights(lik.n_gh)
+        F = mu[:, None] + np.sqrt(v)[:, None] * z
+        r_ = Y - F
+        sc, df = float(lik.scale), lik.df
+        d_lik = s * np.sum((-1.0 / sc + (df + 1.0) * np.square(r_) / (sc * (df * sc * sc + np.square(r_)))) * w)
+    else:
+        d_lik = None
+    if np.asarray(kernel.lengthscales).size == 1:
+        d_ls = np.array([np.sum(d_ls)])
+    return elbo, dict(variance=d_var, lengthscales=d_ls, Z=d_Z, likelihood=d_lik)

@@ -49,7 +49,7 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue(const GemmP& p, double (&acc)[8][4][2], double* smem, int ti, int tj, int bz, int ks,
                                               int tid, int warp, int g, int t, int wm, int wn) {
-    if (EPI == EPI_STORE) {
+    if (EPI == EPI_STORE || EPI == EPI_STORE_COLNORM) {
         const bool split = p.ksplit > 1;
         double* Cg = split ? p.part + (long)ks * p.part_stride + (long)bz * p.sC
                            : ((p.C2 != nullptr && ks == 1) ? p.C2 : p.C) + (long)bz * p.sC;
@@ -72,7 +72,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmP& p, double (&acc)[8][4
                 *ptr = o;
             }
         }
-    } else {
+    }
+    if (EPI == EPI_COLNORM || EPI == EPI_STORE_COLNORM) {
         // column sums of squares over this tile's 128 rows -> norm_out[ti][col]
         double cs[4][2];
 #pragma unroll
@@ -347,6 +348,7 @@ int gemm_init() {
     e |= init_inst<true, true, true, EPI_STORE>();
     e |= init_inst<false, false, false, EPI_STORE>();
     e |= init_inst<false, false, false, EPI_COLNORM>();
+    e |= init_inst<false, false, false, EPI_STORE_COLNORM>();
     e |= init_inst<true, false, false, EPI_STORE>();
     return e;
 }
@@ -408,6 +410,7 @@ int gemm_launch(const GemmP& p, cudaStream_t stream) {
     if (scale) return -1;
     if (!p.a_kc && !p.b_kc) {
         if (p.epilogue == EPI_COLNORM) return p.ksplit == 1 ? launch_inst<false, false, false, EPI_COLNORM>(p, stream) : -1;
+        if (p.epilogue == EPI_STORE_COLNORM) return p.ksplit == 1 && !p.C2 ? launch_inst<false, false, false, EPI_STORE_COLNORM>(p, stream) : -1;
         return launch_inst<false, false, false, EPI_STORE>(p, stream);
     }
     if (p.a_kc && !p.b_kc) {

@@ -14,7 +14,7 @@
 
 namespace tsvgp {
 
-enum { EPI_STORE = 0, EPI_COLNORM = 1 };
+enum { EPI_STORE = 0, EPI_COLNORM = 1, EPI_STORE_COLNORM = 2 };   // 2: store C and also reduce its column norms
 
 struct GemmP {
     const double* A = nullptr; long lda = 0; int a_kc = 1;

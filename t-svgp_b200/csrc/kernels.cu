@@ -83,26 +83,32 @@ __device__ __forceinline__ double sqrt_pos(double m) {
     return fma(0.5 * y, e, r);
 }
 
-template <int KIND>
-__device__ __forceinline__ double cov_from_r2(double r2, double variance) {
+// k(r2) and, when asked, dk/d(r2)  (SE: -k/2 ; Matern-5/2: -(5/6) variance (1 + sqrt5 r) exp(-sqrt5 r))
+template <int KIND, bool DERIV>
+__device__ __forceinline__ double cov_from_r2(double r2, double variance, double& dk) {
     if (KIND == KERN_SE) {
-        return variance * exp_nonpos(-0.5 * r2);
+        const double k = variance * exp_nonpos(-0.5 * r2);
+        if (DERIV) dk = -0.5 * k;
+        return k;
     } else {
         const double r = sqrt_pos(fmax(r2, 1e-36));
         const double sqrt5 = 2.23606797749978969641;
-        return variance * fma(5.0 / 3.0, r * r, fma(sqrt5, r, 1.0)) * exp_nonpos(-sqrt5 * r);
+        const double e = variance * exp_nonpos(-sqrt5 * r);
+        if (DERIV) dk = (-5.0 / 6.0) * fma(sqrt5, r, 1.0) * e;
+        return fma(5.0 / 3.0, r * r, fma(sqrt5, r, 1.0)) * e;
     }
 }
 
 constexpr int KUF_DC = 16;   // feature chunk staged in shared memory
 constexpr int KUF_ROWS = 64; // inducing rows per CTA: 4 thread groups of 16 rows; each thread owns 16 rows x 2 columns
 
-template <int KIND>
+template <int KIND, bool DERIV>
 __global__ void __launch_bounds__(256, 2) kuf_kernel(double variance, const double* __restrict__ XsT, long ldx,
                                                      const double* __restrict__ x2, long n0, long n_valid,
                                                      const double* __restrict__ Zs, const double* __restrict__ z2, int M, int D,
                                                      const double* __restrict__ alpha, double* __restrict__ K, long ldk,
-                                                     double* __restrict__ mu_part, long ldmu, int pad_identity) {
+                                                     double* __restrict__ mu_part, long ldmu, int pad_identity,
+                                                     double* __restrict__ Kp) {
     __shared__ double sx[KUF_DC][128];
     __shared__ __align__(16) double sz[KUF_ROWS][KUF_DC];
     __shared__ double smu[4][128];
@@ -153,13 +159,18 @@ __global__ void __launch_bounds__(256, 2) kuf_kernel(double variance, const doub
     for (int r = 0; r < 16; ++r) {
         const int i = ibase + rbase + r;
         const double zi2 = z2[i];
-        double ka = cov_from_r2<KIND>(fma(-2.0, dot[r][0], xa2 + zi2), variance);
-        double kb = cov_from_r2<KIND>(fma(-2.0, dot[r][1], xb2 + zi2), variance);
+        double dka = 0.0, dkb = 0.0;
+        double ka = cov_from_r2<KIND, DERIV>(fma(-2.0, dot[r][0], xa2 + zi2), variance, dka);
+        double kb = cov_from_r2<KIND, DERIV>(fma(-2.0, dot[r][1], xb2 + zi2), variance, dkb);
         const bool row_ok = i < M;
-        if (!(row_ok && oka)) ka = (pad_identity && (long)i == na) ? 1.0 : 0.0;
-        if (!(row_ok && okb)) kb = (pad_identity && (long)i == nb) ? 1.0 : 0.0;
+        if (!(row_ok && oka)) { ka = (pad_identity && (long)i == na) ? 1.0 : 0.0; dka = 0.0; }
+        if (!(row_ok && okb)) { kb = (pad_identity && (long)i == nb) ? 1.0 : 0.0; dkb = 0.0; }
         K[(long)i * ldk + c0 + tx] = ka;
         K[(long)i * ldk + c0 + tx + 64] = kb;
+        if (DERIV) {
+            Kp[(long)i * ldk + c0 + tx] = dka;
+            Kp[(long)i * ldk + c0 + tx + 64] = dkb;
+        }
         if (alpha) {
             const double al = alpha[i];
             mua = fma(al, ka, mua);
@@ -176,14 +187,15 @@ __global__ void __launch_bounds__(256, 2) kuf_kernel(double variance, const doub
 
 int kuf_launch(int kind, double variance, const double* XsT, long ldx, const double* x2, long n0, long n_valid, int ncols,
                const double* Zs, const double* z2, int M, int Mp, int D, const double* alpha, double* K, long ldk,
-               double* mu_part, long ldmu, int pad_identity, cudaStream_t s) {
+               double* mu_part, long ldmu, int pad_identity, cudaStream_t s, double* Kp) {
     dim3 grid(ncols / 128, Mp / KUF_ROWS);
-    if (kind == KERN_SE)
-        kuf_kernel<KERN_SE><<<grid, 256, 0, s>>>(variance, XsT, ldx, x2, n0, n_valid, Zs, z2, M, D, alpha, K, ldk, mu_part, ldmu, pad_identity);
-    else if (kind == KERN_MATERN52)
-        kuf_kernel<KERN_MATERN52><<<grid, 256, 0, s>>>(variance, XsT, ldx, x2, n0, n_valid, Zs, z2, M, D, alpha, K, ldk, mu_part, ldmu, pad_identity);
-    else
-        return -1;
+#define KUF_ARGS variance, XsT, ldx, x2, n0, n_valid, Zs, z2, M, D, alpha, K, ldk, mu_part, ldmu, pad_identity, Kp
+    if (kind == KERN_SE && !Kp) kuf_kernel<KERN_SE, false><<<grid, 256, 0, s>>>(KUF_ARGS);
+    else if (kind == KERN_SE) kuf_kernel<KERN_SE, true><<<grid, 256, 0, s>>>(KUF_ARGS);
+    else if (kind == KERN_MATERN52 && !Kp) kuf_kernel<KERN_MATERN52, false><<<grid, 256, 0, s>>>(KUF_ARGS);
+    else if (kind == KERN_MATERN52) kuf_kernel<KERN_MATERN52, true><<<grid, 256, 0, s>>>(KUF_ARGS);
+    else return -1;
+#undef KUF_ARGS
     return count_launch();
 }
 
@@ -215,7 +227,7 @@ template <int LIK>
 __global__ void __launch_bounds__(256) point_stats_kernel(LikSpec lk, PointArgs a, GHTable gh) {
     __shared__ double sred[8];
     const int c = blockIdx.x * 256 + threadIdx.x;
-    double ve = 0.0;
+    double ve = 0.0, hsum = 0.0, lsum = 0.0;
     if (c < a.ncols) {
         const bool valid = c < a.n_valid;
         double mu = 0.0, q = 0.0;
@@ -247,10 +259,36 @@ __global__ void __launch_bounds__(256) point_stats_kernel(LikSpec lk, PointArgs 
                 }
                 gv = gs / (2.0 * sd);
             }
-            gv = fmin(gv, -1e-8);
+            if (a.clip) gv = fmin(gv, -1e-8);
+            hsum = gv;
+            if (a.aux_blocks) {   // d ve / d likelihood parameter (Gaussian: variance ; Student-t: scale), M-step gradients
+                if (LIK == LIK_GAUSSIAN) {
+                    const double s2 = lk.p0, r = y - mean;
+                    lsum = -0.5 / s2 + 0.5 * (r * r + var) / (s2 * s2);
+                } else if (LIK == LIK_STUDENT_T) {
+                    const double sd = sqrt(var), sc = lk.p0, df = lk.p1;
+                    for (int k = 0; k < lk.n_gh; ++k) {
+                        const double rr = y - (mean + sd * gh.z[k]);
+                        lsum = fma(gh.w[k], -1.0 / sc + (df + 1.0) * rr * rr / (sc * (df * sc * sc + rr * rr)), lsum);
+                    }
+                }
+            }
         }
         if (a.g) { a.g[c] = valid ? gm : 0.0; a.h[c] = valid ? gv : 0.0; }
         if (!valid) ve = 0.0;
+    }
+    if (a.aux_blocks) {
+        __shared__ double sred2[2][8];
+        hsum = warp_sum(hsum);
+        lsum = warp_sum(lsum);
+        if ((threadIdx.x & 31) == 0) { sred2[0][threadIdx.x >> 5] = hsum; sred2[1][threadIdx.x >> 5] = lsum; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int w = 0; w < 8; ++w) { s0 += sred2[0][w]; s1 += sred2[1][w]; }
+            a.aux_blocks[2 * blockIdx.x] = s0;
+            a.aux_blocks[2 * blockIdx.x + 1] = s1;
+        }
     }
     if (a.ve_blocks) {
         ve = warp_sum(ve);
@@ -858,15 +896,86 @@ int probe_vector_launch(double* v, int M, int Mp, cudaStream_t s) {
     return count_launch();
 }
 // stats tail: out[0] = sum of ve partials, out[1] = flags[0] as a double
-__global__ void __launch_bounds__(256) stats_tail_kernel(const double* ve_blocks, long nblocks, const int* flags, double* out) {
+__global__ void __launch_bounds__(256) stats_tail_kernel(const double* ve_blocks, long nblocks, const int* flags, const double* aux,
+                                                         double* out) {
     __shared__ double sred[8];
     double s = 0.0;
     for (long i = threadIdx.x; i < nblocks; i += 256) s += ve_blocks[i];
     s = block_sum_256(s, sred);
     if (threadIdx.x == 0) { out[0] = s; out[1] = flags[0] ? 1.0 : 0.0; }
+    double s2 = 0.0, s3 = 0.0;
+    if (aux)
+        for (long i = threadIdx.x; i < nblocks; i += 256) { s2 += aux[2 * i]; s3 += aux[2 * i + 1]; }
+    s2 = block_sum_256(s2, sred);
+    s3 = block_sum_256(s3, sred);
+    if (threadIdx.x == 0) { out[2] = s2; out[3] = s3; }
 }
-int stats_tail_launch(const double* ve_blocks, long nblocks, const int* flags, double* out, cudaStream_t s) {
-    stats_tail_kernel<<<1, 256, 0, s>>>(ve_blocks, nblocks, flags, out);
+int stats_tail_launch(const double* ve_blocks, long nblocks, const int* flags, const double* aux, double* out, cudaStream_t s) {
+    stats_tail_kernel<<<1, 256, 0, s>>>(ve_blocks, nblocks, flags, aux, out);
+    return count_launch();
+}
+
+// ---- M-step gradient helpers ------------------------------------------------------------------------------------
+// E[i][c] = scale * (alpha[i] g[c] - 2 h[c] U[i][c]) * Kp[i][c]   in place on U   (dELBO/dKuf times dk/dr2)
+__global__ void egrad_uf_kernel(double* __restrict__ U, const double* __restrict__ Kp, long ld, int Mp, int ncols,
+                                const double* __restrict__ alpha, const double* __restrict__ g, const double* __restrict__ h, double scale) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i0 = blockIdx.y * 16;
+    if (c >= ncols) return;
+    const double gc = g[c], hc2 = 2.0 * h[c];
+    for (int i = i0; i < i0 + 16 && i < Mp; ++i) {
+        const long o = (long)i * ld + c;
+        U[o] = scale * (alpha[i] * gc - hc2 * U[o]) * Kp[o];
+    }
+}
+int egrad_uf_launch(double* U, const double* Kp, long ld, int Mp, int ncols, const double* alpha, const double* g, const double* h,
+                    double scale, cudaStream_t s) {
+    egrad_uf_kernel<<<dim3((ncols + 255) / 256, (Mp + 15) / 16), 256, 0, s>>>(U, Kp, ld, Mp, ncols, alpha, g, h, scale);
+    return count_launch();
+}
+// Xa[c][j] (row-major [ncols][128]) = xs_j | 1 | xs_j^2 | 0 ... of point n0 + c (zero rows for c >= nvalid)
+__global__ void xaug_kernel(const double* __restrict__ XsT, long ldx, long n0, long nvalid, int ncols, int D, double* __restrict__ Xa) {
+    __shared__ double tile[32][33];
+    // block: 32 points x 128 aug columns; transposes through shared memory so both sides stay coalesced
+    const int c0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 256 threads = 8 rows of 32
+    for (int jb = 0; jb < 128; jb += 32) {
+        for (int r = ty; r < 32; r += 8) {   // r = aug column within the 32-block, tx = point
+            const int j = jb + r;
+            const long c = c0 + tx;
+            double v = 0.0;
+            if (c < nvalid) {
+                if (j < D) v = XsT[(long)j * ldx + n0 + c];
+                else if (j == D) v = 1.0;
+                else if (j <= 2 * D) { const double x = XsT[(long)(j - D - 1) * ldx + n0 + c]; v = x * x; }
+            }
+            tile[r][tx] = v;
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {   // r = point, tx = aug column
+            if (c0 + r < ncols) Xa[(long)(c0 + r) * 128 + jb + tx] = tile[tx][r];
+        }
+        __syncthreads();
+    }
+}
+int xaug_launch(const double* XsT, long ldx, long n0, long nvalid, int ncols, int D, double* Xa, cudaStream_t s) {
+    xaug_kernel<<<(ncols + 31) / 32, 256, 0, s>>>(XsT, ldx, n0, nvalid, ncols, D, Xa);
+    return count_launch();
+}
+// Gamma[i][j] = scale (QBQ_ij - (qb_i a_j + qb_j a_i)/2) - (a_i a_j - (qm_i a_j + qm_j a_i) + QKQ_ij)/2   (dELBO/dKuu, symmetric)
+// E[i][j] = Gamma[i][j] * Kp[i][j] off the diagonal, 0 on it
+__global__ void gamma_uu_kernel(const double* QBQ, const double* QKQ, const double* qb, const double* qm, const double* al,
+                                const double* Kp, double* Gamma, double* E, long ld, int n, double scale) {
+    EW_IJ;
+    const long o = (long)i * ld + j;
+    const double ai = al[i], aj = al[j];
+    const double gmm = scale * (0.5 * (QBQ[o] + QBQ[(long)j * ld + i]) - 0.5 * (qb[i] * aj + qb[j] * ai)) -
+                       0.5 * (ai * aj - (qm[i] * aj + qm[j] * ai) + 0.5 * (QKQ[o] + QKQ[(long)j * ld + i]));
+    Gamma[o] = gmm;
+    E[o] = i == j ? 0.0 : gmm * Kp[o];
+}
+int gamma_uu_launch(const double* QBQ, const double* QKQ, const double* qb, const double* qm, const double* al, const double* Kp,
+                    double* Gamma, double* E, long ld, int n, double scale, cudaStream_t s) {
+    gamma_uu_kernel<<<EW_GRID(n), 0, s>>>(QBQ, QKQ, qb, qm, al, Kp, Gamma, E, ld, n, scale);
     return count_launch();
 }
 

@@ -26,7 +26,7 @@ int scale_points_launch(const double* X, long n, int D, const double* ls, double
 // mu_part[i/64][c] = sum_{i in 64-row group} alpha[i] K[i][c].
 int kuf_launch(int kind, double variance, const double* XsT, long ldx, const double* x2, long n0, long n_valid, int ncols,
                const double* ZsT_rows /*Zs [Mp][D]*/, const double* z2, int M, int Mp, int D, const double* alpha, double* K,
-               long ldk, double* mu_part, long ldmu, int pad_identity, cudaStream_t s);
+               long ldk, double* mu_part, long ldmu, int pad_identity, cudaStream_t s, double* Kp = nullptr /* dk/dr2 slab */);
 
 struct PointArgs {
     const double* mu_part; int n_mu_part; long ldmu;   // partial means   [n_mu_part][ldmu]
@@ -39,6 +39,8 @@ struct PointArgs {
     double* g; double* h;       // out: d ve/d mean, clipped d ve/d var  (zero for padding columns), may be null
     double* mean_out; double* var_out;   // out (predict), may be null; written only for c < n_valid
     double* ve_blocks;          // out: per-block sum of ve   [gridDim.x]
+    double* aux_blocks = nullptr;   // out (M-step): per-block [sum h, sum d ve / d likelihood parameter]   [2 * gridDim.x]
+    int clip = 1;               // clip d ve / d var at -1e-8 (natgrad_step, tsvgp.py:262-263); the ELBO gradient does not
     int* flags;                 // flags[0] |= 1 if any var <= 0
 };
 struct GHTable { double z[MAX_GH]; double w[MAX_GH]; };   // nodes sqrt(2) x_k and weights w_k / sqrt(pi), passed by value
@@ -87,6 +89,12 @@ int init_update_launch(const double* G, double* P, long ld, int M, int Mp, doubl
 int set_scaled_identity_launch(double* A, long ld, int M, int Mp, double v, double vpad, cudaStream_t s);
 int probe_vector_launch(double* v, int M, int Mp, cudaStream_t s);
 int vadd_inplace_launch(double* dst, const double* src, long n, cudaStream_t s);
-int stats_tail_launch(const double* ve_blocks, long nblocks, const int* flags, double* out, cudaStream_t s);
+int stats_tail_launch(const double* ve_blocks, long nblocks, const int* flags, const double* aux, double* out, cudaStream_t s);
+// M-step gradient helpers (see tsvgp_elbo_grad)
+int egrad_uf_launch(double* U, const double* Kp, long ld, int Mp, int ncols, const double* alpha, const double* g, const double* h,
+                    double scale, cudaStream_t s);
+int xaug_launch(const double* XsT, long ldx, long n0, long nvalid, int ncols, int D, double* Xa, cudaStream_t s);
+int gamma_uu_launch(const double* QBQ, const double* QKQ, const double* qb, const double* qm, const double* al, const double* Kp,
+                    double* Gamma, double* E, long ld, int n, double scale, cudaStream_t s);
 
 }  // namespace tsvgp

@@ -53,11 +53,11 @@ struct Pool {
     }
 };
 
-enum { MODE_STATS = 0, MODE_ELBO = 1, MODE_PREDICT = 2 };
+enum { MODE_STATS = 0, MODE_ELBO = 1, MODE_PREDICT = 2, MODE_GRAD = 3 };   // MODE_GRAD: statistics with unclipped h + dELBO/dKuf sums
 enum { INFO_W = 0, INFO_K9 = 1, INFO_P = 2, INFO_S = 3, N_INFO = 4 };
 enum { EV_T0 = 0, EV_PREP, EV_STREAM, EV_REDUCE, EV_DENSE, N_EV };
 // device scalars
-enum { SC_LOGDIAG_W = 0, SC_M_ALPHA, SC_TR_QK, SC_PK0, SC_PK1, SC_PI0, SC_PI1, N_SCAL = 8 };
+enum { SC_LOGDIAG_W = 0, SC_M_ALPHA, SC_TR_QK, SC_PK0, SC_PK1, SC_PI0, SC_PI1, SC_G_K, SC_TR_QB, SC_A_B, N_SCAL = 12 };
 enum { ROUTE_AUTO = 0, ROUTE_FUSED = 1, ROUTE_WHITENED = 2 };
 
 }  // namespace
@@ -100,6 +100,7 @@ struct tsvgp_ctx {
     double *stats2[2] = {nullptr, nullptr};  // second B accumulator per stream: the split-off k piece of the balanced SYRK
     double *alpha = nullptr, *mZ = nullptr, *mq = nullptr, *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *gwork = nullptr;
     double *scal = nullptr;
+    double *zaug = nullptr, *fuu = nullptr;   // M-step: [zs | 1 | zs^2] and the Kuu counterpart of F
     double *tmp2 = nullptr, *dinv2 = nullptr, *pv1 = nullptr, *pv2 = nullptr, *gwork2 = nullptr, *scal2 = nullptr;   // side-stream workspace (K9 factor)
     bool k9_pending = false;   // K9 work enqueued on the side stream, probe not read yet
     int* info = nullptr;    // [N_INFO]
@@ -128,6 +129,10 @@ struct tsvgp_ctx {
     double *slab[2] = {}, *mu_part[2] = {}, *q_part[2] = {}, *gbuf[2] = {}, *hbuf[2] = {};
     double* ve_blocks = nullptr;
     long ve_cap = 0;
+    double *kpslab[2] = {}, *vslab[2] = {}, *uslab[2] = {}, *xaug[2] = {}, *fpart[2] = {}, *facc[2] = {};   // M-step gradient workspace
+    double* aux_blocks = nullptr;
+    int fsplit = 1;
+    bool grad_ws = false;
     double* kpart[2] = {};     // split-K partial tiles of the SYRK when M is so small that its tiles cannot fill the SMs
     int ksplit = 1;
 
@@ -136,6 +141,7 @@ struct tsvgp_ctx {
     int world = 1, rank = 0;
 
     double timings[16] = {};
+    double grad_scale = 1.0;
     int profile = 0;
     std::vector<cudaEvent_t> pev;   // profile-mode event pool
     double kprof[12] = {};
@@ -198,6 +204,7 @@ int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     NEED(c->alpha = p.get(mp)); NEED(c->mZ = p.get(mp)); NEED(c->mq = p.get(mp)); NEED(c->v1 = p.get(mp)); NEED(c->v2 = p.get(mp));
     NEED(c->v3 = p.get(mp)); NEED(c->gwork = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal = p.get(N_SCAL));
     NEED(c->info = (int*)p.get(N_INFO)); NEED(c->flags = (int*)p.get(2));
+    NEED(c->zaug = p.get(mp * 128)); NEED(c->fuu = p.get(mp * 128));
     NEED(c->tmp2 = p.get((size_t)((c->Mp / 128 + 1) / 2) * 128 * mp)); NEED(c->dinv2 = p.get((size_t)(c->Mp / 128) * 128 * 128));
     NEED(c->pv1 = p.get(mp)); NEED(c->pv2 = p.get(mp)); NEED(c->gwork2 = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal2 = p.get(N_SCAL));
     c->sites_set = c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = false;
@@ -338,12 +345,13 @@ long pick_chunk(const tsvgp_ctx* c) {
     return nc;
 }
 
-int ensure_slabs(tsvgp_ctx* c, long n_points) {
+int ensure_slabs(tsvgp_ctx* c, long n_points, bool need_grad = false) {
     const long nc = pick_chunk(c);
     const long nchunks = (n_points + nc - 1) / nc;
     const long ve_need = (nchunks + 1) * ((nc + 255) / 256);
     const bool need_w = c->route == ROUTE_WHITENED;
-    if (c->chunk == nc && c->chunk_Mp == c->Mp && c->ve_cap >= ve_need && (!need_w || c->wslab[0])) return TSVGP_OK;
+    if (c->chunk == nc && c->chunk_Mp == c->Mp && c->ve_cap >= ve_need && (!need_w || c->wslab[0]) && (!need_grad || c->grad_ws))
+        return TSVGP_OK;
     CU(cudaStreamSynchronize(c->s_main));
     c->pc.release();
     c->wslab[0] = c->wslab[1] = nullptr;
@@ -373,6 +381,21 @@ int ensure_slabs(tsvgp_ctx* c, long n_points) {
         }
     }
     NEED(c->ve_blocks = p.get(ve_need));
+    c->grad_ws = false;
+    if (need_grad) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->dev);
+        c->fsplit = sms / (c->Mp / 128);
+        if (c->fsplit > (int)(nc / 256)) c->fsplit = (int)(nc / 256);
+        if (c->fsplit < 1) c->fsplit = 1;
+        for (int s = 0; s < 2; ++s) {
+            NEED(c->kpslab[s] = p.get((size_t)c->Mp * nc)); NEED(c->vslab[s] = p.get((size_t)c->Mp * nc));
+            NEED(c->uslab[s] = p.get((size_t)c->Mp * nc)); NEED(c->xaug[s] = p.get((size_t)nc * 128));
+            NEED(c->fpart[s] = p.get((size_t)c->fsplit * c->Mp * 128)); NEED(c->facc[s] = p.get((size_t)c->Mp * 128));
+        }
+        NEED(c->aux_blocks = p.get(2 * ve_need));
+        c->grad_ws = true;
+    }
     c->ve_cap = ve_need;
     c->chunk = nc;
     c->chunk_Mp = c->Mp;
@@ -382,7 +405,9 @@ int ensure_slabs(tsvgp_ctx* c, long n_points) {
 // The streaming pass over `N` points whose scaled, feature-major coordinates are XsT/x2.
 int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, long N, const double* y, const double* mean_off,
                 int mode, double* mean_out, double* var_out) {
-    OK(ensure_slabs(c, N));
+    const bool grad = mode == MODE_GRAD;
+    const bool stats = mode == MODE_STATS || grad;
+    OK(ensure_slabs(c, N, grad));
     const long nc = c->chunk;
     const int Mp = c->Mp;
     const int nstr = (c->n_streams == 1 || c->profile) ? 1 : 2;
@@ -403,11 +428,13 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
 
     CU(cudaMemsetAsync(c->flags, 0, 2 * sizeof(int), sm));
     CU(cudaMemsetAsync(c->ve_blocks, 0, sizeof(double) * (size_t)(nchunks * vstride), sm));
-    if (mode == MODE_STATS)
+    if (stats)
         for (int s = 0; s < nstr; ++s) {
             CU(cudaMemsetAsync(c->stats[s], 0, sizeof(double) * ((size_t)Mp * Mp + Mp + 4), sm));
             CU(cudaMemsetAsync(c->stats2[s], 0, sizeof(double) * (size_t)Mp * Mp, sm));
+            if (grad) CU(cudaMemsetAsync(c->facc[s], 0, sizeof(double) * (size_t)Mp * 128, sm));
         }
+    if (grad) CU(cudaMemsetAsync(c->aux_blocks, 0, sizeof(double) * (size_t)(2 * nchunks * vstride), sm));
     CU(cudaEventRecord(c->ev_fork, sm));
     for (int s = 0; s < nstr; ++s) CU(cudaStreamWaitEvent(c->s_pp[s], c->ev_fork, 0));
 
@@ -420,14 +447,15 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
         if (mark(s)) FAIL(TSVGP_ERR_CUDA, "profile event");
         // (a) covariance slab K[Mp x ncols] and the partial means sum_i alpha_i K[i][n]
         LA(kuf_launch(c->kern_kind, c->kern_var, XsT, ldx, x2, n0, N, ncols, c->Zs, c->z2, c->M, Mp, c->D, c->alpha, c->slab[b],
-                      nc, c->mu_part[b], nc, 0, s));
+                      nc, c->mu_part[b], nc, 0, s, grad ? c->kpslab[b] : nullptr));
         mark(s);
         {   // (b) |T^T k_n|^2 : upper-triangular T^T times the slab, reduced to column norms in the epilogue
             GemmP p;
             p.A = c->T; p.lda = Mp; p.a_kc = 0; p.a_tri = 2;
             p.B = c->slab[b]; p.ldb = nc; p.b_kc = 0;
             p.m = Mp; p.n = ncols; p.k = Mp;
-            p.epilogue = EPI_COLNORM; p.norm_out = c->q_part[b]; p.ldn = nc;
+            p.epilogue = grad ? EPI_STORE_COLNORM : EPI_COLNORM; p.norm_out = c->q_part[b]; p.ldn = nc;
+            if (grad) { p.C = c->vslab[b]; p.ldc = nc; }   // the M-step also needs V = T^T K itself
             LA(gemm_launch(p, s));
         }
         mark(s);
@@ -439,16 +467,18 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
             a.mean_off = mean_off ? mean_off + n0 : nullptr;
             a.kdiag = c->kern_var;
             a.n_valid = nvalid; a.ncols = ncols;
-            a.g = mode == MODE_STATS ? c->gbuf[b] : nullptr; a.h = mode == MODE_STATS ? c->hbuf[b] : nullptr;
+            a.g = stats ? c->gbuf[b] : nullptr; a.h = stats ? c->hbuf[b] : nullptr;
+            a.clip = grad ? 0 : 1;
+            a.aux_blocks = grad ? c->aux_blocks + 2 * ci * vstride : nullptr;
             a.mean_out = mean_out ? mean_out + n0 : nullptr; a.var_out = var_out ? var_out + n0 : nullptr;
             a.ve_blocks = c->ve_blocks + ci * vstride;
             a.flags = c->flags;
             LA(point_stats_launch(c->lik, a, c->gh, s));
         }
         mark(s);
-        if (mode == MODE_STATS) {
+        if (stats) {
             const double* stat_slab = c->slab[b];
-            if (c->route == ROUTE_WHITENED) {   // (c') whitened slab  C9^-1 K  (reference order: A = K9^-1 Kuf first, tsvgp.py:271)
+            if (c->route == ROUTE_WHITENED && !grad) {   // (c') whitened slab  C9^-1 K  (reference order: A = K9^-1 Kuf first, tsvgp.py:271)
                 GemmP p;
                 p.A = c->C9inv; p.lda = Mp; p.a_kc = 1; p.a_tri = 1;
                 p.B = c->slab[b]; p.ldb = nc; p.b_kc = 0;
@@ -480,6 +510,30 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
             LA(gemv_n_launch(stat_slab, nc, Mp, ncols, c->gbuf[b], 1.0, 1.0, c->stats[b] + (size_t)Mp * Mp, s));
             mark(s);
         }
+        if (grad) {
+            {   // U = T V = Q K  (lower-triangular T times the stored V)
+                GemmP p;
+                p.A = c->T; p.lda = Mp; p.a_kc = 1; p.a_tri = 1;
+                p.B = c->vslab[b]; p.ldb = nc; p.b_kc = 0;
+                p.C = c->uslab[b]; p.ldc = nc; p.m = Mp; p.n = ncols; p.k = Mp;
+                LA(gemm_launch(p, s));
+            }
+            // E = scale (alpha g^T - 2 U diag(h)) .* dK/dr2   (in place), then F += E [xs | 1 | xs^2]
+            LA(egrad_uf_launch(c->uslab[b], c->kpslab[b], nc, Mp, ncols, c->alpha, c->gbuf[b], c->hbuf[b], c->grad_scale, s));
+            LA(xaug_launch(XsT, ldx, n0, nvalid, ncols, c->D, c->xaug[b], s));
+            GemmP p;
+            p.A = c->uslab[b]; p.lda = nc; p.a_kc = 1;
+            p.B = c->xaug[b]; p.ldb = 128; p.b_kc = 0;
+            p.C = c->facc[b]; p.ldc = 128; p.m = Mp; p.n = 128; p.k = ncols; p.beta = 1.0;
+            const int fs = c->fsplit < ncols / 256 ? c->fsplit : ncols / 256;
+            if (fs > 1) {
+                p.ksplit = fs; p.part = c->fpart[b]; p.part_stride = (long)Mp * 128;
+                LA(gemm_launch(p, s));
+                LA(splitk_reduce_launch(p, s));
+            } else {
+                LA(gemm_launch(p, s));
+            }
+        }
     }
     if (prof) {   // 7 events per slab: [start, kuf, var, point, whiten, syrk, gemv]
         CU(cudaStreamSynchronize(c->s_pp[0]));
@@ -498,11 +552,12 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
         CU(cudaStreamWaitEvent(sm, c->ev_join[s], 0));
     }
     const size_t mm = (size_t)Mp * Mp;
-    if (mode == MODE_STATS) {
+    if (stats) {
         if (nstr == 2) LA(vadd_inplace_launch(c->stats[0], c->stats[1], (long)(mm + Mp), sm));
+        if (grad && nstr == 2) LA(vadd_inplace_launch(c->facc[0], c->facc[1], (long)Mp * 128, sm));
         for (int s = 0; s < nstr && c->balance; ++s) LA(vadd_inplace_launch(c->stats[0], c->stats2[s], (long)mm, sm));
     }
-    LA(stats_tail_launch(c->ve_blocks, nchunks * vstride, c->flags, c->stats[0] + mm + Mp, sm));
+    LA(stats_tail_launch(c->ve_blocks, nchunks * vstride, c->flags, grad ? c->aux_blocks : nullptr, c->stats[0] + mm + Mp, sm));
     return TSVGP_OK;
 }
 
@@ -1005,6 +1060,105 @@ int tsvgp_prior_kl(tsvgp_ctx* c, double* out) {
     CU(cudaStreamSynchronize(s));
     OK(check_info(c, info_h));
     *out = kl_from_scalars(sc);
+    return TSVGP_OK;
+}
+
+int tsvgp_elbo_grad(tsvgp_ctx* c, double scale, double* elbo, double* d_variance, double* d_lengthscales, double* d_Z, double* d_lik) {
+    if (!c || !elbo || !d_variance || !d_lengthscales || !d_Z || !d_lik) return TSVGP_ERR_INVALID;
+    OK(require_model(c, true));
+    if (2 * c->D + 1 > 128) FAIL(TSVGP_ERR_INVALID, "elbo_grad supports D <= 63 (D = %d)", c->D);
+    CU(cudaSetDevice(c->dev));
+    cudaStream_t s = c->s_main;
+    const int n = c->Mp, M = c->M, D = c->D;
+    const long ld = n;
+    const size_t mm = (size_t)n * n;
+    CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
+    OK(ensure_xs(c));
+    OK(ensure_posterior(c));
+    OK(ensure_kl_terms(c));
+    c->grad_scale = scale;
+    OK(stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_GRAD, nullptr, nullptr));
+    OK(all_reduce(c, c->stats[0], mm + n + 4));
+    OK(all_reduce(c, c->facc[0], (size_t)n * 128));
+    double* B = c->stats[0];
+    double* bvec = c->stats[0] + mm;
+    LA(mirror_lower_launch(B, ld, n, s));
+    {   // Q = T T^T  (symmetric, = (Lambda_2^-1 + K6)^-1)
+        GemmP p;
+        p.A = c->T; p.lda = ld; p.a_kc = 1; p.a_tri = 1;
+        p.B = c->T; p.ldb = ld; p.b_kc = 1; p.b_tri = 1;
+        p.C = c->Wm; p.ldc = ld; p.m = p.n = p.k = n; p.lower_out = 1;
+        LA(gemm_launch(p, s));
+    }
+    LA(mirror_lower_launch(c->Wm, ld, n, s));
+    auto full_gemm = [&](const double* A, const double* Bm, double* C) {   // C = A * Bm, all symmetric-or-full row-major
+        GemmP p;
+        p.A = A; p.lda = ld; p.a_kc = 1;
+        p.B = Bm; p.ldb = ld; p.b_kc = 0;
+        p.C = C; p.ldc = ld; p.m = p.n = p.k = n;
+        return gemm_launch(p, s);
+    };
+    LA(full_gemm(c->Wm, B, c->X1));        // Q B
+    LA(full_gemm(c->X1, c->Wm, c->X2));    // Q B Q
+    LA(full_gemm(c->Wm, c->K6, c->G2));    // Q K6
+    LA(full_gemm(c->G2, c->Wm, c->P));     // Q K6 Q
+    LA(gemv_n_launch(c->Wm, ld, n, n, bvec, 1.0, 0.0, c->v1, s));     // Q b
+    LA(gemv_n_launch(c->Wm, ld, n, n, c->mq, 1.0, 0.0, c->v2, s));    // Q m_q
+    // dk/dr2 of Kuu (K itself is recomputed into a scratch matrix: V is not needed once T exists)
+    LA(kuf_launch(c->kern_kind, c->kern_var, c->ZsT, n, c->z2, 0, M, n, c->Zs, c->z2, M, n, D, nullptr, c->V, n, nullptr, 0, 0, s, c->Wf));
+    LA(gamma_uu_launch(c->X2, c->P, c->v1, c->v2, c->alpha, c->Wf, c->X1, c->G2, ld, n, scale, s));   // X1 = Gamma, G2 = E_uu
+    LA(matdot_launch(c->X1, c->K, ld, n, c->scal + SC_G_K, s));
+    LA(matdot_launch(c->Wm, B, ld, n, c->scal + SC_TR_QB, s));
+    LA(dot_launch(c->alpha, bvec, n, c->scal + SC_A_B, s));
+    LA(xaug_launch(c->ZsT, n, 0, M, n, D, c->zaug, s));
+    {   // F_uu = E_uu [zs | 1 | zs^2]
+        GemmP p;
+        p.A = c->G2; p.lda = ld; p.a_kc = 1;
+        p.B = c->zaug; p.ldb = 128; p.b_kc = 0;
+        p.C = c->fuu; p.ldc = 128; p.m = n; p.n = 128; p.k = n;
+        LA(gemm_launch(p, s));
+    }
+    std::vector<double> Fuf((size_t)n * 128), Fuu((size_t)n * 128), Zs((size_t)n * D), ls(D), dZ((size_t)M * D);
+    double tail[4], sc[N_SCAL];
+    int info_h[N_INFO];
+    CU(cudaMemcpyAsync(Fuf.data(), c->facc[0], sizeof(double) * n * 128, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(Fuu.data(), c->fuu, sizeof(double) * n * 128, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(Zs.data(), c->Zs, sizeof(double) * n * D, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(ls.data(), c->ls_dev, sizeof(double) * D, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(tail, c->stats[0] + mm + n, sizeof tail, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(sc, c->scal, sizeof sc, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(info_h, c->info, sizeof info_h, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    c->kl_valid = false;   // X1 was reused
+    OK(check_info(c, info_h));
+    if (tail[1] != 0.0) FAIL(TSVGP_ERR_NONPOSITIVE_VARIANCE, "predict_f: non-positive predictive variance");
+    *elbo = scale * tail[0] - kl_from_scalars(sc);
+    *d_variance = (scale * (sc[SC_A_B] - 2.0 * sc[SC_TR_QB]) + sc[SC_G_K]) / c->kern_var + scale * tail[2];
+    *d_lik = scale * tail[3];
+    // d r2 / d lengthscale_d = -2 delta_d^2 / l_d, d r2 / d z_id = 2 delta_d / l_d with delta = zs - xs (scaled coordinates);
+    // sums over points expanded through F = E [xs | 1 | xs^2]:  sum_n E delta = zs S1 - EX ; sum E delta^2 = zs^2 S1 - 2 zs EX + C2
+    std::vector<double> dls(D, 0.0);
+    for (int d = 0; d < D; ++d) {
+        double acc = 0.0;
+        for (int i = 0; i < M; ++i) {
+            const double z = Zs[(size_t)i * D + d];
+            const double* fu = &Fuf[(size_t)i * 128];
+            const double* fz = &Fuu[(size_t)i * 128];
+            acc += z * z * fu[D] - 2.0 * z * fu[d] + fu[D + 1 + d];
+            acc += z * z * fz[D] - 2.0 * z * fz[d] + fz[D + 1 + d];
+            dZ[(size_t)i * D + d] = (2.0 / ls[d]) * (z * fu[D] - fu[d]) + (4.0 / ls[d]) * (z * fz[D] - fz[d]);
+        }
+        dls[d] = -(2.0 / ls[d]) * acc;
+    }
+    if (c->ls_host.size() == 1) {
+        double t = 0.0;
+        for (int d = 0; d < D; ++d) t += dls[d];
+        double one = t;
+        CU(cudaMemcpy(d_lengthscales, &one, sizeof(double), cudaMemcpyDefault));
+    } else {
+        CU(cudaMemcpy(d_lengthscales, dls.data(), sizeof(double) * D, cudaMemcpyDefault));
+    }
+    CU(cudaMemcpy(d_Z, dZ.data(), sizeof(double) * (size_t)M * D, cudaMemcpyDefault));
     return TSVGP_OK;
 }
 

@@ -273,6 +273,25 @@ class t_SVGP:
         self._check(self._lib.tsvgp_elbo(self._ctx, self._scale(n, global_minibatch_size), C.byref(out)))
         return out.value
 
+    def elbo_and_grad(self, data=None, *, global_minibatch_size=None):
+        """M-step objective and its gradient with the sites held fixed (what the reference gets from TensorFlow autodiff of
+        `elbo` / `training_loss_closure`; tsvgp.py:72-95, tests/models/test_tsvgp.py:168-188).
+        -> (elbo, {"variance", "lengthscales" (shape of kernel.lengthscales), "Z" [M, D], "likelihood"}), gradients w.r.t. the
+        constrained parameter values (chain your own positive transform); "likelihood" is d/d variance (Gaussian),
+        d/d scale (StudentT) or None (Bernoulli)."""
+        self._sync_objects()
+        if self._mean_fn(np.zeros((1, self._D))) is not None:
+            raise NotImplementedError("elbo_and_grad with a non-zero mean_function")
+        n = self._ingest(data)
+        kind, _, ls = _kernel_spec(self.kernel)
+        e, dv, dl = C.c_double(), C.c_double(), C.c_double()
+        dls, dZ = np.empty(ls.size), np.empty((self._M, self._D))
+        self._check(self._lib.tsvgp_elbo_grad(self._ctx, self._scale(n, global_minibatch_size), C.byref(e), C.byref(dv),
+                                              dls.ctypes.data, dZ.ctypes.data, C.byref(dl)))
+        lik = _likelihood_spec(self.likelihood)[0]
+        return e.value, {"variance": dv.value, "lengthscales": dls.reshape(np.shape(_value(self.kernel.lengthscales)) or ()),
+                         "Z": dZ, "likelihood": None if lik == _lib.LIK_BERNOULLI_PROBIT else dl.value}
+
     def maximum_log_likelihood_objective(self, data=None):  # tsvgp.py:72-77
         return self.elbo(data)
 

@@ -1,0 +1,57 @@
+"""
+GPU: M-step gradients (tsvgp_elbo_grad through t_SVGP.elbo_and_grad) against the oracle's analytic gradients
+(oracle.elbo_gradients, themselves pinned by central differences of the reference-order ELBO on the CPU).
+Tolerance 1e-9 norm-wise relative, as for the rest of the path.
+"""
+import numpy as np
+import pytest
+
+from oracle import tsvgp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+CASES = [  # config, rows, M, num_data, ARD lengthscales?, library options
+    ("cfg1", 3000, 50, None, False, {}),
+    ("cfg2", 2500, 200, 25_000, True, {}),
+    ("cfg3", 3000, 384, 30_000, False, {"chunk": 1024}),
+    ("cfg5", 2000, 256, 50_000, True, {}),
+]
+
+
+@pytest.mark.parametrize("name,n,M,num_data,ard,opts", CASES)
+def test_elbo_gradients_match_oracle(name, n, M, num_data, ard, opts):
+    import tsvgp_b200 as tb
+    import tsvgp_b200.synth as synth
+    cfg = synth.describe(name)
+    X, Y, Z = synth.make_minibatch(cfg, n_rows=n, M=M)
+    kernel, lik = synth.build_objects(cfg, orc)
+    if ard:
+        kernel.lengthscales = orc._param(cfg["ls"] * np.linspace(0.9, 1.2, cfg["D"]))
+    ref = orc.OracleTSVGP(kernel, lik, orc.InducingPoints(Z.copy()), num_data=num_data)
+    for _ in range(2):
+        ref.natgrad_step((X, Y), lr=cfg["lr"])
+    dev = tb.t_SVGP(kernel, lik, Z.copy(), num_data=num_data, lambda_1=ref.lambda_1, lambda_2_sqrt=ref.lambda_2_sqrt)
+    for k, v in opts.items():
+        dev.set_option(k, v)
+    e_ref, g_ref = orc.elbo_gradients(ref, (X, Y))
+    e_dev, g_dev = dev.elbo_and_grad((X, Y))
+    errs = {"elbo": abs(e_dev - e_ref) / abs(e_ref), "variance": abs(g_dev["variance"] - g_ref["variance"]) / abs(g_ref["variance"]),
+            "lengthscales": relerr(np.ravel(g_dev["lengthscales"]), g_ref["lengthscales"]), "Z": relerr(g_dev["Z"], g_ref["Z"])}
+    if g_ref["likelihood"] is None:
+        assert g_dev["likelihood"] is None
+    else:
+        errs["likelihood"] = abs(g_dev["likelihood"] - g_ref["likelihood"]) / abs(g_ref["likelihood"])
+    assert np.shape(g_dev["lengthscales"]) == np.shape(np.asarray(kernel.lengthscales))
+    bad = {k: v for k, v in errs.items() if not v <= 1e-9}
+    assert not bad, (bad, errs)
+    # the gradient call does not disturb the state: a natgrad step afterwards still matches the oracle
+    dev.natgrad_step((X, Y), lr=cfg["lr"])
+    ref.natgrad_step((X, Y), lr=cfg["lr"])
+    assert relerr(dev.lambda_1, ref.lambda_1) < 1e-9 and relerr(dev.lambda_2, ref.lambda_2) < 1e-9
+    dev.close()
