@@ -475,6 +475,41 @@ def gpr_predict_f(kernel, X, Y, noise_variance, Xnew):
     return fmean, fvar[:, None]
 
 
+def predict_y(model, Xnew):
+    """gpflow.models.GPModel.predict_y -> likelihood.predict_mean_and_var [GPflow-recalled]: Gaussian (mu, var + s2);
+    Bernoulli(inv_probit): p = inv_probit(mu / sqrt(1 + var)), p - p^2; StudentT by quadrature = (mu, var + scale^2 df/(df-2))."""
+    mu, var = model.predict_f(Xnew)
+    lik = model.likelihood
+    if isinstance(lik, Gaussian):
+        return mu, var + float(lik.variance)
+    if isinstance(lik, Bernoulli):
+        p = inv_probit(mu / np.sqrt(1.0 + var))
+        return p, p - np.square(p)
+    z, w = gh_points_and_weights(lik.n_gh)   # ScalarLikelihood._predict_mean_and_var: quadrature of E[y|f] = f and Var[y|f] + f^2
+    F = mu[..., None] + np.sqrt(var)[..., None] * z
+    cv = float(lik.scale) ** 2 * lik.df / (lik.df - 2.0)
+    Ey = np.sum(F * w, axis=-1)
+    Ey2 = np.sum((cv + np.square(F)) * w, axis=-1)
+    return Ey, Ey2 - np.square(Ey)
+
+
+def predict_log_density(model, data):
+    """gpflow.models.GPModel.predict_log_density [GPflow-recalled]."""
+    from scipy.special import logsumexp
+    X, Y = data
+    mu, var = model.predict_f(X)
+    lik = model.likelihood
+    if isinstance(lik, Gaussian):
+        v = var + float(lik.variance)
+        return np.sum(-0.5 * (np.log(2 * np.pi) + np.log(v) + np.square(Y - mu) / v), axis=-1)
+    if isinstance(lik, Bernoulli):
+        p, _ = predict_y(model, X)
+        return np.sum(np.log(np.where(Y == 1, p, 1 - p)), axis=-1)
+    z, w = gh_points_and_weights(lik.n_gh)
+    F = mu[..., None] + np.sqrt(var)[..., None] * z
+    return np.sum(logsumexp(lik._logp(F, Y[..., None]) + np.log(w), axis=-1), axis=-1)
+
+
 # ----------------------------------------------------------------------------------------
 # M-step: gradients of the ELBO w.r.t. kernel variance, lengthscales, inducing inputs and
 # likelihood parameters with the sites held fixed.  The reference obtains them by TensorFlow

@@ -322,6 +322,52 @@ class t_SVGP:
                                               mean.ctypes.data, var.ctypes.data))
         return mean, var
 
+    # ---- inherited GPModel surface built on predict_f (used by the reference's callers: experiments/uci_regression.py:114,142,
+    # 145,251).  O(N) host arithmetic on the GPU's predict_f output; GPflow 2.2.1 likelihood semantics [GPflow-recalled]:
+    # Gaussian closed forms; Bernoulli(inv_probit) analytic mean; Student-t / generic via 20-point Gauss-Hermite. -------------
+    def _gh(self):
+        n = int(getattr(self.likelihood, "num_gauss_hermite_points", DEFAULT_N_GH))
+        x, w = np.polynomial.hermite.hermgauss(n)
+        return x * np.sqrt(2.0), w / np.sqrt(np.pi)
+
+    def predict_y(self, Xnew, full_cov=False, full_output_cov=False):
+        """GPModel.predict_y -> likelihood.predict_mean_and_var(f_mean, f_var)."""
+        from math import erf
+        mu, var = self.predict_f(Xnew, full_cov, full_output_cov)
+        name = type(self.likelihood).__name__
+        if name == "Gaussian":
+            return mu, var + float(_value(self.likelihood.variance))
+        if name == "Bernoulli":
+            p = 0.5 * (1.0 + np.vectorize(erf)(mu / np.sqrt(1.0 + var) / np.sqrt(2.0))) * (1 - 2e-3) + 1e-3
+            return p, p - np.square(p)
+        sc, df = float(_value(self.likelihood.scale)), float(_value(self.likelihood.df))   # StudentT: E[y|f] = f, Var[y|f] = scale^2 df/(df-2)
+        return mu, var + sc * sc * df / (df - 2.0)
+
+    def predict_log_density(self, data, full_cov=False, full_output_cov=False):
+        """GPModel.predict_log_density -> log int p(y | f) q(f) df per point, [N]."""
+        from math import lgamma
+        X, Y = data
+        Y = np.asarray(Y, dtype=np.float64)
+        mu, var = self.predict_f(X, full_cov, full_output_cov)
+        name = type(self.likelihood).__name__
+        if name == "Gaussian":
+            v = var + float(_value(self.likelihood.variance))
+            return np.sum(-0.5 * (np.log(2 * np.pi) + np.log(v) + np.square(Y - mu) / v), axis=-1)
+        if name == "Bernoulli":
+            p, _ = self.predict_y(X)
+            return np.sum(np.log(np.where(Y == 1, p, 1 - p)), axis=-1)
+        z, w = self._gh()
+        sc, df = float(_value(self.likelihood.scale)), float(_value(self.likelihood.df))
+        F = mu[..., None] + np.sqrt(var)[..., None] * z
+        const = lgamma((df + 1) * 0.5) - lgamma(df * 0.5) - 0.5 * (np.log(sc * sc) + np.log(df) + np.log(np.pi))
+        logp = const - 0.5 * (df + 1) * np.log1p(np.square((Y[..., None] - F) / sc) / df) + np.log(w)
+        mx = logp.max(axis=-1, keepdims=True)
+        return np.sum(mx[..., 0] + np.log(np.sum(np.exp(logp - mx), axis=-1)), axis=-1)
+
+    def training_loss_closure(self, data=None):
+        """GPModel.training_loss_closure: a zero-argument callable returning -ELBO on `data`."""
+        return lambda: self.training_loss(data)
+
     # ---- multi-GPU: one model (context) per rank ------------------------------------------------------------------------
     def init_comm(self, world_size, rank, unique_id: bytes):
         buf = C.create_string_buffer(bytes(unique_id), 128)

@@ -276,3 +276,25 @@ def test_cuda_is_as_close_to_exact_arithmetic_as_the_oracle(lengthscale):
     # whitened route: the reference's own eps * cond
     assert e_dev <= max(20.0 * e_ref + 1e-13, 1e-10), (e_dev, e_ref)
     dev.close()
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg5"])
+def test_predict_y_and_log_density(name):
+    # the inherited GPModel surface used by the reference's experiment scripts (uci_regression.py:114,142,145,251)
+    import tsvgp_b200 as tb
+    import tsvgp_b200.synth as synth
+    cfg = synth.describe(name)
+    X, Y, Z = synth.make_minibatch(cfg, n_rows=1500, M=64)
+    kernel, lik = synth.build_objects(cfg, orc)
+    ref = orc.OracleTSVGP(kernel, lik, orc.InducingPoints(Z.copy()))
+    dev = tb.t_SVGP(kernel, lik, Z.copy())
+    for _ in range(2):
+        ref.natgrad_step((X, Y), lr=0.5)
+        dev.natgrad_step((X, Y), lr=0.5)
+    my_d, vy_d = dev.predict_y(X[:200])
+    my_r, vy_r = orc.predict_y(ref, X[:200])
+    errs = {"y_mean": relerr(my_d, my_r), "y_var": relerr(vy_d, vy_r),
+            "log_density": relerr(dev.predict_log_density((X[:200], Y[:200])), orc.predict_log_density(ref, (X[:200], Y[:200])))}
+    check(errs)
+    assert abs(dev.training_loss_closure((X, Y))() + ref.elbo((X, Y))) <= 1e-9 * abs(ref.elbo((X, Y)))
+    dev.close()
