@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <map>
+#include <type_traits>
 #include <utility>
 #include <vector>
 #include <stdlib.h>
@@ -21,7 +22,7 @@ template <bool A_KC, bool B_KC, bool SCALE>
 struct Smem {
     static constexpr int A_ELEMS = A_KC ? KC_ELEMS : MC_ELEMS;
     static constexpr int B_ELEMS = B_KC ? KC_ELEMS : MC_ELEMS;
-    static constexpr int STAGE = A_ELEMS + B_ELEMS + (SCALE ? BK : 0);
+    static constexpr int STAGE = A_ELEMS + B_ELEMS + (SCALE ? 2 * BK : 0);   // + per-k scale and mat-vec vectors
     static constexpr int BYTES = STAGE * STAGES * 8;
 };
 
@@ -97,8 +98,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmP& p, double (&acc)[8][4
         if (g == 0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                red[(warp & 1) * BN + wn + 8 * j + 2 * t] = cs[j][0];
-                red[(warp & 1) * BN + wn + 8 * j + 2 * t + 1] = cs[j][1];
+                red[(wm >> 6) * BN + wn + 8 * j + 2 * t] = cs[j][0];
+                red[(wm >> 6) * BN + wn + 8 * j + 2 * t + 1] = cs[j][1];
             }
         }
         __syncthreads();
@@ -141,6 +142,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(GemmP p) {
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    const bool matvec = SCALE && p.gvec != nullptr && tj == 0 && wn == 0;   // the two warps of the first tile column that cover all 128 rows
+    double bacc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bacc[i] = 0.0;
 
     auto issue = [&](int kt) {
         if (kt < KT) {
@@ -150,6 +155,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(GemmP p) {
             load_tile<A_KC>(sa, Ag, p.lda, ti * BM, k0, tid);
             load_tile<B_KC>(sb, Bg, p.ldb, tj * BN, k0, tid);
             if (SCALE && tid < BK / 2) cp_async16(sb + S::B_ELEMS + tid * 2, p.kscale + k0 + tid * 2);
+            if (SCALE && tid >= 32 && tid < 32 + BK / 2 && p.gvec) cp_async16(sb + S::B_ELEMS + BK + (tid - 32) * 2, p.gvec + k0 + (tid - 32) * 2);
         }
         cp_async_commit();
     };
@@ -177,6 +183,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(GemmP p) {
                 const double h = ssc[kk + t];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) b[j] *= h;
+                if (matvec) {
+                    const double gk = ssc[BK + kk + t];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) bacc[i] = fma(a[i], gk, bacc[i]);
+                }
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -187,6 +198,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(GemmP p) {
     cp_async_wait<0>();
     __syncthreads();   // every global read of this CTA is complete: C may alias A (in-place panel solves)
 
+    if (SCALE && matvec) {   // rows wm + 8 i + g : sum the 4 lanes that split k, then one lane adds into the (CTA-private) rows of b
+        double* bo = (p.C2 != nullptr && ks == 1) ? p.bout2 : p.bout;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double v = bacc[i];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (t == 0) bo[ti * BM + wm + 8 * i + g] += v;
+        }
+    }
     gemm_epilogue<EPI>(p, acc, smem, ti, tj, bz, ks, tid, warp, g, t, wm, wn);
 }
 
@@ -201,8 +222,8 @@ template <bool A_KC, bool B_KC, bool SCALE, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
     using S = Smem<A_KC, B_KC, SCALE>;
     extern __shared__ __align__(16) double smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGE * PSTAGES);
-    uint64_t* empty = full + PSTAGES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGE * PSTAGES);
+    uint64_t* empty = full_bar + PSTAGES;
 
     const int tj = blockIdx.x, ti = blockIdx.y;
     if (p.lower_out && tj > ti) return;
@@ -227,11 +248,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
     const int KT = max(ke - kb, 0) / BK;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    // warps w and w + 4 share an SM sub-partition: give each sub-partition one warp of the upper and one of the lower row half,
+    // with the column quarters rotated by two, so that the 8x8 blocks skipped below (zero blocks of triangular operands, the
+    // strictly upper blocks of a diagonal output tile) are spread evenly over the four DMMA pipes
     const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+    const bool plain = p.a_tri == 0 && p.b_tri == 0;
+    const int dj = (p.lower_out && ti == tj && plain) ? (wm - wn) / 8 : 64;   // diagonal tile of a symmetric product: (i, j) needed iff j <= i + dj
+    const int dj_pat = dj >= 3 ? 0 : (dj == 0 ? 1 : (dj == -4 ? 2 : 3));
+    const bool tri_a2 = p.a_tri == 2 && p.b_tri == 0 && !p.lower_out;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < PSTAGES; ++s) { mbar_init(&full[s], NTHREADS); mbar_init(&empty[s], NTHREADS / 32); }
+        for (int s = 0; s < PSTAGES; ++s) { mbar_init(&full_bar[s], NTHREADS); mbar_init(&empty[s], NTHREADS / 32); }
     }
     __syncthreads();
 
@@ -240,6 +268,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    const bool matvec = SCALE && p.gvec != nullptr && tj == 0 && wn == 0;   // the two warps of the first tile column that cover all 128 rows
+    double bacc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bacc[i] = 0.0;
 
     int ps = 0, pround = 0, L = 0;          // producer cursor: tile L goes to stage ps, the pround-th use of that stage
     auto produce = [&]() {
@@ -251,7 +283,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
             load_tile<A_KC>(sa, Ag, p.lda, ti * BM, k0, tid);
             load_tile<B_KC>(sb, Bg, p.ldb, tj * BN, k0, tid);
             if (SCALE && tid < BK / 2) cp_async16(sb + S::B_ELEMS + tid * 2, p.kscale + k0 + tid * 2);
-            cp_async_mbar_arrive(&full[ps]);
+            if (SCALE && tid >= 32 && tid < 32 + BK / 2 && p.gvec) cp_async16(sb + S::B_ELEMS + BK + (tid - 32) * 2, p.gvec + k0 + (tid - 32) * 2);
+            cp_async_mbar_arrive(&full_bar[ps]);
         }
         ++L;
         if (++ps == PSTAGES) { ps = 0; ++pround; }
@@ -262,35 +295,76 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
     int cs = 0, cph = 0;
     for (int kt = 0; kt < KT; ++kt) {
         produce();
-        mbar_wait(&full[cs], cph);
+        // which 8x8 blocks of this warp's 64x32 tile are identically zero / not needed in this k-tile (compile-time patterns only:
+        // run-time predicates around single DMMAs cost more than the DMMAs they save)
+        //   IHI < 8 : A(i,k) = 0 for row blocks i >= IHI (upper-triangular A^T, k-tile inside the diagonal k-block)
+        //   DJ      : diagonal tile of a symmetric (lower_out) product: block (i, j) needed iff j <= i + DJ
+        int ihi = 8;
+        if (tri_a2) ihi = min(8, max(0, ((kb + kt * BK - ti * BM - wm + BK - 1) >> 3) + 1));
+        mbar_wait(&full_bar[cs], cph);
         const double* sa = smem + cs * S::STAGE;
         const double* sb = sa + S::A_ELEMS;
         const double* ssc = sb + S::B_ELEMS;
+        auto k_tile = [&](auto ihi_tag, auto dj_tag, auto mv_tag) {
+            constexpr int IHI = decltype(ihi_tag)::value, DJ = decltype(dj_tag)::value;
+            constexpr bool MV = decltype(mv_tag)::value;
 #pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
-            double a[8], b[4];
+            for (int kk = 0; kk < BK; kk += 4) {
+                double a[8], b[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                a[i] = A_KC ? sa[(wm + 8 * i + g) * KC_LD + kk + t] : sa[(kk + t) * MC_LD + wm + 8 * i + g];
+                for (int i = 0; i < 8; ++i)
+                    a[i] = A_KC ? sa[(wm + 8 * i + g) * KC_LD + kk + t] : sa[(kk + t) * MC_LD + wm + 8 * i + g];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                b[j] = B_KC ? sb[(wn + 8 * j + g) * KC_LD + kk + t] : sb[(kk + t) * MC_LD + wn + 8 * j + g];
-            if (SCALE) {
-                const double h = ssc[kk + t];
+                for (int j = 0; j < 4; ++j)
+                    b[j] = B_KC ? sb[(wn + 8 * j + g) * KC_LD + kk + t] : sb[(kk + t) * MC_LD + wn + 8 * j + g];
+                if (SCALE) {
+                    const double h = ssc[kk + t];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] *= h;
+                    for (int j = 0; j < 4; ++j) b[j] *= h;
+                    if (MV) {
+                        const double gk = ssc[BK + kk + t];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) bacc[i] = fma(a[i], gk, bacc[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (i < IHI && j <= i + DJ) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        };
+        using I8 = std::integral_constant<int, 8>;
+        using FULLJ = std::integral_constant<int, 64>;
+        using NoMV = std::false_type;
+        if (SCALE && matvec) {   // the two warps per row block that also carry b += A g (first tile column only)
+            if (dj_pat == 1) k_tile(I8{}, std::integral_constant<int, 0>{}, std::true_type{});
+            else k_tile(I8{}, FULLJ{}, std::true_type{});
         }
+        else if (dj_pat == 0 && ihi == 8) k_tile(I8{}, FULLJ{}, NoMV{});                          // the common case
+        else if (dj_pat == 1) k_tile(I8{}, std::integral_constant<int, 0>{}, NoMV{});            // j <= i
+        else if (dj_pat == 2) k_tile(I8{}, std::integral_constant<int, -4>{}, NoMV{});           // j <= i - 4
+        else if (dj_pat == 3) {}                                                                   // nothing needed
+        else if (ihi >= 6) k_tile(std::integral_constant<int, 6>{}, FULLJ{}, NoMV{});
+        else if (ihi >= 4) k_tile(std::integral_constant<int, 4>{}, FULLJ{}, NoMV{});
+        else if (ihi >= 2) k_tile(std::integral_constant<int, 2>{}, FULLJ{}, NoMV{});
+        // ihi == 0 : every A block of this warp is zero in this k-tile
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[cs]);
         if (++cs == PSTAGES) { cs = 0; cph ^= 1; }
     }
     __syncthreads();   // every global read of this CTA has landed and every warp is out of the pipeline buffers
 
+    if (SCALE && matvec) {   // rows wm + 8 i + g : sum the 4 lanes that split k, then one lane adds into the (CTA-private) rows of b
+        double* bo = (p.C2 != nullptr && ks == 1) ? p.bout2 : p.bout;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double v = bacc[i];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (t == 0) bo[ti * BM + wm + 8 * i + g] += v;
+        }
+    }
     gemm_epilogue<EPI>(p, acc, smem, ti, tj, bz, ks, tid, warp, g, t, wm, wn);
 }
 
@@ -400,6 +474,7 @@ int balanced_ksplit(int tiles, int k) {
 }
 
 int gemm_launch(const GemmP& p, cudaStream_t stream) {
+    if (p.gvec && (!p.kscale || !p.bout || (p.C2 && !p.bout2) || p.ksplit != 1 || !p.lower_out)) return -1;
     if (p.C2 && (p.ksplit != 1 || p.epilogue != EPI_STORE || p.ksp % BK || p.ksp <= 0 || p.ksp >= p.k)) return -1;
     if (p.m % BM || p.n % BN || p.k % BK || p.m <= 0 || p.n <= 0) return -1;
     const bool scale = p.kscale != nullptr;

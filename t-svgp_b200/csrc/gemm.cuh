@@ -25,6 +25,9 @@ struct GemmP {
     int lower_out = 0;
     int a_tri = 0, b_tri = 0;
     const double* kscale = nullptr;   // optional [k] weights on the contraction index (the h_n of the weighted SYRK)
+    // with kscale: optional fused mat-vec  bout[i] += sum_k A(i,k) gvec[k]  (b += Kuf g of the statistics pass), computed from the A
+    // fragments the first tile column already holds in registers; the split-off k piece (C2) accumulates into bout2
+    const double* gvec = nullptr; double* bout = nullptr; double* bout2 = nullptr;
     int epilogue = EPI_STORE;
     double* norm_out = nullptr; long ldn = 0;   // EPI_COLNORM: norm_out[tile_i * ldn + j] = sum_{i in tile} C(i,j)^2
     int ksplit = 1; double* part = nullptr; long part_stride = 0;   // split-K partial slabs [ksplit][m*ldc]; caller reduces

@@ -36,6 +36,7 @@ thread_local std::string g_create_error;
 constexpr double GPFLOW_DEFAULT_JITTER = 1e-6;   // gpflow.config.default_jitter() (GPflow 2.2.1), tsvgp.py:209-211
 
 inline long round_up(long v, long m) { return (v + m - 1) / m * m; }
+constexpr int MAXS = 4;   // slab streams (option "streams"; default 2)
 
 struct Pool {
     std::vector<void*> ptrs;
@@ -64,14 +65,15 @@ enum { ROUTE_AUTO = 0, ROUTE_FUSED = 1, ROUTE_WHITENED = 2 };
 
 struct tsvgp_ctx {
     int dev = 0;
-    cudaStream_t s_main = nullptr, s_pp[2] = {nullptr, nullptr}, s_side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev[N_EV] = {}, ev_kuu = nullptr, ev_side = nullptr;
+    cudaStream_t s_main = nullptr, s_pp[MAXS] = {}, s_side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join[MAXS] = {}, ev[N_EV] = {}, ev_kuu = nullptr, ev_side = nullptr;
     std::string err;
     int last_info = 0;
 
     // options
     long chunk_opt = 0;        // 0 = automatic
     int n_streams = 2;
+    int fuse_b = 1;            // accumulate b += Kuf g inside the SYRK kernel instead of a separate mat-vec pass over the slab
     int balance = 1;           // split the SYRK's contraction in two pieces so that every SM gets equal work
     int cache_factors = 1;     // keep chol(K9) and the posterior factors between calls while their inputs are unchanged
     int route_opt = ROUTE_AUTO;     // statistics route: fused (B = Kuf H Kfu, then K9^-1 B K9^-1) or whitened (C9^-1 Kuf first)
@@ -96,8 +98,8 @@ struct tsvgp_ctx {
     double *K = nullptr, *K6 = nullptr, *L2 = nullptr, *lam1 = nullptr;
     double *Wm = nullptr, *Wf = nullptr, *V = nullptr, *T = nullptr, *X1 = nullptr, *X2 = nullptr, *C9 = nullptr, *C9inv = nullptr;
     double *G2 = nullptr, *P = nullptr, *tmp = nullptr, *dinv = nullptr;
-    double *stats[2] = {nullptr, nullptr};   // [B (Mp*Mp) | b (Mp) | tail (4)] per ping-pong stream
-    double *stats2[2] = {nullptr, nullptr};  // second B accumulator per stream: the split-off k piece of the balanced SYRK
+    double *stats[MAXS] = {};   // [B (Mp*Mp) | b (Mp) | tail (4)] per ping-pong stream
+    double *stats2[MAXS] = {};  // second B accumulator per stream: the split-off k piece of the balanced SYRK
     double *alpha = nullptr, *mZ = nullptr, *mq = nullptr, *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *gwork = nullptr;
     double *scal = nullptr;
     double *zaug = nullptr, *fuu = nullptr;   // M-step: [zs | 1 | zs^2] and the Kuu counterpart of F
@@ -125,15 +127,16 @@ struct tsvgp_ctx {
     long chunk = 0;
     int chunk_Mp = 0;
     int chunk_route = 0;
-    double *wslab[2] = {};
-    double *slab[2] = {}, *mu_part[2] = {}, *q_part[2] = {}, *gbuf[2] = {}, *hbuf[2] = {};
+    int slab_streams = 0;
+    double *wslab[MAXS] = {};
+    double *slab[MAXS] = {}, *mu_part[MAXS] = {}, *q_part[MAXS] = {}, *gbuf[MAXS] = {}, *hbuf[MAXS] = {};
     double* ve_blocks = nullptr;
     long ve_cap = 0;
-    double *kpslab[2] = {}, *vslab[2] = {}, *uslab[2] = {}, *xaug[2] = {}, *fpart[2] = {}, *facc[2] = {};   // M-step gradient workspace
+    double *kpslab[MAXS] = {}, *vslab[MAXS] = {}, *uslab[MAXS] = {}, *xaug[MAXS] = {}, *fpart[MAXS] = {}, *facc[MAXS] = {};   // M-step gradient workspace
     double* aux_blocks = nullptr;
     int fsplit = 1;
     bool grad_ws = false;
-    double* kpart[2] = {};     // split-K partial tiles of the SYRK when M is so small that its tiles cannot fill the SMs
+    double* kpart[MAXS] = {};     // split-K partial tiles of the SYRK when M is so small that its tiles cannot fill the SMs
     int ksplit = 1;
 
     // multi-GPU
@@ -200,7 +203,7 @@ int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     NEED(c->X1 = p.get(mm)); NEED(c->X2 = p.get(mm)); NEED(c->C9 = p.get(mm)); NEED(c->C9inv = p.get(mm));
     NEED(c->G2 = p.get(mm)); NEED(c->P = p.get(mm)); NEED(c->tmp = p.get((size_t)((c->Mp / 128 + 1) / 2) * 128 * mp));   // trtri_lower: ceil(nblk/2) block rows
     NEED(c->dinv = p.get((size_t)(c->Mp / 128) * 128 * 128));
-    for (int s = 0; s < 2; ++s) { NEED(c->stats[s] = p.get(mm + mp + 4)); NEED(c->stats2[s] = p.get(mm)); }
+    for (int s = 0; s < MAXS; ++s) { NEED(c->stats[s] = p.get(mm + mp + 4)); NEED(c->stats2[s] = p.get(mm + mp)); }
     NEED(c->alpha = p.get(mp)); NEED(c->mZ = p.get(mp)); NEED(c->mq = p.get(mp)); NEED(c->v1 = p.get(mp)); NEED(c->v2 = p.get(mp));
     NEED(c->v3 = p.get(mp)); NEED(c->gwork = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal = p.get(N_SCAL));
     NEED(c->info = (int*)p.get(N_INFO)); NEED(c->flags = (int*)p.get(2));
@@ -350,13 +353,17 @@ int ensure_slabs(tsvgp_ctx* c, long n_points, bool need_grad = false) {
     const long nchunks = (n_points + nc - 1) / nc;
     const long ve_need = (nchunks + 1) * ((nc + 255) / 256);
     const bool need_w = c->route == ROUTE_WHITENED;
-    if (c->chunk == nc && c->chunk_Mp == c->Mp && c->ve_cap >= ve_need && (!need_w || c->wslab[0]) && (!need_grad || c->grad_ws))
+    const int want_streams = c->profile ? 1 : (c->n_streams < 1 ? 1 : (c->n_streams > MAXS ? MAXS : c->n_streams));
+    if (c->chunk == nc && c->chunk_Mp == c->Mp && c->ve_cap >= ve_need && (!need_w || c->wslab[0]) && (!need_grad || c->grad_ws) &&
+        c->slab_streams >= want_streams)
         return TSVGP_OK;
     CU(cudaStreamSynchronize(c->s_main));
     c->pc.release();
-    c->wslab[0] = c->wslab[1] = nullptr;
+    for (int s = 0; s < MAXS; ++s) c->wslab[s] = nullptr;
     Pool& p = c->pc;
-    for (int s = 0; s < 2; ++s) {
+    const int ns = c->profile ? 1 : (c->n_streams < 1 ? 1 : (c->n_streams > MAXS ? MAXS : c->n_streams));
+    c->slab_streams = ns;
+    for (int s = 0; s < ns; ++s) {
         NEED(c->slab[s] = p.get((size_t)c->Mp * nc));
         if (need_w) NEED(c->wslab[s] = p.get((size_t)c->Mp * nc));
         NEED(c->mu_part[s] = p.get((size_t)(c->Mp / 64) * nc));
@@ -375,7 +382,7 @@ int ensure_slabs(tsvgp_ctx* c, long n_points, bool need_grad = false) {
             if (c->ksplit > max_split) c->ksplit = max_split;
             if (c->ksplit < 2) c->ksplit = 1;
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < ns; ++s) {
             c->kpart[s] = nullptr;
             if (c->ksplit > 1) NEED(c->kpart[s] = p.get((size_t)c->ksplit * c->Mp * c->Mp));
         }
@@ -388,7 +395,7 @@ int ensure_slabs(tsvgp_ctx* c, long n_points, bool need_grad = false) {
         c->fsplit = sms / (c->Mp / 128);
         if (c->fsplit > (int)(nc / 256)) c->fsplit = (int)(nc / 256);
         if (c->fsplit < 1) c->fsplit = 1;
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < ns; ++s) {
             NEED(c->kpslab[s] = p.get((size_t)c->Mp * nc)); NEED(c->vslab[s] = p.get((size_t)c->Mp * nc));
             NEED(c->uslab[s] = p.get((size_t)c->Mp * nc)); NEED(c->xaug[s] = p.get((size_t)nc * 128));
             NEED(c->fpart[s] = p.get((size_t)c->fsplit * c->Mp * 128)); NEED(c->facc[s] = p.get((size_t)c->Mp * 128));
@@ -410,7 +417,7 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
     OK(ensure_slabs(c, N, grad));
     const long nc = c->chunk;
     const int Mp = c->Mp;
-    const int nstr = (c->n_streams == 1 || c->profile) ? 1 : 2;
+    const int nstr = c->profile ? 1 : (c->n_streams < 1 ? 1 : (c->n_streams > MAXS ? MAXS : c->n_streams));
     const bool prof = c->profile && mode == MODE_STATS;
     size_t pev_used = 0;
     auto mark = [&](cudaStream_t st) -> int {   // profile mode: one event between consecutive kernels
@@ -431,7 +438,7 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
     if (stats)
         for (int s = 0; s < nstr; ++s) {
             CU(cudaMemsetAsync(c->stats[s], 0, sizeof(double) * ((size_t)Mp * Mp + Mp + 4), sm));
-            CU(cudaMemsetAsync(c->stats2[s], 0, sizeof(double) * (size_t)Mp * Mp, sm));
+            CU(cudaMemsetAsync(c->stats2[s], 0, sizeof(double) * ((size_t)Mp * Mp + Mp), sm));
             if (grad) CU(cudaMemsetAsync(c->facc[s], 0, sizeof(double) * (size_t)Mp * 128, sm));
         }
     if (grad) CU(cudaMemsetAsync(c->aux_blocks, 0, sizeof(double) * (size_t)(2 * nchunks * vstride), sm));
@@ -495,6 +502,7 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
                 p.beta = 1.0; p.lower_out = 1; p.kscale = c->hbuf[b];
                 const int nt = Mp / 128;
                 const int ks_here = c->ksplit < ncols / 256 ? c->ksplit : ncols / 256;
+                bool fused_b = false;
                 if (ks_here > 1) {
                     p.ksplit = ks_here; p.part = c->kpart[b]; p.part_stride = (long)Mp * Mp;
                     LA(gemm_launch(p, s));
@@ -502,12 +510,16 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
                 } else {
                     const int ksp = c->balance ? balanced_ksplit(nt * (nt + 1) / 2, ncols) : ncols;
                     if (ksp < ncols) { p.ksp = ksp; p.C2 = c->stats2[b]; }
+                    if (c->fuse_b) {   // (e) b += K g rides on the A fragments of the SYRK's first tile column
+                        p.gvec = c->gbuf[b]; p.bout = c->stats[b] + (size_t)Mp * Mp; p.bout2 = c->stats2[b] + (size_t)Mp * Mp;
+                        fused_b = true;
+                    }
                     LA(gemm_launch(p, s));
                 }
+                mark(s);
+                // (e) b += K g as its own kernel when the SYRK ran split-K
+                if (!fused_b) LA(gemv_n_launch(stat_slab, nc, Mp, ncols, c->gbuf[b], 1.0, 1.0, c->stats[b] + (size_t)Mp * Mp, s));
             }
-            mark(s);
-            // (e) b += K g
-            LA(gemv_n_launch(stat_slab, nc, Mp, ncols, c->gbuf[b], 1.0, 1.0, c->stats[b] + (size_t)Mp * Mp, s));
             mark(s);
         }
         if (grad) {
@@ -553,9 +565,9 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
     }
     const size_t mm = (size_t)Mp * Mp;
     if (stats) {
-        if (nstr == 2) LA(vadd_inplace_launch(c->stats[0], c->stats[1], (long)(mm + Mp), sm));
-        if (grad && nstr == 2) LA(vadd_inplace_launch(c->facc[0], c->facc[1], (long)Mp * 128, sm));
-        for (int s = 0; s < nstr && c->balance; ++s) LA(vadd_inplace_launch(c->stats[0], c->stats2[s], (long)mm, sm));
+        for (int s = 1; s < nstr; ++s) LA(vadd_inplace_launch(c->stats[0], c->stats[s], (long)(mm + Mp), sm));
+        for (int s = 1; s < nstr && grad; ++s) LA(vadd_inplace_launch(c->facc[0], c->facc[s], (long)Mp * 128, sm));
+        for (int s = 0; s < nstr && c->balance; ++s) LA(vadd_inplace_launch(c->stats[0], c->stats2[s], (long)(mm + Mp), sm));
     }
     LA(stats_tail_launch(c->ve_blocks, nchunks * vstride, c->flags, grad ? c->aux_blocks : nullptr, c->stats[0] + mm + Mp, sm));
     return TSVGP_OK;
@@ -771,7 +783,7 @@ int tsvgp_create(tsvgp_ctx** out, int device_id) {
     c->dev = device_id;
     bool ok = cudaSetDevice(device_id) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking) == cudaSuccess;
-    for (int s = 0; s < 2 && ok; ++s) {
+    for (int s = 0; s < MAXS && ok; ++s) {
         ok = ok && cudaStreamCreateWithFlags(&c->s_pp[s], cudaStreamNonBlocking) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&c->ev_join[s], cudaEventDisableTiming) == cudaSuccess;
     }
@@ -796,7 +808,7 @@ void tsvgp_destroy(tsvgp_ctx* c) {
     cudaDeviceSynchronize();
     if (c->comm) nccl_api().CommDestroy(c->comm);
     c->pm.release(); c->pd.release(); c->pc.release();
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < MAXS; ++s) {
         if (c->s_pp[s]) cudaStreamDestroy(c->s_pp[s]);
         if (c->ev_join[s]) cudaEventDestroy(c->ev_join[s]);
     }
@@ -819,9 +831,10 @@ int tsvgp_last_info(const tsvgp_ctx* c) { return c ? c->last_info : 0; }
 int tsvgp_set_option(tsvgp_ctx* c, const char* name, double value) {
     if (!c || !name) return TSVGP_ERR_INVALID;
     if (!strcmp(name, "chunk")) { c->chunk_opt = (long)value; return TSVGP_OK; }
-    if (!strcmp(name, "streams")) { c->n_streams = value >= 2 ? 2 : 1; return TSVGP_OK; }
+    if (!strcmp(name, "streams")) { c->n_streams = value < 1 ? 1 : (value > MAXS ? MAXS : (int)value); return TSVGP_OK; }
     if (!strcmp(name, "route")) { c->route_opt = (int)value; c->k9_valid = false; return TSVGP_OK; }
     if (!strcmp(name, "route_cond_max")) { c->route_cond_max = value; return TSVGP_OK; }
+    if (!strcmp(name, "fuse_b")) { c->fuse_b = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "balance")) { c->balance = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "profile")) { c->profile = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "cache_factors")) { c->cache_factors = value != 0.0; return TSVGP_OK; }
