@@ -86,6 +86,12 @@ TSVGP_API int tsvgp_get_lambda_2(tsvgp_ctx* ctx, double* lambda_2);             
 /* X [N, D], Y [N] (= [N,1]), mean_X [N] = mean_function(X) or NULL. Host data is copied; device data is aliased.        */
 TSVGP_API int tsvgp_set_data(tsvgp_ctx* ctx, const double* X, const double* Y, int64_t N, int D, const double* mean_X);
 
+/* Input pipeline (stands in for the tf.data prefetch of the reference's minibatch callers, docs/notebooks/mnist.py:85,150):
+ * stage_data copies the NEXT minibatch into a second set of device buffers on a copy stream and returns at once (host
+ * buffers should be pinned and must stay valid until commit_staged); commit_staged makes it the resident minibatch.       */
+TSVGP_API int tsvgp_stage_data(tsvgp_ctx* ctx, const double* X, const double* Y, int64_t N, int D, const double* mean_X);
+TSVGP_API int tsvgp_commit_staged(tsvgp_ctx* ctx);
+
 /* ---- the hot path ----------------------------------------------------------------------------------------------------- */
 /* t_SVGP.natgrad_step (tsvgp.py:234-304) on the resident data and sites.  scale = num_data / minibatch_size or 1
  * (tsvgp.py:286-291) with minibatch_size summed over ranks.  elbo_before (may be NULL) receives the ELBO of the

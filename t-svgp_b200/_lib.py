@@ -59,6 +59,8 @@ _SIGNATURES = {
     "tsvgp_get_sites": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tsvgp_get_lambda_2": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tsvgp_set_data": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "tsvgp_stage_data": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "tsvgp_commit_staged": (C.c_int, [C.c_void_p]),
     "tsvgp_natgrad_step": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp]),
     "tsvgp_elbo": (C.c_int, [C.c_void_p, C.c_double, _dp]),
     "tsvgp_prior_kl": (C.c_int, [C.c_void_p, _dp]),

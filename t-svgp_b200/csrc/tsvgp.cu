@@ -22,6 +22,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace tsvgp {
@@ -117,9 +118,18 @@ struct tsvgp_ctx {
     int dataD = 0;
     const double *X = nullptr, *Y = nullptr, *meanX = nullptr;
     double *Xown = nullptr, *Yown = nullptr, *meanXown = nullptr;
+    // prefetch: the next minibatch is copied into a second set of buffers on a copy stream while the current step computes
+    Pool ps;
+    double *Xst = nullptr, *Yst = nullptr, *meanXst = nullptr;
+    long st_cap_x = 0, st_cap_n = 0, st_N = 0;
+    int st_D = 0;
+    bool st_has_mean = false, st_ready = false;
+    cudaStream_t s_copy = nullptr;
+    cudaEvent_t ev_copy = nullptr;
     long cap_x = 0, cap_n = 0;
     double *XsT = nullptr, *x2 = nullptr;
-    long cap_xs = 0;
+    Pool pxs;
+    long xs_cap = 0, xs_cap_n = 0;
     bool xs_valid = false;
 
     // slab workspace
@@ -807,7 +817,9 @@ void tsvgp_destroy(tsvgp_ctx* c) {
     cudaSetDevice(c->dev);
     cudaDeviceSynchronize();
     if (c->comm) nccl_api().CommDestroy(c->comm);
-    c->pm.release(); c->pd.release(); c->pc.release();
+    c->pm.release(); c->pd.release(); c->pc.release(); c->ps.release(); c->pxs.release();
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     for (int s = 0; s < MAXS; ++s) {
         if (c->s_pp[s]) cudaStreamDestroy(c->s_pp[s]);
         if (c->ev_join[s]) cudaEventDestroy(c->ev_join[s]);
@@ -963,7 +975,12 @@ int tsvgp_set_data(tsvgp_ctx* c, const double* X, const double* Y, int64_t N, in
         c->pd.release();
         c->cap_n = npad; c->cap_x = (long)N * D;
         NEED(c->Xown = c->pd.get((size_t)N * D)); NEED(c->Yown = c->pd.get(npad)); NEED(c->meanXown = c->pd.get(npad));
-        NEED(c->XsT = c->pd.get((size_t)D * npad)); NEED(c->x2 = c->pd.get(npad));
+    }
+    if (npad > c->xs_cap_n || (long)D * npad > c->xs_cap) {
+        CU(cudaStreamSynchronize(s));
+        c->pxs.release();
+        c->xs_cap_n = npad; c->xs_cap = (long)D * npad;
+        NEED(c->XsT = c->pxs.get((size_t)D * npad)); NEED(c->x2 = c->pxs.get(npad));
     }
     if (is_device_ptr(X)) c->X = X;
     else { CU(cudaMemcpyAsync(c->Xown, X, sizeof(double) * (size_t)N * D, cudaMemcpyHostToDevice, s)); c->X = c->Xown; }
@@ -975,6 +992,55 @@ int tsvgp_set_data(tsvgp_ctx* c, const double* X, const double* Y, int64_t N, in
     c->N = N; c->n_pad = npad;
     c->dataD = D;
     c->xs_valid = false;
+    return TSVGP_OK;
+}
+
+int tsvgp_stage_data(tsvgp_ctx* c, const double* X, const double* Y, int64_t N, int D, const double* mean_X) {
+    if (!c) return TSVGP_ERR_INVALID;
+    if (!X || !Y || N < 1) FAIL(TSVGP_ERR_INVALID, "X [N >= 1, D] and Y [N] are required");
+    if (c->D > 0 && D != c->D) FAIL(TSVGP_ERR_INVALID, "X has D=%d but the inducing points have D=%d", D, c->D);
+    CU(cudaSetDevice(c->dev));
+    if (!c->s_copy) {
+        CU(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+    }
+    const long npad = round_up(N, 128);
+    if (npad > c->st_cap_n || (long)N * D > c->st_cap_x) {
+        CU(cudaStreamSynchronize(c->s_copy));
+        c->ps.release();
+        c->st_cap_n = npad; c->st_cap_x = (long)N * D;
+        NEED(c->Xst = c->ps.get((size_t)N * D)); NEED(c->Yst = c->ps.get(npad)); NEED(c->meanXst = c->ps.get(npad));
+    }
+    CU(cudaMemcpyAsync(c->Xst, X, sizeof(double) * (size_t)N * D, cudaMemcpyDefault, c->s_copy));
+    CU(cudaMemcpyAsync(c->Yst, Y, sizeof(double) * N, cudaMemcpyDefault, c->s_copy));
+    if (mean_X) CU(cudaMemcpyAsync(c->meanXst, mean_X, sizeof(double) * N, cudaMemcpyDefault, c->s_copy));
+    CU(cudaEventRecord(c->ev_copy, c->s_copy));
+    c->st_N = N; c->st_D = D; c->st_has_mean = mean_X != nullptr; c->st_ready = true;
+    return TSVGP_OK;
+}
+
+int tsvgp_commit_staged(tsvgp_ctx* c) {
+    if (!c) return TSVGP_ERR_INVALID;
+    if (!c->st_ready) FAIL(TSVGP_ERR_STATE, "no staged minibatch (tsvgp_stage_data)");
+    CU(cudaSetDevice(c->dev));
+    CU(cudaStreamWaitEvent(c->s_main, c->ev_copy, 0));
+    // the staged buffers become the resident ones; the old resident buffers become the next staging area
+    std::swap(c->Xown, c->Xst); std::swap(c->Yown, c->Yst); std::swap(c->meanXown, c->meanXst);
+    std::swap(c->cap_x, c->st_cap_x);
+    std::swap(c->pd.ptrs, c->ps.ptrs);
+    const long npad = round_up(c->st_N, 128);
+    // XsT / x2 stay with the context (pool pd owned them before the swap): re-home them if their capacity is too small
+    if (npad > c->xs_cap_n || (long)c->st_D * npad > c->xs_cap) {
+        CU(cudaStreamSynchronize(c->s_main));
+        c->pxs.release();
+        c->xs_cap_n = npad; c->xs_cap = (long)c->st_D * npad;
+        NEED(c->XsT = c->pxs.get((size_t)c->st_D * npad)); NEED(c->x2 = c->pxs.get(npad));
+    }
+    std::swap(c->cap_n, c->st_cap_n);
+    c->X = c->Xown; c->Y = c->Yown; c->meanX = c->st_has_mean ? c->meanXown : nullptr;
+    c->N = c->st_N; c->n_pad = npad; c->dataD = c->st_D;
+    c->xs_valid = false;
+    c->st_ready = false;
     return TSVGP_OK;
 }
 

@@ -242,6 +242,26 @@ class t_SVGP:
         self._resident = (N, (tx, ty, mean_x))
         return N
 
+    def stage_data(self, data):
+        """Start copying the NEXT minibatch to the GPU on a copy stream while the current step computes (use pinned host
+        arrays, `tsvgp_b200.pinned_empty`, for a truly asynchronous copy); `commit_staged()` makes it resident."""
+        X, Y = data
+        tx, ty = as_tensor(X, "X"), as_tensor(Y, "Y")
+        N, D = tx.shape
+        if int(np.prod(ty.shape)) != N:
+            raise _lib.InvalidArgumentError(_lib.ERR_INVALID, "Y must be [N, 1]")
+        if self._mean_fn(np.zeros((1, D))) is not None:
+            raise NotImplementedError("stage_data with a non-zero mean_function")
+        self._check(self._lib.tsvgp_stage_data(self._ctx, tx.ptr, ty.ptr, N, D, None))
+        self._staged = (N, (tx, ty))
+        return N
+
+    def commit_staged(self):
+        self._check(self._lib.tsvgp_commit_staged(self._ctx))
+        self._resident = (self._staged[0], self._staged[1] + (None,))
+        self._staged = None
+        return self._resident[0]
+
     def _scale(self, n_local, global_minibatch_size):
         n = n_local if global_minibatch_size is None else int(global_minibatch_size)
         if global_minibatch_size is None and self.world_size > 1:
@@ -485,12 +505,42 @@ class MultiLatent_t_SVGP(t_SVGP):
     def init_comm(self, world_size, rank, unique_id):
         raise NotImplementedError("sharding with num_latent_gps > 1")
 
+    def stage_data(self, data):
+        raise NotImplementedError("stage_data with num_latent_gps > 1")
+
+    def elbo_and_grad(self, data=None, *, global_minibatch_size=None):
+        raise NotImplementedError("elbo_and_grad with num_latent_gps > 1")
+
     def timings(self):
         return self._parts[-1].timings()
 
     def sync(self):
         for p in self._parts:
             p.sync()
+
+
+def stream_minibatches(model, batches):
+    """Input pipeline: iterate `batches` (an iterable of (X, Y) host arrays, ideally pinned) so that batch i + 1 is being copied
+    to the GPU while the caller's loop body works on batch i.  Yields the number of rows of the now-resident minibatch:
+
+        for n in stream_minibatches(model, loader):
+            model.natgrad_step(lr=0.5)          # data=None: the resident minibatch
+    """
+    it = iter(batches)
+    try:
+        model.stage_data(next(it))
+    except StopIteration:
+        return
+    while True:
+        n = model.commit_staged()
+        try:
+            model.stage_data(next(it))
+            more = True
+        except StopIteration:
+            more = False
+        yield n
+        if not more:
+            return
 
 
 def comm_unique_id() -> bytes:

@@ -298,3 +298,33 @@ def test_predict_y_and_log_density(name):
     check(errs)
     assert abs(dev.training_loss_closure((X, Y))() + ref.elbo((X, Y))) <= 1e-9 * abs(ref.elbo((X, Y)))
     dev.close()
+
+
+def test_prefetched_minibatch_stream_equals_direct_calls():
+    # the input pipeline (stage_data / commit_staged / stream_minibatches) feeds exactly the same steps as passing data directly
+    import tsvgp_b200 as tb
+    import tsvgp_b200.synth as synth
+    cfg = synth.describe("cfg3")
+    kernel, lik = _objects(cfg)
+    batches = []
+    Z = None
+    for i, n in enumerate([1500, 1500, 900, 2100]):          # ragged sizes: the staging buffers must re-grow
+        X, Y, Zi = synth.make_minibatch(cfg, n_rows=n, M=160, seed_offset=i)
+        Z = Zi if Z is None else Z
+        px, py = tb.pinned_empty(X.shape), tb.pinned_empty(Y.shape)
+        px[...] = X; py[...] = Y
+        batches.append((px, py))
+    a = tb.t_SVGP(kernel, lik, Z.copy(), num_data=60_000)
+    b = tb.t_SVGP(kernel, lik, Z.copy(), num_data=60_000)
+    for batch in batches:
+        a.natgrad_step(batch, lr=0.5)
+    rows = []
+    for n in tb.stream_minibatches(b, batches):
+        rows.append(n)
+        b.natgrad_step(lr=0.5)
+    assert rows == [1500, 1500, 900, 2100]
+    np.testing.assert_array_equal(a.lambda_1, b.lambda_1)
+    np.testing.assert_array_equal(a.lambda_2_sqrt, b.lambda_2_sqrt)
+    for px, py in batches:
+        tb.pinned_free(px); tb.pinned_free(py)
+    a.close(); b.close()
