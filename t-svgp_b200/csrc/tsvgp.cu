@@ -98,7 +98,7 @@ struct tsvgp_ctx {
     bool has_meanZ = false;
     double *K = nullptr, *K6 = nullptr, *L2 = nullptr, *lam1 = nullptr;
     double *Wm = nullptr, *Wf = nullptr, *V = nullptr, *T = nullptr, *X1 = nullptr, *X2 = nullptr, *C9 = nullptr, *C9inv = nullptr;
-    double *G2 = nullptr, *P = nullptr, *tmp = nullptr, *dinv = nullptr;
+    double *G2 = nullptr, *P = nullptr, *tmp = nullptr, *dinv = nullptr, *K9inv = nullptr;
     double *stats[MAXS] = {};   // [B (Mp*Mp) | b (Mp) | tail (4)] per ping-pong stream
     double *stats2[MAXS] = {};  // second B accumulator per stream: the split-off k piece of the balanced SYRK
     double *alpha = nullptr, *mZ = nullptr, *mq = nullptr, *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *gwork = nullptr;
@@ -211,7 +211,7 @@ int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     NEED(c->K = p.get(mm)); NEED(c->K6 = p.get(mm)); NEED(c->L2 = p.get(mm)); NEED(c->lam1 = p.get(mp));
     NEED(c->Wm = p.get(mm)); NEED(c->Wf = p.get(mm)); NEED(c->V = p.get(mm)); NEED(c->T = p.get(mm));
     NEED(c->X1 = p.get(mm)); NEED(c->X2 = p.get(mm)); NEED(c->C9 = p.get(mm)); NEED(c->C9inv = p.get(mm));
-    NEED(c->G2 = p.get(mm)); NEED(c->P = p.get(mm)); NEED(c->tmp = p.get((size_t)((c->Mp / 128 + 1) / 2) * 128 * mp));   // trtri_lower: ceil(nblk/2) block rows
+    NEED(c->G2 = p.get(mm)); NEED(c->P = p.get(mm)); NEED(c->K9inv = p.get(mm)); NEED(c->tmp = p.get((size_t)((c->Mp / 128 + 1) / 2) * 128 * mp));   // trtri_lower: ceil(nblk/2) block rows
     NEED(c->dinv = p.get((size_t)(c->Mp / 128) * 128 * 128));
     for (int s = 0; s < MAXS; ++s) { NEED(c->stats[s] = p.get(mm + mp + 4)); NEED(c->stats2[s] = p.get(mm + mp)); }
     NEED(c->alpha = p.get(mp)); NEED(c->mZ = p.get(mp)); NEED(c->mq = p.get(mp)); NEED(c->v1 = p.get(mp)); NEED(c->v2 = p.get(mp));
@@ -602,6 +602,14 @@ int start_k9(tsvgp_ctx* c, double jitter) {
     LA(copy_add_diag_launch(c->K, c->C9, c->Mp, c->Mp, jitter, s));
     LA(chol_lower(c->C9, c->Mp, c->Mp, c->dinv2, c->info + INFO_K9, s));
     LA(trtri_lower(c->C9, c->Mp, c->Mp, c->dinv2, c->C9inv, c->tmp2, s));
+    {   // K9^-1 = C9^-T C9^-1 (symmetric): the fused route then needs two M^3 products per step instead of four
+        GemmP p;
+        p.A = c->C9inv; p.lda = c->Mp; p.a_kc = 0; p.a_tri = 2;
+        p.B = c->C9inv; p.ldb = c->Mp; p.b_kc = 0; p.b_tri = 2;
+        p.C = c->K9inv; p.ldc = c->Mp; p.m = p.n = p.k = c->Mp; p.lower_out = 1;
+        LA(gemm_launch(p, s));
+        LA(mirror_lower_launch(c->K9inv, c->Mp, c->Mp, s));
+    }
     c->k9_valid = true;
     c->k9_jitter = jitter;
     c->cond_est = 0.0;
@@ -660,44 +668,42 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale) {
     const double* bad = c->stats[0] + mm + n + 1;
     LA(mirror_lower_launch(B, ld, n, s));
     if (c->route == ROUTE_FUSED) {
-        {   // X1 = C9^-1 B
+        {   // X1 = K9^-1 B
             GemmP p;
-            p.A = c->C9inv; p.lda = ld; p.a_kc = 1; p.a_tri = 1;
+            p.A = c->K9inv; p.lda = ld; p.a_kc = 1;
             p.B = B; p.ldb = ld; p.b_kc = 0;
             p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
             LA(gemm_launch(p, s));
         }
-        {   // X2 = X1 C9^-T  (symmetric; lower tiles then mirrored)
+        {   // G2 = X1 K9^-1  (symmetric; lower tiles then mirrored)
             GemmP p;
             p.A = c->X1; p.lda = ld; p.a_kc = 1;
-            p.B = c->C9inv; p.ldb = ld; p.b_kc = 1; p.b_tri = 1;
-            p.C = c->X2; p.ldc = ld; p.m = p.n = p.k = n;
+            p.B = c->K9inv; p.ldb = ld; p.b_kc = 0;
+            p.C = c->G2; p.ldc = ld; p.m = p.n = p.k = n;
             p.lower_out = 1;
             LA(gemm_launch(p, s));
         }
-        LA(mirror_lower_launch(c->X2, ld, n, s));
-        LA(gemv_n_launch(c->C9inv, ld, n, n, bvec, 1.0, 0.0, c->v1, s));   // v1 = C9^-1 b
-    }
-    const double* Bw = c->route == ROUTE_FUSED ? c->X2 : B;      // C9^-1 (Kuf H Kfu) C9^-T, symmetric
-    const double* bw = c->route == ROUTE_FUSED ? c->v1 : bvec;   // C9^-1 Kuf g
-    {   // X1 = C9^-T Bw
-        GemmP p;
-        p.A = c->C9inv; p.lda = ld; p.a_kc = 0; p.a_tri = 2;
-        p.B = Bw; p.ldb = ld; p.b_kc = 0;
-        p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
-        LA(gemm_launch(p, s));
-    }
-    {   // G2 = X1 C9^-1  (symmetric)
-        GemmP p;
-        p.A = c->X1; p.lda = ld; p.a_kc = 1;
-        p.B = c->C9inv; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
-        p.C = c->G2; p.ldc = ld; p.m = p.n = p.k = n;
-        p.lower_out = 1;
-        LA(gemm_launch(p, s));
+        LA(gemv_n_launch(c->K9inv, ld, n, n, bvec, 1.0, 0.0, c->v2, s));   // G1 = K9^-1 b
+    } else {
+        const double* Bw = B;      // C9^-1 (Kuf H Kfu) C9^-T accumulated by the whitened pass, symmetric
+        {   // X1 = C9^-T Bw
+            GemmP p;
+            p.A = c->C9inv; p.lda = ld; p.a_kc = 0; p.a_tri = 2;
+            p.B = Bw; p.ldb = ld; p.b_kc = 0;
+            p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
+            LA(gemm_launch(p, s));
+        }
+        {   // G2 = X1 C9^-1  (symmetric)
+            GemmP p;
+            p.A = c->X1; p.lda = ld; p.a_kc = 1;
+            p.B = c->C9inv; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
+            p.C = c->G2; p.ldc = ld; p.m = p.n = p.k = n;
+            p.lower_out = 1;
+            LA(gemm_launch(p, s));
+        }
+        LA(gemv_t_launch(c->C9inv, ld, n, n, bvec, c->v2, c->gwork, s));   // G1 = C9^-T (C9^-1 Kuf g)
     }
     LA(mirror_lower_launch(c->G2, ld, n, s));
-    // G1 = C9^-T bw ; G2 mZ
-    LA(gemv_t_launch(c->C9inv, ld, n, n, bw, c->v2, c->gwork, s));
     LA(gemv_n_launch(c->G2, ld, n, n, c->mZ, 1.0, 0.0, c->v3, s));
     // P = (1-lr) L2 L2^T - 2 lr scale G2 + jitter I                                     tsvgp.py:293-300
     LA(init_update_launch(c->G2, c->P, ld, c->M, n, -2.0 * lr * scale, jitter, s));
