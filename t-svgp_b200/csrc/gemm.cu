@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
     const bool matvec = SCALE && p.gvec != nullptr && tj == 0 && wn == 0;   // the two warps of the first tile column that cover all 128 rows
+    const bool use_scale = SCALE && p.kscale != nullptr;
     double bacc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) bacc[i] = 0.0;
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
             const int k0 = kb + L * BK;
             load_tile<A_KC>(sa, Ag, p.lda, ti * BM, k0, tid);
             load_tile<B_KC>(sb, Bg, p.ldb, tj * BN, k0, tid);
-            if (SCALE && tid < BK / 2) cp_async16(sb + S::B_ELEMS + tid * 2, p.kscale + k0 + tid * 2);
+            if (SCALE && tid < BK / 2 && p.kscale) cp_async16(sb + S::B_ELEMS + tid * 2, p.kscale + k0 + tid * 2);
             if (SCALE && tid >= 32 && tid < 32 + BK / 2 && p.gvec) cp_async16(sb + S::B_ELEMS + BK + (tid - 32) * 2, p.gvec + k0 + (tid - 32) * 2);
             cp_async_mbar_arrive(&full_bar[ps]);
         }
@@ -305,9 +306,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
         const double* sa = smem + cs * S::STAGE;
         const double* sb = sa + S::A_ELEMS;
         const double* ssc = sb + S::B_ELEMS;
-        auto k_tile = [&](auto ihi_tag, auto dj_tag, auto mv_tag) {
+        auto k_tile = [&](auto ihi_tag, auto dj_tag, auto mv_tag, auto sc_tag) {
             constexpr int IHI = decltype(ihi_tag)::value, DJ = decltype(dj_tag)::value;
-            constexpr bool MV = decltype(mv_tag)::value;
+            constexpr bool MV = decltype(mv_tag)::value, SC = decltype(sc_tag)::value;
 #pragma unroll
             for (int kk = 0; kk < BK; kk += 4) {
                 double a[8], b[4];
@@ -318,9 +319,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
                 for (int j = 0; j < 4; ++j)
                     b[j] = B_KC ? sb[(wn + 8 * j + g) * KC_LD + kk + t] : sb[(kk + t) * MC_LD + wn + 8 * j + g];
                 if (SCALE) {
-                    const double h = ssc[kk + t];
+                    if (SC) {
+                        const double h = ssc[kk + t];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) b[j] *= h;
+                        for (int j = 0; j < 4; ++j) b[j] *= h;
+                    }
                     if (MV) {
                         const double gk = ssc[BK + kk + t];
 #pragma unroll
@@ -336,18 +339,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
         };
         using I8 = std::integral_constant<int, 8>;
         using FULLJ = std::integral_constant<int, 64>;
-        using NoMV = std::false_type;
-        if (SCALE && matvec) {   // the two warps per row block that also carry b += A g (first tile column only)
-            if (dj_pat == 1) k_tile(I8{}, std::integral_constant<int, 0>{}, std::true_type{});
-            else k_tile(I8{}, FULLJ{}, std::true_type{});
+        using J0 = std::integral_constant<int, 0>;
+        using Jm4 = std::integral_constant<int, -4>;
+        using Yes = std::true_type;
+        using No = std::false_type;
+        if (SCALE) {   // statistics products: optional per-k weights (absent when the weights are one constant, Gaussian likelihood)
+            if (matvec) {   // the two warps per row block that also carry b += A g (first tile column only)
+                if (use_scale) { if (dj_pat == 1) k_tile(I8{}, J0{}, Yes{}, Yes{}); else k_tile(I8{}, FULLJ{}, Yes{}, Yes{}); }
+                else { if (dj_pat == 1) k_tile(I8{}, J0{}, Yes{}, No{}); else k_tile(I8{}, FULLJ{}, Yes{}, No{}); }
+            } else if (use_scale) {
+                if (dj_pat == 0) k_tile(I8{}, FULLJ{}, No{}, Yes{});
+                else if (dj_pat == 1) k_tile(I8{}, J0{}, No{}, Yes{});
+                else if (dj_pat == 2) k_tile(I8{}, Jm4{}, No{}, Yes{});
+            } else {
+                if (dj_pat == 0) k_tile(I8{}, FULLJ{}, No{}, No{});
+                else if (dj_pat == 1) k_tile(I8{}, J0{}, No{}, No{});
+                else if (dj_pat == 2) k_tile(I8{}, Jm4{}, No{}, No{});
+            }
         }
-        else if (dj_pat == 0 && ihi == 8) k_tile(I8{}, FULLJ{}, NoMV{});                          // the common case
-        else if (dj_pat == 1) k_tile(I8{}, std::integral_constant<int, 0>{}, NoMV{});            // j <= i
-        else if (dj_pat == 2) k_tile(I8{}, std::integral_constant<int, -4>{}, NoMV{});           // j <= i - 4
-        else if (dj_pat == 3) {}                                                                   // nothing needed
-        else if (ihi >= 6) k_tile(std::integral_constant<int, 6>{}, FULLJ{}, NoMV{});
-        else if (ihi >= 4) k_tile(std::integral_constant<int, 4>{}, FULLJ{}, NoMV{});
-        else if (ihi >= 2) k_tile(std::integral_constant<int, 2>{}, FULLJ{}, NoMV{});
+        else if (dj_pat == 0 && ihi == 8) k_tile(I8{}, FULLJ{}, No{}, No{});                      // the common case
+        else if (dj_pat == 1) k_tile(I8{}, J0{}, No{}, No{});                                    // j <= i
+        else if (dj_pat == 2) k_tile(I8{}, Jm4{}, No{}, No{});                                   // j <= i - 4
+        else if (dj_pat == 3) {}                                                                  // nothing needed
+        else if (ihi >= 6) k_tile(std::integral_constant<int, 6>{}, FULLJ{}, No{}, No{});
+        else if (ihi >= 4) k_tile(std::integral_constant<int, 4>{}, FULLJ{}, No{}, No{});
+        else if (ihi >= 2) k_tile(std::integral_constant<int, 2>{}, FULLJ{}, No{}, No{});
         // ihi == 0 : every A block of this warp is zero in this k-tile
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[cs]);
@@ -397,6 +413,7 @@ constexpr int mb_bytes() { return Smem<A_KC, B_KC, SCALE>::STAGE * PSTAGES * 8 +
 template <bool A_KC, bool B_KC, bool SCALE, int EPI>
 int launch_inst(const GemmP& p, cudaStream_t stream) {
     dim3 grid(p.n / BN, p.m / BM, p.batch * (p.C2 ? 2 : p.ksplit));
+    if (g_variant != 1 && SCALE && !p.kscale) return -1;
     if (g_variant == 1)
         gemm_kernel_mb<A_KC, B_KC, SCALE, EPI><<<grid, NTHREADS, mb_bytes<A_KC, B_KC, SCALE>(), stream>>>(p);
     else
@@ -474,10 +491,10 @@ int balanced_ksplit(int tiles, int k) {
 }
 
 int gemm_launch(const GemmP& p, cudaStream_t stream) {
-    if (p.gvec && (!p.kscale || !p.bout || (p.C2 && !p.bout2) || p.ksplit != 1 || !p.lower_out)) return -1;
+    if (p.gvec && (!p.bout || (p.C2 && !p.bout2) || p.ksplit != 1 || !p.lower_out)) return -1;
     if (p.C2 && (p.ksplit != 1 || p.epilogue != EPI_STORE || p.ksp % BK || p.ksp <= 0 || p.ksp >= p.k)) return -1;
     if (p.m % BM || p.n % BN || p.k % BK || p.m <= 0 || p.n <= 0) return -1;
-    const bool scale = p.kscale != nullptr;
+    const bool scale = p.kscale != nullptr || p.gvec != nullptr;   // the variant that stages per-k vectors
     if (p.a_kc && p.b_kc) {
         if (p.epilogue != EPI_STORE) return -1;
         return scale ? launch_inst<true, true, true, EPI_STORE>(p, stream) : launch_inst<true, true, false, EPI_STORE>(p, stream);

@@ -510,6 +510,10 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
                 p.B = stat_slab; p.ldb = nc; p.b_kc = 1;
                 p.C = c->stats[b]; p.ldc = Mp; p.m = p.n = Mp; p.k = ncols;
                 p.beta = 1.0; p.lower_out = 1; p.kscale = c->hbuf[b];
+                // Gaussian likelihood: h_n is the same constant -1/(2 s2) for every point (tsvgp.py:256-263 with the closed-form
+                // variational expectation), so it multiplies the product once instead of every B fragment
+                const bool const_h = c->lik.kind == LIK_GAUSSIAN && c->fuse_b && !grad;
+                if (const_h) { p.kscale = nullptr; p.alpha = fmin(-0.5 / c->lik.p0, -1e-8); }
                 const int nt = Mp / 128;
                 const int ks_here = c->ksplit < ncols / 256 ? c->ksplit : ncols / 256;
                 bool fused_b = false;
