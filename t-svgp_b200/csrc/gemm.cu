@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(GemmP p) {
 
     const int tj = blockIdx.x, ti = blockIdx.y;
     if (p.lower_out && tj > ti) return;
+    if (p.row_mod > 1 && ti % p.row_mod != p.row_rem) return;
     const int zdiv = p.C2 != nullptr ? 2 : p.ksplit;
     const int bz = blockIdx.z / zdiv, ks = blockIdx.z % zdiv;
     const double* Ag = p.A + (long)bz * p.sA;
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
 
     const int tj = blockIdx.x, ti = blockIdx.y;
     if (p.lower_out && tj > ti) return;
+    if (p.row_mod > 1 && ti % p.row_mod != p.row_rem) return;
     const int zdiv = p.C2 != nullptr ? 2 : p.ksplit;
     const int bz = blockIdx.z / zdiv, ks = blockIdx.z % zdiv;
     const double* Ag = p.A + (long)bz * p.sA;
@@ -387,6 +389,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
 __global__ void splitk_reduce_kernel(GemmP p) {
     const int tj = blockIdx.x, ti = blockIdx.y;
     if (p.lower_out && tj > ti) return;
+    if (p.row_mod > 1 && ti % p.row_mod != p.row_rem) return;
     // 256 threads, each handles a 64-element strip of the 128x128 tile
     for (int e = threadIdx.x; e < BM * BN / 2; e += blockDim.x) {
         const int r = e / (BN / 2), c = (e % (BN / 2)) * 2;

@@ -36,6 +36,9 @@ struct GemmP {
     // blockIdx.z == 1 contract [ksp, k) into C2 (same layout, same beta).  The z = 0 pieces are dispatched first; with
     // ksp / k = (T / P) / ceil(T / P) for T output tiles on P SMs, greedy in-order dispatch fills every SM equally.
     int ksp = 0; double* C2 = nullptr;
+    // Row-cyclic partition over ranks (distributed dense phase): only tile rows with ti % row_mod == row_rem are computed; the caller
+    // zeroes C first and sums the ranks' pieces with one all-reduce (adding zeros is exact, so every rank gets identical bits)
+    int row_mod = 1, row_rem = 0;
 };
 
 // Launch on `stream`. Returns cudaError_t as int (0 = ok), -1 for an unsupported combination.

@@ -74,6 +74,7 @@ struct tsvgp_ctx {
     // options
     long chunk_opt = 0;        // 0 = automatic
     int n_streams = 2;
+    int dist_min_m = 4096;     // distribute the dense M x M products over the ranks from this (padded) M upwards
     int fuse_b = 1;            // accumulate b += Kuf g inside the SYRK kernel instead of a separate mat-vec pass over the slab
     int balance = 1;           // split the SYRK's contraction in two pieces so that every SM gets equal work
     int cache_factors = 1;     // keep chol(K9) and the posterior factors between calls while their inputs are unchanged
@@ -191,6 +192,10 @@ namespace {
         if (!(p)) FAIL(TSVGP_ERR_CUDA, "device allocation failed (%s:%d)", __FILE__, __LINE__); \
     } while (0)
 
+int all_reduce(tsvgp_ctx* c, double* buf, size_t count);
+bool dist_active(const tsvgp_ctx* c);
+int dense_gemm(tsvgp_ctx* c, GemmP p, cudaStream_t s);
+
 bool is_device_ptr(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -275,16 +280,22 @@ int ensure_posterior(tsvgp_ctx* c) {
         p.A = c->K6; p.lda = ld; p.a_kc = 1;
         p.B = c->L2; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
         p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
-        LA(gemm_launch(p, s));
+        OK(dense_gemm(c, p, s));
     }
-    LA(set_scaled_identity_launch(c->Wm, ld, n, n, 1.0, 1.0, s));
     {   // W = I + L2^T X1 (lower tiles)
         GemmP p;
         p.A = c->L2; p.lda = ld; p.a_kc = 0; p.a_tri = 2;
         p.B = c->X1; p.ldb = ld; p.b_kc = 0;
         p.C = c->Wm; p.ldc = ld; p.m = p.n = p.k = n;
-        p.beta = 1.0; p.lower_out = 1;
-        LA(gemm_launch(p, s));
+        p.lower_out = 1;
+        if (dist_active(c)) {
+            OK(dense_gemm(c, p, s));
+            LA(add_diag_launch(c->Wm, ld, n, 1.0, s));
+        } else {
+            LA(set_scaled_identity_launch(c->Wm, ld, n, n, 1.0, 1.0, s));
+            p.beta = 1.0;
+            LA(gemm_launch(p, s));
+        }
     }
     // reverse Cholesky W = Uw Uw^T through the index flip J W J = Lr Lr^T
     LA(flip_sym_launch(c->Wm, c->Wf, ld, n, s));
@@ -299,7 +310,7 @@ int ensure_posterior(tsvgp_ctx* c) {
         p.B = c->V; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
         p.C = c->T; p.ldc = ld; p.m = p.n = p.k = n;
         p.lower_out = 1;
-        LA(gemm_launch(p, s));
+        OK(dense_gemm(c, p, s));
     }
     // alpha = lambda_1 - T T^T K6 lambda_1
     LA(gemv_n_launch(c->K6, ld, n, n, c->lam1, 1.0, 0.0, c->v1, s));
@@ -595,6 +606,23 @@ int all_reduce(tsvgp_ctx* c, double* buf, size_t count) {
     return TSVGP_OK;
 }
 
+// An M x M product of the dense phase.  With several ranks and a large M it is DISTRIBUTED: tile rows are dealt out cyclically,
+// each rank computes its rows into a zeroed C, and one all-reduce assembles the matrix on every rank (bit-identical everywhere:
+// each entry is one rank's value plus zeros).  Below `dist_min_m` the product is latency-bound and stays replicated.
+// Requires p.beta == 0 and every rank calling in the same order.
+bool dist_active(const tsvgp_ctx* c) { return c->world > 1 && c->Mp >= c->dist_min_m; }
+
+int dense_gemm(tsvgp_ctx* c, GemmP p, cudaStream_t s) {
+    if (!dist_active(c) || p.beta != 0.0) {
+        LA(gemm_launch(p, s));
+        return TSVGP_OK;
+    }
+    CU(cudaMemsetAsync(p.C, 0, sizeof(double) * (size_t)p.m * p.ldc, s));
+    p.row_mod = c->world; p.row_rem = c->rank;
+    LA(gemm_launch(p, s));
+    return all_reduce(c, p.C, (size_t)p.m * p.ldc);
+}
+
 // K9 = K + jitter I = C9 C9^T and C9^-1 (tsvgp.py:268-271), kept while kernel, Z and jitter are unchanged.  It depends on the
 // kernel matrix only, so it is factored on a SIDE stream (own workspace) while the main stream builds the posterior factors
 // from the sites; both chains are latency-bound, so running them side by side nearly halves the prepare phase.
@@ -677,7 +705,7 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale) {
             p.A = c->K9inv; p.lda = ld; p.a_kc = 1;
             p.B = B; p.ldb = ld; p.b_kc = 0;
             p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
-            LA(gemm_launch(p, s));
+            OK(dense_gemm(c, p, s));
         }
         {   // G2 = X1 K9^-1  (symmetric; lower tiles then mirrored)
             GemmP p;
@@ -685,7 +713,7 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale) {
             p.B = c->K9inv; p.ldb = ld; p.b_kc = 0;
             p.C = c->G2; p.ldc = ld; p.m = p.n = p.k = n;
             p.lower_out = 1;
-            LA(gemm_launch(p, s));
+            OK(dense_gemm(c, p, s));
         }
         LA(gemv_n_launch(c->K9inv, ld, n, n, bvec, 1.0, 0.0, c->v2, s));   // G1 = K9^-1 b
     } else {
@@ -695,7 +723,7 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale) {
             p.A = c->C9inv; p.lda = ld; p.a_kc = 0; p.a_tri = 2;
             p.B = Bw; p.ldb = ld; p.b_kc = 0;
             p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
-            LA(gemm_launch(p, s));
+            OK(dense_gemm(c, p, s));
         }
         {   // G2 = X1 C9^-1  (symmetric)
             GemmP p;
@@ -703,7 +731,7 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale) {
             p.B = c->C9inv; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
             p.C = c->G2; p.ldc = ld; p.m = p.n = p.k = n;
             p.lower_out = 1;
-            LA(gemm_launch(p, s));
+            OK(dense_gemm(c, p, s));
         }
         LA(gemv_t_launch(c->C9inv, ld, n, n, bvec, c->v2, c->gwork, s));   // G1 = C9^-T (C9^-1 Kuf g)
     }
@@ -716,8 +744,15 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale) {
         p.A = c->L2; p.lda = ld; p.a_kc = 1; p.a_tri = 1;
         p.B = c->L2; p.ldb = ld; p.b_kc = 1; p.b_tri = 1;
         p.C = c->P; p.ldc = ld; p.m = p.n = p.k = n;
-        p.alpha = 1.0 - lr; p.beta = 1.0; p.lower_out = 1;
-        LA(gemm_launch(p, s));
+        p.alpha = 1.0 - lr; p.lower_out = 1;
+        if (dist_active(c)) {   // (1 - lr) L2 L2^T assembled from the ranks' rows, then added
+            p.C = c->X2;
+            OK(dense_gemm(c, p, s));
+            LA(vadd_inplace_launch(c->P, c->X2, (long)n * ld, s));
+        } else {
+            p.beta = 1.0;
+            LA(gemm_launch(p, s));
+        }
     }
     LA(chol_lower(c->P, ld, n, c->dinv, c->info + INFO_P, s));
     // commit (skipped on the device if any variance was non-positive or a factorisation failed)
@@ -856,6 +891,7 @@ int tsvgp_set_option(tsvgp_ctx* c, const char* name, double value) {
     if (!strcmp(name, "streams")) { c->n_streams = value < 1 ? 1 : (value > MAXS ? MAXS : (int)value); return TSVGP_OK; }
     if (!strcmp(name, "route")) { c->route_opt = (int)value; c->k9_valid = false; return TSVGP_OK; }
     if (!strcmp(name, "route_cond_max")) { c->route_cond_max = value; return TSVGP_OK; }
+    if (!strcmp(name, "dist_min_m")) { c->dist_min_m = (int)value; return TSVGP_OK; }
     if (!strcmp(name, "fuse_b")) { c->fuse_b = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "balance")) { c->balance = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "profile")) { c->profile = value != 0.0; return TSVGP_OK; }

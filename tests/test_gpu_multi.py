@@ -31,11 +31,13 @@ def _case():
     return cfg, X, Y, Z, kernel, lik
 
 
-def _rank(rank, world, conn, out):
+def _rank(rank, world, conn, out, opts):
     sys.path.insert(0, ROOT)
     import tsvgp_b200 as tb
     cfg, X, Y, Z, kernel, lik = _case()
     m = tb.t_SVGP(kernel, lik, Z, num_data=50_010, device=rank)
+    for k, v in opts.items():
+        m.set_option(k, v)
     if rank == 0:
         uid = tb.comm_unique_id()
         for c in conn:
@@ -54,12 +56,15 @@ def _rank(rank, world, conn, out):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs >= 2 GPUs")
-def test_two_gpu_sharded_step_matches_single_gpu():
+@pytest.mark.parametrize("opts", [{}, {"dist_min_m": 128}], ids=["replicated_dense", "distributed_dense"])
+def test_two_gpu_sharded_step_matches_single_gpu(opts):
+    # distributed_dense: the M x M products of the dense phase are dealt out row-cyclically over the ranks and assembled by
+    # all-reduce (forced here at small M; by default from M >= 4096)
     import tsvgp_b200 as tb
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     a, b = ctx.Pipe()
-    procs = [ctx.Process(target=_rank, args=(0, 2, [a], out)), ctx.Process(target=_rank, args=(1, 2, b, out))]
+    procs = [ctx.Process(target=_rank, args=(0, 2, [a], out, opts)), ctx.Process(target=_rank, args=(1, 2, b, out, opts))]
     for p in procs:
         p.start()
     res = sorted([out.get(timeout=300) for _ in procs], key=lambda r: r[0])
