@@ -106,6 +106,7 @@ struct tsvgp_ctx {
     double *scal = nullptr;
     double *zaug = nullptr, *fuu = nullptr;   // M-step: [zs | 1 | zs^2] and the Kuu counterpart of F
     double *tmp2 = nullptr, *dinv2 = nullptr, *pv1 = nullptr, *pv2 = nullptr, *gwork2 = nullptr, *scal2 = nullptr;   // side-stream workspace (K9 factor)
+    bool k9inv_valid = false;  // K9inv = C9inv^T C9inv formed (on the main stream, on first use by the fused route)
     bool k9_pending = false;   // K9 work enqueued on the side stream, probe not read yet
     int* info = nullptr;    // [N_INFO]
     int* flags = nullptr;   // [2]
@@ -634,13 +635,15 @@ int start_k9(tsvgp_ctx* c, double jitter) {
     LA(copy_add_diag_launch(c->K, c->C9, c->Mp, c->Mp, jitter, s));
     LA(chol_lower(c->C9, c->Mp, c->Mp, c->dinv2, c->info + INFO_K9, s));
     LA(trtri_lower(c->C9, c->Mp, c->Mp, c->dinv2, c->C9inv, c->tmp2, s));
-    {   // K9^-1 = C9^-T C9^-1 (symmetric): the fused route then needs two M^3 products per step instead of four
+    c->k9inv_valid = false;
+    if (!dist_active(c)) {   // single rank / small M: form K9^-1 here, hidden behind the main stream's posterior preparation
         GemmP p;
         p.A = c->C9inv; p.lda = c->Mp; p.a_kc = 0; p.a_tri = 2;
         p.B = c->C9inv; p.ldb = c->Mp; p.b_kc = 0; p.b_tri = 2;
         p.C = c->K9inv; p.ldc = c->Mp; p.m = p.n = p.k = c->Mp; p.lower_out = 1;
         LA(gemm_launch(p, s));
         LA(mirror_lower_launch(c->K9inv, c->Mp, c->Mp, s));
+        c->k9inv_valid = true;
     }
     c->k9_valid = true;
     c->k9_jitter = jitter;
@@ -700,6 +703,15 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale) {
     const double* bad = c->stats[0] + mm + n + 1;
     LA(mirror_lower_launch(B, ld, n, s));
     if (c->route == ROUTE_FUSED) {
+        if (!c->k9inv_valid) {   // K9^-1 = C9^-T C9^-1 (symmetric): two M^3 products per step instead of four; kept with chol(K9)
+            GemmP p;
+            p.A = c->C9inv; p.lda = ld; p.a_kc = 0; p.a_tri = 2;
+            p.B = c->C9inv; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
+            p.C = c->K9inv; p.ldc = ld; p.m = p.n = p.k = n; p.lower_out = 1;
+            OK(dense_gemm(c, p, s));
+            LA(mirror_lower_launch(c->K9inv, ld, n, s));
+            c->k9inv_valid = true;
+        }
         {   // X1 = K9^-1 B
             GemmP p;
             p.A = c->K9inv; p.lda = ld; p.a_kc = 1;
