@@ -55,3 +55,18 @@ def test_elbo_gradients_match_oracle(name, n, M, num_data, ard, opts):
     ref.natgrad_step((X, Y), lr=cfg["lr"])
     assert relerr(dev.lambda_1, ref.lambda_1) < 1e-9 and relerr(dev.lambda_2, ref.lambda_2) < 1e-9
     dev.close()
+
+
+def test_variational_em_learns_hyperparameters():
+    # the E-step / M-step loop of the reference's callers (experiments/uci_regression.py:112-146) on the toy problem of
+    # docs/notebooks/regression_1D.py: the ELBO rises and the noise variance moves from 1.0 towards the true 0.09
+    import importlib.util, os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "vem_regression_1d.py")
+    spec = importlib.util.spec_from_file_location("vem_regression_1d", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    e0, e1, noise, rmse, trace = mod.main(n_iters=15, verbose=False)
+    assert e1 > e0 + 50.0
+    assert 0.05 < noise < 0.2
+    assert rmse < 0.25
+    assert trace[-1] > trace[0]
