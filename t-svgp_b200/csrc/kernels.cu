@@ -109,12 +109,18 @@ __global__ void __launch_bounds__(256, 2) kuf_kernel(double variance, const doub
                                                      const double* __restrict__ alpha, double* __restrict__ K, long ldk,
                                                      double* __restrict__ mu_part, long ldmu, int pad_identity,
                                                      double* __restrict__ Kp) {
-    __shared__ double sx[KUF_DC][128];
-    __shared__ __align__(16) double sz[KUF_ROWS][KUF_DC];
+    __shared__ __align__(128) double sx[KUF_DC][128];
+    __shared__ __align__(128) double sz[KUF_ROWS][KUF_DC];
     __shared__ double smu[4][128];
+    __shared__ __align__(8) uint64_t tma_bar;
     const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
     const long c0 = (long)blockIdx.x * 128;          // chunk-local first column of this tile
     const int ibase = blockIdx.y * KUF_ROWS, rbase = ty * 16;
+    if (tid == 0) {
+        mbar_init(&tma_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");   // make the initialised barrier visible to the async proxy
+    }
+    uint32_t tma_phase = 0;
 
     double dot[16][2];
 #pragma unroll
@@ -122,16 +128,36 @@ __global__ void __launch_bounds__(256, 2) kuf_kernel(double variance, const doub
 
     for (int dc = 0; dc < D; dc += KUF_DC) {
         const int dlen = min(KUF_DC, D - dc);
-        __syncthreads();
-        for (int e = tid; e < KUF_DC * 128; e += 256) {
-            const int d = e >> 7, c = e & 127;
-            sx[d][c] = d < dlen ? XsT[(long)(dc + d) * ldx + n0 + c0 + c] : 0.0;
+        __syncthreads();   // previous chunk consumed (and the barrier initialised)
+        // X and Z tiles are staged by TMA bulk copies (one 1 KB row of scaled coordinates per feature, one feature chunk per
+        // inducing row) whenever the pieces are 16-byte multiples; otherwise (odd D, e.g. D = 1) by plain loads
+        const bool tma_ok = (dlen & 1) == 0 && (D & 1) == 0;
+        if (tma_ok) {
+            if (tid < 32) {
+                if (tid == 0) mbar_expect_tx(&tma_bar, (uint32_t)(dlen * 128 * 8 + KUF_ROWS * dlen * 8));
+                __syncwarp();
+                for (int d = tid; d < dlen; d += 32) tma_bulk_g2s(&sx[d][0], XsT + (long)(dc + d) * ldx + n0 + c0, 128 * 8, &tma_bar);
+                for (int r = tid; r < KUF_ROWS; r += 32)
+                    tma_bulk_g2s(&sz[r][0], Zs + (long)(ibase + r) * D + dc, (uint32_t)(dlen * 8), &tma_bar);
+            }
+            if (dlen < KUF_DC) {   // zero the unused feature slots once (they are never overwritten by the bulk copies)
+                for (int e = tid; e < (KUF_DC - dlen) * 128; e += 256) sx[dlen + (e >> 7)][e & 127] = 0.0;
+                for (int e = tid; e < KUF_ROWS * (KUF_DC - dlen); e += 256) sz[e / (KUF_DC - dlen)][dlen + e % (KUF_DC - dlen)] = 0.0;
+            }
+            mbar_wait(&tma_bar, tma_phase);
+            tma_phase ^= 1;
+            __syncthreads();   // the zero fill above
+        } else {
+            for (int e = tid; e < KUF_DC * 128; e += 256) {
+                const int d = e >> 7, c = e & 127;
+                sx[d][c] = d < dlen ? XsT[(long)(dc + d) * ldx + n0 + c0 + c] : 0.0;
+            }
+            for (int e = tid; e < KUF_ROWS * KUF_DC; e += 256) {
+                const int r = e / KUF_DC, d = e % KUF_DC;
+                sz[r][d] = d < dlen ? Zs[(long)(ibase + r) * D + dc + d] : 0.0;
+            }
+            __syncthreads();
         }
-        for (int e = tid; e < KUF_ROWS * KUF_DC; e += 256) {
-            const int r = e / KUF_DC, d = e % KUF_DC;
-            sz[r][d] = d < dlen ? Zs[(long)(ibase + r) * D + dc + d] : 0.0;
-        }
-        __syncthreads();
         const int dl4 = (dlen + 3) & ~3;
         for (int d4 = 0; d4 < dl4; d4 += 4) {
             double xa[4], xb[4];
