@@ -64,6 +64,8 @@ TSVGP_API int tsvgp_set_option(tsvgp_ctx* ctx, const char* name, double value); 
  * "invalidate" (any value: drop every cached factor now),
  * "route" (0 = automatic, 1 = fused: B = Kuf diag(h) Kfu then K9^-1 B K9^-1 — 2 M^2 flops per point, rounding ~ eps cond(Kuu)^2;
  *          2 = whitened: C9^-1 Kuf first, as the reference's order A = K9^-1 Kuf — 3 M^2 flops per point, rounding ~ eps cond),
+ * "white" (1 = the whitened sibling t_SVGP_white, reference src/models/tsvgp_white.py: the second site argument of
+ *          set_sites / get_sites / get_lambda_2 is then the full matrix Lambda_2; switching resets the sites),
  * "dist_min_m" (multi-GPU: distribute the dense M x M products over the ranks from this padded M upwards; default 4096),
  * "streams" up to 4, "balance" / "fuse_b" (0 switches the balanced SYRK split / the fused b += Kuf g off, for A/B timing),
  * "route_cond_max" (automatic: fused while the power-iteration estimate of cond(Kuu + jitter I) is below this; default 1e4) */

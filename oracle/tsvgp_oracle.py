@@ -588,3 +588,120 @@ def elbo_gradients(model, data):
     if np.asarray(kernel.lengthscales).size == 1:
         d_ls = np.array([np.sum(d_ls)])
     return elbo, dict(variance=d_var, lengthscales=d_ls, Z=d_Z, likelihood=d_lik)
+
+
+# ----------------------------------------------------------------------------------------
+# Whitened sibling: t_SVGP_white (reference src/models/tsvgp_white.py) and its three helpers
+# (reference src/util.py:11-88, 239-291, 394-426).  Second "next" row of SURVEY 8f.
+# ----------------------------------------------------------------------------------------
+def conditional_from_precision_sites_white(Kuu_, Kff, Kuf_, l, L2, jitter=1e-9):
+    """reference src/util.py:11-88 (L2 given): mean [N, L], cov [N, L]."""
+    M = Kuu_.shape[-1]
+    Id = np.eye(M)
+    LA = cholesky(Kuu_)
+    tmp2 = triangular_solve(LA, Kuf_)
+    means, covs = [], []
+    for i in range(L2.shape[0]):
+        LR = cholesky(L2[i] + Kuu_ + Id * jitter)
+        tmp1 = triangular_solve(LR, Kuf_)
+        covs.append(Kff[:, 0] - (np.sum(np.square(tmp2), axis=0) - np.sum(np.square(tmp1), axis=0)))
+        means.append(Kuf_.T @ cholesky_solve(LR, l[:, i]))
+    return np.stack(means, -1), np.stack(covs, -1)
+
+
+def kl_from_precision_sites_white(A, l, L2):
+    """reference src/util.py:239-291 (L2 given)."""
+    M = A.shape[-1]
+    LA = cholesky(A)
+    kl = 0.0
+    for i in range(L2.shape[0]):
+        LR = cholesky(L2[i] + A)
+        log_det = np.sum(np.log(np.square(np.diag(LR)))) - np.sum(np.log(np.square(np.diag(LA))))
+        tmp = triangular_solve(LR, LA)
+        trace_plus_const = np.sum(np.square(tmp)) - M
+        mahalanobis = np.sum(np.square(LA.T @ cholesky_solve(LR, l[:, i])))
+        kl += 0.5 * (log_det + trace_plus_const + mahalanobis)
+    return kl
+
+
+def posterior_from_dense_site_white(K, lambda_1, lambda_2, jitter=1e-9):
+    """reference src/util.py:394-426."""
+    M = K.shape[-1]
+    Id = np.eye(M)
+    m_q = np.empty_like(lambda_1)
+    chol_S = np.empty_like(lambda_2)
+    for i in range(lambda_2.shape[0]):
+        LR = cholesky(K + lambda_2[i] + Id * jitter)
+        iLRK = triangular_solve(LR, K)
+        chol_S[i] = cholesky(iLRK.T @ iLRK)
+        m_q[:, i] = K @ cholesky_solve(LR, lambda_1[:, i])
+    return m_q, chol_S
+
+
+class OracleTSVGPWhite:
+    """The reference's ``t_SVGP_white`` (src/models/tsvgp_white.py:23-246) on NumPy arrays."""
+
+    def __init__(self, kernel, likelihood, inducing_variable, *, mean_function=None, num_latent_gps=1, lambda_1=None,
+                 lambda_2=None, num_data=None):
+        self.kernel, self.likelihood, self.mean_function, self.num_data = kernel, likelihood, mean_function, num_data
+        self.inducing_variable = inducing_variable if hasattr(inducing_variable, "Z") else InducingPoints(inducing_variable)
+        self.num_inducing = M = self.inducing_variable.num_inducing
+        self.num_latent_gps = num_latent_gps
+        if lambda_2 is None:                                                  # :79-85
+            lambda_2 = np.array([np.eye(M) * 1e-10 for _ in range(num_latent_gps)])
+        else:
+            assert lambda_2.ndim == 3
+            self.num_latent_gps = lambda_2.shape[0]
+        self.lambda_1 = np.zeros((M, self.num_latent_gps)) if lambda_1 is None else np.array(lambda_1, dtype=np.float64)
+        self.lambda_2 = np.array(lambda_2, dtype=np.float64)
+
+    def _mean_fn(self, X):
+        return 0.0 if self.mean_function is None else np.asarray(self.mean_function(X), dtype=np.float64).reshape(X.shape[0], -1)
+
+    def get_mean_chol_cov_inducing_posterior(self):                           # :99-109
+        return posterior_from_dense_site_white(Kuu(self.inducing_variable, self.kernel, jitter=DEFAULT_JITTER), self.lambda_1, self.lambda_2)
+
+    def prior_kl(self):                                                       # :116-120
+        return kl_from_precision_sites_white(Kuu(self.inducing_variable, self.kernel, jitter=DEFAULT_JITTER), self.lambda_1, self.lambda_2)
+
+    def predict_f(self, Xnew, full_cov=False, full_output_cov=False):         # :122-132
+        Xnew = np.asarray(Xnew, dtype=np.float64)
+        K_uu = Kuu(self.inducing_variable, self.kernel, jitter=DEFAULT_JITTER)
+        K_uf = Kuf(self.inducing_variable, self.kernel, Xnew)
+        K_ff = self.kernel.K_diag(Xnew)[..., None]
+        mu, var = conditional_from_precision_sites_white(K_uu, K_ff, K_uf, self.lambda_1, self.lambda_2)
+        if not np.all(var > 0):
+            raise FloatingPointError("predict_f: non-positive predictive variance")
+        return mu + self._mean_fn(Xnew), var
+
+    def elbo(self, data):                                                     # :162-177
+        X, Y = (np.asarray(a, dtype=np.float64) for a in data)
+        kl = self.prior_kl()
+        f_mean, f_var = self.predict_f(X)
+        var_exp = self.likelihood.variational_expectations(f_mean, f_var, Y)
+        scale_ = self.num_data / X.shape[0] if self.num_data is not None else 1.0
+        return np.sum(var_exp) * scale_ - kl
+
+    def compute_data_natural_params(self, data, jitter=1e-9):                 # :183-212 (no clipping of the variance gradient here)
+        X, Y = (np.asarray(a, dtype=np.float64) for a in data)
+        mean, var = self.predict_f(X)
+        meanZ, _ = self.predict_f(np.asarray(self.inducing_variable.Z))
+        _, g_mean, g_var = self.likelihood.ve_and_grads(mean, var, Y)
+        M = self.num_inducing
+        K_uu = Kuu(self.inducing_variable, self.kernel)
+        K_uf = Kuf(self.inducing_variable, self.kernel, X)
+        chol_Kuu = cholesky(K_uu + np.eye(M) * jitter)
+        A = cholesky_solve(chol_Kuu, K_uf).T
+        G1 = A.T @ g_mean
+        G2 = np.stack([(A * g_var[:, l:l + 1]).T @ A for l in range(g_var.shape[1])])
+        return gradient_transformation_mean_var_to_expectation(meanZ, (G1, G2))
+
+    def natgrad_step(self, dataset, lr=0.1, jitter=1e-9):                     # :215-246
+        X, Y = dataset
+        grad_mu = self.compute_data_natural_params((X, Y))
+        K_uu = Kuu(self.inducing_variable, self.kernel)
+        scale_ = self.num_data / np.asarray(X).shape[0] if self.num_data is not None else 1.0
+        lambda_2 = -0.5 * self.lambda_2
+        self.lambda_1 = (1.0 - lr) * self.lambda_1 + lr * scale_ * K_uu @ grad_mu[0]
+        lambda_2 = (1.0 - lr) * lambda_2 + lr * scale_ * np.stack([K_uu @ grad_mu[1][l] @ K_uu for l in range(lambda_2.shape[0])])
+        self.lambda_2 = -2.0 * lambda_2

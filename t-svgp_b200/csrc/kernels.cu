@@ -259,6 +259,11 @@ __global__ void __launch_bounds__(256) point_stats_kernel(LikSpec lk, PointArgs 
         double mu = 0.0, q = 0.0;
         for (int p = 0; p < a.n_mu_part; ++p) mu += a.mu_part[(long)p * a.ldmu + c];
         for (int p = 0; p < a.n_q_part; ++p) q += a.q_part[(long)p * a.ldq + c];
+        if (a.q2_part) {
+            double q2 = 0.0;
+            for (int p = 0; p < a.n_q_part; ++p) q2 += a.q2_part[(long)p * a.ldq + c];
+            q -= q2;   // var = k(x,x) - |LA^-1 k|^2 + |LR^-1 k|^2   (reference util.py:83-85)
+        }
         const double mean = mu + (a.mean_off ? a.mean_off[c] : 0.0);
         const double var = a.kdiag - q;
         if (valid && !(var > 0.0)) atomicOr(a.flags, 1);
@@ -835,6 +840,23 @@ int update_lambda1_launch(double* l1, const double* G1, const double* G2mZ, int 
     update_lambda1_kernel<<<(n + 255) / 256, 256, 0, s>>>(l1, G1, G2mZ, n, lr, scale, bad, info);
     return count_launch();
 }
+__global__ void lincomb_kernel(double* y, double a, const double* x1, double b, const double* x2, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = a * x1[i] + b * x2[i];
+}
+int lincomb_launch(double* y, double a, const double* x1, double b, const double* x2, int n, cudaStream_t s) {
+    lincomb_kernel<<<(n + 255) / 256, 256, 0, s>>>(y, a, x1, b, x2, n);
+    return count_launch();
+}
+__global__ void axpby_vec_guarded_kernel(double* y, const double* x, int n, double a, double b, const double* bad, const int* info) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((bad && bad[0] != 0.0) || (info && (info[0] | info[1] | info[2] | info[3]))) return;
+    if (i < n) y[i] = a * y[i] + b * x[i];
+}
+int axpby_vec_guarded_launch(double* y, const double* x, int n, double a, double b, const double* bad, const int* info, cudaStream_t s) {
+    axpby_vec_guarded_kernel<<<(n + 255) / 256, 256, 0, s>>>(y, x, n, a, b, bad, info);
+    return count_launch();
+}
 __global__ void vsub_kernel(const double* a, const double* b, double* y, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = a[i] - b[i];
@@ -902,6 +924,16 @@ __global__ void set_scaled_identity_kernel(double* A, long ld, int M, int n, dou
 int set_scaled_identity_launch(double* A, long ld, int M, int Mp, double v, double vpad, cudaStream_t s) {
     const int n = Mp;
     set_scaled_identity_kernel<<<EW_GRID(n), 0, s>>>(A, ld, M, Mp, v, vpad);
+    return count_launch();
+}
+__global__ void axpby_guarded_kernel(double* P, const double* X, long ld, int n, double a, double b, const double* bad, const int* info) {
+    EW_IJ;
+    if ((bad && bad[0] != 0.0) || (info && (info[0] | info[1] | info[2] | info[3]))) return;
+    P[(long)i * ld + j] = a * P[(long)i * ld + j] + b * X[(long)i * ld + j];
+}
+int axpby_guarded_launch(double* P, const double* X, long ld, int M, double a, double b, const double* bad, const int* info, cudaStream_t s) {
+    const int n = M;
+    axpby_guarded_kernel<<<EW_GRID(n), 0, s>>>(P, X, ld, n, a, b, bad, info);
     return count_launch();
 }
 __global__ void vadd_inplace_kernel(double* dst, const double* src, long n) {

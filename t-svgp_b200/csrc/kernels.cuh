@@ -30,7 +30,8 @@ int kuf_launch(int kind, double variance, const double* XsT, long ldx, const dou
 
 struct PointArgs {
     const double* mu_part; int n_mu_part; long ldmu;   // partial means   [n_mu_part][ldmu]
-    const double* q_part; int n_q_part; long ldq;      // partial |T^T k|^2 [n_q_part][ldq]
+    const double* q_part; int n_q_part; long ldq;      // partial |T^T k|^2 [n_q_part][ldq]   (subtracted from k(x,x))
+    const double* q2_part = nullptr;                   // optional second set, same shape, ADDED (whitened sibling: + |LR^-1 k|^2)
     const double* y;            // [ncols] (chunk-local pointer) or null (predict)
     const double* mean_off;     // [ncols] mean_function(X) or null
     double kdiag;               // k(x,x) = kernel variance
@@ -79,6 +80,9 @@ int sum_launch(const double* x, long n, double* out, cudaStream_t s);
 // lambda_1 <- (1-lr) lambda_1 + lr*scale*(G1 - 2 G2mZ)
 int update_lambda1_launch(double* l1, const double* G1, const double* G2mZ, int n, double lr, double scale, const double* bad,
                           const int* info, cudaStream_t s);
+// y = a x1 + b x2 ;  guarded y = a y + b x (skipped on the device after a failed step)
+int lincomb_launch(double* y, double a, const double* x1, double b, const double* x2, int n, cudaStream_t s);
+int axpby_vec_guarded_launch(double* y, const double* x, int n, double a, double b, const double* bad, const int* info, cudaStream_t s);
 // y = a - b
 int vsub_launch(const double* a, const double* b, double* y, int n, cudaStream_t s);
 
@@ -88,6 +92,8 @@ int logdiag_launch(const double* A, long lda, int n, double* out, cudaStream_t s
 int init_update_launch(const double* G, double* P, long ld, int M, int Mp, double coef, double jitter, cudaStream_t s);
 int set_scaled_identity_launch(double* A, long ld, int M, int Mp, double v, double vpad, cudaStream_t s);
 int probe_vector_launch(double* v, int M, int Mp, cudaStream_t s);
+// P = a P + b X on [0,M)^2 unless *bad != 0 or any info slot != 0 (guarded commit of the whitened sibling's Lambda_2)
+int axpby_guarded_launch(double* P, const double* X, long ld, int M, double a, double b, const double* bad, const int* info, cudaStream_t s);
 int vadd_inplace_launch(double* dst, const double* src, long n, cudaStream_t s);
 int stats_tail_launch(const double* ve_blocks, long nblocks, const int* flags, const double* aux, double* out, cudaStream_t s);
 // M-step gradient helpers (see tsvgp_elbo_grad)

@@ -104,6 +104,9 @@ struct tsvgp_ctx {
     double *stats2[MAXS] = {};  // second B accumulator per stream: the split-off k piece of the balanced SYRK
     double *alpha = nullptr, *mZ = nullptr, *mq = nullptr, *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *gwork = nullptr;
     double *scal = nullptr;
+    int white = 0;             // 1: the whitened sibling t_SVGP_white (reference src/models/tsvgp_white.py): L2 holds the full Lambda_2
+    double *C6 = nullptr, *C6inv = nullptr;   // chol(K6) and its inverse (whitened sibling)
+    bool c6_valid = false, wpost_valid = false, wkl_valid = false;
     double *zaug = nullptr, *fuu = nullptr;   // M-step: [zs | 1 | zs^2] and the Kuu counterpart of F
     double *tmp2 = nullptr, *dinv2 = nullptr, *pv1 = nullptr, *pv2 = nullptr, *gwork2 = nullptr, *scal2 = nullptr;   // side-stream workspace (K9 factor)
     bool k9inv_valid = false;  // K9inv = C9inv^T C9inv formed (on the main stream, on first use by the fused route)
@@ -141,7 +144,7 @@ struct tsvgp_ctx {
     int chunk_route = 0;
     int slab_streams = 0;
     double *wslab[MAXS] = {};
-    double *slab[MAXS] = {}, *mu_part[MAXS] = {}, *q_part[MAXS] = {}, *gbuf[MAXS] = {}, *hbuf[MAXS] = {};
+    double *slab[MAXS] = {}, *mu_part[MAXS] = {}, *q_part[MAXS] = {}, *q2_part[MAXS] = {}, *gbuf[MAXS] = {}, *hbuf[MAXS] = {};
     double* ve_blocks = nullptr;
     long ve_cap = 0;
     double *kpslab[MAXS] = {}, *vslab[MAXS] = {}, *uslab[MAXS] = {}, *xaug[MAXS] = {}, *fpart[MAXS] = {}, *facc[MAXS] = {};   // M-step gradient workspace
@@ -194,6 +197,10 @@ namespace {
     } while (0)
 
 int all_reduce(tsvgp_ctx* c, double* buf, size_t count);
+int ensure_posterior_white(tsvgp_ctx* c);
+int ensure_kl_terms_white(tsvgp_ctx* c);
+int dense_update_white(tsvgp_ctx* c, double lr, double scale);
+double kl_white_from_scalars(const tsvgp_ctx* c, const double* sc);
 bool dist_active(const tsvgp_ctx* c);
 int dense_gemm(tsvgp_ctx* c, GemmP p, cudaStream_t s);
 
@@ -224,18 +231,21 @@ int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     NEED(c->v3 = p.get(mp)); NEED(c->gwork = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal = p.get(N_SCAL));
     NEED(c->info = (int*)p.get(N_INFO)); NEED(c->flags = (int*)p.get(2));
     NEED(c->zaug = p.get(mp * 128)); NEED(c->fuu = p.get(mp * 128));
+    NEED(c->C6 = p.get(mm)); NEED(c->C6inv = p.get(mm));
+    c->c6_valid = c->wpost_valid = c->wkl_valid = false;
     NEED(c->tmp2 = p.get((size_t)((c->Mp / 128 + 1) / 2) * 128 * mp)); NEED(c->dinv2 = p.get((size_t)(c->Mp / 128) * 128 * 128));
     NEED(c->pv1 = p.get(mp)); NEED(c->pv2 = p.get(mp)); NEED(c->gwork2 = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal2 = p.get(N_SCAL));
-    c->sites_set = c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = false;
+    c->sites_set = c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = c->c6_valid = c->wpost_valid = c->wkl_valid = false;
     c->chunk = 0;   // slab workspace depends on Mp
     return TSVGP_OK;
 }
 
 int default_sites(tsvgp_ctx* c) {   // tsvgp.py:174-180 : lambda_1 = 0, lambda_2_sqrt = -1e-10 I
     CU(cudaMemsetAsync(c->lam1, 0, sizeof(double) * c->Mp, c->s_main));
-    LA(set_scaled_identity_launch(c->L2, c->Mp, c->M, c->Mp, -1e-10, 0.0, c->s_main));
+    // tsvgp.py:174-180 : lambda_2_sqrt = -1e-10 I ;  tsvgp_white.py:79-85 : lambda_2 = +1e-10 I
+    LA(set_scaled_identity_launch(c->L2, c->Mp, c->M, c->Mp, c->white ? 1e-10 : -1e-10, 0.0, c->s_main));
     c->sites_set = true;
-    c->post_valid = c->kl_valid = false;
+    c->post_valid = c->kl_valid = c->wpost_valid = c->wkl_valid = false;
     return TSVGP_OK;
 }
 
@@ -263,13 +273,14 @@ int ensure_kuu(tsvgp_ctx* c) {
                   c->K, c->Mp, nullptr, 0, 1, s));
     LA(copy_add_diag_launch(c->K, c->K6, c->Mp, c->Mp, GPFLOW_DEFAULT_JITTER, s));
     c->kuu_valid = true;
-    c->post_valid = c->kl_valid = c->k9_valid = false;
+    c->post_valid = c->kl_valid = c->k9_valid = c->c6_valid = c->wpost_valid = c->wkl_valid = false;
     return TSVGP_OK;
 }
 
 // Posterior factors of q(u) from the dense sites (replaces posterior_from_dense_site, util.py:349-391, and the
 // conditional's use of it, tsvgp.py:102-112): T, alpha, mZ, log det W.
 int ensure_posterior(tsvgp_ctx* c) {
+    if (c->white) return ensure_posterior_white(c);
     OK(ensure_kuu(c));
     if (c->post_valid && c->cache_factors) return TSVGP_OK;
     if (!c->sites_set) OK(default_sites(c));
@@ -330,6 +341,7 @@ int ensure_posterior(tsvgp_ctx* c) {
 // KL[q(u) || p(u)] = 1/2 ( m^T alpha - tr(Q K6) + log det W )   (gauss_kl with K6; tsvgp.py:65-70). Scalars stay on the
 // device until the caller's final synchronisation.
 int ensure_kl_terms(tsvgp_ctx* c) {
+    if (c->white) return ensure_kl_terms_white(c);
     if (c->kl_valid && c->cache_factors) return TSVGP_OK;
     cudaStream_t s = c->s_main;
     const int n = c->Mp;
@@ -347,7 +359,112 @@ int ensure_kl_terms(tsvgp_ctx* c) {
     return TSVGP_OK;
 }
 
-double kl_from_scalars(const double* sc) { return 0.5 * (sc[SC_M_ALPHA] - sc[SC_TR_QK] + 2.0 * sc[SC_LOGDIAG_W]); }
+double kl_value(const tsvgp_ctx* c, const double* sc) {
+    if (c->white) return kl_white_from_scalars(c, sc);
+    return 0.5 * (sc[SC_M_ALPHA] - sc[SC_TR_QK] + 2.0 * sc[SC_LOGDIAG_W]);
+}
+
+
+// =====================================================================================================================
+// Whitened sibling t_SVGP_white (reference src/models/tsvgp_white.py; util.py:11-88, 239-291, 394-426).  Sites (lambda_1, P) with
+// P = Lambda_2 a full symmetric matrix kept in c->L2.  R = P + K6 + 1e-9 I = LR LR^T, K6 = LA LA^T:
+//   mu_n = k_n^T R^-1 lambda_1 ;  v_n = k_nn - |LA^-1 k_n|^2 + |LR^-1 k_n|^2       (two triangular DMMA products per slab)
+// The statistics (b, B, G1, G2) are those of the plain model; the update needs no factorisation:
+//   lambda_1 <- (1-lr) lambda_1 + lr s K (G1 - 2 G2 mZ) ;  P <- (1-lr) P - 2 lr s K G2 K
+// =====================================================================================================================
+int ensure_posterior_white(tsvgp_ctx* c) {
+    OK(ensure_kuu(c));
+    if (!c->sites_set) OK(default_sites(c));
+    cudaStream_t s = c->s_main;
+    const int n = c->Mp;
+    const long ld = n;
+    if (!c->c6_valid || !c->cache_factors) {   // LA = chol(K6), LA^-1 : kernel only
+        CU(cudaMemcpyAsync(c->C6, c->K6, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, s));
+        LA(chol_lower(c->C6, ld, n, c->dinv, c->info + INFO_W, s));
+        LA(trtri_lower(c->C6, ld, n, c->dinv, c->C6inv, c->tmp, s));
+        c->c6_valid = true;
+    }
+    if (c->wpost_valid && c->cache_factors) return TSVGP_OK;
+    // R = P + K6 + 1e-9 I -> Wm = LR, T = LR^-1     (util.py:74-76, jitter default 1e-9)
+    CU(cudaMemcpyAsync(c->Wm, c->K6, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, s));
+    LA(vadd_inplace_launch(c->Wm, c->L2, (long)n * ld, s));
+    LA(add_diag_launch(c->Wm, ld, n, 1e-9, s));
+    LA(chol_lower(c->Wm, ld, n, c->dinv, c->info + INFO_S, s));
+    LA(trtri_lower(c->Wm, ld, n, c->dinv, c->T, c->tmp, s));
+    // alpha = R^-1 lambda_1 ; mZ = K alpha (predict_f(Z), un-jittered Kuf) ; m_q = K6 alpha
+    LA(gemv_n_launch(c->T, ld, n, n, c->lam1, 1.0, 0.0, c->v1, s));
+    LA(gemv_t_launch(c->T, ld, n, n, c->v1, c->alpha, c->gwork, s));
+    LA(gemv_n_launch(c->K, ld, n, n, c->alpha, 1.0, 0.0, c->mZ, s));
+    if (c->has_meanZ) LA(vadd_inplace_launch(c->mZ, c->meanZ_off, c->M, s));
+    LA(gemv_n_launch(c->K6, ld, n, n, c->alpha, 1.0, 0.0, c->mq, s));
+    c->wpost_valid = true;
+    c->wkl_valid = false;
+    return TSVGP_OK;
+}
+
+// kl_from_precision_sites_white (util.py:239-291) with A = K6 and R0 = P + K6 (no extra jitter here): scalars
+//   SC_LOGDIAG_W = sum log diag LR0 - sum log diag LA ; SC_TR_QK = |LR0^-1 LA|_F^2 ; SC_M_ALPHA = |LA^T R0^-1 lambda_1|^2
+int ensure_kl_terms_white(tsvgp_ctx* c) {
+    if (c->wkl_valid && c->cache_factors) return TSVGP_OK;
+    cudaStream_t s = c->s_main;
+    const int n = c->Mp;
+    const long ld = n;
+    CU(cudaMemcpyAsync(c->Wf, c->K6, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, s));
+    LA(vadd_inplace_launch(c->Wf, c->L2, (long)n * ld, s));
+    LA(chol_lower(c->Wf, ld, n, c->dinv, c->info + INFO_P, s));
+    LA(trtri_lower(c->Wf, ld, n, c->dinv, c->V, c->tmp, s));       // V = LR0^-1
+    LA(logdiag_launch(c->Wf, ld, n, c->scal + SC_LOGDIAG_W, s));
+    LA(logdiag_launch(c->C6, ld, n, c->scal + SC_PK0, s));
+    {   // X1 = LR0^-1 LA  (lower x lower)
+        GemmP p;
+        p.A = c->V; p.lda = ld; p.a_kc = 1; p.a_tri = 1;
+        p.B = c->C6; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
+        p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
+        CU(cudaMemsetAsync(c->X1, 0, sizeof(double) * (size_t)n * ld, s));
+        p.lower_out = 1;
+        LA(gemm_launch(p, s));
+    }
+    LA(matdot_launch(c->X1, c->X1, ld, n, c->scal + SC_TR_QK, s));
+    LA(gemv_n_launch(c->V, ld, n, n, c->lam1, 1.0, 0.0, c->v1, s));
+    LA(gemv_t_launch(c->V, ld, n, n, c->v1, c->v2, c->gwork, s));   // R0^-1 lambda_1
+    LA(gemv_t_launch(c->C6, ld, n, n, c->v2, c->v3, c->gwork, s));  // LA^T (.)
+    LA(dot_launch(c->v3, c->v3, n, c->scal + SC_M_ALPHA, s));
+    c->wkl_valid = true;
+    return TSVGP_OK;
+}
+
+double kl_white_from_scalars(const tsvgp_ctx* c, const double* sc) {
+    return 0.5 * (2.0 * (sc[SC_LOGDIAG_W] - sc[SC_PK0]) + sc[SC_TR_QK] - (double)c->Mp + sc[SC_M_ALPHA]);
+}
+
+// tsvgp_white.py:215-246 after the statistics are complete in stats[0]
+int dense_update_white(tsvgp_ctx* c, double lr, double scale) {
+    cudaStream_t s = c->s_main;
+    const int n = c->Mp;
+    const long ld = n;
+    const size_t mm = (size_t)n * n;
+    const double* bad = c->stats[0] + mm + n + 1;
+    // v3 = K (G1 - 2 G2 mZ) : v2 = G1, v3 = G2 mZ were left by the shared part of the update
+    LA(lincomb_launch(c->v1, 1.0, c->v2, -2.0, c->v3, n, s));          // g0 = G1 - 2 G2 mZ   (util.py:438)
+    LA(gemv_n_launch(c->K, ld, n, c->M, c->v1, 1.0, 0.0, c->mq, s));   // K g0 (un-jittered Kuu, tsvgp_white.py:227,241)
+    {   // X1 = K G2 ; X2 = X1 K (symmetric)
+        GemmP p;
+        p.A = c->K; p.lda = ld; p.a_kc = 1;
+        p.B = c->G2; p.ldb = ld; p.b_kc = 0;
+        p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
+        OK(dense_gemm(c, p, s));
+        GemmP q;
+        q.A = c->X1; q.lda = ld; q.a_kc = 1;
+        q.B = c->K; q.ldb = ld; q.b_kc = 0;
+        q.C = c->X2; q.ldc = ld; q.m = q.n = q.k = n; q.lower_out = 1;
+        OK(dense_gemm(c, q, s));
+        LA(mirror_lower_launch(c->X2, ld, n, s));
+    }
+    // commit (skipped on the device after a non-positive variance or a failed factorisation)
+    LA(axpby_guarded_launch(c->L2, c->X2, ld, c->M, 1.0 - lr, -2.0 * lr * scale, bad, c->info, s));
+    LA(axpby_vec_guarded_launch(c->lam1, c->mq, c->M, 1.0 - lr, lr * scale, bad, c->info, s));
+    return TSVGP_OK;
+}
 
 // ---- data ----------------------------------------------------------------------------------------------------------
 int ensure_xs(tsvgp_ctx* c) {
@@ -390,6 +507,7 @@ int ensure_slabs(tsvgp_ctx* c, long n_points, bool need_grad = false) {
         if (need_w) NEED(c->wslab[s] = p.get((size_t)c->Mp * nc));
         NEED(c->mu_part[s] = p.get((size_t)(c->Mp / 64) * nc));
         NEED(c->q_part[s] = p.get((size_t)(c->Mp / 128) * nc));
+        NEED(c->q2_part[s] = p.get((size_t)(c->Mp / 128) * nc));
         NEED(c->gbuf[s] = p.get(nc));
         NEED(c->hbuf[s] = p.get(nc));
     }
@@ -478,7 +596,7 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
         LA(kuf_launch(c->kern_kind, c->kern_var, XsT, ldx, x2, n0, N, ncols, c->Zs, c->z2, c->M, Mp, c->D, c->alpha, c->slab[b],
                       nc, c->mu_part[b], nc, 0, s, grad ? c->kpslab[b] : nullptr));
         mark(s);
-        {   // (b) |T^T k_n|^2 : upper-triangular T^T times the slab, reduced to column norms in the epilogue
+        if (!c->white) {   // (b) |T^T k_n|^2 : upper-triangular T^T times the slab, reduced to column norms in the epilogue
             GemmP p;
             p.A = c->T; p.lda = Mp; p.a_kc = 0; p.a_tri = 2;
             p.B = c->slab[b]; p.ldb = nc; p.b_kc = 0;
@@ -486,18 +604,28 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
             p.epilogue = grad ? EPI_STORE_COLNORM : EPI_COLNORM; p.norm_out = c->q_part[b]; p.ldn = nc;
             if (grad) { p.C = c->vslab[b]; p.ldc = nc; }   // the M-step also needs V = T^T K itself
             LA(gemm_launch(p, s));
+        } else {           // (b') whitened sibling: |LA^-1 k_n|^2 and |LR^-1 k_n|^2, two lower-triangular products (util.py:78-85)
+            for (int which = 0; which < 2; ++which) {
+                GemmP p;
+                p.A = which == 0 ? c->C6inv : c->T; p.lda = Mp; p.a_kc = 1; p.a_tri = 1;
+                p.B = c->slab[b]; p.ldb = nc; p.b_kc = 0;
+                p.m = Mp; p.n = ncols; p.k = Mp;
+                p.epilogue = EPI_COLNORM; p.norm_out = which == 0 ? c->q_part[b] : c->q2_part[b]; p.ldn = nc;
+                LA(gemm_launch(p, s));
+            }
         }
         mark(s);
         {   // (c) marginals -> likelihood expectations and gradients
             PointArgs a;
             a.mu_part = c->mu_part[b]; a.n_mu_part = Mp / 64; a.ldmu = nc;
             a.q_part = c->q_part[b]; a.n_q_part = Mp / 128; a.ldq = nc;
+            a.q2_part = c->white ? c->q2_part[b] : nullptr;
             a.y = y ? y + n0 : nullptr;
             a.mean_off = mean_off ? mean_off + n0 : nullptr;
             a.kdiag = c->kern_var;
             a.n_valid = nvalid; a.ncols = ncols;
             a.g = stats ? c->gbuf[b] : nullptr; a.h = stats ? c->hbuf[b] : nullptr;
-            a.clip = grad ? 0 : 1;
+            a.clip = (grad || c->white) ? 0 : 1;   // tsvgp_white.py:183-212 does not clip the variance gradient
             a.aux_blocks = grad ? c->aux_blocks + 2 * ci * vstride : nullptr;
             a.mean_out = mean_out ? mean_out + n0 : nullptr; a.var_out = var_out ? var_out + n0 : nullptr;
             a.ve_blocks = c->ve_blocks + ci * vstride;
@@ -749,6 +877,7 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale) {
     }
     LA(mirror_lower_launch(c->G2, ld, n, s));
     LA(gemv_n_launch(c->G2, ld, n, n, c->mZ, 1.0, 0.0, c->v3, s));
+    if (c->white) return dense_update_white(c, lr, scale);
     // P = (1-lr) L2 L2^T - 2 lr scale G2 + jitter I                                     tsvgp.py:293-300
     LA(init_update_launch(c->G2, c->P, ld, c->M, n, -2.0 * lr * scale, jitter, s));
     if (lr != 1.0) {
@@ -774,12 +903,14 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale) {
 }
 
 int check_info(tsvgp_ctx* c, const int* info_h) {
-    static const char* what[N_INFO] = {"I + L2^T K6 L2 (posterior)", "Kuu + jitter I", "-2 lambda_2 + jitter I (site update)", "S_q"};
+    static const char* what[N_INFO] = {"I + L2^T K6 L2 (posterior; Kuu + 1e-6 I for the whitened sibling)", "Kuu + jitter I",
+                                       "-2 lambda_2 + jitter I (site update; Lambda_2 + Kuu or S_q for the whitened sibling)",
+                                       "S_q (Lambda_2 + Kuu + 1e-9 I for the whitened sibling)"};
     for (int i = 0; i < N_INFO; ++i)
         if (info_h[i]) {
             c->last_info = info_h[i];
             if (i == INFO_K9) c->k9_valid = false;
-            c->post_valid = c->kl_valid = false;
+            c->post_valid = c->kl_valid = c->wpost_valid = c->wkl_valid = false;
             FAIL(TSVGP_ERR_NOT_POSITIVE_DEFINITE, "Cholesky of %s failed at pivot %d", what[i], info_h[i]);
         }
     return TSVGP_OK;
@@ -903,12 +1034,18 @@ int tsvgp_set_option(tsvgp_ctx* c, const char* name, double value) {
     if (!strcmp(name, "streams")) { c->n_streams = value < 1 ? 1 : (value > MAXS ? MAXS : (int)value); return TSVGP_OK; }
     if (!strcmp(name, "route")) { c->route_opt = (int)value; c->k9_valid = false; return TSVGP_OK; }
     if (!strcmp(name, "route_cond_max")) { c->route_cond_max = value; return TSVGP_OK; }
+    if (!strcmp(name, "white")) {   // switch the context to the whitened sibling model (resets the sites to its defaults)
+        c->white = value != 0.0;
+        c->sites_set = false;
+        c->post_valid = c->kl_valid = c->wpost_valid = c->wkl_valid = false;
+        return TSVGP_OK;
+    }
     if (!strcmp(name, "dist_min_m")) { c->dist_min_m = (int)value; return TSVGP_OK; }
     if (!strcmp(name, "fuse_b")) { c->fuse_b = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "balance")) { c->balance = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "profile")) { c->profile = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "cache_factors")) { c->cache_factors = value != 0.0; return TSVGP_OK; }
-    if (!strcmp(name, "invalidate")) { c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = false; return TSVGP_OK; }
+    if (!strcmp(name, "invalidate")) { c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = c->c6_valid = c->wpost_valid = c->wkl_valid = false; return TSVGP_OK; }
     FAIL(TSVGP_ERR_INVALID, "unknown option '%s'", name);
 }
 
@@ -920,7 +1057,7 @@ int tsvgp_set_kernel(tsvgp_ctx* c, int kind, double variance, const double* leng
         if (!(lengthscales[i] > 0.0)) FAIL(TSVGP_ERR_INVALID, "lengthscales must be positive");
     c->kern_kind = kind; c->kern_var = variance;
     c->ls_host.assign(lengthscales, lengthscales + n_ls);
-    c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = false;
+    c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = c->c6_valid = c->wpost_valid = c->wkl_valid = false;
     c->xs_valid = false;
     return TSVGP_OK;
 }
@@ -963,7 +1100,7 @@ int tsvgp_set_inducing(tsvgp_ctx* c, const double* Z, int M, int D, const double
         CU(cudaMemcpyAsync(c->meanZ_off, mean_Z, sizeof(double) * M, cudaMemcpyDefault, c->s_main));
     }
     CU(cudaStreamSynchronize(c->s_main));
-    c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = false;
+    c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = c->c6_valid = c->wpost_valid = c->wkl_valid = false;
     return TSVGP_OK;
 }
 
@@ -981,11 +1118,11 @@ int tsvgp_set_sites(tsvgp_ctx* c, const double* lambda_1, const double* lambda_2
         CU(cudaMemsetAsync(c->L2, 0, sizeof(double) * (size_t)c->Mp * c->Mp, s));
         CU(cudaMemcpy2DAsync(c->L2, sizeof(double) * c->Mp, lambda_2_sqrt, sizeof(double) * c->M, sizeof(double) * c->M, c->M,
                              cudaMemcpyDefault, s));
-        LA(zero_upper_launch(c->L2, c->Mp, c->Mp, s));   // sites.py:63 — the triangular() transform keeps the lower triangle
+        if (!c->white) LA(zero_upper_launch(c->L2, c->Mp, c->Mp, s));   // sites.py:63 — the triangular() transform keeps the lower triangle
     }
     CU(cudaStreamSynchronize(s));
     c->sites_set = true;
-    c->post_valid = c->kl_valid = false;
+    c->post_valid = c->kl_valid = c->wpost_valid = c->wkl_valid = false;
     return TSVGP_OK;
 }
 
@@ -1010,6 +1147,11 @@ int tsvgp_get_lambda_2(tsvgp_ctx* c, double* lambda_2) {
     if (!c->sites_set) OK(default_sites(c));
     cudaStream_t s = c->s_main;
     const int n = c->Mp;
+    if (c->white) {   // the whitened sibling stores Lambda_2 itself
+        CU(cudaMemcpy2DAsync(lambda_2, sizeof(double) * c->M, c->L2, sizeof(double) * n, sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
+        CU(cudaStreamSynchronize(s));
+        return TSVGP_OK;
+    }
     GemmP p;   // L2 L2^T (tsvgp.py:197-200), lower tiles then mirrored
     p.A = c->L2; p.lda = n; p.a_kc = 1; p.a_tri = 1;
     p.B = c->L2; p.ldb = n; p.b_kc = 1; p.b_tri = 1;
@@ -1140,7 +1282,7 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
     CU(cudaMemcpyAsync(info_h, c->info, sizeof info_h, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     // the step consumed the posterior factors of the old sites
-    c->post_valid = c->kl_valid = false;
+    c->post_valid = c->kl_valid = c->wpost_valid = c->wkl_valid = false;
     float ms = 0;
     for (int i = 0; i < 4; ++i) { cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]); c->timings[1 + i] = ms; }
     cudaEventElapsedTime(&ms, c->ev[EV_T0], c->ev[EV_DENSE]);
@@ -1151,10 +1293,10 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
     c->timings[8] = c->cond_est;
     OK(check_info(c, info_h));
     if (tail[1] != 0.0) {
-        c->post_valid = c->kl_valid = false;
+        c->post_valid = c->kl_valid = c->wpost_valid = c->wkl_valid = false;
         FAIL(TSVGP_ERR_NONPOSITIVE_VARIANCE, "predict_f: non-positive predictive variance (sites unchanged)");
     }
-    if (elbo_before) *elbo_before = scale * tail[0] - kl_from_scalars(sc);
+    if (elbo_before) *elbo_before = scale * tail[0] - kl_value(c, sc);
     return TSVGP_OK;
 }
 
@@ -1178,7 +1320,7 @@ int tsvgp_elbo(tsvgp_ctx* c, double scale, double* out) {
     CU(cudaStreamSynchronize(s));
     OK(check_info(c, info_h));
     if (tail[1] != 0.0) FAIL(TSVGP_ERR_NONPOSITIVE_VARIANCE, "predict_f: non-positive predictive variance");
-    *out = scale * tail[0] - kl_from_scalars(sc);
+    *out = scale * tail[0] - kl_value(c, sc);
     return TSVGP_OK;
 }
 
@@ -1196,7 +1338,7 @@ int tsvgp_prior_kl(tsvgp_ctx* c, double* out) {
     CU(cudaMemcpyAsync(info_h, c->info, sizeof info_h, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     OK(check_info(c, info_h));
-    *out = kl_from_scalars(sc);
+    *out = kl_value(c, sc);
     return TSVGP_OK;
 }
 
@@ -1204,6 +1346,7 @@ int tsvgp_elbo_grad(tsvgp_ctx* c, double scale, double* elbo, double* d_variance
     if (!c || !elbo || !d_variance || !d_lengthscales || !d_Z || !d_lik) return TSVGP_ERR_INVALID;
     OK(require_model(c, true));
     if (2 * c->D + 1 > 128) FAIL(TSVGP_ERR_INVALID, "elbo_grad supports D <= 63 (D = %d)", c->D);
+    if (c->white) FAIL(TSVGP_ERR_INVALID, "elbo_grad is not available for the whitened sibling model");
     CU(cudaSetDevice(c->dev));
     cudaStream_t s = c->s_main;
     const int n = c->Mp, M = c->M, D = c->D;
@@ -1269,7 +1412,7 @@ int tsvgp_elbo_grad(tsvgp_ctx* c, double scale, double* elbo, double* d_variance
     c->kl_valid = false;   // X1 was reused
     OK(check_info(c, info_h));
     if (tail[1] != 0.0) FAIL(TSVGP_ERR_NONPOSITIVE_VARIANCE, "predict_f: non-positive predictive variance");
-    *elbo = scale * tail[0] - kl_from_scalars(sc);
+    *elbo = scale * tail[0] - kl_value(c, sc);
     *d_variance = (scale * (sc[SC_A_B] - 2.0 * sc[SC_TR_QB]) + sc[SC_G_K]) / c->kern_var + scale * tail[2];
     *d_lik = scale * tail[3];
     // d r2 / d lengthscale_d = -2 delta_d^2 / l_d, d r2 / d z_id = 2 delta_d / l_d with delta = zs - xs (scaled coordinates);
@@ -1347,7 +1490,21 @@ int tsvgp_posterior(tsvgp_ctx* c, double* m, double* chol_S) {
     CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
     OK(ensure_posterior(c));
     if (m) CU(cudaMemcpyAsync(m, c->mq, sizeof(double) * c->M, cudaMemcpyDefault, s));
-    if (chol_S) {   // S = K6 - (K6 T)(K6 T)^T   (util.py:387-388)
+    if (chol_S && c->white) {   // S = (LR^-1 K6)^T (LR^-1 K6)   (util.py:421-424)
+        GemmP p;
+        p.A = c->T; p.lda = n; p.a_kc = 1; p.a_tri = 1;
+        p.B = c->K6; p.ldb = n; p.b_kc = 0;
+        p.C = c->X1; p.ldc = n; p.m = p.n = p.k = n;
+        LA(gemm_launch(p, s));
+        GemmP q;
+        q.A = c->X1; q.lda = n; q.a_kc = 0;
+        q.B = c->X1; q.ldb = n; q.b_kc = 0;
+        q.C = c->X2; q.ldc = n; q.m = q.n = q.k = n; q.lower_out = 1;
+        LA(gemm_launch(q, s));
+        c->wkl_valid = false;
+        LA(chol_lower(c->X2, n, n, c->dinv, c->info + INFO_P, s));
+        CU(cudaMemcpy2DAsync(chol_S, sizeof(double) * c->M, c->X2, sizeof(double) * n, sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
+    } else if (chol_S) {   // S = K6 - (K6 T)(K6 T)^T   (util.py:387-388)
         GemmP p;
         p.A = c->K6; p.lda = n; p.a_kc = 1;
         p.B = c->T; p.ldb = n; p.b_kc = 0; p.b_tri = 2;

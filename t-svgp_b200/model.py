@@ -519,6 +519,50 @@ class MultiLatent_t_SVGP(t_SVGP):
             p.sync()
 
 
+class t_SVGP_white(t_SVGP):
+    """Drop-in for the reference's whitened sibling `t_SVGP_white` (src/models/tsvgp_white.py:23-246): sites
+    t(u) with natural parameters (lambda_1, Lambda_2) in the K-scaled parameterisation, Lambda_2 a full symmetric matrix
+    (`lambda_2 [1, M, M]`, default 1e-10 I), updated without any factorisation:
+        lambda_1 <- (1-lr) lambda_1 + lr s K (G1 - 2 G2 mZ) ;  Lambda_2 <- (1-lr) Lambda_2 - 2 lr s K G2 K.
+    Same constructor / natgrad_step / elbo / predict_f / prior_kl / get_mean_chol_cov_inducing_posterior surface
+    (num_latent_gps = 1; `predict_f_extra_data` and `elbo_and_grad` are not built)."""
+
+    def __new__(cls, *a, **k):
+        return object.__new__(cls)
+
+    def __init__(self, kernel, likelihood, inducing_variable, *, mean_function=None, num_latent_gps=1, lambda_1=None,
+                 lambda_2=None, num_data=None, device=0):
+        if lambda_2 is not None:
+            lambda_2 = np.asarray(lambda_2, dtype=np.float64)
+            assert lambda_2.ndim == 3  # tsvgp_white.py:87
+            num_latent_gps = lambda_2.shape[0]
+        if num_latent_gps != 1:
+            raise NotImplementedError("t_SVGP_white with num_latent_gps > 1")
+        super().__init__(kernel, likelihood, inducing_variable, mean_function=mean_function, num_data=num_data, device=device)
+        self.name = "t_svgp_white"
+        self.set_option("white", 1)
+        if lambda_1 is not None or lambda_2 is not None:
+            self.assign_sites(lambda_1, None if lambda_2 is None else lambda_2[0])
+
+    @property
+    def lambda_2_sqrt(self):
+        raise AttributeError("t_SVGP_white stores lambda_2 itself (src/models/tsvgp_white.py:91-97)")
+
+    def assign_sites(self, lambda_1=None, lambda_2=None):
+        l1 = l2 = None
+        if lambda_1 is not None:
+            l1 = np.ascontiguousarray(np.asarray(lambda_1, dtype=np.float64).reshape(-1))
+        if lambda_2 is not None:
+            l2 = np.ascontiguousarray(np.asarray(lambda_2, dtype=np.float64).reshape(-1, self._M, self._M)[0])
+        self._check(self._lib.tsvgp_set_sites(self._ctx, None if l1 is None else l1.ctypes.data, None if l2 is None else l2.ctypes.data))
+
+    def elbo_and_grad(self, data=None, *, global_minibatch_size=None):
+        raise NotImplementedError("elbo_and_grad for t_SVGP_white")
+
+    def predict_f_extra_data(self, Xnew, extra_data, jitter=1e-6):
+        raise NotImplementedError("predict_f_extra_data (src/models/tsvgp_white.py:134-158) is not built")
+
+
 def stream_minibatches(model, batches):
     """Input pipeline: iterate `batches` (an iterable of (X, Y) host arrays, ideally pinned) so that batch i + 1 is being copied
     to the GPU while the caller's loop body works on batch i.  Yields the number of rows of the now-resident minibatch:
