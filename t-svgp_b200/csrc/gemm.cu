@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <map>
+#include <mutex>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -475,7 +476,9 @@ int balanced_ksplit(int tiles, int k) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
-    static std::map<std::pair<int, int>, int> cache;   // one host thread per context; a race would only recompute
+    static std::map<std::pair<int, int>, int> cache;
+    static std::mutex cache_mutex;   // contexts of different host threads share this table
+    std::lock_guard<std::mutex> lock(cache_mutex);
     const auto key = std::make_pair(tiles, k);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;

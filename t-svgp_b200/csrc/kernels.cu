@@ -646,22 +646,18 @@ __global__ void __launch_bounds__(256) diag_trtri_kernel(const double* L, long l
     tri_inverse_regs(S, Dinv + (long)blockIdx.x * DB * DB);
 }
 
-static bool g_diag_attr_set = false;
-static int diag_attr() {
-    if (g_diag_attr_set) return 0;
+// opt in to the large dynamic shared memory of the diagonal-block kernels on the CURRENT device (call once per context)
+int diag_init() {
     int e = (int)cudaFuncSetAttribute(diag_potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB * DB_LD * 8);
     e |= (int)cudaFuncSetAttribute(diag_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB * DB_LD * 8);
-    if (e == 0) g_diag_attr_set = true;
     return e;
 }
 
 int diag_potrf_inv_launch(double* A, long lda, double* Dinv, int blk_index, int* info, cudaStream_t s) {
-    if (int e = diag_attr()) return e;
     diag_potrf_inv_kernel<<<1, 256, DB * DB_LD * 8, s>>>(A, lda, Dinv, blk_index, info);
     return count_launch();
 }
 int diag_trtri_launch(const double* L, long lda, double* Dinv, int nblk, cudaStream_t s) {
-    if (int e = diag_attr()) return e;
     diag_trtri_kernel<<<nblk, 256, DB * DB_LD * 8, s>>>(L, lda, Dinv);
     return count_launch();
 }
@@ -791,16 +787,7 @@ __global__ void __launch_bounds__(256) frob_logdiag_finish_kernel(const double* 
     l = block_sum_256(l, sred);
     if (threadIdx.x == 0) out[1] = l;
 }
-static double* g_red_part[16] = {nullptr};
-static double* red_scratch() {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 16) return nullptr;
-    if (!g_red_part[dev]) cudaMalloc(&g_red_part[dev], RED_BLOCKS * sizeof(double));
-    return g_red_part[dev];
-}
-int frob_logdiag_launch(const double* A, long lda, int n, double* out, cudaStream_t s) {
-    double* part = red_scratch();
+int frob_logdiag_launch(const double* A, long lda, int n, double* out, double* part, cudaStream_t s) {
     if (!part) return -1;
     frob_part_kernel<<<RED_BLOCKS, 256, 0, s>>>(A, lda, n, part);
     frob_logdiag_finish_kernel<<<1, 256, 0, s>>>(A, lda, n, part, out);
@@ -885,8 +872,7 @@ __global__ void __launch_bounds__(256) sum_parts_kernel(const double* part, doub
     s = block_sum_256(s, sred);
     if (threadIdx.x == 0) out[0] = s;
 }
-int matdot_launch(const double* A, const double* B, long ld, int n, double* out, cudaStream_t s) {
-    double* part = red_scratch();
+int matdot_launch(const double* A, const double* B, long ld, int n, double* out, double* part, cudaStream_t s) {
     if (!part) return -1;
     matdot_part_kernel<<<RED_BLOCKS, 256, 0, s>>>(A, B, ld, n, part);
     sum_parts_kernel<<<1, 256, 0, s>>>(part, out);

@@ -55,6 +55,7 @@ int gemv_t_launch(const double* A, long lda, int m, int n, const double* x, doub
 // Zs[i][d] = ZsT[d][i]  (row-major copy of the scaled inducing inputs, [Mp][D])
 int unpack_rows_launch(const double* ZsT, long ldz, int Mp, int D, double* Zs, cudaStream_t s);
 
+int diag_init();   // once per device/context: opt in to the dynamic shared memory of the diagonal-block kernels
 // --- diagonal blocks --------------------------------------------------------------------------------------------
 // In-place lower Cholesky of the 128x128 block at A (lda) and its inverse into Dinv (ld 128, dense lower).
 // info[0] = first failing global pivot index + 1 (blk_index*128 + k + 1), left untouched on success.
@@ -74,7 +75,7 @@ int finalize_sites_launch(const double* P, double* L2, long ld, int M, int Mp, c
 int place_block_launch(const double* src, long lds, double* dst, long ldd, int rows, int cols, cudaStream_t s);  // dst[0:rows,0:cols] = src
 int copy_lower_launch(const double* src, long lds, int M, double* dst, long ldd, int Mp, cudaStream_t s);  // dst = [[tril(src),0],[0,0]]
 // scalars: out[0] = sum_ij A^2 ; out[1] = sum_i log(diag A) ; single block, deterministic
-int frob_logdiag_launch(const double* A, long lda, int n, double* out, cudaStream_t s);
+int frob_logdiag_launch(const double* A, long lda, int n, double* out, double* part /* [128] caller-owned scratch */, cudaStream_t s);
 int dot_launch(const double* x, const double* y, int n, double* out, cudaStream_t s);
 int sum_launch(const double* x, long n, double* out, cudaStream_t s);
 // lambda_1 <- (1-lr) lambda_1 + lr*scale*(G1 - 2 G2mZ)
@@ -86,7 +87,8 @@ int axpby_vec_guarded_launch(double* y, const double* x, int n, double a, double
 // y = a - b
 int vsub_launch(const double* a, const double* b, double* y, int n, cudaStream_t s);
 
-int matdot_launch(const double* A, const double* B, long ld, int n, double* out, cudaStream_t s);   // sum_ij A_ij B_ij
+int matdot_launch(const double* A, const double* B, long ld, int n, double* out, double* part /* [128] caller-owned scratch */,
+                  cudaStream_t s);   // sum_ij A_ij B_ij
 int logdiag_launch(const double* A, long lda, int n, double* out, cudaStream_t s);                  // sum_i log A_ii
 // P = coef*G + jitter*I on [0,M)^2, identity on the padding block
 int init_update_launch(const double* G, double* P, long ld, int M, int Mp, double coef, double jitter, cudaStream_t s);

@@ -103,7 +103,7 @@ struct tsvgp_ctx {
     double *stats[MAXS] = {};   // [B (Mp*Mp) | b (Mp) | tail (4)] per ping-pong stream
     double *stats2[MAXS] = {};  // second B accumulator per stream: the split-off k piece of the balanced SYRK
     double *alpha = nullptr, *mZ = nullptr, *mq = nullptr, *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *gwork = nullptr;
-    double *scal = nullptr;
+    double *scal = nullptr, *red = nullptr;   // device scalars; [128] scratch of the two-stage reductions (per context)
     int white = 0;             // 1: the whitened sibling t_SVGP_white (reference src/models/tsvgp_white.py): L2 holds the full Lambda_2
     double *C6 = nullptr, *C6inv = nullptr;   // chol(K6) and its inverse (whitened sibling)
     bool c6_valid = false, wpost_valid = false, wkl_valid = false;
@@ -228,7 +228,7 @@ int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     NEED(c->dinv = p.get((size_t)(c->Mp / 128) * 128 * 128));
     for (int s = 0; s < MAXS; ++s) { NEED(c->stats[s] = p.get(mm + mp + 4)); NEED(c->stats2[s] = p.get(mm + mp)); }
     NEED(c->alpha = p.get(mp)); NEED(c->mZ = p.get(mp)); NEED(c->mq = p.get(mp)); NEED(c->v1 = p.get(mp)); NEED(c->v2 = p.get(mp));
-    NEED(c->v3 = p.get(mp)); NEED(c->gwork = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal = p.get(N_SCAL));
+    NEED(c->v3 = p.get(mp)); NEED(c->gwork = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal = p.get(N_SCAL)); NEED(c->red = p.get(128));
     NEED(c->info = (int*)p.get(N_INFO)); NEED(c->flags = (int*)p.get(2));
     NEED(c->zaug = p.get(mp * 128)); NEED(c->fuu = p.get(mp * 128));
     NEED(c->C6 = p.get(mm)); NEED(c->C6inv = p.get(mm));
@@ -353,7 +353,7 @@ int ensure_kl_terms(tsvgp_ctx* c) {
         p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
         LA(gemm_launch(p, s));
     }
-    LA(matdot_launch(c->T, c->X1, ld, n, c->scal + SC_TR_QK, s));
+    LA(matdot_launch(c->T, c->X1, ld, n, c->scal + SC_TR_QK, c->red, s));
     LA(dot_launch(c->mq, c->alpha, n, c->scal + SC_M_ALPHA, s));
     c->kl_valid = true;
     return TSVGP_OK;
@@ -424,7 +424,7 @@ int ensure_kl_terms_white(tsvgp_ctx* c) {
         p.lower_out = 1;
         LA(gemm_launch(p, s));
     }
-    LA(matdot_launch(c->X1, c->X1, ld, n, c->scal + SC_TR_QK, s));
+    LA(matdot_launch(c->X1, c->X1, ld, n, c->scal + SC_TR_QK, c->red, s));
     LA(gemv_n_launch(c->V, ld, n, n, c->lam1, 1.0, 0.0, c->v1, s));
     LA(gemv_t_launch(c->V, ld, n, n, c->v1, c->v2, c->gwork, s));   // R0^-1 lambda_1
     LA(gemv_t_launch(c->C6, ld, n, n, c->v2, c->v3, c->gwork, s));  // LA^T (.)
@@ -990,7 +990,7 @@ int tsvgp_create(tsvgp_ctx** out, int device_id) {
     ok = ok && cudaEventCreateWithFlags(&c->ev_kuu, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < N_EV && ok; ++i) ok = ok && cudaEventCreate(&c->ev[i]) == cudaSuccess;
-    ok = ok && gemm_init() == 0;
+    ok = ok && gemm_init() == 0 && diag_init() == 0;
     if (!ok) {
         g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
         delete c;
@@ -1387,8 +1387,8 @@ int tsvgp_elbo_grad(tsvgp_ctx* c, double scale, double* elbo, double* d_variance
     // dk/dr2 of Kuu (K itself is recomputed into a scratch matrix: V is not needed once T exists)
     LA(kuf_launch(c->kern_kind, c->kern_var, c->ZsT, n, c->z2, 0, M, n, c->Zs, c->z2, M, n, D, nullptr, c->V, n, nullptr, 0, 0, s, c->Wf));
     LA(gamma_uu_launch(c->X2, c->P, c->v1, c->v2, c->alpha, c->Wf, c->X1, c->G2, ld, n, scale, s));   // X1 = Gamma, G2 = E_uu
-    LA(matdot_launch(c->X1, c->K, ld, n, c->scal + SC_G_K, s));
-    LA(matdot_launch(c->Wm, B, ld, n, c->scal + SC_TR_QB, s));
+    LA(matdot_launch(c->X1, c->K, ld, n, c->scal + SC_G_K, c->red, s));
+    LA(matdot_launch(c->Wm, B, ld, n, c->scal + SC_TR_QB, c->red, s));
     LA(dot_launch(c->alpha, bvec, n, c->scal + SC_A_B, s));
     LA(xaug_launch(c->ZsT, n, 0, M, n, D, c->zaug, s));
     {   // F_uu = E_uu [zs | 1 | zs^2]
