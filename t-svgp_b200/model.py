@@ -509,7 +509,20 @@ class MultiLatent_t_SVGP(t_SVGP):
         raise NotImplementedError("stage_data with num_latent_gps > 1")
 
     def elbo_and_grad(self, data=None, *, global_minibatch_size=None):
-        raise NotImplementedError("elbo_and_grad with num_latent_gps > 1")
+        """Sum over the latent GPs (shared kernel, inducing inputs and likelihood): the ELBO and every gradient add up."""
+        parts = self._split(data) if data is not None else [None] * self.num_latent_gps
+        total, grads = 0.0, None
+        for p, d in zip(self._parts, parts):
+            e, g = p.elbo_and_grad(d, global_minibatch_size=global_minibatch_size)
+            total += e
+            if grads is None:
+                grads = g
+            else:
+                for k in ("variance", "lengthscales", "Z"):
+                    grads[k] = grads[k] + g[k]
+                if g["likelihood"] is not None:
+                    grads["likelihood"] += g["likelihood"]
+        return total, grads
 
     def timings(self):
         return self._parts[-1].timings()

@@ -70,3 +70,34 @@ def test_variational_em_learns_hyperparameters():
     assert 0.05 < noise < 0.2
     assert rmse < 0.25
     assert trace[-1] > trace[0]
+
+
+def test_multi_latent_gradients_add_up():
+    # L = 2 with a shared kernel: the ELBO and its gradients are sums over the latents; checked against central differences of
+    # the oracle's L = 2 ELBO for the kernel variance and one lengthscale
+    import copy
+    import tsvgp_b200 as tb
+    rng = np.random.RandomState(5)
+    N, M = 300, 16
+    X = rng.randn(N, 2)
+    Y = np.stack([np.sin(X[:, 0]), np.cos(X[:, 1])], 1) + 0.2 * rng.randn(N, 2)
+    Z = X[:M].copy()
+    kernel, lik = orc.SquaredExponential(variance=1.2, lengthscales=np.array([1.1, 1.4])), orc.Gaussian(variance=0.1)
+    ref = orc.OracleTSVGP(kernel, lik, orc.InducingPoints(Z.copy()), num_latent_gps=2)
+    for _ in range(2):
+        ref.natgrad_step((X, Y), lr=0.7)
+    dev = tb.t_SVGP(kernel, lik, Z.copy(), lambda_1=ref.lambda_1, lambda_2_sqrt=ref.lambda_2_sqrt)
+    e, g = dev.elbo_and_grad((X, Y))
+    assert abs(e - ref.elbo((X, Y))) < 1e-9 * abs(e)
+
+    def fd(setter, x0, h=1e-5):
+        def f(x):
+            m = copy.copy(ref)
+            m.kernel = copy.deepcopy(ref.kernel)
+            setter(m.kernel, x)
+            return m.elbo((X, Y))
+        return (f(x0 + h) - f(x0 - h)) / (2 * h)
+
+    np.testing.assert_allclose(g["variance"], fd(lambda k, x: setattr(k, "variance", orc._param(x)), 1.2), rtol=2e-6)
+    np.testing.assert_allclose(g["lengthscales"][1], fd(lambda k, x: setattr(k, "lengthscales", orc._param(np.array([1.1, x]))), 1.4), rtol=2e-6)
+    dev.close()
