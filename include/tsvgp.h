@@ -114,6 +114,11 @@ TSVGP_API int tsvgp_elbo_grad(tsvgp_ctx* ctx, double scale, double* elbo, double
                               double* d_Z, double* d_lik);
 /* base_SVGP.predict_f, full_cov = False (tsvgp.py:97-114): mean_out, var_out [N]                                        */
 TSVGP_API int tsvgp_predict_f(tsvgp_ctx* ctx, const double* Xnew, int64_t N, int D, const double* mean_X, double* mean_out, double* var_out);
+/* t_SVGP_white.predict_f_extra_data (tsvgp_white.py:134-158; whitened sibling only): predictions at Xnew after conditioning the
+ * current sites on the RESIDENT minibatch (the "extra data") without changing them; jitter is the reference's argument
+ * (default gpflow default_jitter = 1e-6; its test passes 0).                                                              */
+TSVGP_API int tsvgp_predict_f_extra_data(tsvgp_ctx* ctx, const double* Xnew, int64_t N, int D, const double* mean_X, double jitter,
+                                         double* mean_out, double* var_out);
 /* t_SVGP.get_mean_chol_cov_inducing_posterior (tsvgp.py:202-212): m [M], chol_S [M, M]                                  */
 TSVGP_API int tsvgp_posterior(tsvgp_ctx* ctx, double* m, double* chol_S);
 

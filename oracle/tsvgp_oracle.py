@@ -674,6 +674,18 @@ class OracleTSVGPWhite:
             raise FloatingPointError("predict_f: non-positive predictive variance")
         return mu + self._mean_fn(Xnew), var
 
+    def predict_f_extra_data(self, Xnew, extra_data, jitter=DEFAULT_JITTER):  # :134-158
+        Xnew = np.asarray(Xnew, dtype=np.float64)
+        grad_mu = self.compute_data_natural_params(extra_data)
+        lambda_2 = -0.5 * self.lambda_2
+        K_uu = Kuu(self.inducing_variable, self.kernel, jitter=jitter)
+        lambda_1c = self.lambda_1 + K_uu @ grad_mu[0]
+        lambda_2c = -2 * (lambda_2 + np.stack([K_uu @ grad_mu[1][l] @ K_uu for l in range(lambda_2.shape[0])]))
+        K_uf = Kuf(self.inducing_variable, self.kernel, Xnew)
+        K_ff = self.kernel.K_diag(Xnew)[..., None]
+        mu, var = conditional_from_precision_sites_white(K_uu, K_ff, K_uf, lambda_1c, lambda_2c)
+        return mu + self._mean_fn(Xnew), var
+
     def elbo(self, data):                                                     # :162-177
         X, Y = (np.asarray(a, dtype=np.float64) for a in data)
         kl = self.prior_kl()

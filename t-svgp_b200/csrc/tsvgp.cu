@@ -104,6 +104,8 @@ struct tsvgp_ctx {
     double *stats2[MAXS] = {};  // second B accumulator per stream: the split-off k piece of the balanced SYRK
     double *alpha = nullptr, *mZ = nullptr, *mq = nullptr, *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *gwork = nullptr;
     double *scal = nullptr, *red = nullptr;   // device scalars; [128] scratch of the two-stage reductions (per context)
+    double jit6 = GPFLOW_DEFAULT_JITTER;   // jitter of K6 (gpflow default_jitter; predict_f_extra_data passes its own)
+    double* lam1_bak = nullptr;
     int white = 0;             // 1: the whitened sibling t_SVGP_white (reference src/models/tsvgp_white.py): L2 holds the full Lambda_2
     double *C6 = nullptr, *C6inv = nullptr;   // chol(K6) and its inverse (whitened sibling)
     bool c6_valid = false, wpost_valid = false, wkl_valid = false;
@@ -200,6 +202,7 @@ int all_reduce(tsvgp_ctx* c, double* buf, size_t count);
 int ensure_posterior_white(tsvgp_ctx* c);
 int ensure_kl_terms_white(tsvgp_ctx* c);
 int dense_update_white(tsvgp_ctx* c, double lr, double scale);
+int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale, bool only_G);
 double kl_white_from_scalars(const tsvgp_ctx* c, const double* sc);
 bool dist_active(const tsvgp_ctx* c);
 int dense_gemm(tsvgp_ctx* c, GemmP p, cudaStream_t s);
@@ -231,7 +234,7 @@ int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     NEED(c->v3 = p.get(mp)); NEED(c->gwork = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal = p.get(N_SCAL)); NEED(c->red = p.get(128));
     NEED(c->info = (int*)p.get(N_INFO)); NEED(c->flags = (int*)p.get(2));
     NEED(c->zaug = p.get(mp * 128)); NEED(c->fuu = p.get(mp * 128));
-    NEED(c->C6 = p.get(mm)); NEED(c->C6inv = p.get(mm));
+    NEED(c->C6 = p.get(mm)); NEED(c->C6inv = p.get(mm)); NEED(c->lam1_bak = p.get(mp));
     c->c6_valid = c->wpost_valid = c->wkl_valid = false;
     NEED(c->tmp2 = p.get((size_t)((c->Mp / 128 + 1) / 2) * 128 * mp)); NEED(c->dinv2 = p.get((size_t)(c->Mp / 128) * 128 * 128));
     NEED(c->pv1 = p.get(mp)); NEED(c->pv2 = p.get(mp)); NEED(c->gwork2 = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal2 = p.get(N_SCAL));
@@ -271,7 +274,7 @@ int ensure_kuu(tsvgp_ctx* c) {
     LA(unpack_rows_launch(c->ZsT, c->Mp, c->Mp, c->D, c->Zs, s));
     LA(kuf_launch(c->kern_kind, c->kern_var, c->ZsT, c->Mp, c->z2, 0, c->M, c->Mp, c->Zs, c->z2, c->M, c->Mp, c->D, nullptr,
                   c->K, c->Mp, nullptr, 0, 1, s));
-    LA(copy_add_diag_launch(c->K, c->K6, c->Mp, c->Mp, GPFLOW_DEFAULT_JITTER, s));
+    LA(copy_add_diag_launch(c->K, c->K6, c->Mp, c->Mp, c->jit6, s));
     c->kuu_valid = true;
     c->post_valid = c->kl_valid = c->k9_valid = c->c6_valid = c->wpost_valid = c->wkl_valid = false;
     return TSVGP_OK;
@@ -821,7 +824,7 @@ int choose_route(tsvgp_ctx* c, double jitter) {
 }
 
 // tsvgp.py:268-303 after the statistics are complete in stats[0]
-int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale) {
+int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale, bool only_G) {
     cudaStream_t s = c->s_main;
     const int n = c->Mp;
     const long ld = c->Mp;
@@ -877,6 +880,7 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale) {
     }
     LA(mirror_lower_launch(c->G2, ld, n, s));
     LA(gemv_n_launch(c->G2, ld, n, n, c->mZ, 1.0, 0.0, c->v3, s));
+    if (only_G) return TSVGP_OK;   // G2 (mirrored) in c->G2, G1 in c->v2, G2 mZ in c->v3
     if (c->white) return dense_update_white(c, lr, scale);
     // P = (1-lr) L2 L2^T - 2 lr scale G2 + jitter I                                     tsvgp.py:293-300
     LA(init_update_launch(c->G2, c->P, ld, c->M, n, -2.0 * lr * scale, jitter, s));
@@ -1272,7 +1276,7 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
     CU(cudaEventRecord(c->ev[EV_STREAM], s));
     OK(all_reduce(c, c->stats[0], mm + c->Mp + 4));
     CU(cudaEventRecord(c->ev[EV_REDUCE], s));
-    OK(dense_update(c, lr, jitter, scale));
+    OK(dense_update(c, lr, jitter, scale, false));
     CU(cudaEventRecord(c->ev[EV_DENSE], s));
 
     double tail[4], sc[N_SCAL];
@@ -1479,6 +1483,61 @@ int tsvgp_predict_f(tsvgp_ctx* c, const double* Xnew, int64_t N, int D, const do
     OK(check_info(c, info_h));
     if (tail[1] != 0.0) FAIL(TSVGP_ERR_NONPOSITIVE_VARIANCE, "predict_f: non-positive predictive variance");
     return TSVGP_OK;
+}
+
+int tsvgp_predict_f_extra_data(tsvgp_ctx* c, const double* Xnew, int64_t N, int D, const double* mean_X, double jitter,
+                               double* mean_out, double* var_out) {
+    if (!c) return TSVGP_ERR_INVALID;
+    if (!c->white) FAIL(TSVGP_ERR_STATE, "predict_f_extra_data belongs to the whitened sibling model (option \"white\")");
+    OK(require_model(c, true));
+    CU(cudaSetDevice(c->dev));
+    cudaStream_t s = c->s_main;
+    const int n = c->Mp;
+    const long ld = n;
+    const size_t mm = (size_t)n * n;
+    // (1) natural parameters of the resident (extra) data under the current sites: tsvgp_white.py:183-212
+    CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
+    OK(ensure_xs(c));
+    OK(ensure_kuu(c));
+    OK(start_k9(c, 1e-9));
+    OK(ensure_posterior(c));
+    OK(choose_route(c, 1e-9));
+    OK(stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_STATS, nullptr, nullptr));
+    OK(all_reduce(c, c->stats[0], mm + n + 4));
+    OK(dense_update(c, 1.0, 1e-9, 1.0, true));
+    LA(lincomb_launch(c->v1, 1.0, c->v2, -2.0, c->v3, n, s));          // g0 = G1 - 2 G2 mZ
+    // (2) K_j = Kuu + jitter I ; combined sites lambda_1 + K_j g0, Lambda_2 - 2 K_j G2 K_j     (tsvgp_white.py:144-150)
+    CU(cudaMemcpyAsync(c->lam1_bak, c->lam1, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(c->P, c->L2, sizeof(double) * mm, cudaMemcpyDeviceToDevice, s));
+    const double jit_saved = c->jit6;
+    c->jit6 = jitter;
+    LA(copy_add_diag_launch(c->K, c->K6, n, n, jitter, s));
+    c->c6_valid = c->wpost_valid = c->wkl_valid = false;
+    LA(gemv_n_launch(c->K6, ld, n, c->M, c->v1, 1.0, 0.0, c->mq, s));
+    LA(axpby_vec_guarded_launch(c->lam1, c->mq, c->M, 1.0, 1.0, nullptr, nullptr, s));
+    {
+        GemmP p;
+        p.A = c->K6; p.lda = ld; p.a_kc = 1;
+        p.B = c->G2; p.ldb = ld; p.b_kc = 0;
+        p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
+        LA(gemm_launch(p, s));
+        GemmP q;
+        q.A = c->X1; q.lda = ld; q.a_kc = 1;
+        q.B = c->K6; q.ldb = ld; q.b_kc = 0;
+        q.C = c->X2; q.ldc = ld; q.m = q.n = q.k = n; q.lower_out = 1;
+        LA(gemm_launch(q, s));
+        LA(mirror_lower_launch(c->X2, ld, n, s));
+    }
+    LA(axpby_guarded_launch(c->L2, c->X2, ld, c->M, 1.0, -2.0, nullptr, nullptr, s));
+    // (3) the conditional at Xnew with the combined sites, then everything back as it was
+    const int rc = tsvgp_predict_f(c, Xnew, N, D, mean_X, mean_out, var_out);
+    CU(cudaMemcpyAsync(c->lam1, c->lam1_bak, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(c->L2, c->P, sizeof(double) * mm, cudaMemcpyDeviceToDevice, s));
+    c->jit6 = jit_saved;
+    LA(copy_add_diag_launch(c->K, c->K6, n, n, c->jit6, s));
+    c->c6_valid = c->wpost_valid = c->wkl_valid = false;
+    CU(cudaStreamSynchronize(s));
+    return rc;
 }
 
 int tsvgp_posterior(tsvgp_ctx* c, double* m, double* chol_S) {

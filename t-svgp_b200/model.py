@@ -538,7 +538,7 @@ class t_SVGP_white(t_SVGP):
     (`lambda_2 [1, M, M]`, default 1e-10 I), updated without any factorisation:
         lambda_1 <- (1-lr) lambda_1 + lr s K (G1 - 2 G2 mZ) ;  Lambda_2 <- (1-lr) Lambda_2 - 2 lr s K G2 K.
     Same constructor / natgrad_step / elbo / predict_f / prior_kl / get_mean_chol_cov_inducing_posterior surface
-    (num_latent_gps = 1; `predict_f_extra_data` and `elbo_and_grad` are not built)."""
+    (+ `predict_f_extra_data`; num_latent_gps = 1; `elbo_and_grad` is not built for this parameterisation)."""
 
     def __new__(cls, *a, **k):
         return object.__new__(cls)
@@ -573,7 +573,17 @@ class t_SVGP_white(t_SVGP):
         raise NotImplementedError("elbo_and_grad for t_SVGP_white")
 
     def predict_f_extra_data(self, Xnew, extra_data, jitter=1e-6):
-        raise NotImplementedError("predict_f_extra_data (src/models/tsvgp_white.py:134-158) is not built")
+        """tsvgp_white.py:134-158: predictions at Xnew after conditioning the current sites on `extra_data` (the sites themselves
+        are left unchanged; `extra_data` becomes the resident minibatch)."""
+        self._sync_objects()
+        self.set_data(extra_data)
+        tx = as_tensor(Xnew, "Xnew")
+        N, D = tx.shape
+        if self._mean_fn(np.zeros((1, D))) is not None:
+            raise NotImplementedError("predict_f_extra_data with a non-zero mean_function")
+        mean, var = np.empty((N, 1)), np.empty((N, 1))
+        self._check(self._lib.tsvgp_predict_f_extra_data(self._ctx, tx.ptr, N, D, None, float(jitter), mean.ctypes.data, var.ctypes.data))
+        return mean, var
 
 
 def stream_minibatches(model, batches):

@@ -89,3 +89,28 @@ def test_white_model_fails_like_the_reference_when_lambda_2_turns_indefinite():
         assert relerr(dev.lambda_1, ref.lambda_1) < 1e-9 and relerr(dev.lambda_2, ref.lambda_2) < 1e-9
     assert failed_ref == failed_dev
     dev.close()
+
+
+@pytest.mark.parametrize("jitter", [1e-6, 0.0])
+def test_predict_f_extra_data(jitter):
+    # tsvgp_white.py:134-158 (the reference's test_condit.py:101 calls it with jitter = 0): conditioning on extra data for the
+    # prediction only; the sites are left as they were
+    import tsvgp_b200 as tb
+    import tsvgp_b200.synth as synth
+    cfg = synth.describe("cfg3")
+    X, Y, Z = synth.make_minibatch(cfg, n_rows=3000, M=160)
+    kernel, lik = synth.build_objects(cfg, orc)
+    ref = orc.OracleTSVGPWhite(kernel, lik, orc.InducingPoints(Z.copy()))
+    dev = tb.t_SVGP_white(kernel, lik, Z.copy())
+    ref.natgrad_step((X[:1500], Y[:1500]), lr=0.6)
+    dev.natgrad_step((X[:1500], Y[:1500]), lr=0.6)
+    l1, l2 = dev.lambda_1, dev.lambda_2
+    mu_r, var_r = ref.predict_f_extra_data(X[:300] + 0.1, (X[1500:], Y[1500:]), jitter=jitter)
+    mu_d, var_d = dev.predict_f_extra_data(X[:300] + 0.1, (X[1500:], Y[1500:]), jitter=jitter)
+    assert relerr(mu_d, mu_r) < 1e-9 and relerr(var_d, var_r) < 1e-9
+    np.testing.assert_array_equal(dev.lambda_1, l1)
+    np.testing.assert_array_equal(dev.lambda_2, l2)
+    mu0_d, var0_d = dev.predict_f(X[:300] + 0.1)                # and ordinary predictions are back to the unconditioned ones
+    mu0_r, var0_r = ref.predict_f(X[:300] + 0.1)
+    assert relerr(mu0_d, mu0_r) < 1e-9 and relerr(var0_d, var0_r) < 1e-9
+    dev.close()
