@@ -5,6 +5,11 @@ bench.py — natgrad_step datapoints/s of the B200 t-SVGP path (BASELINE.json me
   python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg3] [--impl ours|reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
+Workload: BASELINE.json's metric is quoted "at 1/2/4/8 B200", which is configs[2] (cfg3: N=10M, M=2048, D=16, Matern-5/2, minibatch 1M
+"sharded over 1/2/4/8 B200"); configs[1] (cfg2) is pinned to one B200 and holds 0.15 ms of FP64 work per step, so it measures launch
+latency rather than the path.  cfg3 fits one GPU and is the default; the default N=1 run also measures cfg2 (configs[1]) and reports it
+under `other_configs`; `--config cfgK` selects any config as the main line.
+
 A "step" is one `t_SVGP.natgrad_step` (posterior factors + streaming statistics pass + all-reduce + dense site update) over
 one minibatch of the named config, sharded by rows over the N ranks (strong scaling: the minibatch is fixed).
   value : minibatch rows / step time with the minibatch resident in HBM when the clock starts (4 distinct minibatches rotate)
@@ -385,6 +390,8 @@ def main():
         "dtype": "f64", "data": "synthetic", "config": workload_config(cfg, M, Nb, world), "clocks": clocks, "e2e": e2e,
         "gpu_launches": launches, "roofline": roofline, "detail": extra,
     }
+    if rank == 0 and world == 1 and args.config == "cfg3" and args.minibatch is None and args.M is None and not args.no_e2e:
+        line["other_configs"] = {"cfg2": quick_config(tb, st, synth, "cfg2", local_rank)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, M, Nb)
     if rank == 0:
@@ -392,6 +399,45 @@ def main():
     model.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def quick_config(tb, st, synth, name, device):
+    """configs[1] measured in the same run: natgrad_step datapoints/s, device-resident and end to end (pinned host buffers)."""
+    cfg = synth.describe(name)
+    M, Nb = cfg["M"], cfg["Nb"]
+    kernel, lik = synth.build_objects(cfg, st)
+    X, Y, Z = synth.make_minibatch(cfg)
+    m = tb.t_SVGP(kernel, lik, Z, num_data=cfg["N"], device=device)
+    xd, yd = m.device_array(X), m.device_array(Y)
+    px, py = tb.pinned_empty(X.shape), tb.pinned_empty(Y.shape)
+    px[...] = X; py[...] = Y
+
+    def resident():
+        m.set_option("invalidate", 1)
+        m.set_data((xd, yd))
+        m.natgrad_step(lr=cfg["lr"])
+
+    def e2e():
+        m.set_option("invalidate", 1)
+        e = m.natgrad_step((px, py), lr=cfg["lr"], return_elbo=True)
+        return e, m.lambda_1
+
+    out = {}
+    for key, fn in (("value", resident), ("e2e", e2e)):
+        for _ in range(5):
+            fn()
+        m.sync()
+        m.timer_start()
+        for _ in range(30):
+            fn()
+        ms = m.timer_stop() / 30
+        out[key] = Nb / (ms * 1e-3)
+        out[key + "_ms_per_step"] = ms
+    q = lik_q(cfg)
+    out.update(unit="datapoints/s", workload=f"{name}: {cfg['lik']} GH-20, D={cfg['D']}, M={M}, minibatch {Nb} (BASELINE configs[1])",
+               step_fp64_frac=(Nb * synth.flops_per_point(M, cfg["D"], q) + synth.dense_flops(M)) / (out["value_ms_per_step"] * 1e-3) / (FP64_PEAK_TFLOPS * 1e12))
+    m.close()
+    return out
 
 
 def lik_q(cfg):
