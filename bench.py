@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--M", type=int, default=None, help="override the number of inducing points (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-grad", action="store_true", help="skip the (reported, untimed-in-the-metric) M-step gradient measurement")
     ap.add_argument("--keep-cache", action="store_true", help="do not invalidate the kernel-matrix factors every step")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (tsvgp_set_option), repeatable")
     return ap.parse_args()
@@ -336,7 +337,7 @@ def main():
 
     # ---------- M-step gradient pass (next-row feature; reported, not part of the metric) ----------
     grad_ms = None
-    if world == 1 and cfg["D"] <= 63:
+    if world == 1 and cfg["D"] <= 63 and not args.no_grad:
         model.set_data(mbs_dev[0])
         model.elbo_and_grad(global_minibatch_size=Nb)
         model.timer_start()
