@@ -334,6 +334,8 @@ class t_SVGP:
         if len(tx.shape) != 2:
             raise _lib.InvalidArgumentError(_lib.ERR_INVALID, "Xnew must be [N, D]")
         N, D = tx.shape
+        if N == 0:   # an empty query returns empty moments, as the reference's conditional does
+            return np.empty((0, 1)), np.empty((0, 1))
         mean_x = None
         if self._mean_fn(np.zeros((1, D))) is not None:
             mean_x = self._mean_fn(np.asarray(Xnew, dtype=np.float64))

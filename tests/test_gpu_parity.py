@@ -203,6 +203,12 @@ def test_errors_leave_sites_unchanged():
     np.testing.assert_array_equal(m.lambda_2_sqrt, l2)
     with pytest.raises(tb.InvalidArgumentError):
         m.predict_f(np.zeros((3, 5)))     # wrong D
+    with pytest.raises(tb.InvalidArgumentError):
+        m.natgrad_step((np.zeros((0, 2)), np.zeros((0, 1))))     # empty minibatch
+    with pytest.raises(tb.InvalidArgumentError):
+        m.natgrad_step((X, Y[:-1]))       # ragged X / Y
+    assert m.predict_f(np.zeros((0, 2)))[0].shape == (0, 1)
+    np.testing.assert_array_equal(m.lambda_1, l1)
     m.natgrad_step((X, Y), lr=0.5)         # the context is still usable
     m.close()
 
