@@ -63,3 +63,27 @@ def test_cfg5_quadrature_step_improves_elbo_at_scale():
     l2s = m.lambda_2_sqrt[0]
     assert np.all(np.diagonal(l2s) < 0) and np.all(np.isfinite(l2s))
     m.close()
+
+
+def test_cfg4_m8192_dense_phase_properties():
+    # the Cholesky-bound config at its full M = 8192 (64 tile rows: deepest blocked Cholesky / triangular-inverse recursion the
+    # library runs) on a reduced minibatch: the Gaussian lr = 1 fixed point, ELBO consistency, finite negative-diagonal factor
+    import tsvgp_b200 as tb
+    import tsvgp_b200.synth as synth
+    from tsvgp_b200 import standins as st
+    cfg = synth.describe("cfg4")
+    X, Y, Z = synth.make_minibatch(cfg, n_rows=16_384, M=cfg["M"])
+    kernel, lik = synth.build_objects(cfg, st)
+    m = tb.t_SVGP(kernel, lik, Z, num_data=cfg["N"])
+    m.set_data((m.device_array(X), m.device_array(Y)))
+    e0 = m.natgrad_step(lr=1.0, return_elbo=True)
+    l1 = m.lambda_1
+    e1 = m.natgrad_step(lr=1.0, return_elbo=True)
+    assert e1 > e0
+    assert relerr(m.lambda_1, l1) < 1e-6                          # one full Gaussian step is already the optimum
+    assert abs(m.elbo() - e1) < 1e-8 * abs(e1)
+    d = np.diagonal(m.lambda_2_sqrt[0])
+    assert np.all(np.isfinite(d)) and np.all(d < 0)
+    mu, var = m.predict_f(X[:2048])
+    assert np.all(var > 0) and np.sqrt(np.mean((mu - Y[:2048]) ** 2)) < 0.6
+    m.close()
