@@ -121,3 +121,23 @@ def test_synthetic_configs_have_the_survey_shapes():
         X, Y, Z = synth.make_minibatch(cfg, n_rows=300, M=40)
         assert X.shape == (300, D) and Y.shape == (300, 1) and Z.shape == (40, D)
     assert synth.flops_per_point(2048, 16) == 2 * 2048 ** 2 + 2048 * 38 + 4 * 2048
+
+
+def test_header_is_plain_c_and_the_c_example_links():
+    # the boundary is a C ABI: the header must compile as C, and a C client must link against the library
+    import shutil
+    import tempfile
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    import tsvgp_b200
+    tsvgp_b200.load()
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "c_api_example")
+        cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_api_example.c"),
+               "-o", exe, "-L", os.path.join(ROOT, "t-svgp_b200"), "-ltsvgp", "-Wl,-rpath," + os.path.join(ROOT, "t-svgp_b200"), "-lm"]
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+        assert res.returncode == 0, res.stderr
+        if not have_gpu():   # without a device the client must fail loudly in tsvgp_create (no CPU fallback)
+            run = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+            assert run.returncode != 0 and "no CUDA device" in run.stderr
