@@ -63,12 +63,15 @@ TSVGP_API int tsvgp_set_option(tsvgp_ctx* ctx, const char* name, double value); 
  * "cache_factors" (1 = keep chol(Kuu+jitter I) and the posterior factors while kernel, Z and sites are unchanged),
  * "invalidate" (any value: drop every cached factor now),
  * "route" (0 = automatic, 1 = fused: B = Kuf diag(h) Kfu then K9^-1 B K9^-1 — 2 M^2 flops per point, rounding ~ eps cond(Kuu)^2;
- *          2 = whitened: C9^-1 Kuf first, as the reference's order A = K9^-1 Kuf — 3 M^2 flops per point, rounding ~ eps cond),
+ *          2 = whitened: C9^-1 Kuf first, as the reference's order A = K9^-1 Kuf — 3 M^2 flops per point, rounding ~ eps cond;
+ *          3 = exact: A = K9^-1 Kuf formed per slab, then the Gram product A^T diag(h) A — the reference's order literally
+ *              (tsvgp.py:271-281), 4 M^2 flops per point; keeps -2 Lambda_2 positive definite where the reference's does),
  * "white" (1 = the whitened sibling t_SVGP_white, reference src/models/tsvgp_white.py: the second site argument of
  *          set_sites / get_sites / get_lambda_2 is then the full matrix Lambda_2; switching resets the sites),
  * "dist_min_m" (multi-GPU: distribute the dense M x M products over the ranks from this padded M upwards; default 4096),
  * "streams" up to 4, "balance" / "fuse_b" (0 switches the balanced SYRK split / the fused b += Kuf g off, for A/B timing),
- * "route_cond_max" (automatic: fused while the power-iteration estimate of cond(Kuu + jitter I) is below this; default 1e4) */
+ * "route_cond_max" (automatic: fused while the power-iteration estimate of cond(Kuu + jitter I) is below this; default 1e4),
+ * "route_exact_min" (automatic: exact above this estimate, whitened in between; default 1e8) */
 
 /* ---- model objects read by the path (tsvgp.py:209,268-269; GPflow kernel / likelihood / inducing attributes) ------ */
 /* lengthscales: HOST pointer, n_ls = 1 (isotropic) or D (ARD)                                                          */
@@ -130,7 +133,7 @@ TSVGP_API int tsvgp_comm_size(const tsvgp_ctx* ctx);
 /* ---- measurement ------------------------------------------------------------------------------------------------------ */
 /* CUDA-event durations (ms) of the last natgrad_step, on the context's stream.  out[0..n):
  *  0 total, 1 prepare (posterior factors), 2 streaming pass, 3 all-reduce, 4 dense update, 5 number of slabs,
- *  6 kernels launched by the step, 7 route used (1 fused, 2 whitened), 8 estimated cond(Kuu + jitter I) (0 if not probed) */
+ *  6 kernels launched by the step, 7 route used (1 fused, 2 whitened, 3 exact), 8 estimated cond(Kuu + jitter I) (0 if not probed) */
 TSVGP_API int tsvgp_get_timings(tsvgp_ctx* ctx, double* out, int n);
 TSVGP_API int tsvgp_sync(tsvgp_ctx* ctx);
 /* With option "profile" = 1 the streaming pass runs on one stream and brackets every kernel with CUDA events.  After a

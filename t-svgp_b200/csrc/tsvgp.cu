@@ -60,7 +60,7 @@ enum { INFO_W = 0, INFO_K9 = 1, INFO_P = 2, INFO_S = 3, N_INFO = 4 };
 enum { EV_T0 = 0, EV_PREP, EV_STREAM, EV_REDUCE, EV_DENSE, N_EV };
 // device scalars
 enum { SC_LOGDIAG_W = 0, SC_M_ALPHA, SC_TR_QK, SC_PK0, SC_PK1, SC_PI0, SC_PI1, SC_G_K, SC_TR_QB, SC_A_B, N_SCAL = 12 };
-enum { ROUTE_AUTO = 0, ROUTE_FUSED = 1, ROUTE_WHITENED = 2 };
+enum { ROUTE_AUTO = 0, ROUTE_FUSED = 1, ROUTE_WHITENED = 2, ROUTE_EXACT = 3 };
 
 }  // namespace
 
@@ -81,6 +81,9 @@ struct tsvgp_ctx {
     int route_opt = ROUTE_AUTO;     // statistics route: fused (B = Kuf H Kfu, then K9^-1 B K9^-1) or whitened (C9^-1 Kuf first)
     double route_cond_max = 1e4;    // auto: fused while the estimated cond(Kuu + jitter I) is below this (measured fused error
                                     // <= 4e-18 cond^2, tests/test_gpu_parity.py arbiter test: 4e-10 at the threshold)
+    double route_exact_min = 1e8;   // auto: above this estimate even the two-sided product C9^-T Bw C9^-1 of the whitened route loses
+                                    // the positive definiteness the reference gets from forming A = K9^-1 Kuf first and then the
+                                    // Gram product A^T diag(h) A (tsvgp.py:271-281): take that order literally (4 M^2 flops per point)
     int route = ROUTE_FUSED;        // route of the current / last step
     double cond_est = 0.0;
 
@@ -494,7 +497,7 @@ int ensure_slabs(tsvgp_ctx* c, long n_points, bool need_grad = false) {
     const long nc = pick_chunk(c);
     const long nchunks = (n_points + nc - 1) / nc;
     const long ve_need = (nchunks + 1) * ((nc + 255) / 256);
-    const bool need_w = c->route == ROUTE_WHITENED;
+    const bool need_w = c->route == ROUTE_WHITENED || c->route == ROUTE_EXACT;
     const int want_streams = c->profile ? 1 : (c->n_streams < 1 ? 1 : (c->n_streams > MAXS ? MAXS : c->n_streams));
     if (c->chunk == nc && c->chunk_Mp == c->Mp && c->ve_cap >= ve_need && (!need_w || c->wslab[0]) && (!need_grad || c->grad_ws) &&
         c->slab_streams >= want_streams)
@@ -638,13 +641,21 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
         mark(s);
         if (stats) {
             const double* stat_slab = c->slab[b];
-            if (c->route == ROUTE_WHITENED && !grad) {   // (c') whitened slab  C9^-1 K  (reference order: A = K9^-1 Kuf first, tsvgp.py:271)
+            if ((c->route == ROUTE_WHITENED || c->route == ROUTE_EXACT) && !grad) {   // (c') whitened slab  C9^-1 K  (reference order: A = K9^-1 Kuf first, tsvgp.py:271)
                 GemmP p;
                 p.A = c->C9inv; p.lda = Mp; p.a_kc = 1; p.a_tri = 1;
                 p.B = c->slab[b]; p.ldb = nc; p.b_kc = 0;
                 p.C = c->wslab[b]; p.ldc = nc; p.m = Mp; p.n = ncols; p.k = Mp;
                 LA(gemm_launch(p, s));
                 stat_slab = c->wslab[b];
+                if (c->route == ROUTE_EXACT) {   // (c'') A = C9^-T (C9^-1 K) = K9^-1 Kuf itself, written over the covariance slab (no longer needed)
+                    GemmP q;
+                    q.A = c->C9inv; q.lda = Mp; q.a_kc = 0; q.a_tri = 2;
+                    q.B = c->wslab[b]; q.ldb = nc; q.b_kc = 0;
+                    q.C = c->slab[b]; q.ldc = nc; q.m = Mp; q.n = ncols; q.k = Mp;
+                    LA(gemm_launch(q, s));
+                    stat_slab = c->slab[b];
+                }
             }
             mark(s);
             {   // (d) B += K diag(h) K^T, lower tiles
@@ -711,7 +722,7 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
             for (int k = 0; k < 6; ++k) {
                 float ms = 0;
                 cudaEventElapsedTime(&ms, c->pev[e + k], c->pev[e + k + 1]);
-                if (k == 3 && c->route != ROUTE_WHITENED) continue;
+                if (k == 3 && c->route != ROUTE_WHITENED && c->route != ROUTE_EXACT) continue;
                 c->kprof[2 * k] += ms;
                 c->kprof[2 * k + 1] += 1.0;
             }
@@ -818,7 +829,8 @@ int choose_route(tsvgp_ctx* c, double jitter) {
         CU(cudaStreamWaitEvent(c->s_main, c->ev_side, 0));
         c->k9_pending = false;
     }
-    if (c->route_opt == ROUTE_AUTO) c->route = c->cond_est <= c->route_cond_max ? ROUTE_FUSED : ROUTE_WHITENED;
+    if (c->route_opt == ROUTE_AUTO)
+        c->route = c->cond_est <= c->route_cond_max ? ROUTE_FUSED : (c->cond_est <= c->route_exact_min ? ROUTE_WHITENED : ROUTE_EXACT);
     else c->route = c->route_opt;
     return TSVGP_OK;
 }
@@ -859,6 +871,9 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale, bool only
             OK(dense_gemm(c, p, s));
         }
         LA(gemv_n_launch(c->K9inv, ld, n, n, bvec, 1.0, 0.0, c->v2, s));   // G1 = K9^-1 b
+    } else if (c->route == ROUTE_EXACT) {   // the pass accumulated G2 = A^T diag(h) A and G1 = A^T g themselves (tsvgp.py:273-281)
+        CU(cudaMemcpyAsync(c->G2, B, sizeof(double) * mm, cudaMemcpyDeviceToDevice, s));
+        CU(cudaMemcpyAsync(c->v2, bvec, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
     } else {
         const double* Bw = B;      // C9^-1 (Kuf H Kfu) C9^-T accumulated by the whitened pass, symmetric
         {   // X1 = C9^-T Bw
@@ -1038,6 +1053,7 @@ int tsvgp_set_option(tsvgp_ctx* c, const char* name, double value) {
     if (!strcmp(name, "streams")) { c->n_streams = value < 1 ? 1 : (value > MAXS ? MAXS : (int)value); return TSVGP_OK; }
     if (!strcmp(name, "route")) { c->route_opt = (int)value; c->k9_valid = false; return TSVGP_OK; }
     if (!strcmp(name, "route_cond_max")) { c->route_cond_max = value; return TSVGP_OK; }
+    if (!strcmp(name, "route_exact_min")) { c->route_exact_min = value; return TSVGP_OK; }
     if (!strcmp(name, "white")) {   // switch the context to the whitened sibling model (resets the sites to its defaults)
         c->white = value != 0.0;
         c->sites_set = false;

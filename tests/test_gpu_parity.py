@@ -142,6 +142,43 @@ def test_ill_conditioned_inducing_points_take_the_whitened_route():
     check(errs, tol=1e-6)
 
 
+def test_exact_route_matches_too():
+    # route 3: A = K9^-1 Kuf formed per slab and the Gram product A^T diag(h) A accumulated directly (tsvgp.py:271-281 literally)
+    import tsvgp_b200.synth as synth
+    check(run_pair(synth.describe("cfg3"), n_rows=3000, M=384, steps=2, num_data=30_000, options={"route": 3}))
+    check(run_pair(synth.describe("cfg2"), n_rows=2000, M=200, steps=2, options={"route": 3, "chunk": 512}))
+
+
+def test_extreme_conditioning_keeps_the_reference_error_behaviour():
+    # examples/c_api_example.c's data: 40 inducing points 0.05 apart under an SE kernel of lengthscale 0.2 — cond(Kuu) = 5e17,
+    # cond(Kuu + 1e-9 I) = 9e9.  The reference's order (A first, then the Gram product) keeps -2 Lambda_2 + jitter I positive
+    # definite here and the step succeeds; the two-sided product of the whitened route does not (min eigenvalue -7e-4).  The
+    # automatic route must therefore take the exact route and must not raise.  Results agree with the oracle at the level two
+    # float64 implementations can agree at this conditioning (the oracle itself is ~1e-3 from exact arithmetic here).
+    import tsvgp_b200 as tb
+    N, M = 2000, 40
+    s = 12345
+    X, Y = np.zeros((N, 1)), np.zeros((N, 1))
+    for i in range(N):
+        s = (s * 1664525 + 1013904223) & 0xFFFFFFFF
+        X[i] = 2.0 * (s >> 8) / 16777216.0 - 1.0
+        s = (s * 1664525 + 1013904223) & 0xFFFFFFFF
+        Y[i] = np.sin(6.0 * X[i]) + 0.2 * ((s >> 8) / 16777216.0 - 0.5)
+    Z = np.linspace(-1.0, 1.0, M)[:, None]
+    k, lik = orc.SquaredExponential(lengthscales=0.2, variance=1.0), orc.Gaussian(variance=0.05)
+    dev = tb.t_SVGP(k, lik, orc.InducingPoints(Z.copy()))
+    ref = orc.OracleTSVGP(k, lik, orc.InducingPoints(Z.copy()))
+    for _ in range(3):
+        dev.natgrad_step((X, Y), lr=0.9)
+        ref.natgrad_step((X, Y), lr=0.9)
+    assert dev.timings()["route"] == 3 and dev.timings()["cond_est"] > 1e8
+    Xs = np.linspace(-0.9, 0.9, 50)[:, None]
+    mu_d, var_d = dev.predict_f(Xs)
+    mu_r, var_r = ref.predict_f(Xs)
+    assert relerr(mu_d, mu_r) < 1e-3 and np.max(np.abs(mu_d[:, 0] - np.sin(6.0 * Xs[:, 0]))) < 0.05
+    dev.close()
+
+
 def test_lr_one_and_ard_and_mean_function():
     import tsvgp_b200.synth as synth
     cfg = synth.describe("cfg5")
