@@ -2,6 +2,7 @@
 #include "kernels.cuh"
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace tsvgp {
 
@@ -646,15 +647,253 @@ __global__ void __launch_bounds__(256) diag_trtri_kernel(const double* L, long l
     tri_inverse_regs(S, Dinv + (long)blockIdx.x * DB * DB);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Blocked variant of the same operation (Cholesky of one 128x128 block AND X = L^-1): 4 x 4 sub-blocks of 32 x 32 in shared
+// memory (row stride 36 doubles = 4 mod 16, so the DMMA fragment loads below are bank-conflict-free in both orientations).
+// Per block step j:
+//   (1) ONE warp factors the 32 x 32 diagonal sub-block with lane r owning row r in registers: per pivot one shuffle (the
+//       pivot), rsqrt, the scaled column published through a double-buffered shared column (one __syncwarp, no CTA barrier),
+//       FMAs only; the right-looking elimination of L X = I rides on the same pivot, so X_jj = L_jj^-1 comes out of the same loop;
+//   (2) all 8 warps, DMMA: panel L_ij = A_ij X_jj^T (i > j) and the finished block row of the inverse X_jc = X_jj Xcur_jc (c < j);
+//   (3) all 8 warps, DMMA: trailing A_ik -= L_ij L_kj^T (j < k <= i) and the inverse's elimination Xcur_ic -= L_ij X_jc (c <= j).
+// 11 CTA barriers instead of 128, and the O(n^3) part runs on the FP64 tensor pipe.  The per-pivot kernel above is latency-bound
+// on its barrier chain (77 us per block, 13 us of arithmetic: tools/diag_bench).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int QB = 32, QLD = 36, QBLK = QB * QLD, QNB = DB / QB;
+#ifdef TSVGP_DIAG_TIMING   // tools/diag_bench only: cycle stamps of the phases of one block (thread 0)
+__device__ long long g_diag_clk[32];
+#define DIAG_STAMP(i) do { if (threadIdx.x == 0) g_diag_clk[i] = clock64(); } while (0)
+#else
+#define DIAG_STAMP(i) do { } while (0)
+#endif
+__device__ __forceinline__ int qidx(int i, int j) { return (i * (i + 1) / 2 + j) * QBLK; }
+
+// One warp: the (8 TM) x (8 TN) region at (r0, n0) of the 32 x 32 block C from the 32 x 32 blocks A ([r][k]) and B
+// (NT: stored [n][k];  !NT: stored [k][n]).   mode 0: C = A B,  1: C -= A B,  2: C = -A B.   k runs over [klo, 32).
+// TRI = 1: B is a lower-triangular block used as B^T (NT) with n0 = 0 — tile column j needs k < 8 (j + 1) only;
+// TRI = 2: A is a lower-triangular block with r0 = 0 — tile row i needs k < 8 (i + 1) only.
+// Every operand element is read before the warp stores (C may alias A when the region spans whole rows, or B when it spans
+// whole columns).
+template <int TM, int TN, bool NT, int TRI>
+__device__ __forceinline__ void qblk_mma(double* C, const double* A, const double* B, int r0, int n0, int mode, int klo, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    double acc[TM][TN][2];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < QB; ks += 4) {
+        if (ks >= klo) {   // warp-uniform
+            double a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = (TRI == 2 && ks >= 8 * (i + 1)) ? 0.0 : A[(r0 + 8 * i + g) * QLD + ks + t];
+#pragma unroll
+            for (int j = 0; j < TN; ++j)
+                b[j] = (TRI == 1 && ks >= 8 * (j + 1)) ? 0.0 : (NT ? B[(n0 + 8 * j + g) * QLD + ks + t] : B[(ks + t) * QLD + n0 + 8 * j + g]);
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    if (TRI == 1 && ks >= 8 * (j + 1)) continue;
+                    if (TRI == 2 && ks >= 8 * (i + 1)) continue;
+                    dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            double2* dst = reinterpret_cast<double2*>(C + (r0 + 8 * i + g) * QLD + n0 + 8 * j + 2 * t);
+            double2 v;
+            if (mode == 1) {
+                v = *dst;
+                v.x -= acc[i][j][0];
+                v.y -= acc[i][j][1];
+            } else if (mode == 2) {
+                v.x = -acc[i][j][0];
+                v.y = -acc[i][j][1];
+            } else {
+                v.x = acc[i][j][0];
+                v.y = acc[i][j][1];
+            }
+            *dst = v;
+        }
+}
+
+// Warp 0: in-place Cholesky of the 32 x 32 block Ajj (lower; the upper part is written as zeros).  Lane r owns ROW r of A
+// (a[c], c < r) and its diagonal element d.  Per pivot k the dependent chain is shuffle(d from lane k) -> rsqrt -> l = a[k] rs ->
+// d -= l^2: the next pivot never waits on shared memory.  The scaled column k and 1 / L[k][k] are published in colbuf[k][.] /
+// rsbuf[k] and signalled on mbarrier k, which is all warp 1 (below) needs to run the inverse one pivot behind on another scheduler.
+// Returns 0, or k + 1 for the first non-positive (or NaN) pivot k.
+__device__ __forceinline__ int warp_potrf_32(double* Ajj, double* colbuf, double* rsbuf, uint64_t* bars, int lane) {
+    double a[QB];
+#pragma unroll
+    for (int c = 0; c < QB; ++c) a[c] = c < lane ? Ajj[lane * QLD + c] : 0.0;
+    double d = Ajj[lane * QLD + lane], dl = 0.0;
+    int fail = 0;
+#pragma unroll
+    for (int k = 0; k < QB; ++k) {
+        const double piv = __shfl_sync(0xffffffffu, d, k);
+        if (!(piv > 0.0) && fail == 0) fail = k + 1;   // uniform across the warp
+        const double rs = rsqrt(piv);
+        const double lk = lane > k ? a[k] * rs : 0.0;
+        d = fma(-lk, lk, d);
+        a[k] = lk;
+        if (lane == k) dl = piv * rs;
+        colbuf[k * QB + lane] = lk;
+        if (lane == 0) rsbuf[k] = rs;
+        mbar_arrive(bars + k);   // release: the column and rs are visible to whoever observes the completed phase
+        __syncwarp();
+#pragma unroll
+        for (int c = k + 1; c < QB; ++c) a[c] = fma(-lk, colbuf[k * QB + c], a[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < QB; ++c) Ajj[lane * QLD + c] = c < lane ? a[c] : (c == lane ? dl : 0.0);
+    return fail;
+}
+
+// Warp 1: Xjj = Ljj^-1 by right-looking elimination of L X = I, lane c owning COLUMN c of X, consuming the columns of L as warp 0
+// publishes them:  X[k][c] *= 1 / L[k][k] ;  X[r][c] -= L[r][k] X[k][c]  (r > k).
+__device__ __forceinline__ void warp_trtri_32(double* Xjj, const double* colbuf, const double* rsbuf, uint64_t* bars, uint32_t parity,
+                                              int lane) {
+    double x[QB];
+#pragma unroll
+    for (int c = 0; c < QB; ++c) x[c] = c == lane ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < QB; ++k) {
+        mbar_wait(bars + k, parity);
+        const double xk = x[k] * rsbuf[k];   // X[k][lane], final
+        x[k] = xk;
+#pragma unroll
+        for (int c = k + 1; c < QB; ++c) x[c] = fma(-colbuf[k * QB + c], xk, x[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < QB; ++c) Xjj[c * QLD + lane] = x[c];   // zero above the diagonal by construction
+}
+
+__global__ void __launch_bounds__(256) diag_potrf_inv_blocked_kernel(double* A, long lda, double* Dinv, int blk, int* info) {
+    extern __shared__ __align__(16) double S[];
+    double* As = S;                                       // 10 lower sub-blocks of A -> L
+    double* Xs = S + (QNB * (QNB + 1) / 2) * QBLK;        // 10 lower sub-blocks of X = L^-1
+    __shared__ __align__(16) double colbuf[QB * QB];   // scaled columns of the diagonal sub-block being factored
+    __shared__ __align__(16) double rsbuf[QB];
+    __shared__ __align__(8) uint64_t bars[QB];          // one per pivot: warp 0 -> warp 1 hand-over (phase = block step)
+    __shared__ int sfail;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) sfail = 0;
+    if (tid < QB) mbar_init(bars + tid, 32);
+    DIAG_STAMP(0);
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Dinv) | (uintptr_t)(lda * 8)) & 15) == 0;
+    if (vec_ok) {   // all 16-byte pieces of the lower sub-blocks in flight at once
+        for (int u = tid; u < DB * (DB / 2); u += 256) {
+            const int r = u >> 6, c = (u & 63) * 2;
+            if ((c >> 5) <= (r >> 5)) cp_async16(As + qidx(r >> 5, c >> 5) + (r & 31) * QLD + (c & 31), A + (long)r * lda + c);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+    } else {
+        for (int e = tid; e < DB * DB; e += 256) {
+            const int r = e >> 7, c = e & 127;
+            if ((c >> 5) <= (r >> 5)) As[qidx(r >> 5, c >> 5) + (r & 31) * QLD + (c & 31)] = A[(long)r * lda + c];
+        }
+    }
+    __syncthreads();
+    DIAG_STAMP(1);
+#pragma unroll 1
+    for (int j = 0; j < QNB; ++j) {
+        if (warp == 0) {
+            const int f = warp_potrf_32(As + qidx(j, j), colbuf, rsbuf, bars, lane);
+            if (f && lane == 0) sfail = j * QB + f;
+        } else if (warp == 1) {
+            warp_trtri_32(Xs + qidx(j, j), colbuf, rsbuf, bars, (uint32_t)(j & 1), lane);
+        }
+        __syncthreads();
+        DIAG_STAMP(2 + 3 * j);
+        if (sfail) break;   // uniform
+        {   // (2) panel rows below (row halves: the product is in place on A_ij) and the finished block row j of X (column halves)
+            int tsk = 0;
+            for (int i = j + 1; i < QNB; ++i)
+                for (int h = 0; h < 2; ++h)
+                    if ((tsk++ & 7) == warp)
+                        qblk_mma<2, 4, true, 1>(As + qidx(i, j), As + qidx(i, j), Xs + qidx(j, j), 16 * h, 0, 0, 0, lane);
+            for (int c = 0; c < j; ++c)
+                for (int h = 0; h < 2; ++h)
+                    if ((tsk++ & 7) == warp)
+                        qblk_mma<4, 2, false, 2>(Xs + qidx(j, c), Xs + qidx(j, j), Xs + qidx(j, c), 0, 16 * h, 0, 0, lane);
+        }
+        __syncthreads();
+        DIAG_STAMP(3 + 3 * j);
+        if (j + 1 < QNB) {   // (3) trailing update of A and the elimination step of L X = I, in 16 x 16 quarters
+            int tsk = 0;
+            for (int i = j + 1; i < QNB; ++i) {
+                for (int k = j + 1; k <= i; ++k)
+                    for (int qd = 0; qd < 4; ++qd) {
+                        if (i == k && qd == 1) continue;   // strictly upper quarter of a diagonal block
+                        if ((tsk++ & 7) == warp)
+                            qblk_mma<2, 2, true, 0>(As + qidx(i, k), As + qidx(i, j), As + qidx(k, j), 16 * (qd >> 1), 16 * (qd & 1), 1, 0, lane);
+                    }
+                for (int c = 0; c <= j; ++c)
+                    for (int qd = 0; qd < 4; ++qd)
+                        if ((tsk++ & 7) == warp)   // c == j: X_jj is lower triangular, rows k < n0 contribute nothing
+                            qblk_mma<2, 2, false, 0>(Xs + qidx(i, c), As + qidx(i, j), Xs + qidx(j, c), 16 * (qd >> 1), 16 * (qd & 1),
+                                                     c == j ? 2 : 1, c == j ? 16 * (qd & 1) : 0, lane);
+            }
+            __syncthreads();
+            DIAG_STAMP(4 + 3 * j);
+        }
+    }
+    if (sfail) {
+        if (tid == 0) atomicCAS(info, 0, blk * DB + sfail);
+        return;
+    }
+    if (vec_ok) {
+#pragma unroll 4
+        for (int u = tid; u < DB * (DB / 2); u += 256) {
+            const int r = u >> 6, c = (u & 63) * 2;
+            if ((c >> 5) > (r >> 5)) continue;   // strictly upper sub-blocks: A's are zeroed by the caller (chol_lower), Dinv's stay zero
+            const int o = qidx(r >> 5, c >> 5) + (r & 31) * QLD + (c & 31);
+            double2 l = *reinterpret_cast<const double2*>(As + o);
+            double2 x = *reinterpret_cast<const double2*>(Xs + o);
+            if (c > r) l.x = x.x = 0.0;
+            if (c + 1 > r) l.y = x.y = 0.0;
+            *reinterpret_cast<double2*>(A + (long)r * lda + c) = l;
+            *reinterpret_cast<double2*>(Dinv + r * DB + c) = x;
+        }
+    } else {
+        for (int e = tid; e < DB * DB; e += 256) {
+            const int r = e >> 7, c = e & 127;
+            if ((c >> 5) > (r >> 5)) continue;
+            const int o = qidx(r >> 5, c >> 5) + (r & 31) * QLD + (c & 31);
+            A[(long)r * lda + c] = c <= r ? As[o] : 0.0;
+            Dinv[e] = c <= r ? Xs[o] : 0.0;
+        }
+    }
+    DIAG_STAMP(14);
+}
+
+#ifdef TSVGP_DIAG_TIMING
+int diag_read_stamps(long long* out32) { return (int)cudaMemcpyFromSymbol(out32, g_diag_clk, sizeof(long long) * 32); }
+#endif
+static int g_diag_variant = 1;   // 1 = blocked (DMMA) kernel, 0 = per-pivot register kernel (kept for A/B timing: tools/diag_bench)
+void diag_set_variant(int v) { g_diag_variant = v; }
+constexpr int DIAG_BLOCKED_SMEM = 2 * (QNB * (QNB + 1) / 2) * QBLK * 8;
+
 // opt in to the large dynamic shared memory of the diagonal-block kernels on the CURRENT device (call once per context)
 int diag_init() {
     int e = (int)cudaFuncSetAttribute(diag_potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB * DB_LD * 8);
     e |= (int)cudaFuncSetAttribute(diag_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB * DB_LD * 8);
+    e |= (int)cudaFuncSetAttribute(diag_potrf_inv_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_BLOCKED_SMEM);
+    if (const char* v = getenv("TSVGP_DIAG_VARIANT")) g_diag_variant = atoi(v);
     return e;
 }
 
 int diag_potrf_inv_launch(double* A, long lda, double* Dinv, int blk_index, int* info, cudaStream_t s) {
-    diag_potrf_inv_kernel<<<1, 256, DB * DB_LD * 8, s>>>(A, lda, Dinv, blk_index, info);
+    if (g_diag_variant == 1) diag_potrf_inv_blocked_kernel<<<1, 256, DIAG_BLOCKED_SMEM, s>>>(A, lda, Dinv, blk_index, info);
+    else diag_potrf_inv_kernel<<<1, 256, DB * DB_LD * 8, s>>>(A, lda, Dinv, blk_index, info);
     return count_launch();
 }
 int diag_trtri_launch(const double* L, long lda, double* Dinv, int nblk, cudaStream_t s) {

@@ -56,9 +56,12 @@ int gemv_t_launch(const double* A, long lda, int m, int n, const double* x, doub
 int unpack_rows_launch(const double* ZsT, long ldz, int Mp, int D, double* Zs, cudaStream_t s);
 
 int diag_init();   // once per device/context: opt in to the dynamic shared memory of the diagonal-block kernels
+void diag_set_variant(int v);   // 1 = blocked DMMA kernel (default), 0 = per-pivot register kernel (A/B timing; env TSVGP_DIAG_VARIANT)
 // --- diagonal blocks --------------------------------------------------------------------------------------------
 // In-place lower Cholesky of the 128x128 block at A (lda) and its inverse into Dinv (ld 128, dense lower).
 // info[0] = first failing global pivot index + 1 (blk_index*128 + k + 1), left untouched on success.
+// Dinv must have been zero-filled once (cudaMemset) by its owner: the blocked kernel never writes the strictly upper 32 x 32
+// sub-blocks of Dinv, and leaves those of A to the caller (chol_lower zeroes the upper triangle at the end).
 int diag_potrf_inv_launch(double* A, long lda, double* Dinv, int blk_index, int* info, cudaStream_t s);
 // Dinv[b] = inverse of the lower-triangular 128x128 diagonal block b of L, b < nblk (batched)
 int diag_trtri_launch(const double* L, long lda, double* Dinv, int nblk, cudaStream_t s);

@@ -232,6 +232,7 @@ int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     NEED(c->X1 = p.get(mm)); NEED(c->X2 = p.get(mm)); NEED(c->C9 = p.get(mm)); NEED(c->C9inv = p.get(mm));
     NEED(c->G2 = p.get(mm)); NEED(c->P = p.get(mm)); NEED(c->K9inv = p.get(mm)); NEED(c->tmp = p.get((size_t)((c->Mp / 128 + 1) / 2) * 128 * mp));   // trtri_lower: ceil(nblk/2) block rows
     NEED(c->dinv = p.get((size_t)(c->Mp / 128) * 128 * 128));
+    CU(cudaMemset(c->dinv, 0, sizeof(double) * (size_t)(c->Mp / 128) * 128 * 128));   // contract of diag_potrf_inv_launch
     for (int s = 0; s < MAXS; ++s) { NEED(c->stats[s] = p.get(mm + mp + 4)); NEED(c->stats2[s] = p.get(mm + mp)); }
     NEED(c->alpha = p.get(mp)); NEED(c->mZ = p.get(mp)); NEED(c->mq = p.get(mp)); NEED(c->v1 = p.get(mp)); NEED(c->v2 = p.get(mp));
     NEED(c->v3 = p.get(mp)); NEED(c->gwork = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal = p.get(N_SCAL)); NEED(c->red = p.get(128));
@@ -240,6 +241,7 @@ int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     NEED(c->C6 = p.get(mm)); NEED(c->C6inv = p.get(mm)); NEED(c->lam1_bak = p.get(mp));
     c->c6_valid = c->wpost_valid = c->wkl_valid = false;
     NEED(c->tmp2 = p.get((size_t)((c->Mp / 128 + 1) / 2) * 128 * mp)); NEED(c->dinv2 = p.get((size_t)(c->Mp / 128) * 128 * 128));
+    CU(cudaMemset(c->dinv2, 0, sizeof(double) * (size_t)(c->Mp / 128) * 128 * 128));
     NEED(c->pv1 = p.get(mp)); NEED(c->pv2 = p.get(mp)); NEED(c->gwork2 = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal2 = p.get(N_SCAL));
     c->sites_set = c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = c->c6_valid = c->wpost_valid = c->wkl_valid = false;
     c->chunk = 0;   // slab workspace depends on Mp
