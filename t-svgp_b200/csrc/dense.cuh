@@ -9,11 +9,13 @@ namespace tsvgp {
 // dinv: workspace [n/128][128*128], receives the inverses of the diagonal blocks of L.
 // info: device int, set to (failing pivot index + 1) if A is not positive definite (left untouched otherwise).
 // Restates tf.linalg.cholesky as called at reference src/models/tsvgp.py:270,300 and src/util.py:382.
-int chol_lower(double* A, long ld, int n, double* dinv, int* info, cudaStream_t s);
+// ws / ws_doubles: optional split-K workspace (gemm_launch_auto) private to the stream; nullptr = never split.
+int chol_lower(double* A, long ld, int n, double* dinv, int* info, cudaStream_t s, double* ws = nullptr, size_t ws_doubles = 0);
 
 // Linv = L^-1 for lower-triangular L.  dinv must hold the inverses of L's diagonal blocks (from chol_lower, or
 // diag_trtri_launch).  tmp: workspace [ceil(n/256)*128][ld].  Turns tf.linalg.triangular_solve / cholesky_solve
 // (reference tsvgp.py:271, util.py:386) into tensor-core products.
-int trtri_lower(const double* L, long ld, int n, const double* dinv, double* Linv, double* tmp, cudaStream_t s);
+int trtri_lower(const double* L, long ld, int n, const double* dinv, double* Linv, double* tmp, cudaStream_t s, double* ws = nullptr,
+                size_t ws_doubles = 0);
 
 }  // namespace tsvgp

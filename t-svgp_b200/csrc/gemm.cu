@@ -53,8 +53,9 @@ __device__ __forceinline__ void gemm_epilogue(const GemmP& p, double (&acc)[8][4
                                               int tid, int warp, int g, int t, int wm, int wn) {
     if (EPI == EPI_STORE || EPI == EPI_STORE_COLNORM) {
         const bool split = p.ksplit > 1;
-        double* Cg = split ? p.part + (long)ks * p.part_stride + (long)bz * p.sC
+        double* Cg = split ? p.part + (long)ks * p.part_stride + (long)bz * (p.part_sC ? p.part_sC : p.sC)
                            : ((p.C2 != nullptr && ks == 1) ? p.C2 : p.C) + (long)bz * p.sC;
+        const long ldo = (split && p.part_ld) ? p.part_ld : p.ldc;
         const double alpha = p.alpha, beta = split ? 0.0 : p.beta;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -62,7 +63,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmP& p, double (&acc)[8][4
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int col = tj * BN + wn + 8 * j + 2 * t;
-                double2* ptr = reinterpret_cast<double2*>(Cg + row * p.ldc + col);
+                double2* ptr = reinterpret_cast<double2*>(Cg + row * ldo + col);
                 double2 o;
                 o.x = alpha * acc[i][j][0];
                 o.y = alpha * acc[i][j][1];
@@ -387,20 +388,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
     gemm_epilogue<EPI>(p, acc, smem, ti, tj, bz, ks, tid, warp, g, t, wm, wn);
 }
 
-__global__ void splitk_reduce_kernel(GemmP p) {
+constexpr int RED_SLICES = 8;   // row slices per 128 x 128 tile: the reduction is bandwidth work, spread it over 8x the CTAs
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmP p) {
     const int tj = blockIdx.x, ti = blockIdx.y;
     if (p.lower_out && tj > ti) return;
     if (p.row_mod > 1 && ti % p.row_mod != p.row_rem) return;
-    // 256 threads, each handles a 64-element strip of the 128x128 tile
-    for (int e = threadIdx.x; e < BM * BN / 2; e += blockDim.x) {
-        const int r = e / (BN / 2), c = (e % (BN / 2)) * 2;
-        const long off = (long)(ti * BM + r) * p.ldc + tj * BN + c;
+    const int bz = blockIdx.z / RED_SLICES, sl = blockIdx.z % RED_SLICES;
+    const long pld = p.part_ld ? p.part_ld : p.ldc;
+    const double* part = p.part + (long)bz * (p.part_sC ? p.part_sC : p.sC);
+    double* C = p.C + (long)bz * p.sC;
+    constexpr int ROWS = BM / RED_SLICES;
+    // 256 threads over a 16 x 128 strip, two doubles each
+    for (int e = threadIdx.x; e < ROWS * BN / 2; e += blockDim.x) {
+        const int r = sl * ROWS + e / (BN / 2), c = (e % (BN / 2)) * 2;
+        const long poff = (long)(ti * BM + r) * pld + tj * BN + c;
         double2 s = make_double2(0.0, 0.0);
+#pragma unroll 4
         for (int k = 0; k < p.ksplit; ++k) {
-            const double2 v = *reinterpret_cast<const double2*>(p.part + (long)k * p.part_stride + off);
+            const double2 v = *reinterpret_cast<const double2*>(part + (long)k * p.part_stride + poff);
             s.x += v.x; s.y += v.y;
         }
-        double2* ptr = reinterpret_cast<double2*>(p.C + off);
+        double2* ptr = reinterpret_cast<double2*>(C + (long)(ti * BM + r) * p.ldc + tj * BN + c);
         if (p.beta != 0.0) {
             const double2 old = *ptr;
             s.x += p.beta * old.x; s.y += p.beta * old.y;
@@ -521,9 +529,42 @@ int gemm_launch(const GemmP& p, cudaStream_t stream) {
 }
 
 int splitk_reduce_launch(const GemmP& p, cudaStream_t stream) {
-    dim3 grid(p.n / BN, p.m / BM, 1);
+    dim3 grid(p.n / BN, p.m / BM, p.batch * RED_SLICES);
     splitk_reduce_kernel<<<grid, 256, 0, stream>>>(p);
     return count_launch();
+}
+
+int gemm_launch_auto(GemmP p, cudaStream_t stream, double* ws, size_t ws_doubles) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const bool eligible = ws && p.ksplit == 1 && !p.C2 && !p.gvec && !p.kscale && p.epilogue == EPI_STORE && p.m % BM == 0 && p.n % BN == 0;
+    if (eligible) {
+        const long nti = p.m / BM, ntj = p.n / BN;
+        long tiles = p.lower_out ? (ntj >= nti ? nti * (nti + 1) / 2 : nti * ntj - ntj * (ntj - 1) / 2) : nti * ntj;   // tiles with tj <= ti
+        if (p.row_mod > 1) tiles = (tiles + p.row_mod - 1) / p.row_mod;
+        tiles *= p.batch;
+        // contraction length a typical tile sees (triangular operands skip about half of their k-blocks)
+        long keff = p.k;
+        if (p.a_tri || p.b_tri) keff = keff / 2 > BM ? keff / 2 : (keff < BM ? keff : BM);
+        const long kt = keff / BK;
+        long ks = tiles > 0 ? sms / tiles : 1;
+        if (ks > kt / 2) ks = kt / 2;                       // at least two k-tiles per piece
+        const size_t slab = (size_t)p.batch * p.m * p.n;    // compact partial image of C
+        if (slab > 0 && ks > (long)(ws_doubles / slab)) ks = (long)(ws_doubles / slab);
+        if (ks > 16) ks = 16;
+        if (ks >= 2) {
+            p.ksplit = (int)ks; p.part = ws; p.part_stride = (long)slab; p.part_ld = p.n; p.part_sC = (long)p.m * p.n;
+            int e = gemm_launch(p, stream);
+            if (e) return e;
+            return splitk_reduce_launch(p, stream);
+        }
+    }
+    return gemm_launch(p, stream);
 }
 
 }  // namespace tsvgp

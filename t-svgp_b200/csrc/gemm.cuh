@@ -31,6 +31,7 @@ struct GemmP {
     int epilogue = EPI_STORE;
     double* norm_out = nullptr; long ldn = 0;   // EPI_COLNORM: norm_out[tile_i * ldn + j] = sum_{i in tile} C(i,j)^2
     int ksplit = 1; double* part = nullptr; long part_stride = 0;   // split-K partial slabs [ksplit][m*ldc]; caller reduces
+    long part_ld = 0, part_sC = 0;    // row / batch strides of the partial slabs when they are stored more compactly than C (0 = ldc / sC)
     int batch = 1; long sA = 0, sB = 0, sC = 0;
     // Two-piece k split for load balance (no atomics): CTAs with blockIdx.z == 0 contract k in [0, ksp) into C, CTAs with
     // blockIdx.z == 1 contract [ksp, k) into C2 (same layout, same beta).  The z = 0 pieces are dispatched first; with
@@ -46,6 +47,11 @@ int gemm_launch(const GemmP& p, cudaStream_t stream);
 
 // C = beta*C + sum_s part[s]  over the tiles gemm_launch wrote (lower tiles only if lower_out)
 int splitk_reduce_launch(const GemmP& p, cudaStream_t stream);
+
+// gemm_launch that splits the contraction over otherwise idle SMs when the product has few output tiles (the latency-bound
+// M x M phases at small M, Cholesky panels, triangular-inverse nodes): partial tiles go to `ws` (ws_doubles doubles, owned by
+// the caller, one per stream) and are summed by splitk_reduce_launch.  Falls back to the plain launch when nothing is gained.
+int gemm_launch_auto(GemmP p, cudaStream_t stream, double* ws, size_t ws_doubles);
 
 // k split point for `tiles` equal output tiles of contraction length k on this device's SMs (multiple of 16; k = no split)
 int balanced_ksplit(int tiles, int k);

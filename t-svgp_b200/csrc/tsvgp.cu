@@ -106,6 +106,8 @@ struct tsvgp_ctx {
     double *stats[MAXS] = {};   // [B (Mp*Mp) | b (Mp) | tail (4)] per ping-pong stream
     double *stats2[MAXS] = {};  // second B accumulator per stream: the split-off k piece of the balanced SYRK
     double *alpha = nullptr, *mZ = nullptr, *mq = nullptr, *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *gwork = nullptr;
+    double *gws = nullptr, *gws2 = nullptr;   // split-K partial-tile workspaces of the M x M products (main / side stream)
+    size_t gws_doubles = 0;
     double *scal = nullptr, *red = nullptr;   // device scalars; [128] scratch of the two-stage reductions (per context)
     double jit6 = GPFLOW_DEFAULT_JITTER;   // jitter of K6 (gpflow default_jitter; predict_f_extra_data passes its own)
     double* lam1_bak = nullptr;
@@ -209,6 +211,7 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale, bool only
 double kl_white_from_scalars(const tsvgp_ctx* c, const double* sc);
 bool dist_active(const tsvgp_ctx* c);
 int dense_gemm(tsvgp_ctx* c, GemmP p, cudaStream_t s);
+int mm_gemm(tsvgp_ctx* c, const GemmP& p, cudaStream_t s);
 
 bool is_device_ptr(const void* p) {
     cudaPointerAttributes a;
@@ -237,6 +240,8 @@ int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     NEED(c->alpha = p.get(mp)); NEED(c->mZ = p.get(mp)); NEED(c->mq = p.get(mp)); NEED(c->v1 = p.get(mp)); NEED(c->v2 = p.get(mp));
     NEED(c->v3 = p.get(mp)); NEED(c->gwork = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal = p.get(N_SCAL)); NEED(c->red = p.get(128));
     NEED(c->info = (int*)p.get(N_INFO)); NEED(c->flags = (int*)p.get(2));
+    c->gws_doubles = (size_t)4 << 20;   // 32 MB per stream: up to 16 partial images of a 512 x 512 product, 4 of a 1024 x 1024 one
+    NEED(c->gws = p.get(c->gws_doubles)); NEED(c->gws2 = p.get(c->gws_doubles));
     NEED(c->zaug = p.get(mp * 128)); NEED(c->fuu = p.get(mp * 128));
     NEED(c->C6 = p.get(mm)); NEED(c->C6inv = p.get(mm)); NEED(c->lam1_bak = p.get(mp));
     c->c6_valid = c->wpost_valid = c->wkl_valid = false;
@@ -314,14 +319,14 @@ int ensure_posterior(tsvgp_ctx* c) {
         } else {
             LA(set_scaled_identity_launch(c->Wm, ld, n, n, 1.0, 1.0, s));
             p.beta = 1.0;
-            LA(gemm_launch(p, s));
+            LA(mm_gemm(c, p, s));
         }
     }
     // reverse Cholesky W = Uw Uw^T through the index flip J W J = Lr Lr^T
     LA(flip_sym_launch(c->Wm, c->Wf, ld, n, s));
-    LA(chol_lower(c->Wf, ld, n, c->dinv, c->info + INFO_W, s));
+    LA(chol_lower(c->Wf, ld, n, c->dinv, c->info + INFO_W, s, c->gws, c->gws_doubles));
     LA(logdiag_launch(c->Wf, ld, n, c->scal + SC_LOGDIAG_W, s));
-    LA(trtri_lower(c->Wf, ld, n, c->dinv, c->X2, c->tmp, s));
+    LA(trtri_lower(c->Wf, ld, n, c->dinv, c->X2, c->tmp, s, c->gws, c->gws_doubles));
     LA(antitranspose_launch(c->X2, c->V, ld, n, s));   // V = Uw^-T (lower)
     CU(cudaMemsetAsync(c->T, 0, sizeof(double) * (size_t)n * ld, s));
     {   // T = L2 V  (lower x lower)
@@ -359,7 +364,7 @@ int ensure_kl_terms(tsvgp_ctx* c) {
         p.A = c->K6; p.lda = ld; p.a_kc = 1;
         p.B = c->T; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
         p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
-        LA(gemm_launch(p, s));
+        LA(mm_gemm(c, p, s));
     }
     LA(matdot_launch(c->T, c->X1, ld, n, c->scal + SC_TR_QK, c->red, s));
     LA(dot_launch(c->mq, c->alpha, n, c->scal + SC_M_ALPHA, s));
@@ -388,8 +393,8 @@ int ensure_posterior_white(tsvgp_ctx* c) {
     const long ld = n;
     if (!c->c6_valid || !c->cache_factors) {   // LA = chol(K6), LA^-1 : kernel only
         CU(cudaMemcpyAsync(c->C6, c->K6, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, s));
-        LA(chol_lower(c->C6, ld, n, c->dinv, c->info + INFO_W, s));
-        LA(trtri_lower(c->C6, ld, n, c->dinv, c->C6inv, c->tmp, s));
+        LA(chol_lower(c->C6, ld, n, c->dinv, c->info + INFO_W, s, c->gws, c->gws_doubles));
+        LA(trtri_lower(c->C6, ld, n, c->dinv, c->C6inv, c->tmp, s, c->gws, c->gws_doubles));
         c->c6_valid = true;
     }
     if (c->wpost_valid && c->cache_factors) return TSVGP_OK;
@@ -397,8 +402,8 @@ int ensure_posterior_white(tsvgp_ctx* c) {
     CU(cudaMemcpyAsync(c->Wm, c->K6, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, s));
     LA(vadd_inplace_launch(c->Wm, c->L2, (long)n * ld, s));
     LA(add_diag_launch(c->Wm, ld, n, 1e-9, s));
-    LA(chol_lower(c->Wm, ld, n, c->dinv, c->info + INFO_S, s));
-    LA(trtri_lower(c->Wm, ld, n, c->dinv, c->T, c->tmp, s));
+    LA(chol_lower(c->Wm, ld, n, c->dinv, c->info + INFO_S, s, c->gws, c->gws_doubles));
+    LA(trtri_lower(c->Wm, ld, n, c->dinv, c->T, c->tmp, s, c->gws, c->gws_doubles));
     // alpha = R^-1 lambda_1 ; mZ = K alpha (predict_f(Z), un-jittered Kuf) ; m_q = K6 alpha
     LA(gemv_n_launch(c->T, ld, n, n, c->lam1, 1.0, 0.0, c->v1, s));
     LA(gemv_t_launch(c->T, ld, n, n, c->v1, c->alpha, c->gwork, s));
@@ -419,8 +424,8 @@ int ensure_kl_terms_white(tsvgp_ctx* c) {
     const long ld = n;
     CU(cudaMemcpyAsync(c->Wf, c->K6, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, s));
     LA(vadd_inplace_launch(c->Wf, c->L2, (long)n * ld, s));
-    LA(chol_lower(c->Wf, ld, n, c->dinv, c->info + INFO_P, s));
-    LA(trtri_lower(c->Wf, ld, n, c->dinv, c->V, c->tmp, s));       // V = LR0^-1
+    LA(chol_lower(c->Wf, ld, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles));
+    LA(trtri_lower(c->Wf, ld, n, c->dinv, c->V, c->tmp, s, c->gws, c->gws_doubles));       // V = LR0^-1
     LA(logdiag_launch(c->Wf, ld, n, c->scal + SC_LOGDIAG_W, s));
     LA(logdiag_launch(c->C6, ld, n, c->scal + SC_PK0, s));
     {   // X1 = LR0^-1 LA  (lower x lower)
@@ -430,7 +435,7 @@ int ensure_kl_terms_white(tsvgp_ctx* c) {
         p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
         CU(cudaMemsetAsync(c->X1, 0, sizeof(double) * (size_t)n * ld, s));
         p.lower_out = 1;
-        LA(gemm_launch(p, s));
+        LA(mm_gemm(c, p, s));
     }
     LA(matdot_launch(c->X1, c->X1, ld, n, c->scal + SC_TR_QK, c->red, s));
     LA(gemv_n_launch(c->V, ld, n, n, c->lam1, 1.0, 0.0, c->v1, s));
@@ -751,6 +756,11 @@ int all_reduce(tsvgp_ctx* c, double* buf, size_t count) {
     return TSVGP_OK;
 }
 
+// Every M x M product outside the streaming pass goes through here: few output tiles (small M, panels) are split over the idle SMs.
+int mm_gemm(tsvgp_ctx* c, const GemmP& p, cudaStream_t s) {
+    return gemm_launch_auto(p, s, s == c->s_side ? c->gws2 : c->gws, c->gws_doubles);
+}
+
 // An M x M product of the dense phase.  With several ranks and a large M it is DISTRIBUTED: tile rows are dealt out cyclically,
 // each rank computes its rows into a zeroed C, and one all-reduce assembles the matrix on every rank (bit-identical everywhere:
 // each entry is one rank's value plus zeros).  Below `dist_min_m` the product is latency-bound and stays replicated.
@@ -759,12 +769,12 @@ bool dist_active(const tsvgp_ctx* c) { return c->world > 1 && c->Mp >= c->dist_m
 
 int dense_gemm(tsvgp_ctx* c, GemmP p, cudaStream_t s) {
     if (!dist_active(c) || p.beta != 0.0) {
-        LA(gemm_launch(p, s));
+        LA(mm_gemm(c, p, s));
         return TSVGP_OK;
     }
     CU(cudaMemsetAsync(p.C, 0, sizeof(double) * (size_t)p.m * p.ldc, s));
     p.row_mod = c->world; p.row_rem = c->rank;
-    LA(gemm_launch(p, s));
+    LA(mm_gemm(c, p, s));
     return all_reduce(c, p.C, (size_t)p.m * p.ldc);
 }
 
@@ -777,15 +787,15 @@ int start_k9(tsvgp_ctx* c, double jitter) {
     CU(cudaEventRecord(c->ev_kuu, c->s_main));
     CU(cudaStreamWaitEvent(s, c->ev_kuu, 0));
     LA(copy_add_diag_launch(c->K, c->C9, c->Mp, c->Mp, jitter, s));
-    LA(chol_lower(c->C9, c->Mp, c->Mp, c->dinv2, c->info + INFO_K9, s));
-    LA(trtri_lower(c->C9, c->Mp, c->Mp, c->dinv2, c->C9inv, c->tmp2, s));
+    LA(chol_lower(c->C9, c->Mp, c->Mp, c->dinv2, c->info + INFO_K9, s, c->gws2, c->gws_doubles));
+    LA(trtri_lower(c->C9, c->Mp, c->Mp, c->dinv2, c->C9inv, c->tmp2, s, c->gws2, c->gws_doubles));
     c->k9inv_valid = false;
     if (!dist_active(c)) {   // single rank / small M: form K9^-1 here, hidden behind the main stream's posterior preparation
         GemmP p;
         p.A = c->C9inv; p.lda = c->Mp; p.a_kc = 0; p.a_tri = 2;
         p.B = c->C9inv; p.ldb = c->Mp; p.b_kc = 0; p.b_tri = 2;
         p.C = c->K9inv; p.ldc = c->Mp; p.m = p.n = p.k = c->Mp; p.lower_out = 1;
-        LA(gemm_launch(p, s));
+        LA(mm_gemm(c, p, s));
         LA(mirror_lower_launch(c->K9inv, c->Mp, c->Mp, s));
         c->k9inv_valid = true;
     }
@@ -808,8 +818,13 @@ int start_k9(tsvgp_ctx* c, double jitter) {
         LA(probe_vector_launch(a, c->M, n, s));
         for (int it = 0; it < 8; ++it) {
             if (it == 7) LA(dot_launch(a, a, n, c->scal2 + SC_PI0, s));
-            LA(gemv_n_launch(c->C9inv, n, n, n, a, 1.0, 0.0, b, s));
-            LA(gemv_t_launch(c->C9inv, n, n, n, b, a, c->gwork2, s));
+            if (c->k9inv_valid) {   // K9^-1 itself is at hand (formed just above): one mat-vec per iteration instead of two
+                LA(gemv_n_launch(c->K9inv, n, n, n, a, 1.0, 0.0, b, s));
+                double* t = a; a = b; b = t;
+            } else {
+                LA(gemv_n_launch(c->C9inv, n, n, n, a, 1.0, 0.0, b, s));
+                LA(gemv_t_launch(c->C9inv, n, n, n, b, a, c->gwork2, s));
+            }
         }
         LA(dot_launch(a, a, n, c->scal2 + SC_PI1, s));
     }
@@ -913,10 +928,10 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale, bool only
             LA(vadd_inplace_launch(c->P, c->X2, (long)n * ld, s));
         } else {
             p.beta = 1.0;
-            LA(gemm_launch(p, s));
+            LA(mm_gemm(c, p, s));
         }
     }
-    LA(chol_lower(c->P, ld, n, c->dinv, c->info + INFO_P, s));
+    LA(chol_lower(c->P, ld, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles));
     // commit (skipped on the device if any variance was non-positive or a factorisation failed)
     LA(update_lambda1_launch(c->lam1, c->v2, c->v3, c->M, lr, scale, bad, c->info, s));
     LA(finalize_sites_launch(c->P, c->L2, ld, c->M, n, bad, c->info, s));
@@ -1178,7 +1193,7 @@ int tsvgp_get_lambda_2(tsvgp_ctx* c, double* lambda_2) {
     p.A = c->L2; p.lda = n; p.a_kc = 1; p.a_tri = 1;
     p.B = c->L2; p.ldb = n; p.b_kc = 1; p.b_tri = 1;
     p.C = c->X2; p.ldc = n; p.m = p.n = p.k = n; p.lower_out = 1;
-    LA(gemm_launch(p, s));
+    LA(mm_gemm(c, p, s));
     LA(mirror_lower_launch(c->X2, n, n, s));
     CU(cudaMemcpy2DAsync(lambda_2, sizeof(double) * c->M, c->X2, sizeof(double) * n, sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
     CU(cudaStreamSynchronize(s));
@@ -1390,7 +1405,7 @@ int tsvgp_elbo_grad(tsvgp_ctx* c, double scale, double* elbo, double* d_variance
         p.A = c->T; p.lda = ld; p.a_kc = 1; p.a_tri = 1;
         p.B = c->T; p.ldb = ld; p.b_kc = 1; p.b_tri = 1;
         p.C = c->Wm; p.ldc = ld; p.m = p.n = p.k = n; p.lower_out = 1;
-        LA(gemm_launch(p, s));
+        LA(mm_gemm(c, p, s));
     }
     LA(mirror_lower_launch(c->Wm, ld, n, s));
     auto full_gemm = [&](const double* A, const double* Bm, double* C) {   // C = A * Bm, all symmetric-or-full row-major
@@ -1398,7 +1413,7 @@ int tsvgp_elbo_grad(tsvgp_ctx* c, double scale, double* elbo, double* d_variance
         p.A = A; p.lda = ld; p.a_kc = 1;
         p.B = Bm; p.ldb = ld; p.b_kc = 0;
         p.C = C; p.ldc = ld; p.m = p.n = p.k = n;
-        return gemm_launch(p, s);
+        return mm_gemm(c, p, s);
     };
     LA(full_gemm(c->Wm, B, c->X1));        // Q B
     LA(full_gemm(c->X1, c->Wm, c->X2));    // Q B Q
@@ -1418,7 +1433,7 @@ int tsvgp_elbo_grad(tsvgp_ctx* c, double scale, double* elbo, double* d_variance
         p.A = c->G2; p.lda = ld; p.a_kc = 1;
         p.B = c->zaug; p.ldb = 128; p.b_kc = 0;
         p.C = c->fuu; p.ldc = 128; p.m = n; p.n = 128; p.k = n;
-        LA(gemm_launch(p, s));
+        LA(mm_gemm(c, p, s));
     }
     std::vector<double> Fuf((size_t)n * 128), Fuu((size_t)n * 128), Zs((size_t)n * D), ls(D), dZ((size_t)M * D);
     double tail[4], sc[N_SCAL];
@@ -1538,12 +1553,12 @@ int tsvgp_predict_f_extra_data(tsvgp_ctx* c, const double* Xnew, int64_t N, int 
         p.A = c->K6; p.lda = ld; p.a_kc = 1;
         p.B = c->G2; p.ldb = ld; p.b_kc = 0;
         p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
-        LA(gemm_launch(p, s));
+        LA(mm_gemm(c, p, s));
         GemmP q;
         q.A = c->X1; q.lda = ld; q.a_kc = 1;
         q.B = c->K6; q.ldb = ld; q.b_kc = 0;
         q.C = c->X2; q.ldc = ld; q.m = q.n = q.k = n; q.lower_out = 1;
-        LA(gemm_launch(q, s));
+        LA(mm_gemm(c, q, s));
         LA(mirror_lower_launch(c->X2, ld, n, s));
     }
     LA(axpby_guarded_launch(c->L2, c->X2, ld, c->M, 1.0, -2.0, nullptr, nullptr, s));
@@ -1572,21 +1587,21 @@ int tsvgp_posterior(tsvgp_ctx* c, double* m, double* chol_S) {
         p.A = c->T; p.lda = n; p.a_kc = 1; p.a_tri = 1;
         p.B = c->K6; p.ldb = n; p.b_kc = 0;
         p.C = c->X1; p.ldc = n; p.m = p.n = p.k = n;
-        LA(gemm_launch(p, s));
+        LA(mm_gemm(c, p, s));
         GemmP q;
         q.A = c->X1; q.lda = n; q.a_kc = 0;
         q.B = c->X1; q.ldb = n; q.b_kc = 0;
         q.C = c->X2; q.ldc = n; q.m = q.n = q.k = n; q.lower_out = 1;
-        LA(gemm_launch(q, s));
+        LA(mm_gemm(c, q, s));
         c->wkl_valid = false;
-        LA(chol_lower(c->X2, n, n, c->dinv, c->info + INFO_P, s));
+        LA(chol_lower(c->X2, n, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles));
         CU(cudaMemcpy2DAsync(chol_S, sizeof(double) * c->M, c->X2, sizeof(double) * n, sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
     } else if (chol_S) {   // S = K6 - (K6 T)(K6 T)^T   (util.py:387-388)
         GemmP p;
         p.A = c->K6; p.lda = n; p.a_kc = 1;
         p.B = c->T; p.ldb = n; p.b_kc = 0; p.b_tri = 2;
         p.C = c->X1; p.ldc = n; p.m = p.n = p.k = n;
-        LA(gemm_launch(p, s));
+        LA(mm_gemm(c, p, s));
         c->kl_valid = false;   // X1 is shared with the KL terms
         CU(cudaMemcpyAsync(c->X2, c->K6, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, s));
         GemmP q;
@@ -1594,8 +1609,8 @@ int tsvgp_posterior(tsvgp_ctx* c, double* m, double* chol_S) {
         q.B = c->X1; q.ldb = n; q.b_kc = 1;
         q.C = c->X2; q.ldc = n; q.m = q.n = q.k = n;
         q.alpha = -1.0; q.beta = 1.0; q.lower_out = 1;
-        LA(gemm_launch(q, s));
-        LA(chol_lower(c->X2, n, n, c->dinv, c->info + INFO_S, s));
+        LA(mm_gemm(c, q, s));
+        LA(chol_lower(c->X2, n, n, c->dinv, c->info + INFO_S, s, c->gws, c->gws_doubles));
         CU(cudaMemcpy2DAsync(chol_S, sizeof(double) * c->M, c->X2, sizeof(double) * n, sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
     }
     int info_h[N_INFO];

@@ -20,6 +20,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&dA, sizeof(double) * n * n)); CK(cudaMalloc(&dW, sizeof(double) * n * n)); CK(cudaMalloc(&dLinv, sizeof(double) * n * n));
     CK(cudaMalloc(&tmp, sizeof(double) * n * n)); CK(cudaMalloc(&dinv, sizeof(double) * (n / 128) * 128 * 128)); CK(cudaMalloc(&info, 16)); CK(cudaMemset(info, 0, 16)); CK(cudaMemset(dinv, 0, sizeof(double) * (n / 128) * 128 * 128));
     CK(cudaMemcpy(dA, A.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    double* ws; const size_t ws_doubles = (size_t)4 << 20; CK(cudaMalloc(&ws, sizeof(double) * ws_doubles));   // split-K workspace (gemm_launch_auto)
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); float ms;
     for (int variant = 0; variant < 2; ++variant) {
         diag_set_variant(variant);
@@ -83,10 +84,11 @@ int main(int argc, char** argv) {
     }
     for (int rep = 0; rep < 3; ++rep) {
         CK(cudaMemcpy(dW, dA, sizeof(double) * n * n, cudaMemcpyDeviceToDevice));
-        cudaEventRecord(e0); chol_lower(dW, n, n, dinv, info, 0); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
-        cudaEventElapsedTime(&ms, e0, e1); printf("chol_lower n=%d: %.3f ms  (%.2f TFLOP/s of n^3/3)\n", n, ms, (double)n * n * n / 3 / ms / 1e9);
-        cudaEventRecord(e0); trtri_lower(dW, n, n, dinv, dLinv, tmp, 0); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
-        cudaEventElapsedTime(&ms, e0, e1); printf("trtri_lower n=%d: %.3f ms\n", n, ms);
+        double* w = rep == 0 ? nullptr : ws;   // first repetition without split-K, for comparison
+        cudaEventRecord(e0); chol_lower(dW, n, n, dinv, info, 0, w, ws_doubles); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+        cudaEventElapsedTime(&ms, e0, e1); printf("chol_lower n=%d (%s): %.3f ms  (%.2f TFLOP/s of n^3/3)\n", n, w ? "auto split-K" : "no split", ms, (double)n * n * n / 3 / ms / 1e9);
+        cudaEventRecord(e0); trtri_lower(dW, n, n, dinv, dLinv, tmp, 0, w, ws_doubles); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+        cudaEventElapsedTime(&ms, e0, e1); printf("trtri_lower n=%d (%s): %.3f ms\n", n, w ? "auto split-K" : "no split", ms);
     }
     int h; CK(cudaMemcpy(&h, info, 4, cudaMemcpyDeviceToHost)); printf("info %d\n", h);
     std::vector<double> L((size_t)n * n), Li((size_t)n * n);
