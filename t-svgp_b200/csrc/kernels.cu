@@ -367,8 +367,45 @@ __global__ void __launch_bounds__(256) gemv_n_kernel(const double* __restrict__ 
     if (lane == 0) y[row] = alpha * s + (beta != 0.0 ? beta * y[row] : 0.0);
 }
 
+// long rows (the b += Kuf g mat-vec over a slab: n = points per slab): one CTA per row, four 16-byte loads in flight per thread
+__global__ void __launch_bounds__(256) gemv_n_wide_kernel(const double* __restrict__ A, long lda, int m, long n,
+                                                          const double* __restrict__ x, double alpha, double beta,
+                                                          double* __restrict__ y) {
+    __shared__ double sred[8];
+    const int row = blockIdx.x;
+    const double* a = A + (long)row * lda;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    long j = threadIdx.x * 2;
+    for (; j + 1 + 3 * 512 < n; j += 4 * 512) {
+        const double2 a0 = *reinterpret_cast<const double2*>(a + j), a1 = *reinterpret_cast<const double2*>(a + j + 512);
+        const double2 a2 = *reinterpret_cast<const double2*>(a + j + 1024), a3 = *reinterpret_cast<const double2*>(a + j + 1536);
+        const double2 x0 = *reinterpret_cast<const double2*>(x + j), x1 = *reinterpret_cast<const double2*>(x + j + 512);
+        const double2 x2 = *reinterpret_cast<const double2*>(x + j + 1024), x3 = *reinterpret_cast<const double2*>(x + j + 1536);
+        s0 = fma(a0.x, x0.x, s0); s0 = fma(a0.y, x0.y, s0);
+        s1 = fma(a1.x, x1.x, s1); s1 = fma(a1.y, x1.y, s1);
+        s2 = fma(a2.x, x2.x, s2); s2 = fma(a2.y, x2.y, s2);
+        s3 = fma(a3.x, x3.x, s3); s3 = fma(a3.y, x3.y, s3);
+    }
+    for (; j + 1 < n; j += 512) {
+        const double2 av = *reinterpret_cast<const double2*>(a + j);
+        const double2 xv = *reinterpret_cast<const double2*>(x + j);
+        s0 = fma(av.x, xv.x, s0); s0 = fma(av.y, xv.y, s0);
+    }
+    if (j < n) s0 = fma(a[j], x[j], s0);
+    double v = warp_sum((s0 + s1) + (s2 + s3));
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sred[w];
+        y[row] = alpha * t + (beta != 0.0 ? beta * y[row] : 0.0);
+    }
+}
+
 int gemv_n_launch(const double* A, long lda, int m, long n, const double* x, double alpha, double beta, double* y, cudaStream_t s) {
-    gemv_n_kernel<<<(m + 7) / 8, 256, 0, s>>>(A, lda, m, n, x, alpha, beta, y);
+    if (n >= 4096 && (n & 1) == 0 && (lda & 1) == 0) gemv_n_wide_kernel<<<m, 256, 0, s>>>(A, lda, m, n, x, alpha, beta, y);
+    else gemv_n_kernel<<<(m + 7) / 8, 256, 0, s>>>(A, lda, m, n, x, alpha, beta, y);
     return count_launch();
 }
 

@@ -24,6 +24,8 @@
 #include <string>
 #include <utility>
 #include <vector>
+#include <mutex>
+#include <thread>
 
 namespace tsvgp {
 thread_local long g_launches = 0;
@@ -69,12 +71,14 @@ struct tsvgp_ctx {
     cudaStream_t s_main = nullptr, s_pp[MAXS] = {}, s_side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join[MAXS] = {}, ev[N_EV] = {}, ev_kuu = nullptr, ev_side = nullptr;
     std::string err;
+    std::mutex err_mu;            // the side-stream issue thread may report an error too
     int last_info = 0;
 
     // options
     long chunk_opt = 0;        // 0 = automatic
     int n_streams = 2;
     int dist_min_m = 4096;     // distribute the dense M x M products over the ranks from this (padded) M upwards
+    int async_issue = 1;       // small M: enqueue the K9 chain from a helper host thread while this thread enqueues the posterior chain
     int fuse_b = 1;            // accumulate b += Kuf g inside the SYRK kernel instead of a separate mat-vec pass over the slab
     int balance = 1;           // split the SYRK's contraction in two pieces so that every SM gets equal work
     int cache_factors = 1;     // keep chol(K9) and the posterior factors between calls while their inputs are unchanged
@@ -179,7 +183,10 @@ namespace {
     do {                                                  \
         char b_[512];                                     \
         snprintf(b_, sizeof b_, __VA_ARGS__);             \
-        c->err = b_;                                      \
+        {                                                 \
+            std::lock_guard<std::mutex> g_(c->err_mu);    \
+            c->err = b_;                                  \
+        }                                                 \
         return (code);                                    \
     } while (0)
 #define CU(x)                                                                                            \
@@ -500,9 +507,21 @@ long pick_chunk(const tsvgp_ctx* c) {
     return nc;
 }
 
+// Points per slab actually used for a pass over n_points: the allocated width `nc`, shrunk so that the slabs are equal and their
+// number is a multiple of the slab streams (a 10 000-point minibatch runs as 2 x 5 120 side by side instead of 8 192 + 1 808)
+long used_chunk(const tsvgp_ctx* c, long n_points, long nc, int nstr) {
+    long nch = (n_points + nc - 1) / nc;
+    if (c->chunk_opt > 0 || n_points <= 2048 || nstr <= 1) return nc;
+    nch = round_up(nch, nstr);
+    const long ncu = round_up((n_points + nch - 1) / nch, 128);
+    return ncu < nc ? ncu : nc;
+}
+
 int ensure_slabs(tsvgp_ctx* c, long n_points, bool need_grad = false) {
     const long nc = pick_chunk(c);
-    const long nchunks = (n_points + nc - 1) / nc;
+    const int nstr_used = c->profile ? 1 : (c->n_streams < 1 ? 1 : (c->n_streams > MAXS ? MAXS : c->n_streams));
+    const long ncu = used_chunk(c, n_points, nc, nstr_used);
+    const long nchunks = (n_points + ncu - 1) / ncu;
     const long ve_need = (nchunks + 1) * ((nc + 255) / 256);
     const bool need_w = c->route == ROUTE_WHITENED || c->route == ROUTE_EXACT;
     const int want_streams = c->profile ? 1 : (c->n_streams < 1 ? 1 : (c->n_streams > MAXS ? MAXS : c->n_streams));
@@ -583,7 +602,8 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
         return cudaEventRecord(c->pev[pev_used++], st) != cudaSuccess;
     };
     const long vstride = (nc + 255) / 256;
-    const long nchunks = (N + nc - 1) / nc;
+    const long ncu = used_chunk(c, N, nc, nstr);   // slab width of this pass (<= the allocated width nc, which stays the leading dimension)
+    const long nchunks = (N + ncu - 1) / ncu;
     cudaStream_t sm = c->s_main;
 
     CU(cudaMemsetAsync(c->flags, 0, 2 * sizeof(int), sm));
@@ -601,8 +621,8 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
     for (long ci = 0; ci < nchunks; ++ci) {
         const int b = (int)(ci % nstr);
         cudaStream_t s = c->s_pp[b];
-        const long n0 = ci * nc;
-        const long nvalid = N - n0 < nc ? N - n0 : nc;
+        const long n0 = ci * ncu;
+        const long nvalid = N - n0 < ncu ? N - n0 : ncu;
         const int ncols = (int)round_up(nvalid, 128);
         if (mark(s)) FAIL(TSVGP_ERR_CUDA, "profile event");
         // (a) covariance slab K[Mp x ncols] and the partial means sum_i alpha_i K[i][n]
@@ -781,11 +801,53 @@ int dense_gemm(tsvgp_ctx* c, GemmP p, cudaStream_t s) {
 // K9 = K + jitter I = C9 C9^T and C9^-1 (tsvgp.py:268-271), kept while kernel, Z and jitter are unchanged.  It depends on the
 // kernel matrix only, so it is factored on a SIDE stream (own workspace) while the main stream builds the posterior factors
 // from the sites; both chains are latency-bound, so running them side by side nearly halves the prepare phase.
-int start_k9(tsvgp_ctx* c, double jitter) {
-    if (c->k9_valid && c->k9_jitter == jitter && c->cache_factors) return TSVGP_OK;
-    cudaStream_t s = c->s_side;
+bool k9_cached(const tsvgp_ctx* c, double jitter) { return c->k9_valid && c->k9_jitter == jitter && c->cache_factors; }
+
+int k9_fork(tsvgp_ctx* c) {   // the side stream starts after the kernel matrix K is complete on the main stream
     CU(cudaEventRecord(c->ev_kuu, c->s_main));
-    CU(cudaStreamWaitEvent(s, c->ev_kuu, 0));
+    CU(cudaStreamWaitEvent(c->s_side, c->ev_kuu, 0));
+    return TSVGP_OK;
+}
+
+int k9_chain(tsvgp_ctx* c, double jitter);
+
+int start_k9(tsvgp_ctx* c, double jitter) {
+    if (k9_cached(c, jitter)) return TSVGP_OK;
+    OK(k9_fork(c));
+    return k9_chain(c, jitter);
+}
+
+// Both chains of the prepare phase are ~40 dependent small kernels; at small M their GPU time is comparable to the time the host
+// needs to enqueue them, so enqueueing them one after the other delays the second chain by the first one's issue time.  With
+// `async_issue` a helper thread enqueues the K9 chain on the side stream while the calling thread enqueues the posterior chain.
+struct SideIssue {
+    std::thread th;
+    int rc = TSVGP_OK;
+    long launches = 0;
+    bool active = false;
+    void join_into(long& counter) {
+        if (!active) return;
+        th.join();
+        counter += launches;
+        active = false;
+    }
+};
+
+int start_k9_async(tsvgp_ctx* c, double jitter, SideIssue& side) {
+    if (k9_cached(c, jitter)) return TSVGP_OK;
+    OK(k9_fork(c));
+    if (!c->async_issue || c->Mp > 1024) return k9_chain(c, jitter);
+    side.active = true;
+    side.th = std::thread([c, jitter, &side]() {
+        const long l0 = g_launches;
+        side.rc = cudaSetDevice(c->dev) == cudaSuccess ? k9_chain(c, jitter) : TSVGP_ERR_CUDA;
+        side.launches = g_launches - l0;
+    });
+    return TSVGP_OK;
+}
+
+int k9_chain(tsvgp_ctx* c, double jitter) {
+    cudaStream_t s = c->s_side;
     LA(copy_add_diag_launch(c->K, c->C9, c->Mp, c->Mp, jitter, s));
     LA(chol_lower(c->C9, c->Mp, c->Mp, c->dinv2, c->info + INFO_K9, s, c->gws2, c->gws_doubles));
     LA(trtri_lower(c->C9, c->Mp, c->Mp, c->dinv2, c->C9inv, c->tmp2, s, c->gws2, c->gws_doubles));
@@ -1078,6 +1140,7 @@ int tsvgp_set_option(tsvgp_ctx* c, const char* name, double value) {
         return TSVGP_OK;
     }
     if (!strcmp(name, "dist_min_m")) { c->dist_min_m = (int)value; return TSVGP_OK; }
+    if (!strcmp(name, "async_issue")) { c->async_issue = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "fuse_b")) { c->fuse_b = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "balance")) { c->balance = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "profile")) { c->profile = value != 0.0; return TSVGP_OK; }
@@ -1300,9 +1363,15 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
     CU(cudaEventRecord(c->ev[EV_T0], s));
     OK(ensure_xs(c));
     OK(ensure_kuu(c));
-    OK(start_k9(c, jitter));
-    OK(ensure_posterior(c));
-    if (elbo_before) OK(ensure_kl_terms(c));
+    {
+        SideIssue side;
+        int rc = start_k9_async(c, jitter, side);
+        if (rc == TSVGP_OK) rc = ensure_posterior(c);
+        if (rc == TSVGP_OK && elbo_before) rc = ensure_kl_terms(c);
+        side.join_into(g_launches);
+        if (rc != TSVGP_OK) return rc;
+        if (side.rc != TSVGP_OK) return side.rc;
+    }
     OK(choose_route(c, jitter));
     CU(cudaEventRecord(c->ev[EV_PREP], s));
     OK(stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_STATS, nullptr, nullptr));
@@ -1324,7 +1393,11 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
     for (int i = 0; i < 4; ++i) { cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]); c->timings[1 + i] = ms; }
     cudaEventElapsedTime(&ms, c->ev[EV_T0], c->ev[EV_DENSE]);
     c->timings[0] = ms;
-    c->timings[5] = (double)((c->N + c->chunk - 1) / c->chunk);
+    {
+        const int nstr_t = c->profile ? 1 : (c->n_streams < 1 ? 1 : (c->n_streams > MAXS ? MAXS : c->n_streams));
+        const long ncu_t = used_chunk(c, c->N, c->chunk, nstr_t);
+        c->timings[5] = (double)((c->N + ncu_t - 1) / ncu_t);
+    }
     c->timings[6] = (double)(g_launches - launches0);
     c->timings[7] = (double)c->route;
     c->timings[8] = c->cond_est;
