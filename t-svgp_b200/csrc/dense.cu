@@ -85,9 +85,7 @@ static int trtri_level(const double* L, long ld, int lo, int hl, int hr, int bat
 
 int trtri_lower(const double* L, long ld, int n, const double* dinv, double* Linv, double* tmp, cudaStream_t s, double* ws, size_t ws_doubles) {
     const int nblk = n / NB;
-    if (cudaMemsetAsync(Linv, 0, sizeof(double) * (size_t)n * ld, s) != cudaSuccess) return (int)cudaGetLastError();
-    for (int b = 0; b < nblk; ++b)
-        TRY(place_block_launch(dinv + (long)b * NB * NB, NB, Linv + (long)b * NB * ld + (long)b * NB, ld, NB, NB, s));
+    TRY(trtri_seed_launch(dinv, Linv, ld, n, s));
     for (int h = 1; h < nblk; h *= 2) {
         const int full = nblk / (2 * h);                 // nodes with both halves of size h
         const long stride = (long)2 * h * NB * (ld + 1);

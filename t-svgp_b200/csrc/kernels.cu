@@ -1016,6 +1016,16 @@ __global__ void place_block_kernel(const double* src, long lds, double* dst, lon
     const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
     if (i < rows && j < cols) dst[(long)i * ldd + j] = src[(long)i * lds + j];
 }
+// Linv = blockdiag(dinv[0], dinv[1], ...) with zeros elsewhere: the seed of the bottom-up triangular inverse, one launch
+__global__ void trtri_seed_kernel(const double* dinv, double* Linv, long ld, int n) {
+    EW_IJ;
+    const int bi = i >> 7, bj = j >> 7;
+    Linv[(long)i * ld + j] = bi == bj ? dinv[(long)bi * DB * DB + (i & 127) * DB + (j & 127)] : 0.0;
+}
+int trtri_seed_launch(const double* dinv, double* Linv, long ld, int n, cudaStream_t s) {
+    trtri_seed_kernel<<<EW_GRID(n), 0, s>>>(dinv, Linv, ld, n);
+    return count_launch();
+}
 int place_block_launch(const double* src, long lds, double* dst, long ldd, int rows, int cols, cudaStream_t s) {
     place_block_kernel<<<dim3((cols + 31) / 32, (rows + 7) / 8), dim3(32, 8), 0, s>>>(src, lds, dst, ldd, rows, cols);
     return count_launch();

@@ -75,6 +75,7 @@ int antitranspose_launch(const double* Linv, double* V, long ld, int n, cudaStre
 int zero_upper_launch(double* A, long lda, int n, cudaStream_t s);
 // L2 = -tril(P) on [0,M)^2, 0 elsewhere — skipped on the device when *bad != 0 or any of info[0..3] != 0 (failed step keeps old sites)
 int finalize_sites_launch(const double* P, double* L2, long ld, int M, int Mp, const double* bad, const int* info, cudaStream_t s);
+int trtri_seed_launch(const double* dinv, double* Linv, long ld, int n, cudaStream_t s);   // Linv = blockdiag(dinv[b]) (128 x 128 blocks), zero elsewhere
 int place_block_launch(const double* src, long lds, double* dst, long ldd, int rows, int cols, cudaStream_t s);  // dst[0:rows,0:cols] = src
 int copy_lower_launch(const double* src, long lds, int M, double* dst, long ldd, int Mp, cudaStream_t s);  // dst = [[tril(src),0],[0,0]]
 // scalars: out[0] = sum_ij A^2 ; out[1] = sum_i log(diag A) ; single block, deterministic
