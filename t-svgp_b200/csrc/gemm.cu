@@ -75,6 +75,40 @@ __device__ __forceinline__ void gemm_epilogue(const GemmP& p, double (&acc)[8][4
                 *ptr = o;
             }
         }
+        if (EPI == EPI_STORE && split && p.tile_ctr != nullptr) {
+            // Fused split-K reduction: the piece that arrives LAST at this tile's counter sums all partial tiles in the fixed order
+            // k = 0 .. ksplit-1 (deterministic) and writes C; no second kernel.  The counter resets itself for the next launch.
+            __shared__ int s_last;
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                int* ctr = p.tile_ctr + ((long)bz * gridDim.y + ti) * gridDim.x + tj;
+                const int old = atomicAdd(ctr, 1);
+                s_last = old == p.ksplit - 1;
+                if (s_last) *ctr = 0;
+            }
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                const double* part = p.part + (long)bz * (p.part_sC ? p.part_sC : p.sC);
+                double* C = p.C + (long)bz * p.sC;
+                for (int e = tid; e < BM * BN / 2; e += NTHREADS) {
+                    const int r = e / (BN / 2), c = (e % (BN / 2)) * 2;
+                    const long poff = (long)(ti * BM + r) * ldo + tj * BN + c;
+                    double2 sum = make_double2(0.0, 0.0);
+                    for (int k = 0; k < p.ksplit; ++k) {
+                        const double2 v = __ldcg(reinterpret_cast<const double2*>(part + (long)k * p.part_stride + poff));
+                        sum.x += v.x; sum.y += v.y;
+                    }
+                    double2* ptr = reinterpret_cast<double2*>(C + (long)(ti * BM + r) * p.ldc + tj * BN + c);
+                    if (p.beta != 0.0) {
+                        const double2 old = *ptr;
+                        sum.x += p.beta * old.x; sum.y += p.beta * old.y;
+                    }
+                    *ptr = sum;
+                }
+            }
+        }
     }
     if (EPI == EPI_COLNORM || EPI == EPI_STORE_COLNORM) {
         // column sums of squares over this tile's 128 rows -> norm_out[ti][col]
@@ -555,10 +589,20 @@ int gemm_launch_auto(GemmP p, cudaStream_t stream, double* ws, size_t ws_doubles
         long ks = tiles > 0 ? sms / tiles : 1;
         if (ks > kt / 2) ks = kt / 2;                       // at least two k-tiles per piece
         const size_t slab = (size_t)p.batch * p.m * p.n;    // compact partial image of C
-        if (slab > 0 && ks > (long)(ws_doubles / slab)) ks = (long)(ws_doubles / slab);
+        // the last GEMM_WS_COUNTER_DOUBLES doubles of the workspace are the self-resetting tile counters of the fused reduction
+        const size_t ws_part = ws_doubles > GEMM_WS_COUNTER_DOUBLES ? ws_doubles - GEMM_WS_COUNTER_DOUBLES : 0;
+        if (slab > 0 && ks > (long)(ws_part / slab)) ks = (long)(ws_part / slab);
         if (ks > 16) ks = 16;
         if (ks >= 2) {
             p.ksplit = (int)ks; p.part = ws; p.part_stride = (long)slab; p.part_ld = p.n; p.part_sC = (long)p.m * p.n;
+            const long grid_tiles = (long)p.batch * nti * ntj;
+            // Measured slower than the separate 8x-parallel reduction kernel (one SM pulls ksplit x 128 KB of partials through its own
+            // L2 port: chol_lower(2048) 1.19 -> 1.69 ms, cfg2 1.39 -> 1.64 ms), so it is off unless TSVGP_FUSED_SPLITK=1 (A/B timing).
+            static const bool fused = getenv("TSVGP_FUSED_SPLITK") && atoi(getenv("TSVGP_FUSED_SPLITK")) != 0;
+            if (fused && grid_tiles <= (long)GEMM_WS_COUNTER_DOUBLES * 2) {   // one int counter per (batch, ti, tj)
+                p.tile_ctr = reinterpret_cast<int*>(ws + ws_part);
+                return gemm_launch(p, stream);
+            }
             int e = gemm_launch(p, stream);
             if (e) return e;
             return splitk_reduce_launch(p, stream);

@@ -31,6 +31,7 @@ struct GemmP {
     int epilogue = EPI_STORE;
     double* norm_out = nullptr; long ldn = 0;   // EPI_COLNORM: norm_out[tile_i * ldn + j] = sum_{i in tile} C(i,j)^2
     int ksplit = 1; double* part = nullptr; long part_stride = 0;   // split-K partial slabs [ksplit][m*ldc]; caller reduces
+    int* tile_ctr = nullptr;          // split-K with a fused reduction: zero-initialised counters, one per (batch, tile_i, tile_j) of the grid
     long part_ld = 0, part_sC = 0;    // row / batch strides of the partial slabs when they are stored more compactly than C (0 = ldc / sC)
     int batch = 1; long sA = 0, sB = 0, sC = 0;
     // Two-piece k split for load balance (no atomics): CTAs with blockIdx.z == 0 contract k in [0, ksp) into C, CTAs with
@@ -51,6 +52,9 @@ int splitk_reduce_launch(const GemmP& p, cudaStream_t stream);
 // gemm_launch that splits the contraction over otherwise idle SMs when the product has few output tiles (the latency-bound
 // M x M phases at small M, Cholesky panels, triangular-inverse nodes): partial tiles go to `ws` (ws_doubles doubles, owned by
 // the caller, one per stream) and are summed by splitk_reduce_launch.  Falls back to the plain launch when nothing is gained.
+// The last GEMM_WS_COUNTER_DOUBLES doubles of `ws` hold the tile counters of the fused reduction (the piece that finishes a tile
+// last sums the partials — no second kernel): the owner must zero them ONCE (cudaMemset) after allocating the workspace.
+constexpr size_t GEMM_WS_COUNTER_DOUBLES = 2048;
 int gemm_launch_auto(GemmP p, cudaStream_t stream, double* ws, size_t ws_doubles);
 
 // k split point for `tiles` equal output tiles of contraction length k on this device's SMs (multiple of 16; k = no split)

@@ -249,6 +249,8 @@ int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     NEED(c->info = (int*)p.get(N_INFO)); NEED(c->flags = (int*)p.get(2));
     c->gws_doubles = (size_t)4 << 20;   // 32 MB per stream: up to 16 partial images of a 512 x 512 product, 4 of a 1024 x 1024 one
     NEED(c->gws = p.get(c->gws_doubles)); NEED(c->gws2 = p.get(c->gws_doubles));
+    CU(cudaMemset(c->gws + c->gws_doubles - GEMM_WS_COUNTER_DOUBLES, 0, sizeof(double) * GEMM_WS_COUNTER_DOUBLES));    // tile counters
+    CU(cudaMemset(c->gws2 + c->gws_doubles - GEMM_WS_COUNTER_DOUBLES, 0, sizeof(double) * GEMM_WS_COUNTER_DOUBLES));
     NEED(c->zaug = p.get(mp * 128)); NEED(c->fuu = p.get(mp * 128));
     NEED(c->C6 = p.get(mm)); NEED(c->C6inv = p.get(mm)); NEED(c->lam1_bak = p.get(mp));
     c->c6_valid = c->wpost_valid = c->wkl_valid = false;
@@ -550,7 +552,7 @@ int ensure_slabs(tsvgp_ctx* c, long n_points, bool need_grad = false) {
         c->ksplit = 1;
         if (tiles * 2 <= sms) {
             c->ksplit = sms / tiles;
-            const int max_split = (int)(nc / 256);     // at least 16 k-tiles per piece
+            const int max_split = (int)(nc / 128);     // at least 8 k-tiles per piece
             if (c->ksplit > max_split) c->ksplit = max_split;
             if (c->ksplit < 2) c->ksplit = 1;
         }
@@ -696,7 +698,7 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
                 const bool const_h = c->lik.kind == LIK_GAUSSIAN && c->fuse_b && !grad;
                 if (const_h) { p.kscale = nullptr; p.alpha = fmin(-0.5 / c->lik.p0, -1e-8); }
                 const int nt = Mp / 128;
-                const int ks_here = c->ksplit < ncols / 256 ? c->ksplit : ncols / 256;
+                const int ks_here = c->ksplit < ncols / 128 ? c->ksplit : ncols / 128;
                 bool fused_b = false;
                 if (ks_here > 1) {
                     p.ksplit = ks_here; p.part = c->kpart[b]; p.part_stride = (long)Mp * Mp;

@@ -20,7 +20,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&dA, sizeof(double) * n * n)); CK(cudaMalloc(&dW, sizeof(double) * n * n)); CK(cudaMalloc(&dLinv, sizeof(double) * n * n));
     CK(cudaMalloc(&tmp, sizeof(double) * n * n)); CK(cudaMalloc(&dinv, sizeof(double) * (n / 128) * 128 * 128)); CK(cudaMalloc(&info, 16)); CK(cudaMemset(info, 0, 16)); CK(cudaMemset(dinv, 0, sizeof(double) * (n / 128) * 128 * 128));
     CK(cudaMemcpy(dA, A.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
-    double* ws; const size_t ws_doubles = (size_t)4 << 20; CK(cudaMalloc(&ws, sizeof(double) * ws_doubles));   // split-K workspace (gemm_launch_auto)
+    double* ws; const size_t ws_doubles = (size_t)4 << 20; CK(cudaMalloc(&ws, sizeof(double) * ws_doubles)); CK(cudaMemset(ws, 0, sizeof(double) * ws_doubles));   // split-K workspace (gemm_launch_auto)
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); float ms;
     for (int variant = 0; variant < 2; ++variant) {
         diag_set_variant(variant);
