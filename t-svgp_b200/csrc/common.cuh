@@ -79,6 +79,30 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
                  : "memory");
 }
 
+// ---- programmatic dependent launch (sm_90+) --------------------------------------------------------------------------------
+// The M x M phases are chains of ~100 dependent small kernels.  A kernel launched with the programmatic-serialisation attribute may
+// be dispatched (CTAs resident, parameters loaded) as soon as every CTA of its predecessor has started, and blocks in
+// griddepcontrol.wait until the predecessor has completed and its memory is visible: the launch latency leaves the critical path.
+// Every kernel launched through launch_k(pdl = true, ...) MUST run PDL_PROLOGUE() before it touches global memory.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#define PDL_PROLOGUE() pdl_prologue()
+
+extern int g_pdl;   // 1 = use programmatic dependent launch (default), 0 = plain stream order (env TSVGP_PDL=0; A/B timing)
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (pdl && g_pdl) ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through count_launch() / cudaGetLastError
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

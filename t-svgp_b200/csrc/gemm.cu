@@ -145,6 +145,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmP& p, double (&acc)[8][4
 
 template <bool A_KC, bool B_KC, bool SCALE, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(GemmP p) {
+    PDL_PROLOGUE();   // no-op unless launched with the programmatic-serialisation attribute (GemmP::pdl)
     using S = Smem<A_KC, B_KC, SCALE>;
     extern __shared__ __align__(16) double smem[];
 
@@ -257,6 +258,7 @@ constexpr int PSTAGES = 5;
 
 template <bool A_KC, bool B_KC, bool SCALE, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
+    PDL_PROLOGUE();   // no-op unless launched with the programmatic-serialisation attribute (GemmP::pdl)
     using S = Smem<A_KC, B_KC, SCALE>;
     extern __shared__ __align__(16) double smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGE * PSTAGES);
@@ -424,6 +426,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
 
 constexpr int RED_SLICES = 8;   // row slices per 128 x 128 tile: the reduction is bandwidth work, spread it over 8x the CTAs
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmP p) {
+    PDL_PROLOGUE();   // no-op unless launched with the programmatic-serialisation attribute (GemmP::pdl)
     const int tj = blockIdx.x, ti = blockIdx.y;
     if (p.lower_out && tj > ti) return;
     if (p.row_mod > 1 && ti % p.row_mod != p.row_rem) return;
@@ -461,9 +464,9 @@ int launch_inst(const GemmP& p, cudaStream_t stream) {
     dim3 grid(p.n / BN, p.m / BM, p.batch * (p.C2 ? 2 : p.ksplit));
     if (g_variant != 1 && SCALE && !p.kscale) return -1;
     if (g_variant == 1)
-        gemm_kernel_mb<A_KC, B_KC, SCALE, EPI><<<grid, NTHREADS, mb_bytes<A_KC, B_KC, SCALE>(), stream>>>(p);
+        launch_k(p.pdl != 0, gemm_kernel_mb<A_KC, B_KC, SCALE, EPI>, grid, NTHREADS, mb_bytes<A_KC, B_KC, SCALE>(), stream, p);
     else
-        gemm_kernel<A_KC, B_KC, SCALE, EPI><<<grid, NTHREADS, Smem<A_KC, B_KC, SCALE>::BYTES, stream>>>(p);
+        launch_k(p.pdl != 0, gemm_kernel<A_KC, B_KC, SCALE, EPI>, grid, NTHREADS, Smem<A_KC, B_KC, SCALE>::BYTES, stream, p);
     return count_launch();
 }
 
@@ -564,7 +567,7 @@ int gemm_launch(const GemmP& p, cudaStream_t stream) {
 
 int splitk_reduce_launch(const GemmP& p, cudaStream_t stream) {
     dim3 grid(p.n / BN, p.m / BM, p.batch * RED_SLICES);
-    splitk_reduce_kernel<<<grid, 256, 0, stream>>>(p);
+    launch_k(p.pdl != 0, splitk_reduce_kernel, grid, 256, 0, stream, p);
     return count_launch();
 }
 
@@ -576,6 +579,7 @@ int gemm_launch_auto(GemmP p, cudaStream_t stream, double* ws, size_t ws_doubles
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
+    p.pdl = 1;   // the M x M chains: programmatic dependent launch (see common.cuh)
     const bool eligible = ws && p.ksplit == 1 && !p.C2 && !p.gvec && !p.kscale && p.epilogue == EPI_STORE && p.m % BM == 0 && p.n % BN == 0;
     if (eligible) {
         const long nti = p.m / BM, ntj = p.n / BN;

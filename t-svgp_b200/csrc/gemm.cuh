@@ -41,6 +41,7 @@ struct GemmP {
     // Row-cyclic partition over ranks (distributed dense phase): only tile rows with ti % row_mod == row_rem are computed; the caller
     // zeroes C first and sums the ranks' pieces with one all-reduce (adding zeros is exact, so every rank gets identical bits)
     int row_mod = 1, row_rem = 0;
+    int pdl = 0;   // launch with the programmatic-serialisation attribute (the kernels always run the PDL prologue)
 };
 
 // Launch on `stream`. Returns cudaError_t as int (0 = ok), -1 for an unsupported combination.

@@ -351,6 +351,7 @@ int point_stats_launch(const LikSpec& lik, const PointArgs& a, const GHTable& g_
 __global__ void __launch_bounds__(256) gemv_n_kernel(const double* __restrict__ A, long lda, int m, long n,
                                                      const double* __restrict__ x, double alpha, double beta,
                                                      double* __restrict__ y) {
+    PDL_PROLOGUE();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= m) return;
     const double* a = A + (long)row * lda;
@@ -371,6 +372,7 @@ __global__ void __launch_bounds__(256) gemv_n_kernel(const double* __restrict__ 
 __global__ void __launch_bounds__(256) gemv_n_wide_kernel(const double* __restrict__ A, long lda, int m, long n,
                                                           const double* __restrict__ x, double alpha, double beta,
                                                           double* __restrict__ y) {
+    PDL_PROLOGUE();
     __shared__ double sred[8];
     const int row = blockIdx.x;
     const double* a = A + (long)row * lda;
@@ -404,13 +406,14 @@ __global__ void __launch_bounds__(256) gemv_n_wide_kernel(const double* __restri
 }
 
 int gemv_n_launch(const double* A, long lda, int m, long n, const double* x, double alpha, double beta, double* y, cudaStream_t s) {
-    if (n >= 4096 && (n & 1) == 0 && (lda & 1) == 0) gemv_n_wide_kernel<<<m, 256, 0, s>>>(A, lda, m, n, x, alpha, beta, y);
-    else gemv_n_kernel<<<(m + 7) / 8, 256, 0, s>>>(A, lda, m, n, x, alpha, beta, y);
+    if (n >= 4096 && (n & 1) == 0 && (lda & 1) == 0) launch_k(true, gemv_n_wide_kernel, m, 256, 0, s, A, lda, m, n, x, alpha, beta, y);
+    else launch_k(true, gemv_n_kernel, (m + 7) / 8, 256, 0, s, A, lda, m, n, x, alpha, beta, y);
     return count_launch();
 }
 
 __global__ void __launch_bounds__(128) gemv_t_part_kernel(const double* __restrict__ A, long lda, int m, int n,
                                                           const double* __restrict__ x, double* __restrict__ work) {
+    PDL_PROLOGUE();
     const int j = blockIdx.x * 128 + threadIdx.x;
     const int i0 = blockIdx.y * 64;
     if (j >= n) return;
@@ -420,6 +423,7 @@ __global__ void __launch_bounds__(128) gemv_t_part_kernel(const double* __restri
     work[(long)blockIdx.y * n + j] = s;
 }
 __global__ void gemv_t_sum_kernel(const double* __restrict__ work, int nchunk, int n, double* __restrict__ y) {
+    PDL_PROLOGUE();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     double s = 0.0;
@@ -430,8 +434,8 @@ __global__ void gemv_t_sum_kernel(const double* __restrict__ work, int nchunk, i
 int gemv_t_launch(const double* A, long lda, int m, int n, const double* x, double* y, double* work, cudaStream_t s) {
     const int nchunk = (m + 63) / 64;
     dim3 grid((n + 127) / 128, nchunk);
-    gemv_t_part_kernel<<<grid, 128, 0, s>>>(A, lda, m, n, x, work);
-    gemv_t_sum_kernel<<<(n + 255) / 256, 256, 0, s>>>(work, nchunk, n, y);
+    launch_k(true, gemv_t_part_kernel, grid, 128, 0, s, A, lda, m, n, x, work);
+    launch_k(true, gemv_t_sum_kernel, (n + 255) / 256, 256, 0, s, work, nchunk, n, y);
     ++g_launches;
     return count_launch();
 }
@@ -813,6 +817,7 @@ __device__ __forceinline__ void warp_trtri_32(double* Xjj, const double* colbuf,
 }
 
 __global__ void __launch_bounds__(256) diag_potrf_inv_blocked_kernel(double* A, long lda, double* Dinv, int blk, int* info) {
+    PDL_PROLOGUE();
     extern __shared__ __align__(16) double S[];
     double* As = S;                                       // 10 lower sub-blocks of A -> L
     double* Xs = S + (QNB * (QNB + 1) / 2) * QBLK;        // 10 lower sub-blocks of X = L^-1
@@ -929,7 +934,7 @@ int diag_init() {
 }
 
 int diag_potrf_inv_launch(double* A, long lda, double* Dinv, int blk_index, int* info, cudaStream_t s) {
-    if (g_diag_variant == 1) diag_potrf_inv_blocked_kernel<<<1, 256, DIAG_BLOCKED_SMEM, s>>>(A, lda, Dinv, blk_index, info);
+    if (g_diag_variant == 1) launch_k(true, diag_potrf_inv_blocked_kernel, 1, 256, DIAG_BLOCKED_SMEM, s, A, lda, Dinv, blk_index, info);
     else diag_potrf_inv_kernel<<<1, 256, DB * DB_LD * 8, s>>>(A, lda, Dinv, blk_index, info);
     return count_launch();
 }
@@ -945,22 +950,25 @@ int diag_trtri_launch(const double* L, long lda, double* Dinv, int nblk, cudaStr
 #define EW_IJ const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y; if (i >= n || j >= n) return;
 
 __global__ void add_diag_kernel(double* A, long lda, int n, double v) {
+    PDL_PROLOGUE();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) A[(long)i * lda + i] += v;
 }
 int add_diag_launch(double* A, long lda, int n, double v, cudaStream_t s) {
-    add_diag_kernel<<<(n + 255) / 256, 256, 0, s>>>(A, lda, n, v);
+    launch_k(true, add_diag_kernel, (n + 255) / 256, 256, 0, s, A, lda, n, v);
     return count_launch();
 }
 __global__ void copy_add_diag_kernel(const double* A, double* B, long ld, int n, double v) {
+    PDL_PROLOGUE();
     EW_IJ;
     B[(long)i * ld + j] = A[(long)i * ld + j] + (i == j ? v : 0.0);
 }
 int copy_add_diag_launch(const double* A, double* B, long ld, int n, double v, cudaStream_t s) {
-    copy_add_diag_kernel<<<EW_GRID(n), 0, s>>>(A, B, ld, n, v);
+    launch_k(true, copy_add_diag_kernel, EW_GRID(n), 0, s, A, B, ld, n, v);
     return count_launch();
 }
 __global__ void mirror_lower_kernel(double* A, long lda, int n) {
+    PDL_PROLOGUE();
     __shared__ double tile[32][33];
     // block (bx, by) with by >= bx : read lower tile (by, bx), write transposed into (bx, by)
     const int bx = blockIdx.x, by = blockIdx.y;
@@ -973,43 +981,47 @@ __global__ void mirror_lower_kernel(double* A, long lda, int n) {
     }
 }
 int mirror_lower_launch(double* A, long lda, int n, cudaStream_t s) {
-    mirror_lower_kernel<<<dim3(n / 32, n / 32), dim3(32, 8), 0, s>>>(A, lda, n);
+    launch_k(true, mirror_lower_kernel, dim3(n / 32, n / 32), dim3(32, 8), 0, s, A, lda, n);
     return count_launch();
 }
 __global__ void flip_sym_kernel(const double* W, double* Wf, long ld, int n) {
+    PDL_PROLOGUE();
     EW_IJ;
     if (j > i) { Wf[(long)i * ld + j] = 0.0; return; }
     const int a = n - 1 - i, b = n - 1 - j;   // a <= b : take the lower element W[b][a]
     Wf[(long)i * ld + j] = W[(long)b * ld + a];
 }
 int flip_sym_launch(const double* W, double* Wf, long ld, int n, cudaStream_t s) {
-    flip_sym_kernel<<<EW_GRID(n), 0, s>>>(W, Wf, ld, n);
+    launch_k(true, flip_sym_kernel, EW_GRID(n), 0, s, W, Wf, ld, n);
     return count_launch();
 }
 __global__ void antitranspose_kernel(const double* Linv, double* V, long ld, int n) {
+    PDL_PROLOGUE();
     EW_IJ;
     V[(long)i * ld + j] = j <= i ? Linv[(long)(n - 1 - j) * ld + (n - 1 - i)] : 0.0;
 }
 int antitranspose_launch(const double* Linv, double* V, long ld, int n, cudaStream_t s) {
-    antitranspose_kernel<<<EW_GRID(n), 0, s>>>(Linv, V, ld, n);
+    launch_k(true, antitranspose_kernel, EW_GRID(n), 0, s, Linv, V, ld, n);
     return count_launch();
 }
 __global__ void zero_upper_kernel(double* A, long lda, int n) {
+    PDL_PROLOGUE();
     EW_IJ;
     if (j > i) A[(long)i * lda + j] = 0.0;
 }
 int zero_upper_launch(double* A, long lda, int n, cudaStream_t s) {
-    zero_upper_kernel<<<EW_GRID(n), 0, s>>>(A, lda, n);
+    launch_k(true, zero_upper_kernel, EW_GRID(n), 0, s, A, lda, n);
     return count_launch();
 }
 __global__ void finalize_sites_kernel(const double* P, double* L2, long ld, int M, int n, const double* bad, const int* info) {
+    PDL_PROLOGUE();
     EW_IJ;
     if ((bad && bad[0] != 0.0) || (info && (info[0] | info[1] | info[2] | info[3]))) return;   // failed step: the sites stay as they were
     L2[(long)i * ld + j] = (j <= i && i < M) ? -P[(long)i * ld + j] : 0.0;
 }
 int finalize_sites_launch(const double* P, double* L2, long ld, int M, int Mp, const double* bad, const int* info, cudaStream_t s) {
     const int n = Mp;
-    finalize_sites_kernel<<<EW_GRID(n), 0, s>>>(P, L2, ld, M, Mp, bad, info);
+    launch_k(true, finalize_sites_kernel, EW_GRID(n), 0, s, P, L2, ld, M, Mp, bad, info);
     return count_launch();
 }
 __global__ void place_block_kernel(const double* src, long lds, double* dst, long ldd, int rows, int cols) {
@@ -1018,12 +1030,13 @@ __global__ void place_block_kernel(const double* src, long lds, double* dst, lon
 }
 // Linv = blockdiag(dinv[0], dinv[1], ...) with zeros elsewhere: the seed of the bottom-up triangular inverse, one launch
 __global__ void trtri_seed_kernel(const double* dinv, double* Linv, long ld, int n) {
+    PDL_PROLOGUE();
     EW_IJ;
     const int bi = i >> 7, bj = j >> 7;
     Linv[(long)i * ld + j] = bi == bj ? dinv[(long)bi * DB * DB + (i & 127) * DB + (j & 127)] : 0.0;
 }
 int trtri_seed_launch(const double* dinv, double* Linv, long ld, int n, cudaStream_t s) {
-    trtri_seed_kernel<<<EW_GRID(n), 0, s>>>(dinv, Linv, ld, n);
+    launch_k(true, trtri_seed_kernel, EW_GRID(n), 0, s, dinv, Linv, ld, n);
     return count_launch();
 }
 int place_block_launch(const double* src, long lds, double* dst, long ldd, int rows, int cols, cudaStream_t s) {
@@ -1081,6 +1094,7 @@ int frob_logdiag_launch(const double* A, long lda, int n, double* out, double* p
     return count_launch();
 }
 __global__ void __launch_bounds__(256) dot_kernel(const double* x, const double* y, int n, double* out) {
+    PDL_PROLOGUE();
     __shared__ double sred[8];
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) s = fma(x[i], y[i], s);
@@ -1088,7 +1102,7 @@ __global__ void __launch_bounds__(256) dot_kernel(const double* x, const double*
     if (threadIdx.x == 0) out[0] = s;
 }
 int dot_launch(const double* x, const double* y, int n, double* out, cudaStream_t s) {
-    dot_kernel<<<1, 256, 0, s>>>(x, y, n, out);
+    launch_k(true, dot_kernel, 1, 256, 0, s, x, y, n, out);
     return count_launch();
 }
 __global__ void __launch_bounds__(256) sum_kernel(const double* x, long n, double* out) {
@@ -1104,44 +1118,49 @@ int sum_launch(const double* x, long n, double* out, cudaStream_t s) {
 }
 __global__ void update_lambda1_kernel(double* l1, const double* G1, const double* G2mZ, int n, double lr, double scale,
                                       const double* bad, const int* info) {
+    PDL_PROLOGUE();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if ((bad && bad[0] != 0.0) || (info && (info[0] | info[1] | info[2] | info[3]))) return;
     if (i < n) l1[i] = (1.0 - lr) * l1[i] + lr * scale * (G1[i] - 2.0 * G2mZ[i]);
 }
 int update_lambda1_launch(double* l1, const double* G1, const double* G2mZ, int n, double lr, double scale, const double* bad,
                           const int* info, cudaStream_t s) {
-    update_lambda1_kernel<<<(n + 255) / 256, 256, 0, s>>>(l1, G1, G2mZ, n, lr, scale, bad, info);
+    launch_k(true, update_lambda1_kernel, (n + 255) / 256, 256, 0, s, l1, G1, G2mZ, n, lr, scale, bad, info);
     return count_launch();
 }
 __global__ void lincomb_kernel(double* y, double a, const double* x1, double b, const double* x2, int n) {
+    PDL_PROLOGUE();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = a * x1[i] + b * x2[i];
 }
 int lincomb_launch(double* y, double a, const double* x1, double b, const double* x2, int n, cudaStream_t s) {
-    lincomb_kernel<<<(n + 255) / 256, 256, 0, s>>>(y, a, x1, b, x2, n);
+    launch_k(true, lincomb_kernel, (n + 255) / 256, 256, 0, s, y, a, x1, b, x2, n);
     return count_launch();
 }
 __global__ void axpby_vec_guarded_kernel(double* y, const double* x, int n, double a, double b, const double* bad, const int* info) {
+    PDL_PROLOGUE();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if ((bad && bad[0] != 0.0) || (info && (info[0] | info[1] | info[2] | info[3]))) return;
     if (i < n) y[i] = a * y[i] + b * x[i];
 }
 int axpby_vec_guarded_launch(double* y, const double* x, int n, double a, double b, const double* bad, const int* info, cudaStream_t s) {
-    axpby_vec_guarded_kernel<<<(n + 255) / 256, 256, 0, s>>>(y, x, n, a, b, bad, info);
+    launch_k(true, axpby_vec_guarded_kernel, (n + 255) / 256, 256, 0, s, y, x, n, a, b, bad, info);
     return count_launch();
 }
 __global__ void vsub_kernel(const double* a, const double* b, double* y, int n) {
+    PDL_PROLOGUE();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = a[i] - b[i];
 }
 int vsub_launch(const double* a, const double* b, double* y, int n, cudaStream_t s) {
-    vsub_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, y, n);
+    launch_k(true, vsub_kernel, (n + 255) / 256, 256, 0, s, a, b, y, n);
     return count_launch();
 }
 
 
 // out[0] = sum_ij A[i][j] * B[i][j] over the n x n leading block (deterministic two-stage)
 __global__ void __launch_bounds__(256) matdot_part_kernel(const double* A, const double* B, long ld, int n, double* part) {
+    PDL_PROLOGUE();
     __shared__ double sred[8];
     double s = 0.0;
     const long total = (long)n * n;
@@ -1153,6 +1172,7 @@ __global__ void __launch_bounds__(256) matdot_part_kernel(const double* A, const
     if (threadIdx.x == 0) part[blockIdx.x] = s;
 }
 __global__ void __launch_bounds__(256) sum_parts_kernel(const double* part, double* out) {
+    PDL_PROLOGUE();
     __shared__ double sred[8];
     double s = threadIdx.x < RED_BLOCKS ? part[threadIdx.x] : 0.0;
     s = block_sum_256(s, sred);
@@ -1160,12 +1180,13 @@ __global__ void __launch_bounds__(256) sum_parts_kernel(const double* part, doub
 }
 int matdot_launch(const double* A, const double* B, long ld, int n, double* out, double* part, cudaStream_t s) {
     if (!part) return -1;
-    matdot_part_kernel<<<RED_BLOCKS, 256, 0, s>>>(A, B, ld, n, part);
-    sum_parts_kernel<<<1, 256, 0, s>>>(part, out);
+    launch_k(true, matdot_part_kernel, RED_BLOCKS, 256, 0, s, A, B, ld, n, part);
+    launch_k(true, sum_parts_kernel, 1, 256, 0, s, part, out);
     ++g_launches;
     return count_launch();
 }
 __global__ void __launch_bounds__(256) logdiag_kernel(const double* A, long lda, int n, double* out) {
+    PDL_PROLOGUE();
     __shared__ double sred[8];
     double l = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) l += log(A[(long)i * lda + i]);
@@ -1173,11 +1194,12 @@ __global__ void __launch_bounds__(256) logdiag_kernel(const double* A, long lda,
     if (threadIdx.x == 0) out[0] = l;
 }
 int logdiag_launch(const double* A, long lda, int n, double* out, cudaStream_t s) {
-    logdiag_kernel<<<1, 256, 0, s>>>(A, lda, n, out);
+    launch_k(true, logdiag_kernel, 1, 256, 0, s, A, lda, n, out);
     return count_launch();
 }
 // P = coef * G on [0,M)^2 plus jitter on its diagonal; identity on the padding block [M,n)
 __global__ void init_update_kernel(const double* G, double* P, long ld, int M, int n, double coef, double jitter) {
+    PDL_PROLOGUE();
     EW_IJ;
     double v;
     if (i < M && j < M) v = coef * G[(long)i * ld + j] + (i == j ? jitter : 0.0);
@@ -1186,43 +1208,47 @@ __global__ void init_update_kernel(const double* G, double* P, long ld, int M, i
 }
 int init_update_launch(const double* G, double* P, long ld, int M, int Mp, double coef, double jitter, cudaStream_t s) {
     const int n = Mp;
-    init_update_kernel<<<EW_GRID(n), 0, s>>>(G, P, ld, M, Mp, coef, jitter);
+    launch_k(true, init_update_kernel, EW_GRID(n), 0, s, G, P, ld, M, Mp, coef, jitter);
     return count_launch();
 }
 __global__ void set_scaled_identity_kernel(double* A, long ld, int M, int n, double v, double vpad) {
+    PDL_PROLOGUE();
     EW_IJ;
     A[(long)i * ld + j] = i == j ? (i < M ? v : vpad) : 0.0;
 }
 int set_scaled_identity_launch(double* A, long ld, int M, int Mp, double v, double vpad, cudaStream_t s) {
     const int n = Mp;
-    set_scaled_identity_kernel<<<EW_GRID(n), 0, s>>>(A, ld, M, Mp, v, vpad);
+    launch_k(true, set_scaled_identity_kernel, EW_GRID(n), 0, s, A, ld, M, Mp, v, vpad);
     return count_launch();
 }
 __global__ void axpby_guarded_kernel(double* P, const double* X, long ld, int n, double a, double b, const double* bad, const int* info) {
+    PDL_PROLOGUE();
     EW_IJ;
     if ((bad && bad[0] != 0.0) || (info && (info[0] | info[1] | info[2] | info[3]))) return;
     P[(long)i * ld + j] = a * P[(long)i * ld + j] + b * X[(long)i * ld + j];
 }
 int axpby_guarded_launch(double* P, const double* X, long ld, int M, double a, double b, const double* bad, const int* info, cudaStream_t s) {
     const int n = M;
-    axpby_guarded_kernel<<<EW_GRID(n), 0, s>>>(P, X, ld, n, a, b, bad, info);
+    launch_k(true, axpby_guarded_kernel, EW_GRID(n), 0, s, P, X, ld, n, a, b, bad, info);
     return count_launch();
 }
 __global__ void vadd_inplace_kernel(double* dst, const double* src, long n) {
+    PDL_PROLOGUE();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] += src[i];
 }
 int vadd_inplace_launch(double* dst, const double* src, long n, cudaStream_t s) {
-    vadd_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, src, n);
+    launch_k(true, vadd_inplace_kernel, (unsigned)((n + 255) / 256), 256, 0, s, dst, src, n);
     return count_launch();
 }
 // v[i] = 1 + 0.5 sin(1.7 i) for i < M, 0 on the padding: deterministic start vector of the conditioning probe
 __global__ void probe_vector_kernel(double* v, int M, int n) {
+    PDL_PROLOGUE();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] = i < M ? 1.0 + 0.5 * sin(1.7 * (double)i) : 0.0;
 }
 int probe_vector_launch(double* v, int M, int Mp, cudaStream_t s) {
-    probe_vector_kernel<<<(Mp + 255) / 256, 256, 0, s>>>(v, M, Mp);
+    launch_k(true, probe_vector_kernel, (Mp + 255) / 256, 256, 0, s, v, M, Mp);
     return count_launch();
 }
 // stats tail: out[0] = sum of ve partials, out[1] = flags[0] as a double

@@ -30,6 +30,7 @@
 namespace tsvgp {
 thread_local long g_launches = 0;
 int g_debug_sync = 0;
+int g_pdl = 1;
 }
 using namespace tsvgp;
 
@@ -1077,6 +1078,7 @@ int tsvgp_create(tsvgp_ctx** out, int device_id) {
         return TSVGP_ERR_CUDA;
     }
     if (const char* dbg = getenv("TSVGP_DEBUG_SYNC")) g_debug_sync = atoi(dbg);
+    if (const char* v = getenv("TSVGP_PDL")) g_pdl = atoi(v);
     tsvgp_ctx* c = new tsvgp_ctx();
     c->dev = device_id;
     bool ok = cudaSetDevice(device_id) == cudaSuccess;
