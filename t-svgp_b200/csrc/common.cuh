@@ -91,6 +91,9 @@ __device__ __forceinline__ void pdl_prologue() {
 #define PDL_PROLOGUE() pdl_prologue()
 
 extern int g_pdl;   // 1 = use programmatic dependent launch (default), 0 = plain stream order (env TSVGP_PDL=0; A/B timing)
+// set by a host thread while it enqueues two concurrent chains of LARGE kernels (prepare phase at M >= 2048): there the CTAs of a
+// pre-dispatched, still waiting kernel of one chain take SM slots from the running GEMM of the other (measured: +0.16 ms at M = 2048)
+extern thread_local int g_pdl_suspended;
 
 template <typename... KArgs, typename... Args>
 inline void launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
@@ -98,7 +101,7 @@ inline void launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, 
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = (pdl && g_pdl) ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = (pdl && g_pdl && !g_pdl_suspended) ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through count_launch() / cudaGetLastError
 }

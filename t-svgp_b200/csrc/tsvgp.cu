@@ -31,6 +31,7 @@ namespace tsvgp {
 thread_local long g_launches = 0;
 int g_debug_sync = 0;
 int g_pdl = 1;
+thread_local int g_pdl_suspended = 0;
 }
 using namespace tsvgp;
 
@@ -1369,6 +1370,8 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
     OK(ensure_kuu(c));
     {
         SideIssue side;
+        struct PdlGuard { ~PdlGuard() { g_pdl_suspended = 0; } } pdl_guard;
+        if (c->Mp >= 2048 && !k9_cached(c, jitter)) g_pdl_suspended = 1;   // two concurrent chains of large kernels: see common.cuh
         int rc = start_k9_async(c, jitter, side);
         if (rc == TSVGP_OK) rc = ensure_posterior(c);
         if (rc == TSVGP_OK && elbo_before) rc = ensure_kl_terms(c);

@@ -7,7 +7,7 @@
 #include <cuda_runtime.h>
 #include "../t-svgp_b200/csrc/gemm.cuh"
 #include "../t-svgp_b200/csrc/common.cuh"
-namespace tsvgp { thread_local long g_launches = 0; int g_debug_sync = 0; int g_pdl = 1; }
+namespace tsvgp { thread_local long g_launches = 0; int g_debug_sync = 0; int g_pdl = 1; thread_local int g_pdl_suspended = 0; }
 using namespace tsvgp;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1);} } while (0)
 
