@@ -71,7 +71,12 @@ TSVGP_API int tsvgp_set_option(tsvgp_ctx* ctx, const char* name, double value); 
  * "dist_min_m" (multi-GPU: distribute the dense M x M products over the ranks from this padded M upwards; default 4096),
  * "streams" up to 4, "balance" / "fuse_b" (0 switches the balanced SYRK split / the fused b += Kuf g off, for A/B timing),
  * "route_cond_max" (automatic: fused while the power-iteration estimate of cond(Kuu + jitter I) is below this; default 1e4),
- * "route_exact_min" (automatic: exact above this estimate, whitened in between; default 1e8) */
+ * "route_exact_min" (automatic: exact above this estimate, whitened in between; default 1e8),
+ * "async_issue" (1 = at M <= 1024 a helper host thread enqueues the Kuu + jitter I factorisation chain on the side stream while
+ *          the calling thread enqueues the posterior chain; 0 = one thread enqueues both).
+ * Environment (read once, A/B timing): TSVGP_PDL=0 plain stream order instead of programmatic dependent launch for the M x M
+ * kernel chains; TSVGP_DIAG_VARIANT=0 the per-pivot diagonal-block Cholesky kernel; TSVGP_GEMM_VARIANT=0 the CTA-barrier GEMM
+ * pipeline; TSVGP_FUSED_SPLITK=1 the fused (last-CTA) split-K reduction; TSVGP_DEBUG_SYNC=1 synchronise after every launch. */
 
 /* ---- model objects read by the path (tsvgp.py:209,268-269; GPflow kernel / likelihood / inducing attributes) ------ */
 /* lengthscales: HOST pointer, n_ls = 1 (isotropic) or D (ARD)                                                          */

@@ -841,12 +841,16 @@ int start_k9_async(tsvgp_ctx* c, double jitter, SideIssue& side) {
     if (k9_cached(c, jitter)) return TSVGP_OK;
     OK(k9_fork(c));
     if (!c->async_issue || c->Mp > 1024) return k9_chain(c, jitter);
-    side.active = true;
-    side.th = std::thread([c, jitter, &side]() {
-        const long l0 = g_launches;
-        side.rc = cudaSetDevice(c->dev) == cudaSuccess ? k9_chain(c, jitter) : TSVGP_ERR_CUDA;
-        side.launches = g_launches - l0;
-    });
+    try {
+        side.th = std::thread([c, jitter, &side]() {
+            const long l0 = g_launches;
+            side.rc = cudaSetDevice(c->dev) == cudaSuccess ? k9_chain(c, jitter) : TSVGP_ERR_CUDA;
+            side.launches = g_launches - l0;
+        });
+        side.active = true;
+    } catch (...) {   // no thread to be had: enqueue the chain from this thread
+        return k9_chain(c, jitter);
+    }
     return TSVGP_OK;
 }
 

@@ -91,3 +91,59 @@ def natgrad(K, Kuf, g, h, alpha, lambda_1, L2, lr, scale, jitter=1e-9, whiten=Fa
     l1 = (1 - lr) * lambda_1[:, 0] + lr * scale * g0
     P = (1 - lr) * (L2 @ L2.T) + lr * scale * (-2.0 * G2) + jitter * np.eye(M)
     return l1[:, None], -sla.cholesky(P, lower=True)
+
+
+# ---- the three statistics routes ------------------------------------------------------------------------------
+def natural_gradients(K, Kuf, g, h, jitter=1e-9, route="fused"):
+    """(G1, G2) of tsvgp.py:271-281 as each device route forms them.
+    fused    : B = Kuf diag(h) Kfu, then K9^-1 B K9^-1                      (2 M^2 flops per point, rounding ~ eps cond^2)
+    whitened : t = C9^-1 k per slab, Bw = sum h t t^T, then C9^-T Bw C9^-1   (3 M^2, rounding ~ eps cond)
+    exact    : a = C9^-T C9^-1 k per slab, G2 = sum h a a^T                  (4 M^2; a Gram product, as the reference)"""
+    M = K.shape[0]
+    C9 = np.linalg.cholesky(K + jitter * np.eye(M))
+    C9inv = sla.solve_triangular(C9, np.eye(M), lower=True)
+    if route == "fused":
+        K9inv = C9inv.T @ C9inv
+        return K9inv @ (Kuf @ g), K9inv @ ((Kuf * h) @ Kuf.T) @ K9inv
+    Wt = C9inv @ Kuf
+    if route == "whitened":
+        return C9inv.T @ (Wt @ g), C9inv.T @ ((Wt * h) @ Wt.T) @ C9inv
+    A = C9inv.T @ Wt
+    return A @ g, (A * h) @ A.T
+
+
+# ---- block schedule of diag_potrf_inv_blocked_kernel (csrc/kernels.cu) -------------------------------------------------------
+def blocked_potrf_inv(A, q=32):
+    """Cholesky L of a (4q x 4q) block and X = L^-1 in the kernel's order: per block step j the q x q diagonal sub-block is
+    factored column by column with the elimination of L X = I riding on the same pivots; then panel L_ij = A_ij X_jj^T and the
+    finished block row X_jc = X_jj Xcur_jc; then trailing A_ik -= L_ij L_kj^T and Xcur_ic -= L_ij X_jc (overwrite for c = j)."""
+    nb = A.shape[0] // q
+    As = {(i, j): A[i * q:(i + 1) * q, j * q:(j + 1) * q].copy() for i in range(nb) for j in range(i + 1)}
+    Xs = {}
+    rows = np.arange(q)
+    for j in range(nb):
+        a, x = np.tril(As[j, j]).copy(), np.eye(q)
+        for k in range(q):
+            rs = 1.0 / np.sqrt(a[k, k])
+            col = np.where(rows > k, a[:, k] * rs, 0.0)
+            a[:, k] = np.where(rows == k, a[k, k] * rs, col)
+            x[k, :] *= rs
+            a[:, k + 1:] -= np.outer(col, col[k + 1:])
+            x -= np.outer(col, x[k, :])
+        As[j, j], Xs[j, j] = np.tril(a), np.tril(x)
+        for i in range(j + 1, nb):
+            As[i, j] = As[i, j] @ Xs[j, j].T
+        for c in range(j):
+            Xs[j, c] = Xs[j, j] @ Xs[j, c]
+        for i in range(j + 1, nb):
+            for k in range(j + 1, i + 1):
+                As[i, k] -= As[i, j] @ As[k, j].T
+            for c in range(j + 1):
+                Xs[i, c] = -As[i, j] @ Xs[j, c] if c == j else Xs[i, c] - As[i, j] @ Xs[j, c]
+    n = nb * q
+    L, X = np.zeros((n, n)), np.zeros((n, n))
+    for (i, j), blk in As.items():
+        L[i * q:(i + 1) * q, j * q:(j + 1) * q] = blk
+    for (i, j), blk in Xs.items():
+        X[i * q:(i + 1) * q, j * q:(j + 1) * q] = blk
+    return L, X
