@@ -75,7 +75,7 @@ TSVGP_API int tsvgp_set_option(tsvgp_ctx* ctx, const char* name, double value); 
  * "async_issue" (1 = at M <= 1024 a helper host thread enqueues the Kuu + jitter I factorisation chain on the side stream while
  *          the calling thread enqueues the posterior chain; 0 = one thread enqueues both).
  * Environment (read once, A/B timing): TSVGP_PDL=0 plain stream order instead of programmatic dependent launch for the M x M
- * kernel chains; TSVGP_DIAG_VARIANT=0 the per-pivot diagonal-block Cholesky kernel; TSVGP_GEMM_VARIANT=0 the CTA-barrier GEMM
+ * kernel chains; TSVGP_DIAG_VARIANT=0 the per-pivot diagonal-block Cholesky kernel, =2 the blocked kernel with look-ahead; TSVGP_GEMM_VARIANT=0 the CTA-barrier GEMM
  * pipeline; TSVGP_FUSED_SPLITK=1 the fused (last-CTA) split-K reduction; TSVGP_DEBUG_SYNC=1 synchronise after every launch. */
 
 /* ---- model objects read by the path (tsvgp.py:209,268-269; GPflow kernel / likelihood / inducing attributes) ------ */

@@ -917,10 +917,127 @@ __global__ void __launch_bounds__(256) diag_potrf_inv_blocked_kernel(double* A, 
     DIAG_STAMP(14);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Look-ahead variant of the blocked kernel.  The pivot chain of warps 0 / 1 (8 k cycles per 32 x 32 sub-block) is the critical
+// path; everything else is arranged around it:
+//   * the trailing update of step j is split: T_j^A = the blocks step j + 1 needs (block column j + 1 of A, block row j + 1 of the
+//     inverse's work matrix) runs on all warps right after the panel; T_j^B = the rest is DEFERRED and runs on warps 2..7 while
+//     warps 0 / 1 factor sub-block j + 1;
+//   * the same six warps then write back what became final with panel j (block column j of L, block row j of X), so that only
+//     the last column / row is left for the end.
+// Dependencies: F_{j+1} touches A(j+1,j+1), X(j+1,j+1) only; T_j^B writes A(i,k), k >= j+2, and Xcur(i,c), i >= j+2, and reads block
+// column j of L and block row j of X, which nobody writes any more.
+// ---------------------------------------------------------------------------------------------------------------------
+// rows [r0, r0 + nr) of the 32 x 32 sub-block (bi, bj) -> G (row stride ldg); zeros above the diagonal of a diagonal sub-block
+__device__ __forceinline__ void qstore_rows(const double* blk, double* G, long ldg, int bi, int bj, int r0, int nr, int lane) {
+    for (int r = r0; r < r0 + nr; ++r) {
+        double v = blk[r * QLD + lane];
+        if (bi == bj && lane > r) v = 0.0;
+        G[(long)(QB * bi + r) * ldg + QB * bj + lane] = v;
+    }
+}
+
+// trailing tasks of step j; part 0 = T_j^A (needed by step j + 1), part 1 = T_j^B (deferred).  Task t goes to worker (t % nw) + w0.
+__device__ __forceinline__ void qtrailing(double* As, double* Xs, int j, int part, int w0, int nw, int warp, int lane) {
+    int tsk = 0;
+    for (int i = j + 1; i < QNB; ++i) {
+        for (int k = j + 1; k <= i; ++k) {
+            if ((k == j + 1 ? 0 : 1) != part) continue;
+            for (int qd = 0; qd < 4; ++qd) {
+                if (i == k && qd == 1) continue;   // strictly upper quarter of a diagonal block
+                if ((tsk++ % nw) + w0 == warp)
+                    qblk_mma<2, 2, true, 0>(As + qidx(i, k), As + qidx(i, j), As + qidx(k, j), 16 * (qd >> 1), 16 * (qd & 1), 1, 0, lane);
+            }
+        }
+        if ((i == j + 1 ? 0 : 1) != part) continue;
+        for (int c = 0; c <= j; ++c)
+            for (int qd = 0; qd < 4; ++qd)
+                if ((tsk++ % nw) + w0 == warp)
+                    qblk_mma<2, 2, false, 0>(Xs + qidx(i, c), As + qidx(i, j), Xs + qidx(j, c), 16 * (qd >> 1), 16 * (qd & 1),
+                                             c == j ? 2 : 1, c == j ? 16 * (qd & 1) : 0, lane);
+    }
+}
+
+// write back block column j of L and block row j of X (final once panel j is done) in 16-row pieces; piece t -> worker (t % nw) + w0
+__device__ __forceinline__ void qwriteback(const double* As, const double* Xs, double* A, long lda, double* Dinv, int j, int w0, int nw,
+                                           int warp, int lane) {
+    int tsk = 0;
+    for (int i = j; i < QNB; ++i)
+        for (int h = 0; h < 2; ++h)
+            if ((tsk++ % nw) + w0 == warp) qstore_rows(As + qidx(i, j), A, lda, i, j, 16 * h, 16, lane);
+    for (int c = 0; c <= j; ++c)
+        for (int h = 0; h < 2; ++h)
+            if ((tsk++ % nw) + w0 == warp) qstore_rows(Xs + qidx(j, c), Dinv, DB, j, c, 16 * h, 16, lane);
+}
+
+__global__ void __launch_bounds__(256) diag_potrf_inv_lookahead_kernel(double* A, long lda, double* Dinv, int blk, int* info) {
+    PDL_PROLOGUE();
+    extern __shared__ __align__(16) double S[];
+    double* As = S;
+    double* Xs = S + (QNB * (QNB + 1) / 2) * QBLK;
+    __shared__ __align__(16) double colbuf[QB * QB];
+    __shared__ __align__(16) double rsbuf[QB];
+    __shared__ __align__(8) uint64_t bars[QB];
+    __shared__ int sfail;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) sfail = 0;
+    if (tid < QB) mbar_init(bars + tid, 32);
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(A) | (uintptr_t)(lda * 8)) & 15) == 0;
+    if (vec_ok) {
+        for (int u = tid; u < DB * (DB / 2); u += 256) {
+            const int r = u >> 6, c = (u & 63) * 2;
+            if ((c >> 5) <= (r >> 5)) cp_async16(As + qidx(r >> 5, c >> 5) + (r & 31) * QLD + (c & 31), A + (long)r * lda + c);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+    } else {
+        for (int e = tid; e < DB * DB; e += 256) {
+            const int r = e >> 7, c = e & 127;
+            if ((c >> 5) <= (r >> 5)) As[qidx(r >> 5, c >> 5) + (r & 31) * QLD + (c & 31)] = A[(long)r * lda + c];
+        }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < QNB; ++j) {
+        if (warp == 0) {
+            const int f = warp_potrf_32(As + qidx(j, j), colbuf, rsbuf, bars, lane);
+            if (f && lane == 0) sfail = j * QB + f;
+        } else if (warp == 1) {
+            warp_trtri_32(Xs + qidx(j, j), colbuf, rsbuf, bars, (uint32_t)(j & 1), lane);
+        } else if (j > 0) {   // deferred work of step j - 1, in the shadow of the pivot chain
+            qtrailing(As, Xs, j - 1, 1, 2, 6, warp, lane);
+            qwriteback(As, Xs, A, lda, Dinv, j - 1, 2, 6, warp, lane);
+        }
+        __syncthreads();
+        if (sfail) break;   // uniform
+        {   // panel rows below and the finished block row j of X
+            int tsk = 0;
+            for (int i = j + 1; i < QNB; ++i)
+                for (int h = 0; h < 2; ++h)
+                    if ((tsk++ & 7) == warp)
+                        qblk_mma<2, 4, true, 1>(As + qidx(i, j), As + qidx(i, j), Xs + qidx(j, j), 16 * h, 0, 0, 0, lane);
+            for (int c = 0; c < j; ++c)
+                for (int h = 0; h < 2; ++h)
+                    if ((tsk++ & 7) == warp)
+                        qblk_mma<4, 2, false, 2>(Xs + qidx(j, c), Xs + qidx(j, j), Xs + qidx(j, c), 0, 16 * h, 0, 0, lane);
+        }
+        __syncthreads();
+        if (j + 1 < QNB) {
+            qtrailing(As, Xs, j, 0, 0, 8, warp, lane);   // what step j + 1 needs
+            __syncthreads();
+        }
+    }
+    if (sfail) {
+        if (tid == 0) atomicCAS(info, 0, blk * DB + sfail);
+        return;
+    }
+    qwriteback(As, Xs, A, lda, Dinv, QNB - 1, 0, 8, warp, lane);
+}
+
 #ifdef TSVGP_DIAG_TIMING
 int diag_read_stamps(long long* out32) { return (int)cudaMemcpyFromSymbol(out32, g_diag_clk, sizeof(long long) * 32); }
 #endif
-static int g_diag_variant = 1;   // 1 = blocked (DMMA) kernel, 0 = per-pivot register kernel (kept for A/B timing: tools/diag_bench)
+static int g_diag_variant = 1;   // 1 = blocked (DMMA) kernel, 2 = the same with look-ahead, 0 = per-pivot register kernel (A/B timing: tools/diag_bench)
 void diag_set_variant(int v) { g_diag_variant = v; }
 constexpr int DIAG_BLOCKED_SMEM = 2 * (QNB * (QNB + 1) / 2) * QBLK * 8;
 
@@ -929,12 +1046,14 @@ int diag_init() {
     int e = (int)cudaFuncSetAttribute(diag_potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB * DB_LD * 8);
     e |= (int)cudaFuncSetAttribute(diag_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB * DB_LD * 8);
     e |= (int)cudaFuncSetAttribute(diag_potrf_inv_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_BLOCKED_SMEM);
+    e |= (int)cudaFuncSetAttribute(diag_potrf_inv_lookahead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_BLOCKED_SMEM);
     if (const char* v = getenv("TSVGP_DIAG_VARIANT")) g_diag_variant = atoi(v);
     return e;
 }
 
 int diag_potrf_inv_launch(double* A, long lda, double* Dinv, int blk_index, int* info, cudaStream_t s) {
-    if (g_diag_variant == 1) launch_k(true, diag_potrf_inv_blocked_kernel, 1, 256, DIAG_BLOCKED_SMEM, s, A, lda, Dinv, blk_index, info);
+    if (g_diag_variant == 2) launch_k(true, diag_potrf_inv_lookahead_kernel, 1, 256, DIAG_BLOCKED_SMEM, s, A, lda, Dinv, blk_index, info);
+    else if (g_diag_variant == 1) launch_k(true, diag_potrf_inv_blocked_kernel, 1, 256, DIAG_BLOCKED_SMEM, s, A, lda, Dinv, blk_index, info);
     else diag_potrf_inv_kernel<<<1, 256, DB * DB_LD * 8, s>>>(A, lda, Dinv, blk_index, info);
     return count_launch();
 }

@@ -22,12 +22,12 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(dA, A.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
     double* ws; const size_t ws_doubles = (size_t)4 << 20; CK(cudaMalloc(&ws, sizeof(double) * ws_doubles)); CK(cudaMemset(ws, 0, sizeof(double) * ws_doubles));   // split-K workspace (gemm_launch_auto)
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); float ms;
-    for (int variant = 0; variant < 2; ++variant) {
+    for (int variant = 0; variant < 3; ++variant) {
         diag_set_variant(variant);
         for (int rep = 0; rep < 3; ++rep) {
             CK(cudaMemcpy(dW, dA, sizeof(double) * n * n, cudaMemcpyDeviceToDevice));
             cudaEventRecord(e0); diag_potrf_inv_launch(dW, n, dinv, 0, info, 0); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
-            cudaEventElapsedTime(&ms, e0, e1); printf("diag_potrf_inv variant %d (%s, 1 block): %.1f us\n", variant, variant ? "blocked DMMA" : "per-pivot", ms * 1e3);
+            cudaEventElapsedTime(&ms, e0, e1); printf("diag_potrf_inv variant %d (%s, 1 block): %.1f us\n", variant, variant == 2 ? "blocked DMMA + look-ahead" : (variant ? "blocked DMMA" : "per-pivot"), ms * 1e3);
         }
         // the block against a host Cholesky + inverse
         std::vector<double> Lb(128 * 128), Xb(128 * 128), Lh(128 * 128, 0.0);
@@ -66,7 +66,7 @@ int main(int argc, char** argv) {
         }
         printf(" | store %lld | total %lld\n", clk[14] - prev, clk[14] - clk[0]);
     }
-    for (int variant = 0; variant < 2; ++variant) {   // failure reporting: a non-positive pivot at row 70 of block 3
+    for (int variant = 0; variant < 3; ++variant) {   // failure reporting: a non-positive pivot at row 70 of block 3
         diag_set_variant(variant);
         std::vector<double> Bad(128 * 128, 0.0);
         for (int i = 0; i < 128; ++i) Bad[i * 128 + i] = i == 70 ? -1.0 : 2.0;
