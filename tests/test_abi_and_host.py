@@ -141,3 +141,17 @@ def test_header_is_plain_c_and_the_c_example_links():
         if not have_gpu():   # without a device the client must fail loudly in tsvgp_create (no CPU fallback)
             run = subprocess.run([exe], capture_output=True, text=True, timeout=60)
             assert run.returncode != 0 and "no CUDA device" in run.stderr
+
+
+def test_every_library_option_is_documented_in_the_header():
+    # tsvgp_set_option(name, value): the names the library accepts (csrc/tsvgp.cu) and the names include/tsvgp.h documents
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "t-svgp_b200", "csrc", "tsvgp.cu")).read()
+    body = src[src.index("int tsvgp_set_option("):src.index("int tsvgp_set_kernel(")]
+    accepted = set(re.findall(r'strcmp\(name, "([a-z_0-9]+)"\)', body))
+    header = open(os.path.join(root, "include", "tsvgp.h")).read()
+    documented = set(re.findall(r'"([a-z_0-9]+)"', header))
+    assert accepted, "no options found in tsvgp_set_option"
+    internal = {"profile"}   # measurement switch behind tsvgp_get_kernel_profile, described there
+    assert accepted - internal <= documented, sorted(accepted - internal - documented)
