@@ -26,7 +26,7 @@ def test_cfg3_full_minibatch_properties():
     Xd, Yd = m.device_array(X), m.device_array(Y)
     m.set_data((Xd, Yd))
     e0 = m.natgrad_step(lr=1.0, return_elbo=True)
-    assert abs(e0 - m_elbo_default(m, e0)) >= 0.0      # finite
+    assert np.isfinite(e0)
     l1, l2 = m.lambda_1, m.lambda_2
     e1 = m.natgrad_step(lr=1.0, return_elbo=True)      # fixed point of the Gaussian update (reference test_tsvgp.py:134-145)
     assert relerr(m.lambda_1, l1) < 1e-7 and relerr(m.lambda_2, l2) < 1e-7
@@ -42,10 +42,6 @@ def test_cfg3_full_minibatch_properties():
     assert np.all(var > 0) and np.all(var < 1.0 + 1e-12)          # posterior variance within the prior variance
     assert np.sqrt(np.mean((mu - Y[:4096]) ** 2)) < 0.5           # fits the data to about the noise level (sigma = 0.316)
     m.close(); m2.close()
-
-
-def m_elbo_default(m, e):
-    return e
 
 
 def test_cfg5_quadrature_step_improves_elbo_at_scale():
