@@ -59,7 +59,9 @@ TSVGP_API const char* tsvgp_last_error(const tsvgp_ctx* ctx);        /* ctx may 
 TSVGP_API int tsvgp_last_info(const tsvgp_ctx* ctx);                 /* failing pivot of the last TSVGP_ERR_NOT_POSITIVE_DEFINITE   */
 TSVGP_API int tsvgp_set_option(tsvgp_ctx* ctx, const char* name, double value);   /* see below */
 
-/* options: "chunk" (points per Kuf slab; 0 = automatic, ~32 MB slabs that stay in L2), "streams" (1|2 ping-pong streams),
+/* options: "chunk" (points per Kuf slab; 0 = automatic = 8192 points, i.e. Mp x 8192 x 8 B per slab stream — 134 MB at M = 2048,
+ *          larger than the 126 MB L2: the slab is written once and re-read Mp/128 times through L2/HBM by compute-bound DMMA
+ *          products, measured at ~4 % of the HBM roof), "streams" (1|2 ping-pong streams),
  * "cache_factors" (1 = keep chol(Kuu+jitter I) and the posterior factors while kernel, Z and sites are unchanged),
  * "invalidate" (any value: drop every cached factor now),
  * "route" (0 = automatic, 1 = fused: B = Kuf diag(h) Kfu then K9^-1 B K9^-1 — 2 M^2 flops per point, rounding ~ eps cond(Kuu)^2;
@@ -73,7 +75,12 @@ TSVGP_API int tsvgp_set_option(tsvgp_ctx* ctx, const char* name, double value); 
  * "route_cond_max" (automatic: fused while the power-iteration estimate of cond(Kuu + jitter I) is below this; default 1e4),
  * "route_exact_min" (automatic: exact above this estimate, whitened in between; default 1e8),
  * "async_issue" (1 = at M <= 1024 a helper host thread enqueues the Kuu + jitter I factorisation chain on the side stream while
- *          the calling thread enqueues the posterior chain; 0 = one thread enqueues both).
+ *          the calling thread enqueues the posterior chain; 0 = one thread enqueues both),
+ * "speculate" (1 = automatic route: when this context's last conditioning estimate chose the fused route, run the
+ *          Kuu + jitter I chain UNDERNEATH the streaming pass instead of in front of it, read the probe after the pass and
+ *          repeat the pass with the right route if the estimate crossed the threshold; 0 = always probe before the pass),
+ * "early_slabs" (n = Gaussian likelihood, fused route: Kuf and the constant-weight SYRK of the first slab of up to n slab
+ *          streams do not depend on the posterior and are enqueued before the posterior chain; 0 = off).
  * Environment (read once, A/B timing): TSVGP_PDL=0 plain stream order instead of programmatic dependent launch for the M x M
  * kernel chains; TSVGP_DIAG_VARIANT=0 the per-pivot diagonal-block Cholesky kernel, =2 the blocked kernel with look-ahead; TSVGP_GEMM_VARIANT=0 the CTA-barrier GEMM
  * pipeline; TSVGP_FUSED_SPLITK=1 the fused (last-CTA) split-K reduction; TSVGP_DEBUG_SYNC=1 synchronise after every launch. */

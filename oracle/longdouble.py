@@ -95,3 +95,70 @@ def natgrad_step_gaussian(X, Y, Z, variance, lengthscale, noise, lam1, L2, lr, s
     new1 = (1 - LD(lr)) * lam1 + LD(lr) * LD(scale) * g0
     new2 = (1 - LD(lr)) * lam2 + LD(lr) * LD(scale) * G2
     return new1, -chol(-2 * new2 + LD(jitter) * Id)
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# Non-conjugate likelihoods (the Gauss-Hermite path of tsvgp.py:256-263) in extended precision: the arbiter for the quadrature
+# sums, their analytic (mean, variance) gradients and the -1e-8 clip.  The quadrature RULE is the reference's: GPflow's 20 nodes
+# sqrt(2) x_k and weights w_k / sqrt(pi) from numpy.polynomial.hermite.hermgauss (float64 constants), used here as exact numbers.
+# erf has no long-double implementation in NumPy/SciPy: mpmath at 80 bits, element by element (fine for N * 20 <= ~10^4 values).
+# ----------------------------------------------------------------------------------------------------------------------------
+def _erf_ld(x):
+    import mpmath
+    mpmath.mp.prec = 80
+    f = np.frompyfunc(lambda v: LD(str(mpmath.erf(mpmath.mpf(str(v))))), 1, 1)   # decimal strings carry all 64 mantissa bits (21 digits)
+    return f(np.asarray(x, dtype=LD)).astype(LD)
+
+
+def gh_rule(n_gh=20):
+    """The rule constants exactly as the float64 implementations hold them (oracle: tsvgp_oracle.gh_points_and_weights; CUDA:
+    tsvgp_set_likelihood): float64(sqrt(2) x_k), float64(w_k / sqrt(pi)), widened to long double."""
+    x, w = np.polynomial.hermite.hermgauss(n_gh)
+    return np.asarray(x * np.sqrt(2.0), dtype=LD), np.asarray(w / np.sqrt(np.pi), dtype=LD)
+
+
+def ve_grads(lik, mean, var, y):
+    """d E_q[log p(y | f)] / d mean, d / d var (clipped at -1e-8, tsvgp.py:262-263) per point, long double.
+    lik = ("gaussian", variance) | ("bernoulli",) | ("student_t", scale, df)."""
+    kind = lik[0]
+    if kind == "gaussian":
+        return (y - mean) / LD(lik[1]), np.minimum(np.full_like(mean, -0.5 / LD(lik[1])), LD(-1e-8))
+    z, w = gh_rule(20)
+    sd = np.sqrt(var)
+    F = mean[:, None] + sd[:, None] * z[None, :]
+    if kind == "bernoulli":            # inv_probit with GPflow's 1e-3 jitter; labels other than 1 count as class 0
+        PI = LD("3.14159265358979323846264338327950288")
+        p = LD(0.5) * (1 + _erf_ld(F / np.sqrt(LD(2)))) * (1 - 2 * LD(1e-3)) + LD(1e-3)
+        dp = (1 - 2 * LD(1e-3)) * np.exp(-F * F / 2) / np.sqrt(2 * PI)
+        d = np.where(y[:, None] == 1, dp / p, -dp / (1 - p))
+    elif kind == "student_t":
+        sc, df = LD(lik[1]), LD(lik[2])
+        r = y[:, None] - F
+        d = (df + 1) * r / (df * sc * sc + r * r)
+    else:
+        raise ValueError(kind)
+    d = d * w[None, :]
+    return np.sum(d, 1), np.minimum(np.sum(d * z[None, :], 1) / (2 * sd), LD(-1e-8))
+
+
+def natgrad_step(X, Y, Z, variance, lengthscale, lik, lam1, L2, lr, scale=1.0, jitter=1e-9):
+    """One natgrad_step (tsvgp.py:234-304) for any of the three likelihoods, SE kernel, long double; same order as
+    natgrad_step_gaussian."""
+    X, Z = np.asarray(X), np.asarray(Z)
+    lam1, L2, y = np.asarray(lam1, dtype=LD), np.asarray(L2, dtype=LD), np.asarray(Y, dtype=LD).reshape(-1)
+    M = Z.shape[0]
+    Id = np.eye(M, dtype=LD)
+    mean, var = predict_f(X, Z, variance, lengthscale, lam1, L2)
+    meanZ, _ = predict_f(Z, Z, variance, lengthscale, lam1, L2)
+    g_mean, g_var = ve_grads(lik, mean, var, y)
+    K = se_kernel(Z, Z, variance, lengthscale)
+    Kuf = se_kernel(Z, X, variance, lengthscale)
+    C9 = chol(K + LD(jitter) * Id)
+    A = solve_upper(C9.T, solve_lower(C9, Kuf)).T
+    G1 = A.T @ g_mean
+    G2 = (A * g_var[:, None]).T @ A
+    g0 = G1 - 2 * (G2 @ meanZ)
+    lam2 = -(L2 @ L2.T) / 2
+    new1 = (1 - LD(lr)) * lam1 + LD(lr) * LD(scale) * g0
+    new2 = (1 - LD(lr)) * lam2 + LD(lr) * LD(scale) * G2
+    return new1, -chol(-2 * new2 + LD(jitter) * Id)

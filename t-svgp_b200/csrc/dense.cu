@@ -1,6 +1,7 @@
 #include "dense.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include <stdlib.h>
 
 namespace tsvgp {
 
@@ -9,7 +10,65 @@ namespace tsvgp {
 constexpr int NB = 128;
 static int g_chol_outer = 512;   // outer panel width of the two-level blocking (multiple of 128)
 
-int chol_lower(double* A, long ld, int n, double* dinv, int* info, cudaStream_t s, double* ws, size_t ws_doubles) {
+// Right-looking with look-ahead over two streams.  Per block column q, on `s` (the critical path):
+//   diag(q) -> panel(q) = A[q+1:, q] L_qq^-T -> [wait: trailing(q-1) done] -> A[q+1:, q+1] -= panel(q) panel(q)[0]^T  -> diag(q+1) ...
+// and on aux->s2, once panel(q) exists:  A[q+2:, q+2:] -= panel(q)[1:] panel(q)[1:]^T  (lower tiles), hidden under diag(q+1).
+// The two streams always write disjoint block columns (q+1 on `s`, >= q+2 on s2); `s` joins s2 before it returns.
+static int chol_lower_lookahead(double* A, long ld, int n, double* dinv, int* info, cudaStream_t s, double* ws, size_t ws_doubles,
+                                const CholAux& aux) {
+#define CUQ(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+    bool f_pending = false;
+    for (int q = 0; q < n; q += NB) {
+        double* Aqq = A + (long)q * ld + q;
+        double* Dq = dinv + (long)(q / NB) * NB * NB;
+        TRY(diag_potrf_inv_launch(Aqq, ld, Dq, q / NB, info, s));
+        const int below = n - (q + NB);
+        if (below <= 0) break;
+        double* panel = A + (long)(q + NB) * ld + q;
+        {   // panel <- panel * L_qq^-T
+            GemmP p;
+            p.A = panel; p.lda = ld; p.a_kc = 1;
+            p.B = Dq; p.ldb = NB; p.b_kc = 1;
+            p.C = panel; p.ldc = ld;
+            p.m = below; p.n = NB; p.k = NB;
+            TRY(gemm_launch_auto(p, s, ws, ws_doubles));
+        }
+        const int rest = below - NB;   // rows / columns from q + 2 blocks on
+        if (rest > 0) {   // trailing update of the columns >= q+2 on the helper stream
+            CUQ(cudaEventRecord(aux.e, s));
+            CUQ(cudaStreamWaitEvent(aux.s2, aux.e, 0));
+            GemmP p;
+            const double* Lp = panel + (long)NB * ld;
+            p.A = Lp; p.lda = ld; p.a_kc = 1;
+            p.B = Lp; p.ldb = ld; p.b_kc = 1;
+            p.C = A + (long)(q + 2 * NB) * ld + (q + 2 * NB); p.ldc = ld;
+            p.m = rest; p.n = rest; p.k = NB;
+            p.alpha = -1.0; p.beta = 1.0; p.lower_out = 1;
+            // trailing(q-1) precedes it in s2's own order; block column q+1 is written on `s` meanwhile (disjoint)
+            TRY(gemm_launch_auto(p, aux.s2, nullptr, 0));
+        }
+        // block column q+1 on the critical stream; trailing(q-1), which also wrote this column, must be complete
+        if (f_pending) CUQ(cudaStreamWaitEvent(s, aux.f, 0));
+        {
+            GemmP p;
+            p.A = panel; p.lda = ld; p.a_kc = 1;
+            p.B = panel; p.ldb = ld; p.b_kc = 1;
+            p.C = A + (long)(q + NB) * ld + (q + NB); p.ldc = ld;
+            p.m = below; p.n = NB; p.k = NB;
+            p.alpha = -1.0; p.beta = 1.0;
+            TRY(gemm_launch_auto(p, s, ws, ws_doubles));
+        }
+        if (rest > 0) { CUQ(cudaEventRecord(aux.f, aux.s2)); f_pending = true; }
+        else f_pending = false;
+    }
+    if (f_pending) CUQ(cudaStreamWaitEvent(s, aux.f, 0));
+#undef CUQ
+    return zero_upper_launch(A, ld, n, s);
+}
+
+int chol_lower(double* A, long ld, int n, double* dinv, int* info, cudaStream_t s, double* ws, size_t ws_doubles, const CholAux* aux) {
+    static const bool la_off = getenv("TSVGP_CHOL_LOOKAHEAD") && atoi(getenv("TSVGP_CHOL_LOOKAHEAD")) == 0;
+    if (aux && aux->s2 && n >= 4 * NB && !la_off) return chol_lower_lookahead(A, ld, n, dinv, info, s, ws, ws_doubles, *aux);
     const int OB = g_chol_outer;
     for (int P0 = 0; P0 < n; P0 += OB) {
         const int Pend = P0 + OB < n ? P0 + OB : n;

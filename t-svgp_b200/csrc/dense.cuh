@@ -10,7 +10,12 @@ namespace tsvgp {
 // info: device int, set to (failing pivot index + 1) if A is not positive definite (left untouched otherwise).
 // Restates tf.linalg.cholesky as called at reference src/models/tsvgp.py:270,300 and src/util.py:382.
 // ws / ws_doubles: optional split-K workspace (gemm_launch_auto) private to the stream; nullptr = never split.
-int chol_lower(double* A, long ld, int n, double* dinv, int* info, cudaStream_t s, double* ws = nullptr, size_t ws_doubles = 0);
+// aux (optional): a helper stream and two events private to the caller's stream.  With it the factorisation runs with LOOK-AHEAD:
+// after panel q only block column q+1 is updated on `s` (so the next diagonal block can start at once); the rest of the trailing
+// update (columns >= q+2) runs on aux->s2 underneath the next diagonal-block kernel, which is one CTA and leaves 147 SMs idle.
+struct CholAux { cudaStream_t s2 = nullptr; cudaEvent_t e = nullptr, f = nullptr; };
+int chol_lower(double* A, long ld, int n, double* dinv, int* info, cudaStream_t s, double* ws = nullptr, size_t ws_doubles = 0,
+               const CholAux* aux = nullptr);
 
 // Linv = L^-1 for lower-triangular L.  dinv must hold the inverses of L's diagonal blocks (from chol_lower, or
 // diag_trtri_launch).  tmp: workspace [ceil(n/256)*128][ld].  Turns tf.linalg.triangular_solve / cholesky_solve

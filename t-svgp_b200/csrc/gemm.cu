@@ -288,12 +288,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
     const int KT = max(ke - kb, 0) / BK;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    // warps w and w + 4 share an SM sub-partition: give each sub-partition one warp of the upper and one of the lower row half,
-    // with the column quarters rotated by two, so that the 8x8 blocks skipped below (zero blocks of triangular operands, the
-    // strictly upper blocks of a diagonal output tile) are spread evenly over the four DMMA pipes
-    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
     const bool plain = p.a_tri == 0 && p.b_tri == 0;
-    const int dj = (p.lower_out && ti == tj && plain) ? (wm - wn) / 8 : 64;   // diagonal tile of a symmetric product: (i, j) needed iff j <= i + dj
+    const bool diag_tile = p.lower_out && ti == tj && plain;
+    // Warps w and w + 4 share an SM sub-partition, i.e. one DMMA pipe.  The 8x8 blocks skipped below (zero blocks of a triangular
+    // operand inside its diagonal k-block; the strictly upper blocks of a diagonal output tile) must be spread EVENLY over the four
+    // pipes, or the tile runs at the speed of the fullest one:
+    //  * general mapping: the two warps of a sub-partition sit in different row halves (wm 0 / 64), so inside the diagonal k-block of
+    //    an upper-triangular A^T — where row block i is non-zero only from k-tile i/2 on — every pipe sees the same mix;
+    //  * diagonal tile of a symmetric product (needed blocks per warp: 32, 32, 26, 26, 10, 10, 0, 0): the pairs (64,0)+(0,64),
+    //    (64,32)+(0,96), (0,0)+(64,96), (64,64)+(0,32) give 32 / 32 / 36 / 36 DMMAs per k-step and pipe instead of up to 64.
+    int wm, wn;
+    if (diag_tile) { wm = ((0x4B >> warp) & 1) * 64; wn = ((0x7E84 >> (2 * warp)) & 3) * 32; }
+    else if (warp < 4) { wm = (warp & 1) * 64; wn = (warp >> 1) * 32; }
+    else { wm = ((warp & 1) ^ 1) * 64; wn = 64 + ((warp - 4) >> 1) * 32; }
+    const int dj = diag_tile ? (wm - wn) / 8 : 64;   // diagonal tile of a symmetric product: (i, j) needed iff j <= i + dj
     const int dj_pat = dj >= 3 ? 0 : (dj == 0 ? 1 : (dj == -4 ? 2 : 3));
     const bool tri_a2 = p.a_tri == 2 && p.b_tri == 0 && !p.lower_out;
 
@@ -494,20 +502,24 @@ int gemm_init() {
     return e;
 }
 
-// Greedy in-order dispatch of `tiles` big pieces (kt1 k-tiles each) then `tiles` small pieces (kt - kt1 each) onto `sms`
-// single-CTA SMs; every piece also pays `ovh` k-tiles of prologue / epilogue (pipeline fill, C tile read-modify-write).
-static double dispatch_makespan(int tiles, int sms, int kt1, int kt2, double ovh) {
+// Greedy in-order dispatch of the lower tiles of an nt x nt symmetric product onto `sms` single-CTA SMs, first every tile's big
+// piece (kt1 k-tiles), then every tile's small piece (kt2), in launch order (tile rows, diagonal tile last in its row).  A diagonal
+// tile needs only its lower 8x8 blocks and runs at DIAG_COST of a full tile (see the warp mapping in gemm_kernel_mb); every piece
+// also pays `ovh` k-tiles of prologue / epilogue (pipeline fill, C tile read-modify-write).
+constexpr double DIAG_COST = 36.0 / 64.0;
+static double dispatch_makespan(int nt, int sms, int kt1, int kt2, double ovh) {
     std::vector<double> free_at(sms, 0.0);
-    auto run = [&](int count, double len) {
-        for (int i = 0; i < count; ++i) {
-            int best = 0;
-            for (int s = 1; s < sms; ++s)
-                if (free_at[s] < free_at[best]) best = s;
-            free_at[best] += len;
-        }
+    auto run = [&](double kt) {
+        for (int ti = 0; ti < nt; ++ti)
+            for (int tj = 0; tj <= ti; ++tj) {
+                int best = 0;
+                for (int s = 1; s < sms; ++s)
+                    if (free_at[s] < free_at[best]) best = s;
+                free_at[best] += (tj == ti ? DIAG_COST : 1.0) * kt + ovh;
+            }
     };
-    run(tiles, kt1 + ovh);
-    if (kt2 > 0) run(tiles, kt2 + ovh);
+    run(kt1);
+    if (kt2 > 0) run(kt2);
     double m = 0.0;
     for (double f : free_at) m = f > m ? f : m;
     return m;
@@ -527,15 +539,19 @@ int balanced_ksplit(int tiles, int k) {
     const auto key = std::make_pair(tiles, k);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
+    int nt = 1;
+    while (nt * (nt + 1) / 2 < tiles) ++nt;   // tiles = nt (nt + 1) / 2 lower tiles
     const int kt = k / BK;
     const double ovh = 3.0;   // measured: a split-off piece costs about 3 k-tiles beyond its DMMA work (tools/gemm_bench)
     int best = k;
-    double best_t = dispatch_makespan(tiles, sms, kt, 0, ovh);
-    const double waves = (double)tiles / sms, f0 = waves / ceil(waves);
-    for (int d = -6; d <= 14; ++d) {   // candidates around the ideal fraction, biased towards larger first pieces
-        const int kt1 = (int)(f0 * kt) + d * (kt >= 256 ? kt / 128 : 1);
+    double best_t = dispatch_makespan(nt, sms, kt, 0, ovh);
+    const double work = (tiles - nt) + nt * DIAG_COST;   // in full-tile units
+    const double waves = work / sms, f0 = waves / ceil(waves);
+    const int step = kt >= 256 ? kt / 128 : 1;
+    for (int d = -24; d <= 24; ++d) {   // candidates around the ideal fraction
+        const int kt1 = (int)(f0 * kt) + d * step;
         if (kt1 < 1 || kt - kt1 < 4) continue;
-        const double t = dispatch_makespan(tiles, sms, kt1, kt - kt1, ovh);
+        const double t = dispatch_makespan(nt, sms, kt1, kt - kt1, ovh);
         if (t < best_t * 0.985) { best_t = t; best = kt1 * BK; }
     }
     cache[key] = best;

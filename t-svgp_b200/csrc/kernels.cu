@@ -422,6 +422,28 @@ __global__ void __launch_bounds__(128) gemv_t_part_kernel(const double* __restri
     for (int i = i0; i < i1; ++i) s = fma(A[(long)i * lda + j], x[i], s);
     work[(long)blockIdx.y * n + j] = s;
 }
+// the partial stage alone, with its own leading dimension: work[chunk][j] = sum over the 64-row chunk of A[i][j] x[i]  (the layout
+// kuf_kernel gives its partial means)
+__global__ void __launch_bounds__(128) gemv_t_part_ld_kernel(const double* __restrict__ A, long lda, int m, int n,
+                                                             const double* __restrict__ x, double* __restrict__ work, long ldw) {
+    PDL_PROLOGUE();
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    const int i0 = blockIdx.y * 64;
+    if (j >= n) return;
+    double s0 = 0.0, s1 = 0.0;
+    const int i1 = min(i0 + 64, m);
+    for (int i = i0; i + 1 < i1; i += 2) {
+        s0 = fma(A[(long)i * lda + j], x[i], s0);
+        s1 = fma(A[(long)(i + 1) * lda + j], x[i + 1], s1);
+    }
+    if ((i1 - i0) & 1) s0 = fma(A[(long)(i1 - 1) * lda + j], x[i1 - 1], s0);
+    work[(long)blockIdx.y * ldw + j] = s0 + s1;
+}
+int gemv_t_part_launch(const double* A, long lda, int m, int n, const double* x, double* work, long ldw, cudaStream_t s) {
+    dim3 grid((n + 127) / 128, (m + 63) / 64);
+    launch_k(false, gemv_t_part_ld_kernel, grid, 128, 0, s, A, lda, m, n, x, work, ldw);
+    return count_launch();
+}
 __global__ void gemv_t_sum_kernel(const double* __restrict__ work, int nchunk, int n, double* __restrict__ y) {
     PDL_PROLOGUE();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;

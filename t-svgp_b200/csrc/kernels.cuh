@@ -52,6 +52,9 @@ int gemv_n_launch(const double* A, long lda, int m, long n, const double* x, dou
 // y[j] = sum_i A[i][j] x[i]   (uses work [nchunk][n]); deterministic two-stage
 int gemv_t_launch(const double* A, long lda, int m, int n, const double* x, double* y, double* work, cudaStream_t s);
 
+// work[c][j] = sum_{i in 64-row chunk c} A[i][j] x[i], leading dimension ldw  (partial means of a slab that already exists)
+int gemv_t_part_launch(const double* A, long lda, int m, int n, const double* x, double* work, long ldw, cudaStream_t s);
+
 // Zs[i][d] = ZsT[d][i]  (row-major copy of the scaled inducing inputs, [Mp][D])
 int unpack_rows_launch(const double* ZsT, long ldz, int Mp, int D, double* Zs, cudaStream_t s);
 

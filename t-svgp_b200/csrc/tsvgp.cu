@@ -92,6 +92,23 @@ struct tsvgp_ctx {
                                     // Gram product A^T diag(h) A (tsvgp.py:271-281): take that order literally (4 M^2 flops per point)
     int route = ROUTE_FUSED;        // route of the current / last step
     double cond_est = 0.0;
+    // The conditioning probe needs chol(K9), i.e. the whole K9 chain, before the statistics route of the pass can be chosen.  When an
+    // estimate from an earlier step of this context says "fused" (the route that needs nothing of K9 inside the pass), the step
+    // SPECULATES: the K9 chain runs on the side stream underneath the streaming pass instead of in front of it, the probe is read
+    // after the pass, and the pass is repeated with the right route in the (rare) case the estimate crossed the threshold.
+    double cond_hint = 0.0;
+    bool cond_hint_valid = false;
+    int speculate = 1;
+    // Gaussian likelihood, fused route: h_n is a constant, so Kuf and the SYRK of a slab do not depend on the posterior.  The first
+    // slab of every slab stream is enqueued BEFORE the posterior chain (latency-bound, SMs mostly idle) and fills the idle SMs.
+    int early_slabs = 1;
+    int n_early = 0;
+    cudaEvent_t ev_post = nullptr;
+    CholAux la_main, la_side;   // look-ahead helper streams of the Cholesky factorisations on the main / side stream (dense.cuh)
+    // Entry points that every rank calls together (natgrad_step, elbo, elbo_grad, predict_f_extra_data) may distribute the dense
+    // M x M products over the ranks; predict_f / prior_kl / posterior may be called by one rank alone and must not hide a collective.
+    bool collective_ok = false;
+    bool post_collective = false;   // the cached posterior factors were built by a collective call (distributed products)
 
     // kernel / likelihood
     int kern_kind = -1;
@@ -306,8 +323,11 @@ int ensure_kuu(tsvgp_ctx* c) {
 int ensure_posterior(tsvgp_ctx* c) {
     if (c->white) return ensure_posterior_white(c);
     OK(ensure_kuu(c));
-    if (c->post_valid && c->cache_factors) return TSVGP_OK;
+    // cached factors are reused, except that a collective call must not skip the build when this rank's cache was built by a
+    // non-collective call (predict_f on one rank alone): the other ranks are about to run the distributed products' all-reduces
+    if (c->post_valid && c->cache_factors && !(dist_active(c) && !c->post_collective)) return TSVGP_OK;
     if (!c->sites_set) OK(default_sites(c));
+    c->post_collective = dist_active(c);
     cudaStream_t s = c->s_main;
     const int n = c->Mp;
     const long ld = c->Mp;
@@ -335,7 +355,7 @@ int ensure_posterior(tsvgp_ctx* c) {
     }
     // reverse Cholesky W = Uw Uw^T through the index flip J W J = Lr Lr^T
     LA(flip_sym_launch(c->Wm, c->Wf, ld, n, s));
-    LA(chol_lower(c->Wf, ld, n, c->dinv, c->info + INFO_W, s, c->gws, c->gws_doubles));
+    LA(chol_lower(c->Wf, ld, n, c->dinv, c->info + INFO_W, s, c->gws, c->gws_doubles, &c->la_main));
     LA(logdiag_launch(c->Wf, ld, n, c->scal + SC_LOGDIAG_W, s));
     LA(trtri_lower(c->Wf, ld, n, c->dinv, c->X2, c->tmp, s, c->gws, c->gws_doubles));
     LA(antitranspose_launch(c->X2, c->V, ld, n, s));   // V = Uw^-T (lower)
@@ -404,7 +424,7 @@ int ensure_posterior_white(tsvgp_ctx* c) {
     const long ld = n;
     if (!c->c6_valid || !c->cache_factors) {   // LA = chol(K6), LA^-1 : kernel only
         CU(cudaMemcpyAsync(c->C6, c->K6, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, s));
-        LA(chol_lower(c->C6, ld, n, c->dinv, c->info + INFO_W, s, c->gws, c->gws_doubles));
+        LA(chol_lower(c->C6, ld, n, c->dinv, c->info + INFO_W, s, c->gws, c->gws_doubles, &c->la_main));
         LA(trtri_lower(c->C6, ld, n, c->dinv, c->C6inv, c->tmp, s, c->gws, c->gws_doubles));
         c->c6_valid = true;
     }
@@ -413,7 +433,7 @@ int ensure_posterior_white(tsvgp_ctx* c) {
     CU(cudaMemcpyAsync(c->Wm, c->K6, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, s));
     LA(vadd_inplace_launch(c->Wm, c->L2, (long)n * ld, s));
     LA(add_diag_launch(c->Wm, ld, n, 1e-9, s));
-    LA(chol_lower(c->Wm, ld, n, c->dinv, c->info + INFO_S, s, c->gws, c->gws_doubles));
+    LA(chol_lower(c->Wm, ld, n, c->dinv, c->info + INFO_S, s, c->gws, c->gws_doubles, &c->la_main));
     LA(trtri_lower(c->Wm, ld, n, c->dinv, c->T, c->tmp, s, c->gws, c->gws_doubles));
     // alpha = R^-1 lambda_1 ; mZ = K alpha (predict_f(Z), un-jittered Kuf) ; m_q = K6 alpha
     LA(gemv_n_launch(c->T, ld, n, n, c->lam1, 1.0, 0.0, c->v1, s));
@@ -435,7 +455,7 @@ int ensure_kl_terms_white(tsvgp_ctx* c) {
     const long ld = n;
     CU(cudaMemcpyAsync(c->Wf, c->K6, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, s));
     LA(vadd_inplace_launch(c->Wf, c->L2, (long)n * ld, s));
-    LA(chol_lower(c->Wf, ld, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles));
+    LA(chol_lower(c->Wf, ld, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles, &c->la_main));
     LA(trtri_lower(c->Wf, ld, n, c->dinv, c->V, c->tmp, s, c->gws, c->gws_doubles));       // V = LR0^-1
     LA(logdiag_launch(c->Wf, ld, n, c->scal + SC_LOGDIAG_W, s));
     LA(logdiag_launch(c->C6, ld, n, c->scal + SC_PK0, s));
@@ -586,11 +606,16 @@ int ensure_slabs(tsvgp_ctx* c, long n_points, bool need_grad = false) {
 }
 
 // The streaming pass over `N` points whose scaled, feature-major coordinates are XsT/x2.
+// phase 0: the whole pass.  phase 1: set-up plus the posterior-independent head (Kuf slab and constant-weight SYRK of the first slab
+// of every slab stream; Gaussian likelihood, fused route) — enqueued BEFORE the posterior chain.  phase 2: the rest of a pass whose
+// phase 1 has been enqueued: the early slabs only run their posterior-dependent part (means, variance product, point statistics,
+// b += Kuf g).
+enum { PASS_WHOLE = 0, PASS_EARLY = 1, PASS_REST = 2 };
 int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, long N, const double* y, const double* mean_off,
-                int mode, double* mean_out, double* var_out) {
+                int mode, double* mean_out, double* var_out, int phase = PASS_WHOLE) {
     const bool grad = mode == MODE_GRAD;
     const bool stats = mode == MODE_STATS || grad;
-    OK(ensure_slabs(c, N, grad));
+    if (phase != PASS_REST) OK(ensure_slabs(c, N, grad));
     const long nc = c->chunk;
     const int Mp = c->Mp;
     const int nstr = c->profile ? 1 : (c->n_streams < 1 ? 1 : (c->n_streams > MAXS ? MAXS : c->n_streams));
@@ -610,17 +635,72 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
     const long nchunks = (N + ncu - 1) / ncu;
     cudaStream_t sm = c->s_main;
 
-    CU(cudaMemsetAsync(c->flags, 0, 2 * sizeof(int), sm));
-    CU(cudaMemsetAsync(c->ve_blocks, 0, sizeof(double) * (size_t)(nchunks * vstride), sm));
-    if (stats)
+    if (phase != PASS_REST) {
+        CU(cudaMemsetAsync(c->flags, 0, 2 * sizeof(int), sm));
+        CU(cudaMemsetAsync(c->ve_blocks, 0, sizeof(double) * (size_t)(nchunks * vstride), sm));
+        if (grad) CU(cudaMemsetAsync(c->aux_blocks, 0, sizeof(double) * (size_t)(2 * nchunks * vstride), sm));
+        CU(cudaEventRecord(c->ev_fork, sm));
         for (int s = 0; s < nstr; ++s) {
-            CU(cudaMemsetAsync(c->stats[s], 0, sizeof(double) * ((size_t)Mp * Mp + Mp + 4), sm));
-            CU(cudaMemsetAsync(c->stats2[s], 0, sizeof(double) * ((size_t)Mp * Mp + Mp), sm));
-            if (grad) CU(cudaMemsetAsync(c->facc[s], 0, sizeof(double) * (size_t)Mp * 128, sm));
+            CU(cudaStreamWaitEvent(c->s_pp[s], c->ev_fork, 0));
+            if (stats) {   // every slab stream zeroes its own accumulators (off the main stream, which runs the posterior chain)
+                CU(cudaMemsetAsync(c->stats[s], 0, sizeof(double) * ((size_t)Mp * Mp + Mp + 4), c->s_pp[s]));
+                CU(cudaMemsetAsync(c->stats2[s], 0, sizeof(double) * ((size_t)Mp * Mp + Mp), c->s_pp[s]));
+                if (grad) CU(cudaMemsetAsync(c->facc[s], 0, sizeof(double) * (size_t)Mp * 128, c->s_pp[s]));
+            }
         }
-    if (grad) CU(cudaMemsetAsync(c->aux_blocks, 0, sizeof(double) * (size_t)(2 * nchunks * vstride), sm));
-    CU(cudaEventRecord(c->ev_fork, sm));
-    for (int s = 0; s < nstr; ++s) CU(cudaStreamWaitEvent(c->s_pp[s], c->ev_fork, 0));
+        c->n_early = 0;
+    }
+    // the weighted SYRK of one slab (and, fused into it, b += K g unless `with_b` is false)
+    auto syrk = [&](int b, const double* stat_slab, int ncols, bool const_h, bool with_b, bool& fused_b) -> int {
+        cudaStream_t s = c->s_pp[b];
+        GemmP p;
+        p.A = stat_slab; p.lda = nc; p.a_kc = 1;
+        p.B = stat_slab; p.ldb = nc; p.b_kc = 1;
+        p.C = c->stats[b]; p.ldc = Mp; p.m = p.n = Mp; p.k = ncols;
+        p.beta = 1.0; p.lower_out = 1; p.kscale = c->hbuf[b];
+        // Gaussian likelihood: h_n is the same constant -1/(2 s2) for every point (tsvgp.py:256-263 with the closed-form
+        // variational expectation), so it multiplies the product once instead of every B fragment
+        if (const_h) { p.kscale = nullptr; p.alpha = fmin(-0.5 / c->lik.p0, -1e-8); }
+        const int nt = Mp / 128;
+        const int ks_here = c->ksplit < ncols / 128 ? c->ksplit : ncols / 128;
+        fused_b = false;
+        if (ks_here > 1) {
+            p.ksplit = ks_here; p.part = c->kpart[b]; p.part_stride = (long)Mp * Mp;
+            LA(gemm_launch(p, s));
+            LA(splitk_reduce_launch(p, s));
+        } else {
+            const int ksp = c->balance ? balanced_ksplit(nt * (nt + 1) / 2, ncols) : ncols;
+            if (ksp < ncols) { p.ksp = ksp; p.C2 = c->stats2[b]; }
+            if (c->fuse_b && with_b) {   // b += K g rides on the A fragments of the SYRK's first tile column
+                p.gvec = c->gbuf[b]; p.bout = c->stats[b] + (size_t)Mp * Mp; p.bout2 = c->stats2[b] + (size_t)Mp * Mp;
+                fused_b = true;
+            }
+            LA(gemm_launch(p, s));
+        }
+        return TSVGP_OK;
+    };
+    const bool const_h_pass = c->lik.kind == LIK_GAUSSIAN && c->fuse_b && !grad;
+    if (phase == PASS_EARLY) {
+        const bool ok = mode == MODE_STATS && const_h_pass && c->route == ROUTE_FUSED && !c->white && !prof && c->ksplit <= 1 &&
+                        nchunks >= 2 * nstr;
+        const int ne = ok ? (c->early_slabs < nstr ? c->early_slabs : nstr) : 0;
+        for (int ci = 0; ci < ne; ++ci) {
+            const long n0 = ci * ncu;
+            const long nvalid = N - n0 < ncu ? N - n0 : ncu;
+            const int ncols = (int)round_up(nvalid, 128);
+            LA(kuf_launch(c->kern_kind, c->kern_var, XsT, ldx, x2, n0, N, ncols, c->Zs, c->z2, c->M, Mp, c->D, nullptr, c->slab[ci],
+                          nc, nullptr, 0, 0, c->s_pp[ci], nullptr));
+            bool fb;
+            OK(syrk(ci, c->slab[ci], ncols, true, false, fb));
+        }
+        c->n_early = ne;
+        return TSVGP_OK;
+    }
+    if (phase == PASS_REST) {   // the slab streams continue once the posterior factors are complete on the main stream
+        CU(cudaEventRecord(c->ev_post, sm));
+        for (int s = 0; s < nstr; ++s) CU(cudaStreamWaitEvent(c->s_pp[s], c->ev_post, 0));
+    }
+    const int n_early = phase == PASS_REST ? c->n_early : 0;
 
     for (long ci = 0; ci < nchunks; ++ci) {
         const int b = (int)(ci % nstr);
@@ -628,10 +708,14 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
         const long n0 = ci * ncu;
         const long nvalid = N - n0 < ncu ? N - n0 : ncu;
         const int ncols = (int)round_up(nvalid, 128);
+        const bool early = ci < n_early;   // Kuf slab and SYRK already enqueued by phase 1
         if (mark(s)) FAIL(TSVGP_ERR_CUDA, "profile event");
         // (a) covariance slab K[Mp x ncols] and the partial means sum_i alpha_i K[i][n]
-        LA(kuf_launch(c->kern_kind, c->kern_var, XsT, ldx, x2, n0, N, ncols, c->Zs, c->z2, c->M, Mp, c->D, c->alpha, c->slab[b],
-                      nc, c->mu_part[b], nc, 0, s, grad ? c->kpslab[b] : nullptr));
+        if (!early)
+            LA(kuf_launch(c->kern_kind, c->kern_var, XsT, ldx, x2, n0, N, ncols, c->Zs, c->z2, c->M, Mp, c->D, c->alpha, c->slab[b],
+                          nc, c->mu_part[b], nc, 0, s, grad ? c->kpslab[b] : nullptr));
+        else   // the slab exists already: the same per-64-row partial means from a transposed mat-vec over it
+            LA(gemv_t_part_launch(c->slab[b], nc, Mp, ncols, c->alpha, c->mu_part[b], nc, s));
         mark(s);
         if (!c->white) {   // (b) |T^T k_n|^2 : upper-triangular T^T times the slab, reduced to column norms in the epilogue
             GemmP p;
@@ -689,34 +773,11 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
                 }
             }
             mark(s);
-            {   // (d) B += K diag(h) K^T, lower tiles
-                GemmP p;
-                p.A = stat_slab; p.lda = nc; p.a_kc = 1;
-                p.B = stat_slab; p.ldb = nc; p.b_kc = 1;
-                p.C = c->stats[b]; p.ldc = Mp; p.m = p.n = Mp; p.k = ncols;
-                p.beta = 1.0; p.lower_out = 1; p.kscale = c->hbuf[b];
-                // Gaussian likelihood: h_n is the same constant -1/(2 s2) for every point (tsvgp.py:256-263 with the closed-form
-                // variational expectation), so it multiplies the product once instead of every B fragment
-                const bool const_h = c->lik.kind == LIK_GAUSSIAN && c->fuse_b && !grad;
-                if (const_h) { p.kscale = nullptr; p.alpha = fmin(-0.5 / c->lik.p0, -1e-8); }
-                const int nt = Mp / 128;
-                const int ks_here = c->ksplit < ncols / 128 ? c->ksplit : ncols / 128;
+            {   // (d) B += K diag(h) K^T, lower tiles (already enqueued for an early slab)
                 bool fused_b = false;
-                if (ks_here > 1) {
-                    p.ksplit = ks_here; p.part = c->kpart[b]; p.part_stride = (long)Mp * Mp;
-                    LA(gemm_launch(p, s));
-                    LA(splitk_reduce_launch(p, s));
-                } else {
-                    const int ksp = c->balance ? balanced_ksplit(nt * (nt + 1) / 2, ncols) : ncols;
-                    if (ksp < ncols) { p.ksp = ksp; p.C2 = c->stats2[b]; }
-                    if (c->fuse_b) {   // (e) b += K g rides on the A fragments of the SYRK's first tile column
-                        p.gvec = c->gbuf[b]; p.bout = c->stats[b] + (size_t)Mp * Mp; p.bout2 = c->stats2[b] + (size_t)Mp * Mp;
-                        fused_b = true;
-                    }
-                    LA(gemm_launch(p, s));
-                }
+                if (!early) OK(syrk(b, stat_slab, ncols, const_h_pass, true, fused_b));
                 mark(s);
-                // (e) b += K g as its own kernel when the SYRK ran split-K
+                // (e) b += K g as its own kernel when the SYRK ran split-K or ahead of the posterior
                 if (!fused_b) LA(gemv_n_launch(stat_slab, nc, Mp, ncols, c->gbuf[b], 1.0, 1.0, c->stats[b] + (size_t)Mp * Mp, s));
             }
             mark(s);
@@ -789,7 +850,7 @@ int mm_gemm(tsvgp_ctx* c, const GemmP& p, cudaStream_t s) {
 // each rank computes its rows into a zeroed C, and one all-reduce assembles the matrix on every rank (bit-identical everywhere:
 // each entry is one rank's value plus zeros).  Below `dist_min_m` the product is latency-bound and stays replicated.
 // Requires p.beta == 0 and every rank calling in the same order.
-bool dist_active(const tsvgp_ctx* c) { return c->world > 1 && c->Mp >= c->dist_min_m; }
+bool dist_active(const tsvgp_ctx* c) { return c->world > 1 && c->Mp >= c->dist_min_m && c->collective_ok; }
 
 int dense_gemm(tsvgp_ctx* c, GemmP p, cudaStream_t s) {
     if (!dist_active(c) || p.beta != 0.0) {
@@ -857,7 +918,7 @@ int start_k9_async(tsvgp_ctx* c, double jitter, SideIssue& side) {
 int k9_chain(tsvgp_ctx* c, double jitter) {
     cudaStream_t s = c->s_side;
     LA(copy_add_diag_launch(c->K, c->C9, c->Mp, c->Mp, jitter, s));
-    LA(chol_lower(c->C9, c->Mp, c->Mp, c->dinv2, c->info + INFO_K9, s, c->gws2, c->gws_doubles));
+    LA(chol_lower(c->C9, c->Mp, c->Mp, c->dinv2, c->info + INFO_K9, s, c->gws2, c->gws_doubles, &c->la_side));
     LA(trtri_lower(c->C9, c->Mp, c->Mp, c->dinv2, c->C9inv, c->tmp2, s, c->gws2, c->gws_doubles));
     c->k9inv_valid = false;
     if (!dist_active(c)) {   // single rank / small M: form K9^-1 here, hidden behind the main stream's posterior preparation
@@ -902,6 +963,11 @@ int k9_chain(tsvgp_ctx* c, double jitter) {
     return TSVGP_OK;
 }
 
+int route_for(const tsvgp_ctx* c, double cond) {
+    if (c->route_opt != ROUTE_AUTO) return c->route_opt;
+    return cond <= c->route_cond_max ? ROUTE_FUSED : (cond <= c->route_exact_min ? ROUTE_WHITENED : ROUTE_EXACT);
+}
+
 // joins the side stream, reads the conditioning probe (if one ran) and fixes the statistics route of this step
 int choose_route(tsvgp_ctx* c, double jitter) {
     if (c->k9_pending) {
@@ -912,13 +978,13 @@ int choose_route(tsvgp_ctx* c, double jitter) {
             const double lmax = sqrt(sc[SC_PK1] / sc[SC_PK0]) + jitter, inv_lmin = sqrt(sc[SC_PI1] / sc[SC_PI0]);
             c->cond_est = lmax * inv_lmin;
             if (!(c->cond_est == c->cond_est)) c->cond_est = INFINITY;   // failed factorisation: the step will report it
+            c->cond_hint = c->cond_est;
+            c->cond_hint_valid = true;
         }
         CU(cudaStreamWaitEvent(c->s_main, c->ev_side, 0));
         c->k9_pending = false;
     }
-    if (c->route_opt == ROUTE_AUTO)
-        c->route = c->cond_est <= c->route_cond_max ? ROUTE_FUSED : (c->cond_est <= c->route_exact_min ? ROUTE_WHITENED : ROUTE_EXACT);
-    else c->route = c->route_opt;
+    c->route = route_for(c, c->cond_est);
     return TSVGP_OK;
 }
 
@@ -1001,7 +1067,7 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale, bool only
             LA(mm_gemm(c, p, s));
         }
     }
-    LA(chol_lower(c->P, ld, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles));
+    LA(chol_lower(c->P, ld, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles, &c->la_main));
     // commit (skipped on the device if any variance was non-positive or a factorisation failed)
     LA(update_lambda1_launch(c->lam1, c->v2, c->v3, c->M, lr, scale, bad, c->info, s));
     LA(finalize_sites_launch(c->P, c->L2, ld, c->M, n, bad, c->info, s));
@@ -1087,13 +1153,25 @@ int tsvgp_create(tsvgp_ctx** out, int device_id) {
     tsvgp_ctx* c = new tsvgp_ctx();
     c->dev = device_id;
     bool ok = cudaSetDevice(device_id) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking) == cudaSuccess;
+    // the latency-bound M x M chains (main and side stream) outrank the slab streams, whose 1-CTA-per-SM DMMA kernels would
+    // otherwise make every small chain kernel wait for a whole wave
+    int prio_low = 0, prio_high = 0;
+    ok = ok && cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&c->s_main, cudaStreamNonBlocking, prio_high) == cudaSuccess;
     for (int s = 0; s < MAXS && ok; ++s) {
-        ok = ok && cudaStreamCreateWithFlags(&c->s_pp[s], cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&c->s_pp[s], cudaStreamNonBlocking, prio_low) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&c->ev_join[s], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&c->s_side, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_post, cudaEventDisableTiming) == cudaSuccess;
+    // the side chain (Kuu + jitter I) yields to the main chain (posterior, site update) where they meet, and both outrank the slabs
+    const int prio_mid = prio_high < prio_low - 1 ? prio_high + 1 : prio_high;
+    ok = ok && cudaStreamCreateWithPriority(&c->s_side, cudaStreamNonBlocking, prio_mid) == cudaSuccess;
+    for (CholAux* a : {&c->la_main, &c->la_side}) {
+        ok = ok && cudaStreamCreateWithPriority(&a->s2, cudaStreamNonBlocking, a == &c->la_main ? prio_high : prio_mid) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&a->e, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&a->f, cudaEventDisableTiming) == cudaSuccess;
+    }
     ok = ok && cudaEventCreateWithFlags(&c->ev_kuu, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < N_EV && ok; ++i) ok = ok && cudaEventCreate(&c->ev[i]) == cudaSuccess;
@@ -1120,9 +1198,15 @@ void tsvgp_destroy(tsvgp_ctx* c) {
         if (c->ev_join[s]) cudaEventDestroy(c->ev_join[s]);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_post) cudaEventDestroy(c->ev_post);
     if (c->ev_kuu) cudaEventDestroy(c->ev_kuu);
     if (c->ev_side) cudaEventDestroy(c->ev_side);
     if (c->s_side) cudaStreamDestroy(c->s_side);
+    for (CholAux* a : {&c->la_main, &c->la_side}) {
+        if (a->s2) cudaStreamDestroy(a->s2);
+        if (a->e) cudaEventDestroy(a->e);
+        if (a->f) cudaEventDestroy(a->f);
+    }
     for (cudaEvent_t e : c->pev) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i)
         if (c->ev_sw[i]) cudaEventDestroy(c->ev_sw[i]);
@@ -1139,7 +1223,13 @@ int tsvgp_set_option(tsvgp_ctx* c, const char* name, double value) {
     if (!c || !name) return TSVGP_ERR_INVALID;
     if (!strcmp(name, "chunk")) { c->chunk_opt = (long)value; return TSVGP_OK; }
     if (!strcmp(name, "streams")) { c->n_streams = value < 1 ? 1 : (value > MAXS ? MAXS : (int)value); return TSVGP_OK; }
-    if (!strcmp(name, "route")) { c->route_opt = (int)value; c->k9_valid = false; return TSVGP_OK; }
+    if (!strcmp(name, "route")) {
+        if (value != ROUTE_AUTO && value != ROUTE_FUSED && value != ROUTE_WHITENED && value != ROUTE_EXACT)
+            FAIL(TSVGP_ERR_INVALID, "route must be 0 (auto), 1 (fused), 2 (whitened) or 3 (exact)");
+        c->route_opt = (int)value; c->k9_valid = false; return TSVGP_OK;
+    }
+    if (!strcmp(name, "speculate")) { c->speculate = value != 0.0; return TSVGP_OK; }
+    if (!strcmp(name, "early_slabs")) { c->early_slabs = value < 0 ? 0 : (int)value; return TSVGP_OK; }
     if (!strcmp(name, "route_cond_max")) { c->route_cond_max = value; return TSVGP_OK; }
     if (!strcmp(name, "route_exact_min")) { c->route_exact_min = value; return TSVGP_OK; }
     if (!strcmp(name, "white")) {   // switch the context to the whitened sibling model (resets the sites to its defaults)
@@ -1370,22 +1460,43 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
     const size_t mm = (size_t)c->Mp * c->Mp;
     CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
     CU(cudaEventRecord(c->ev[EV_T0], s));
+    c->collective_ok = true;
     OK(ensure_xs(c));
     OK(ensure_kuu(c));
     {
         SideIssue side;
         struct PdlGuard { ~PdlGuard() { g_pdl_suspended = 0; } } pdl_guard;
-        if (c->Mp >= 2048 && !k9_cached(c, jitter)) g_pdl_suspended = 1;   // two concurrent chains of large kernels: see common.cuh
+        const bool k9_runs = !k9_cached(c, jitter);
+        if (c->Mp >= 2048 && k9_runs) g_pdl_suspended = 1;   // two concurrent chains of large kernels: see common.cuh
         int rc = start_k9_async(c, jitter, side);
+        // When is the K9 chain joined?  The fused route needs nothing of it inside the pass, so if the route is fused — forced, or
+        // SPECULATED from this context's last conditioning estimate — the chain runs underneath the pass and is joined after it
+        // (where the probe is read and the guess checked).  Whitened / exact passes need C9^-1: join first, as does a first step.
+        bool join_before = true;
+        if (k9_runs && (c->route_opt == ROUTE_FUSED ||
+                        (c->route_opt == ROUTE_AUTO && c->speculate && c->cond_hint_valid && route_for(c, c->cond_hint) == ROUTE_FUSED))) {
+            c->route = ROUTE_FUSED;
+            join_before = false;
+        }
+        if (rc == TSVGP_OK && !k9_runs) rc = choose_route(c, jitter);   // cached factors: the route is known at once
+        c->n_early = 0;
+        const bool early = rc == TSVGP_OK && c->early_slabs && (!k9_runs || !join_before) && c->route == ROUTE_FUSED;
+        if (early) rc = stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_STATS, nullptr, nullptr, PASS_EARLY);
         if (rc == TSVGP_OK) rc = ensure_posterior(c);
         if (rc == TSVGP_OK && elbo_before) rc = ensure_kl_terms(c);
         side.join_into(g_launches);
         if (rc != TSVGP_OK) return rc;
         if (side.rc != TSVGP_OK) return side.rc;
+        if (k9_runs && join_before) OK(choose_route(c, jitter));
+        CU(cudaEventRecord(c->ev[EV_PREP], s));
+        OK(stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_STATS, nullptr, nullptr, early ? PASS_REST : PASS_WHOLE));
+        if (k9_runs && !join_before) {   // join the K9 chain, read the probe, repeat the pass if the guess was wrong
+            const int guessed = c->route;
+            OK(choose_route(c, jitter));
+            if (c->route != guessed)
+                OK(stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_STATS, nullptr, nullptr));
+        }
     }
-    OK(choose_route(c, jitter));
-    CU(cudaEventRecord(c->ev[EV_PREP], s));
-    OK(stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_STATS, nullptr, nullptr));
     CU(cudaEventRecord(c->ev[EV_STREAM], s));
     OK(all_reduce(c, c->stats[0], mm + c->Mp + 4));
     CU(cudaEventRecord(c->ev[EV_REDUCE], s));
@@ -1425,6 +1536,7 @@ int tsvgp_elbo(tsvgp_ctx* c, double scale, double* out) {
     if (!c || !out) return TSVGP_ERR_INVALID;
     OK(require_model(c, true));
     CU(cudaSetDevice(c->dev));
+    c->collective_ok = true;    // every rank calls elbo together (it all-reduces the expectations)
     cudaStream_t s = c->s_main;
     const size_t mm = (size_t)c->Mp * c->Mp;
     CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
@@ -1449,6 +1561,7 @@ int tsvgp_prior_kl(tsvgp_ctx* c, double* out) {
     if (!c || !out) return TSVGP_ERR_INVALID;
     OK(require_model(c, false));
     CU(cudaSetDevice(c->dev));
+    c->collective_ok = false;   // may be called by one rank alone: no hidden collective (replicated products)
     cudaStream_t s = c->s_main;
     CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
     OK(ensure_posterior(c));
@@ -1469,6 +1582,7 @@ int tsvgp_elbo_grad(tsvgp_ctx* c, double scale, double* elbo, double* d_variance
     if (2 * c->D + 1 > 128) FAIL(TSVGP_ERR_INVALID, "elbo_grad supports D <= 63 (D = %d)", c->D);
     if (c->white) FAIL(TSVGP_ERR_INVALID, "elbo_grad is not available for the whitened sibling model");
     CU(cudaSetDevice(c->dev));
+    c->collective_ok = true;
     cudaStream_t s = c->s_main;
     const int n = c->Mp, M = c->M, D = c->D;
     const long ld = n;
@@ -1569,6 +1683,7 @@ int tsvgp_predict_f(tsvgp_ctx* c, const double* Xnew, int64_t N, int D, const do
     OK(require_model(c, false));
     if (D != c->D) FAIL(TSVGP_ERR_INVALID, "Xnew has D=%d but the inducing points have D=%d", D, c->D);
     CU(cudaSetDevice(c->dev));
+    c->collective_ok = false;   // predict_f needs no collective: one rank may call it alone
     cudaStream_t s = c->s_main;
     CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
     OK(ensure_posterior(c));
@@ -1613,6 +1728,7 @@ int tsvgp_predict_f_extra_data(tsvgp_ctx* c, const double* Xnew, int64_t N, int 
     const long ld = n;
     const size_t mm = (size_t)n * n;
     // (1) natural parameters of the resident (extra) data under the current sites: tsvgp_white.py:183-212
+    c->collective_ok = true;
     CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
     OK(ensure_xs(c));
     OK(ensure_kuu(c));
@@ -1623,10 +1739,30 @@ int tsvgp_predict_f_extra_data(tsvgp_ctx* c, const double* Xnew, int64_t N, int 
     OK(all_reduce(c, c->stats[0], mm + n + 4));
     OK(dense_update(c, 1.0, 1e-9, 1.0, true));
     LA(lincomb_launch(c->v1, 1.0, c->v2, -2.0, c->v3, n, s));          // g0 = G1 - 2 G2 mZ
+    {   // the reference calls predict_f on the extra data here (assert_positive, failed Cholesky raise): check before going on,
+        // the nested predict_f below clears the flags
+        double tail[4];
+        int info_h[N_INFO];
+        CU(cudaMemcpyAsync(tail, c->stats[0] + mm + n, sizeof tail, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(info_h, c->info, sizeof info_h, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        OK(check_info(c, info_h));
+        if (tail[1] != 0.0) FAIL(TSVGP_ERR_NONPOSITIVE_VARIANCE, "predict_f_extra_data: non-positive predictive variance at the extra data");
+    }
     // (2) K_j = Kuu + jitter I ; combined sites lambda_1 + K_j g0, Lambda_2 - 2 K_j G2 K_j     (tsvgp_white.py:144-150)
     CU(cudaMemcpyAsync(c->lam1_bak, c->lam1, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
     CU(cudaMemcpyAsync(c->P, c->L2, sizeof(double) * mm, cudaMemcpyDeviceToDevice, s));
-    const double jit_saved = c->jit6;
+    struct Restore {   // every exit path puts the sites, K6 and its jitter back
+        tsvgp_ctx* c; double jit_saved; int n; size_t mm; cudaStream_t s;
+        ~Restore() {
+            cudaMemcpyAsync(c->lam1, c->lam1_bak, sizeof(double) * n, cudaMemcpyDeviceToDevice, s);
+            cudaMemcpyAsync(c->L2, c->P, sizeof(double) * mm, cudaMemcpyDeviceToDevice, s);
+            c->jit6 = jit_saved;
+            copy_add_diag_launch(c->K, c->K6, n, n, c->jit6, s);
+            c->c6_valid = c->wpost_valid = c->wkl_valid = false;
+            cudaStreamSynchronize(s);
+        }
+    } restore{c, c->jit6, n, mm, s};
     c->jit6 = jitter;
     LA(copy_add_diag_launch(c->K, c->K6, n, n, jitter, s));
     c->c6_valid = c->wpost_valid = c->wkl_valid = false;
@@ -1646,21 +1782,15 @@ int tsvgp_predict_f_extra_data(tsvgp_ctx* c, const double* Xnew, int64_t N, int 
         LA(mirror_lower_launch(c->X2, ld, n, s));
     }
     LA(axpby_guarded_launch(c->L2, c->X2, ld, c->M, 1.0, -2.0, nullptr, nullptr, s));
-    // (3) the conditional at Xnew with the combined sites, then everything back as it was
-    const int rc = tsvgp_predict_f(c, Xnew, N, D, mean_X, mean_out, var_out);
-    CU(cudaMemcpyAsync(c->lam1, c->lam1_bak, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
-    CU(cudaMemcpyAsync(c->L2, c->P, sizeof(double) * mm, cudaMemcpyDeviceToDevice, s));
-    c->jit6 = jit_saved;
-    LA(copy_add_diag_launch(c->K, c->K6, n, n, c->jit6, s));
-    c->c6_valid = c->wpost_valid = c->wkl_valid = false;
-    CU(cudaStreamSynchronize(s));
-    return rc;
+    // (3) the conditional at Xnew with the combined sites; `restore` puts everything back as it was
+    return tsvgp_predict_f(c, Xnew, N, D, mean_X, mean_out, var_out);
 }
 
 int tsvgp_posterior(tsvgp_ctx* c, double* m, double* chol_S) {
     if (!c) return TSVGP_ERR_INVALID;
     OK(require_model(c, false));
     CU(cudaSetDevice(c->dev));
+    c->collective_ok = false;
     cudaStream_t s = c->s_main;
     const int n = c->Mp;
     CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
@@ -1678,7 +1808,7 @@ int tsvgp_posterior(tsvgp_ctx* c, double* m, double* chol_S) {
         q.C = c->X2; q.ldc = n; q.m = q.n = q.k = n; q.lower_out = 1;
         LA(mm_gemm(c, q, s));
         c->wkl_valid = false;
-        LA(chol_lower(c->X2, n, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles));
+        LA(chol_lower(c->X2, n, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles, &c->la_main));
         CU(cudaMemcpy2DAsync(chol_S, sizeof(double) * c->M, c->X2, sizeof(double) * n, sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
     } else if (chol_S) {   // S = K6 - (K6 T)(K6 T)^T   (util.py:387-388)
         GemmP p;
@@ -1694,7 +1824,7 @@ int tsvgp_posterior(tsvgp_ctx* c, double* m, double* chol_S) {
         q.C = c->X2; q.ldc = n; q.m = q.n = q.k = n;
         q.alpha = -1.0; q.beta = 1.0; q.lower_out = 1;
         LA(mm_gemm(c, q, s));
-        LA(chol_lower(c->X2, n, n, c->dinv, c->info + INFO_S, s, c->gws, c->gws_doubles));
+        LA(chol_lower(c->X2, n, n, c->dinv, c->info + INFO_S, s, c->gws, c->gws_doubles, &c->la_main));
         CU(cudaMemcpy2DAsync(chol_S, sizeof(double) * c->M, c->X2, sizeof(double) * n, sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
     }
     int info_h[N_INFO];

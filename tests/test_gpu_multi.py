@@ -49,9 +49,13 @@ def _rank(rank, world, conn, out, opts):
     elbos = []
     for _ in range(2):
         elbos.append(m.natgrad_step((X[lo:hi], Y[lo:hi]), lr=cfg["lr"], global_minibatch_size=X.shape[0], return_elbo=True))
+    # predict_f is not a collective.  Right after a step the posterior factors are stale on every rank; rank 0 ALONE
+    # predicts (it must rebuild them without an all-reduce even when the dense products are distributed), then every rank calls
+    # the collective elbo() — rank 0's privately rebuilt cache must not unbalance the other ranks' collectives.
+    mu_solo = m.predict_f(X[50:100])[0] if rank == 0 else None
     elbos.append(m.elbo((X[lo:hi], Y[lo:hi]), global_minibatch_size=X.shape[0]))
     mu, var = m.predict_f(X[:50])
-    out.put((rank, m.lambda_1, m.lambda_2, elbos, mu, var))
+    out.put((rank, m.lambda_1, m.lambda_2, elbos, mu, var, mu_solo))
     m.close()
 
 
@@ -77,9 +81,11 @@ def test_two_gpu_sharded_step_matches_single_gpu(opts):
     e[2] = single.elbo((X, Y))
     mu, var = single.predict_f(X[:50])
     rel = lambda x, y: float(np.max(np.abs(np.asarray(x) - np.asarray(y))) / np.max(np.abs(y)))  # noqa: E731
-    for rank, l1, l2, elbos, mu_r, var_r in res:
+    for rank, l1, l2, elbos, mu_r, var_r, mu_solo in res:
         assert rel(l1, single.lambda_1) < 1e-11 and rel(l2, single.lambda_2) < 1e-11     # summation order only
         assert rel(elbos, e) < 1e-11 and rel(mu_r, mu) < 1e-11 and rel(var_r, var) < 1e-11
+        if rank == 0:
+            assert rel(mu_solo, single.predict_f(X[50:100])[0]) < 1e-11
     np.testing.assert_array_equal(res[0][1], res[1][1])   # replicated dense phase: both ranks hold identical sites
     np.testing.assert_array_equal(res[0][2], res[1][2])
     single.close()

@@ -371,3 +371,33 @@ def test_prefetched_minibatch_stream_equals_direct_calls():
     for px, py in batches:
         tb.pinned_free(px); tb.pinned_free(py)
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("lik_name", ["bernoulli", "student_t"])
+def test_cuda_quadrature_path_against_the_long_double_arbiter(lik_name):
+    # the non-conjugate path (20-point Gauss-Hermite, analytic gradients, -1e-8 clip; tsvgp.py:256-263): the CUDA result must sit as
+    # close to the 80-bit evaluation of the reference's formulas (oracle/longdouble.py::natgrad_step) as the float64 oracle does
+    import tsvgp_b200 as tb
+    from oracle import longdouble as ld
+    rng = np.random.RandomState(1)
+    N, M, D = 120, 20, 6
+    X, Z = rng.randn(N, D), rng.randn(M, D)
+    f = np.sin(X.sum(1, keepdims=True))
+    kernel = orc.SquaredExponential(variance=1.0, lengthscales=2.0)
+    if lik_name == "bernoulli":
+        lik, spec, Y = orc.Bernoulli(), ("bernoulli",), (f + 0.3 * rng.randn(N, 1) > 0).astype(float)
+    else:
+        lik, spec, Y = orc.StudentT(scale=0.3, df=3.0), ("student_t", 0.3, 3.0), f + 0.3 * rng.standard_t(3.0, size=(N, 1))
+    ref = orc.OracleTSVGP(kernel, lik, orc.InducingPoints(Z), num_data=4 * N)
+    ref.natgrad_step((X, Y), lr=0.6)
+    l1, L2 = ref.lambda_1.copy(), ref.lambda_2_sqrt.copy()
+    t1, tL2 = ld.natgrad_step(X, Y, Z, 1.0, 2.0, spec, l1[:, 0], L2[0], lr=0.6, scale=4.0)
+    truth1, truth2 = np.asarray(t1, dtype=np.float64), np.asarray(tL2 @ tL2.T, dtype=np.float64)
+    ref.natgrad_step((X, Y), lr=0.6)
+    dev = tb.t_SVGP(kernel, lik, Z.copy(), lambda_1=l1, lambda_2_sqrt=L2, num_data=4 * N)
+    dev.natgrad_step((X, Y), lr=0.6)
+    e_ref = max(relerr(ref.lambda_1[:, 0], truth1), relerr(ref.lambda_2[0], truth2))
+    e_dev = max(relerr(dev.lambda_1[:, 0], truth1), relerr(dev.lambda_2[0], truth2))
+    _record({"oracle_vs_longdouble": e_ref, "cuda_vs_longdouble": e_dev, "route": dev.timings()["route"]})
+    assert e_dev <= max(20.0 * e_ref + 1e-13, 1e-10), (e_dev, e_ref)
+    dev.close()

@@ -90,6 +90,18 @@ int main(int argc, char** argv) {
         cudaEventRecord(e0); trtri_lower(dW, n, n, dinv, dLinv, tmp, 0, w, ws_doubles); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
         cudaEventElapsedTime(&ms, e0, e1); printf("trtri_lower n=%d (%s): %.3f ms\n", n, w ? "auto split-K" : "no split", ms);
     }
+    {   // look-ahead over two streams (dense.cuh::CholAux) against the single-stream schedule, on explicit non-blocking streams
+        cudaStream_t s1; CholAux aux;
+        CK(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&aux.s2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&aux.e, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&aux.f, cudaEventDisableTiming));
+        for (int rep = 0; rep < 6; ++rep) {
+            const bool la = rep >= 3;
+            CK(cudaMemcpyAsync(dW, dA, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, s1));
+            cudaEventRecord(e0, s1); chol_lower(dW, n, n, dinv, info, s1, ws, ws_doubles, la ? &aux : nullptr); cudaEventRecord(e1, s1); CK(cudaEventSynchronize(e1));
+            cudaEventElapsedTime(&ms, e0, e1); printf("chol_lower n=%d (%s): %.3f ms\n", n, la ? "look-ahead, 2 streams" : "single stream", ms);
+        }
+        CK(cudaStreamSynchronize(s1));
+    }
     int h; CK(cudaMemcpy(&h, info, 4, cudaMemcpyDeviceToHost)); printf("info %d\n", h);
     std::vector<double> L((size_t)n * n), Li((size_t)n * n);
     CK(cudaMemcpy(L.data(), dW, sizeof(double) * n * n, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(Li.data(), dLinv, sizeof(double) * n * n, cudaMemcpyDeviceToHost));
