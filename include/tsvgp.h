@@ -79,6 +79,8 @@ TSVGP_API int tsvgp_set_option(tsvgp_ctx* ctx, const char* name, double value); 
  * "speculate" (1 = automatic route: when this context's last conditioning estimate chose the fused route, run the
  *          Kuu + jitter I chain UNDERNEATH the streaming pass instead of in front of it, read the probe after the pass and
  *          repeat the pass with the right route if the estimate crossed the threshold; 0 = always probe before the pass),
+ * "k9_defer" (1 = from M = 2048 a Kuu + jitter I chain that is only needed after the pass starts behind the posterior chain
+ *          instead of beside it; 0 = both chains start together, for A/B timing),
  * "early_slabs" (n = Gaussian likelihood, fused route: Kuf and the constant-weight SYRK of the first slab of up to n slab
  *          streams do not depend on the posterior and are enqueued before the posterior chain; 0 = off).
  * Environment (read once, A/B timing): TSVGP_PDL=0 plain stream order instead of programmatic dependent launch for the M x M

@@ -68,7 +68,9 @@ static int chol_lower_lookahead(double* A, long ld, int n, double* dinv, int* in
 
 int chol_lower(double* A, long ld, int n, double* dinv, int* info, cudaStream_t s, double* ws, size_t ws_doubles, const CholAux* aux) {
     static const bool la_off = getenv("TSVGP_CHOL_LOOKAHEAD") && atoi(getenv("TSVGP_CHOL_LOOKAHEAD")) == 0;
-    if (aux && aux->s2 && n >= 4 * NB && !la_off) return chol_lower_lookahead(A, ld, n, dinv, info, s, ws, ws_doubles, *aux);
+    // measured (tools/diag_bench, profiles/diag_r02.txt): 1.12 -> 1.04 ms at n = 2048, 2.98 -> 2.90 ms at n = 4096; at n = 8192 the
+    // single-level trailing updates (k = 128 per pass over the trailing matrix) lose to the two-level blocking below (12.4 vs 10.8 ms)
+    if (aux && aux->s2 && n >= 4 * NB && n <= 4096 && !la_off) return chol_lower_lookahead(A, ld, n, dinv, info, s, ws, ws_doubles, *aux);
     const int OB = g_chol_outer;
     for (int P0 = 0; P0 < n; P0 += OB) {
         const int Pend = P0 + OB < n ? P0 + OB : n;

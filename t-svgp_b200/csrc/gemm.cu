@@ -297,10 +297,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
     //    an upper-triangular A^T — where row block i is non-zero only from k-tile i/2 on — every pipe sees the same mix;
     //  * diagonal tile of a symmetric product (needed blocks per warp: 32, 32, 26, 26, 10, 10, 0, 0): the pairs (64,0)+(0,64),
     //    (64,32)+(0,96), (0,0)+(64,96), (64,64)+(0,32) give 32 / 32 / 36 / 36 DMMAs per k-step and pipe instead of up to 64.
-    int wm, wn;
-    if (diag_tile) { wm = ((0x4B >> warp) & 1) * 64; wn = ((0x7E84 >> (2 * warp)) & 3) * 32; }
-    else if (warp < 4) { wm = (warp & 1) * 64; wn = (warp >> 1) * 32; }
-    else { wm = ((warp & 1) ^ 1) * 64; wn = 64 + ((warp - 4) >> 1) * 32; }
+    // one nibble per warp: bit 2 = row half (wm / 64), bits 0-1 = column quarter (wn / 32); see g_wmap / g_wmap_diag below
+    const unsigned nib = ((diag_tile ? p.wmap_diag : p.wmap) >> (4 * warp)) & 15u;
+    const int wm = (int)(nib >> 2) * 64, wn = (int)(nib & 3u) * 32;
     const int dj = diag_tile ? (wm - wn) / 8 : 64;   // diagonal tile of a symmetric product: (i, j) needed iff j <= i + dj
     const int dj_pat = dj >= 3 ? 0 : (dj == 0 ? 1 : (dj == -4 ? 2 : 3));
     const bool tri_a2 = p.a_tri == 2 && p.b_tri == 0 && !p.lower_out;
@@ -463,6 +462,16 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmP p) {
 }
 
 int g_variant = 1;   // 1 = mbarrier-decoupled pipeline (default), 0 = CTA-barrier pipeline (TSVGP_GEMM_VARIANT=0, for A/B timing)
+// warp -> (row half, column quarter) of the 128 x 128 CTA tile, one nibble per warp (warp 0 in the low nibble).
+// Default: wm = (w & 1) * 64, wn = (w >> 1) * 32.  TSVGP_WMAP / TSVGP_WMAP_DIAG (hex) override them for A/B timing (tools/gemm_bench).
+// Measured on B200 (tools/gemm_bench, profiles/gemm_bench_r02.txt):
+//  * general tiles: any map whose sub-partition partners (warps w, w + 4) sit in the SAME row half is fastest for the triangular
+//    variance product (1.056 ms per 8192-point slab at M = 2048); partners in different row halves cost 5 % (1.107 - 1.111 ms):
+//    inside the diagonal k-block a warp that runs alone on its sub-partition drives the DMMA pipe at only ~64 % of its rate.
+//  * diagonal tile of a symmetric product: its needed 8x8 blocks per 64 x 32 warp tile are 32, 32, 26, 26, 10, 10, 0, 0.  The
+//    default map puts 32 + 26 on one pipe (1.09 x the time of a FULL tile); pairing (64,0)+(0,64), (64,32)+(0,96), (0,0)+(64,96),
+//    (64,64)+(0,32) — 32 / 32 / 36 / 36 per pipe — brings a diagonal tile to 0.78 x a full tile.
+unsigned g_wmap = 0x73625140u, g_wmap_diag = 0x17326054u;
 
 template <bool A_KC, bool B_KC, bool SCALE>
 constexpr int mb_bytes() { return Smem<A_KC, B_KC, SCALE>::STAGE * PSTAGES * 8 + 2 * PSTAGES * 8; }
@@ -471,8 +480,12 @@ template <bool A_KC, bool B_KC, bool SCALE, int EPI>
 int launch_inst(const GemmP& p, cudaStream_t stream) {
     dim3 grid(p.n / BN, p.m / BM, p.batch * (p.C2 ? 2 : p.ksplit));
     if (g_variant != 1 && SCALE && !p.kscale) return -1;
-    if (g_variant == 1)
-        launch_k(p.pdl != 0, gemm_kernel_mb<A_KC, B_KC, SCALE, EPI>, grid, NTHREADS, mb_bytes<A_KC, B_KC, SCALE>(), stream, p);
+    if (g_variant == 1) {
+        GemmP q = p;
+        if (!q.wmap) q.wmap = g_wmap;
+        if (!q.wmap_diag) q.wmap_diag = g_wmap_diag;
+        launch_k(p.pdl != 0, gemm_kernel_mb<A_KC, B_KC, SCALE, EPI>, grid, NTHREADS, mb_bytes<A_KC, B_KC, SCALE>(), stream, q);
+    }
     else
         launch_k(p.pdl != 0, gemm_kernel<A_KC, B_KC, SCALE, EPI>, grid, NTHREADS, Smem<A_KC, B_KC, SCALE>::BYTES, stream, p);
     return count_launch();
@@ -491,6 +504,8 @@ int init_inst() {
 
 int gemm_init() {
     if (const char* v = getenv("TSVGP_GEMM_VARIANT")) g_variant = atoi(v);
+    if (const char* v = getenv("TSVGP_WMAP")) g_wmap = (unsigned)strtoul(v, nullptr, 16);
+    if (const char* v = getenv("TSVGP_WMAP_DIAG")) g_wmap_diag = (unsigned)strtoul(v, nullptr, 16);
     int e = 0;
     e |= init_inst<true, true, false, EPI_STORE>();
     e |= init_inst<true, true, true, EPI_STORE>();
@@ -506,7 +521,7 @@ int gemm_init() {
 // piece (kt1 k-tiles), then every tile's small piece (kt2), in launch order (tile rows, diagonal tile last in its row).  A diagonal
 // tile needs only its lower 8x8 blocks and runs at DIAG_COST of a full tile (see the warp mapping in gemm_kernel_mb); every piece
 // also pays `ovh` k-tiles of prologue / epilogue (pipeline fill, C tile read-modify-write).
-constexpr double DIAG_COST = 36.0 / 64.0;
+constexpr double DIAG_COST = 0.78;   // measured: one diagonal tile / one full tile of the same k (tools/gemm_bench)
 static double dispatch_makespan(int nt, int sms, int kt1, int kt2, double ovh) {
     std::vector<double> free_at(sms, 0.0);
     auto run = [&](double kt) {
@@ -545,14 +560,19 @@ int balanced_ksplit(int tiles, int k) {
     const double ovh = 3.0;   // measured: a split-off piece costs about 3 k-tiles beyond its DMMA work (tools/gemm_bench)
     int best = k;
     double best_t = dispatch_makespan(nt, sms, kt, 0, ovh);
-    const double work = (tiles - nt) + nt * DIAG_COST;   // in full-tile units
-    const double waves = work / sms, f0 = waves / ceil(waves);
-    const int step = kt >= 256 ? kt / 128 : 1;
-    for (int d = -24; d <= 24; ++d) {   // candidates around the ideal fraction
-        const int kt1 = (int)(f0 * kt) + d * step;
-        if (kt1 < 1 || kt - kt1 < 4) continue;
+    // every split point on a k-tile grid; the makespan falls off a cliff just below the optimum (one more round of small pieces)
+    // and rises only slowly above it, so the chosen point sits a little above the model's optimum
+    const int step = kt >= 1024 ? kt / 512 : 1;
+    int best_kt1 = kt;
+    for (int kt1 = kt / 2; kt1 <= kt - 4; kt1 += step) {
         const double t = dispatch_makespan(nt, sms, kt1, kt - kt1, ovh);
-        if (t < best_t * 0.985) { best_t = t; best = kt1 * BK; }
+        if (t < best_t) { best_t = t; best_kt1 = kt1; }
+    }
+    if (best_kt1 < kt) {
+        const int safe = best_kt1 + (kt + 63) / 64;
+        if (safe <= kt - 4 && dispatch_makespan(nt, sms, safe, kt - safe, ovh) < 0.985 * dispatch_makespan(nt, sms, kt, 0, ovh))
+            best = safe * BK;
+        else if (best_t < 0.985 * dispatch_makespan(nt, sms, kt, 0, ovh)) best = best_kt1 * BK;
     }
     cache[key] = best;
     return best;

@@ -42,6 +42,8 @@ struct GemmP {
     // zeroes C first and sums the ranks' pieces with one all-reduce (adding zeros is exact, so every rank gets identical bits)
     int row_mod = 1, row_rem = 0;
     int pdl = 0;   // launch with the programmatic-serialisation attribute (the kernels always run the PDL prologue)
+    // warp -> sub-tile maps (one nibble per warp; 0 = the library default, see gemm.cu): general tiles / diagonal tiles of a symmetric product
+    unsigned wmap = 0, wmap_diag = 0;
 };
 
 // Launch on `stream`. Returns cudaError_t as int (0 = ok), -1 for an unsupported combination.

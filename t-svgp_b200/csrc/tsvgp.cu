@@ -99,6 +99,7 @@ struct tsvgp_ctx {
     double cond_hint = 0.0;
     bool cond_hint_valid = false;
     int speculate = 1;
+    int k9_defer = 0;   // measured slower (M = 2048, 131072 rows: 41.1 vs 39.9 ms): under the pass every chain kernel waits for an SM slot
     // Gaussian likelihood, fused route: h_n is a constant, so Kuf and the SYRK of a slab do not depend on the posterior.  The first
     // slab of every slab stream is enqueued BEFORE the posterior chain (latency-bound, SMs mostly idle) and fills the idle SMs.
     int early_slabs = 1;
@@ -1229,6 +1230,7 @@ int tsvgp_set_option(tsvgp_ctx* c, const char* name, double value) {
         c->route_opt = (int)value; c->k9_valid = false; return TSVGP_OK;
     }
     if (!strcmp(name, "speculate")) { c->speculate = value != 0.0; return TSVGP_OK; }
+    if (!strcmp(name, "k9_defer")) { c->k9_defer = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "early_slabs")) { c->early_slabs = value < 0 ? 0 : (int)value; return TSVGP_OK; }
     if (!strcmp(name, "route_cond_max")) { c->route_cond_max = value; return TSVGP_OK; }
     if (!strcmp(name, "route_exact_min")) { c->route_exact_min = value; return TSVGP_OK; }
@@ -1467,8 +1469,7 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
         SideIssue side;
         struct PdlGuard { ~PdlGuard() { g_pdl_suspended = 0; } } pdl_guard;
         const bool k9_runs = !k9_cached(c, jitter);
-        if (c->Mp >= 2048 && k9_runs) g_pdl_suspended = 1;   // two concurrent chains of large kernels: see common.cuh
-        int rc = start_k9_async(c, jitter, side);
+        int rc = TSVGP_OK;
         // When is the K9 chain joined?  The fused route needs nothing of it inside the pass, so if the route is fused — forced, or
         // SPECULATED from this context's last conditioning estimate — the chain runs underneath the pass and is joined after it
         // (where the probe is read and the guess checked).  Whitened / exact passes need C9^-1: join first, as does a first step.
@@ -1478,12 +1479,19 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
             c->route = ROUTE_FUSED;
             join_before = false;
         }
+        // ... and when does it start?  Side by side with the posterior chain the two latency-bound chains slow each other down
+        // (measured at M = 2048: posterior chain 2.6 ms alone, 3.4 ms beside the K9 chain, programmatic launch suspended).  When the
+        // chain is only needed after the pass it therefore starts once the posterior chain is complete and runs under the pass.
+        const bool defer_k9 = k9_runs && !join_before && c->k9_defer && c->Mp >= 2048;
+        if (c->Mp >= 2048 && k9_runs && !defer_k9) g_pdl_suspended = 1;   // two concurrent chains of large kernels: see common.cuh
+        if (!defer_k9) rc = start_k9_async(c, jitter, side);
         if (rc == TSVGP_OK && !k9_runs) rc = choose_route(c, jitter);   // cached factors: the route is known at once
         c->n_early = 0;
         const bool early = rc == TSVGP_OK && c->early_slabs && (!k9_runs || !join_before) && c->route == ROUTE_FUSED;
         if (early) rc = stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_STATS, nullptr, nullptr, PASS_EARLY);
         if (rc == TSVGP_OK) rc = ensure_posterior(c);
         if (rc == TSVGP_OK && elbo_before) rc = ensure_kl_terms(c);
+        if (rc == TSVGP_OK && defer_k9) rc = start_k9(c, jitter);   // forks from the main stream HERE: behind the posterior chain
         side.join_into(g_launches);
         if (rc != TSVGP_OK) return rc;
         if (side.rc != TSVGP_OK) return side.rc;

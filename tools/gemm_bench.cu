@@ -99,6 +99,40 @@ int main(int argc, char** argv) {
         printf("syrk scale=%d split=%d (ksp %d): %.3f ms  %.2f TFLOP/s algorithmic (%.2f executed)\n", v & 1, (v >> 1) & 1, p.ksp, ms,
                alg / ms / 1e9, alg * (1.0 + 128.0 / M) / ms / 1e9);
     }
+    {   // warp -> sub-tile maps (GemmP::wmap / wmap_diag): which pairing of warps on an SM sub-partition is fastest?
+        const unsigned gmaps[] = {0x73625140u, 0x37265140u, 0x76543210u, 0x76325410u, 0x62735140u, 0x51407362u};
+        const unsigned dmaps[] = {0x73625140u, 0x17326054u, 0x16703524u, 0x10765432u};
+        for (unsigned gm : gmaps) {
+            GemmP p; p.A = T; p.lda = M; p.a_kc = 0; p.a_tri = 2; p.B = K; p.ldb = NC; p.b_kc = 0; p.m = M; p.n = NC; p.k = M;
+            p.epilogue = EPI_COLNORM; p.norm_out = q; p.ldn = NC; p.wmap = gm;
+            double ms = time_launch(p, 20);
+            printf("wmap %08x variance: %.4f ms  %.2f TFLOP/s algorithmic\n", gm, ms, (double)M * M * NC / ms / 1e9);
+            GemmP f; f.A = C0; f.lda = M; f.a_kc = 1; f.B = C0; f.ldb = M; f.b_kc = 1; f.C = C; f.ldc = M; f.m = f.n = f.k = M; f.wmap = gm;
+            ms = time_launch(f, 10);
+            printf("wmap %08x dense full x full^T: %.4f ms  %.2f TFLOP/s\n", gm, ms, 2.0 * M * M * M / ms / 1e9);
+        }
+        for (unsigned dm : dmaps)
+            for (int sc = 0; sc < 2; ++sc) {
+                GemmP p; p.A = K; p.lda = NC; p.a_kc = 1; p.B = K; p.ldb = NC; p.b_kc = 1; p.C = C; p.ldc = M; p.m = p.n = M; p.k = NC;
+                p.beta = 1.0; p.lower_out = 1; p.kscale = sc ? h : nullptr; p.wmap_diag = dm;
+                int nt = M / 128; int ksp = balanced_ksplit(nt * (nt + 1) / 2, NC); if (ksp < NC) { p.ksp = ksp; p.C2 = C0; }
+                double ms = time_launch(p, 20);
+                GemmP d1 = p; d1.ksp = 0; d1.C2 = nullptr;
+                double ms1 = time_launch(d1, 20);
+                printf("wmap_diag %08x syrk scale=%d: split(ksp %d) %.4f ms %.2f TFLOP/s alg | unsplit %.4f ms\n", dm, sc, p.ksp, ms,
+                       (double)M * M * NC / ms / 1e9, ms1);
+            }
+        {   // diagonal tiles alone: a 128-row SYRK (one diagonal tile) against one full off-diagonal tile of the same k
+            for (unsigned dm : dmaps) {
+                GemmP p; p.A = K; p.lda = NC; p.a_kc = 1; p.B = K; p.ldb = NC; p.b_kc = 1; p.C = C; p.ldc = M; p.m = p.n = 128; p.k = NC;
+                p.beta = 1.0; p.lower_out = 1; p.wmap_diag = dm;
+                double ms = time_launch(p, 20);
+                GemmP f = p; f.lower_out = 0;
+                double msf = time_launch(f, 20);
+                printf("wmap_diag %08x single diagonal tile %.4f ms vs full tile %.4f ms (ratio %.3f)\n", dm, ms, msf, ms / msf);
+            }
+        }
+    }
     for (int variant = 0; variant < 3; ++variant) {   // dense M x M x M products as used by the update phase
         GemmP p; p.C = C; p.ldc = M; p.m = p.n = p.k = M;
         const char* name;
