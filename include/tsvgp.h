@@ -47,7 +47,7 @@ enum {
 };
 
 enum { TSVGP_KERNEL_SE = 0, TSVGP_KERNEL_MATERN52 = 1 };                       /* gpflow.kernels.{SquaredExponential,Matern52} */
-enum { TSVGP_LIK_GAUSSIAN = 0, TSVGP_LIK_BERNOULLI_PROBIT = 1, TSVGP_LIK_STUDENT_T = 2 }; /* gpflow.likelihoods.*        */
+enum { TSVGP_LIK_GAUSSIAN = 0, TSVGP_LIK_BERNOULLI_PROBIT = 1, TSVGP_LIK_STUDENT_T = 2, TSVGP_LIK_SOFTMAX = 3 }; /* gpflow.likelihoods.* */
 
 typedef struct tsvgp_ctx tsvgp_ctx;   /* opaque: owns one CUDA stream, device buffers, optional NCCL communicator */
 
@@ -71,11 +71,15 @@ TSVGP_API int tsvgp_set_option(tsvgp_ctx* ctx, const char* name, double value); 
  * "white" (1 = the whitened sibling t_SVGP_white, reference src/models/tsvgp_white.py: the second site argument of
  *          set_sites / get_sites / get_lambda_2 is then the full matrix Lambda_2; switching resets the sites),
  * "dist_min_m" (multi-GPU: distribute the dense M x M products over the ranks from this padded M upwards; default 4096),
+ * "shard_min_m" (multi-GPU, fused route: from this padded M upwards (default 2048; needs (M/128) % ranks == 0) the statistics are
+ *          reduce-scattered by tile rows, G2 = K9^-1 B K9^-1 is formed on each rank's rows and assembled by two all-gathers,
+ *          instead of an all-reduce followed by the full products on every rank; a huge value switches it off),
  * "streams" up to 4, "balance" / "fuse_b" (0 switches the balanced SYRK split / the fused b += Kuf g off, for A/B timing),
  * "route_cond_max" (automatic: fused while the power-iteration estimate of cond(Kuu + jitter I) is below this; default 1e4),
  * "route_exact_min" (automatic: exact above this estimate, whitened in between; default 1e8),
  * "async_issue" (1 = at M <= 1024 a helper host thread enqueues the Kuu + jitter I factorisation chain on the side stream while
  *          the calling thread enqueues the posterior chain; 0 = one thread enqueues both),
+ * "mc_seed" (Softmax: key of the Monte-Carlo generator; resets the draw counter),
  * "speculate" (1 = automatic route: when this context's last conditioning estimate chose the fused route, run the
  *          Kuu + jitter I chain UNDERNEATH the streaming pass instead of in front of it, read the probe after the pass and
  *          repeat the pass with the right route if the estimate crossed the threshold; 0 = always probe before the pass),
@@ -96,15 +100,29 @@ TSVGP_API int tsvgp_set_kernel(tsvgp_ctx* ctx, int kind, double variance, const 
 TSVGP_API int tsvgp_set_likelihood(tsvgp_ctx* ctx, int kind, double p0, double p1, int n_gh, const double* gh_x, const double* gh_w);
 /* Z [M, D] inducing inputs (inducing_variable.Z); mean_Z [M] = mean_function(Z) or NULL for the Zero mean function     */
 TSVGP_API int tsvgp_set_inducing(tsvgp_ctx* ctx, const double* Z, int M, int D, const double* mean_Z);
+/* num_latent_gps = L (tsvgp.py:122-134, 276-281; default 1): L latent GPs that share the kernel and the inducing inputs, each with
+ * its own site pair, in ONE context — one Kuu / Kuu + jitter I chain and one Kuf slab per launch serve all of them; the variance
+ * product, the weighted SYRK and the site update run per latent.  Layouts follow the reference: lambda_1 [M, L], lambda_2_sqrt
+ * [L, M, M], Y [N, L] (independent likelihood terms, summed over the latent axis) or [N, 1] class labels (Softmax), predictive
+ * moments [N, L].  Resets the sites and drops the resident data.  Not available for the whitened sibling.                       */
+TSVGP_API int tsvgp_set_num_latent(tsvgp_ctx* ctx, int L);
+TSVGP_API int tsvgp_num_latent(const tsvgp_ctx* ctx);
+/* TSVGP_LIK_SOFTMAX (gpflow.likelihoods.Softmax, docs/notebooks/mnist.py:117-122): set_likelihood with p0 = number of classes
+ * (= L) and n_gh = Monte-Carlo points per data point (GPflow: 100).  GPflow draws fresh standard normals [S, N, L] in every
+ * call; here they come from a counter-based generator (Philox4x32-10 + Box-Muller, option "mc_seed", a new draw per call) or,
+ * for reproducible comparisons, from an explicit array eps [S, N, L] (HOST or DEVICE; used whenever a pass runs over exactly
+ * N points; NULL clears it).                                                                                                   */
+TSVGP_API int tsvgp_set_mc_epsilon(tsvgp_ctx* ctx, const double* eps, int S, int64_t N, int L);
 
-/* ---- DenseSites state (src/sites.py:43-80): lambda_1 [M], lambda_2_sqrt [M, M] lower triangular -------------------- */
+/* ---- DenseSites state (src/sites.py:43-80): lambda_1 [M, L], lambda_2_sqrt [L, M, M] lower triangular ------------- */
 /* NULL lambda_1 / lambda_2_sqrt = the reference defaults 0 and -1e-10 * I (tsvgp.py:174-180). Upper triangle ignored.  */
 TSVGP_API int tsvgp_set_sites(tsvgp_ctx* ctx, const double* lambda_1, const double* lambda_2_sqrt);
 TSVGP_API int tsvgp_get_sites(tsvgp_ctx* ctx, double* lambda_1, double* lambda_2_sqrt);     /* either may be NULL                  */
 TSVGP_API int tsvgp_get_lambda_2(tsvgp_ctx* ctx, double* lambda_2);                          /* L2 L2^T (tsvgp.py:197-200)          */
 
 /* ---- data: this rank's rows of the minibatch ------------------------------------------------------------------------ */
-/* X [N, D], Y [N] (= [N,1]), mean_X [N] = mean_function(X) or NULL. Host data is copied; device data is aliased.        */
+/* X [N, D], Y [N, 1] ([N, L] for L latents with independent likelihood terms), mean_X [N] = mean_function(X) or NULL.
+ * Host data is copied; device data is aliased.                                                                          */
 TSVGP_API int tsvgp_set_data(tsvgp_ctx* ctx, const double* X, const double* Y, int64_t N, int D, const double* mean_X);
 
 /* Input pipeline (stands in for the tf.data prefetch of the reference's minibatch callers, docs/notebooks/mnist.py:85,150):
@@ -143,6 +161,10 @@ TSVGP_API int tsvgp_posterior(tsvgp_ctx* ctx, double* m, double* chol_S);
 TSVGP_API int tsvgp_comm_unique_id(void* id_out_128_bytes);                                   /* ncclGetUniqueId                     */
 TSVGP_API int tsvgp_comm_init(tsvgp_ctx* ctx, int world_size, int rank, const void* id_128_bytes);
 TSVGP_API int tsvgp_comm_size(const tsvgp_ctx* ctx);
+/* The CUDA device of the context and its main stream (a cudaStream_t): a DLPack producer is handed this stream
+ * (`tensor.__dlpack__(stream=...)`) so that its pending writes are ordered before the library's first read.            */
+TSVGP_API int tsvgp_device(const tsvgp_ctx* ctx);
+TSVGP_API void* tsvgp_stream(const tsvgp_ctx* ctx);
 
 /* ---- measurement ------------------------------------------------------------------------------------------------------ */
 /* CUDA-event durations (ms) of the last natgrad_step, on the context's stream.  out[0..n):

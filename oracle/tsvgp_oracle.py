@@ -248,6 +248,45 @@ class StudentT(_QuadratureLikelihood):
         return (df + 1.0) * r / (df * sc * sc + np.square(r))
 
 
+class Softmax:
+    """gpflow.likelihoods.Softmax(num_classes) [GPflow-recalled]: a MonteCarloLikelihood with num_monte_carlo_points = 100.
+    variational_expectations = mean over S draws of log softmax(Fmu + sqrt(Fvar) * eps)[y], eps ~ N(0, I) of shape [S, N, L]
+    (MonteCarloLikelihood._mc_quadrature); Y holds integer class labels [N, 1] (sparse_softmax_cross_entropy_with_logits).
+    GPflow draws eps afresh in every call (tf.random.normal); for a reproducible comparison the draws are an attribute here
+    (`epsilon`, GPflow's own optional argument), and the gradients the reference takes by tf.GradientTape (tsvgp.py:256-259)
+    are the analytic derivatives of the same Monte-Carlo sum for fixed eps."""
+
+    name = "softmax"
+
+    def __init__(self, num_classes, num_monte_carlo_points=100, epsilon=None):
+        self.num_classes = int(num_classes)
+        self.num_monte_carlo_points = int(num_monte_carlo_points)
+        self.epsilon = epsilon
+
+    def _eps(self, N):
+        if self.epsilon is None or self.epsilon.shape != (self.num_monte_carlo_points, N, self.num_classes):
+            raise ValueError("Softmax oracle: set .epsilon to an array [S, N, L] (GPflow would draw tf.random.normal here)")
+        return self.epsilon
+
+    def variational_expectations(self, Fmu, Fvar, Y):
+        return self.ve_and_grads(Fmu, Fvar, Y)[0]
+
+    def ve_and_grads(self, Fmu, Fvar, Y):
+        N, L = Fmu.shape
+        eps = self._eps(N)
+        sd = np.sqrt(Fvar)
+        F = Fmu[None] + sd[None] * eps                         # [S, N, L]
+        F = F - F.max(axis=-1, keepdims=True)
+        logp = F - np.log(np.sum(np.exp(F), axis=-1, keepdims=True))
+        y = np.asarray(Y[:, 0], dtype=int)
+        onehot = np.eye(L)[y]                                  # [N, L]
+        ve = np.mean(np.take_along_axis(logp, y[None, :, None], axis=-1)[..., 0], axis=0)
+        d = onehot[None] - np.exp(logp)                        # d log softmax[y] / d f
+        g_mean = np.mean(d, axis=0)
+        g_var = np.mean(d * eps, axis=0) / (2.0 * sd)
+        return ve, g_mean, g_var
+
+
 # ----------------------------------------------------------------------------------------
 # TF linear-algebra ops, as the reference calls them.
 # ----------------------------------------------------------------------------------------

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libtsvgp.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOT_PD, ERR_NONPOS_VAR, ERR_COMM, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 KERNEL_SE, KERNEL_MATERN52 = 0, 1
-LIK_GAUSSIAN, LIK_BERNOULLI_PROBIT, LIK_STUDENT_T = 0, 1, 2
+LIK_GAUSSIAN, LIK_BERNOULLI_PROBIT, LIK_STUDENT_T, LIK_SOFTMAX = 0, 1, 2, 3
 ABI_VERSION = 1
 
 
@@ -55,6 +55,9 @@ _SIGNATURES = {
     "tsvgp_set_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int]),
     "tsvgp_set_likelihood": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, _dp, _dp]),
     "tsvgp_set_inducing": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "tsvgp_set_num_latent": (C.c_int, [C.c_void_p, C.c_int]),
+    "tsvgp_num_latent": (C.c_int, [C.c_void_p]),
+    "tsvgp_set_mc_epsilon": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int]),
     "tsvgp_set_sites": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tsvgp_get_sites": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tsvgp_get_lambda_2": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -71,6 +74,8 @@ _SIGNATURES = {
     "tsvgp_comm_unique_id": (C.c_int, [C.c_void_p]),
     "tsvgp_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "tsvgp_comm_size": (C.c_int, [C.c_void_p]),
+    "tsvgp_device": (C.c_int, [C.c_void_p]),
+    "tsvgp_stream": (C.c_void_p, [C.c_void_p]),
     "tsvgp_get_timings": (C.c_int, [C.c_void_p, _dp, C.c_int]),
     "tsvgp_sync": (C.c_int, [C.c_void_p]),
     "tsvgp_get_kernel_profile": (C.c_int, [C.c_void_p, _dp, C.c_int]),
@@ -190,9 +195,11 @@ def pinned_free(arr):
         load().tsvgp_pinned_free(ptr)
 
 
-def as_tensor(obj, name="tensor"):
+def as_tensor(obj, name="tensor", model=None):
     """numpy arrays / anything with __dlpack__ (cupy, torch, jax ...) -> Tensor.  Host data is made float64-contiguous;
-    device data must already be float64 and compact (the C side validates the DLTensor)."""
+    device data must already be float64 and compact (the C side validates the DLTensor).  With `model`, a device tensor is
+    requested on the context's main stream (DLPack's `stream` argument: the producer orders its pending writes before that
+    stream's next work) and must live on the context's device."""
     lib = load()
     if isinstance(obj, DeviceArray):
         return Tensor(obj.ptr, obj.shape, True, 0, obj)
@@ -203,7 +210,15 @@ def as_tensor(obj, name="tensor"):
             obj = np.ascontiguousarray(obj, dtype=np.float64)
         if not obj.flags.writeable:  # numpy refuses to export read-only arrays through DLPack
             return Tensor(obj.ctypes.data, obj.shape, False, 0, obj)
-    cap = obj.__dlpack__()
+    cap = None
+    if model is not None and not isinstance(obj, np.ndarray):
+        handle = lib.tsvgp_stream(model._ctx)
+        try:
+            cap = obj.__dlpack__(stream=int(handle or 0) or None)
+        except (TypeError, ValueError, RuntimeError, AssertionError, BufferError):   # producers without stream support / host tensors
+            cap = None
+    if cap is None:
+        cap = obj.__dlpack__()
     dlm = _PyCapsule_GetPointer(cap, b"dltensor")
     view = View()
     rc = lib.tsvgp_dlpack_view(dlm, C.byref(view))
@@ -213,5 +228,7 @@ def as_tensor(obj, name="tensor"):
     on_device = view.device_type in (KDL_CUDA, KDL_CUDA_MANAGED)
     if view.device_type not in (KDL_CPU, KDL_CUDA, KDL_CUDA_HOST, KDL_CUDA_MANAGED):
         raise InvalidArgumentError(ERR_INVALID, f"{name}: unsupported DLPack device type {view.device_type}")
+    if on_device and model is not None and view.device_type == KDL_CUDA and view.device_id != lib.tsvgp_device(model._ctx):
+        raise InvalidArgumentError(ERR_INVALID, f"{name}: tensor lives on cuda:{view.device_id}, the model on cuda:{lib.tsvgp_device(model._ctx)}")
     # the capsule is only borrowed (never renamed): when it is collected it runs the producer's deleter itself
     return Tensor(view.data, shape, on_device, view.device_id, (obj, cap))

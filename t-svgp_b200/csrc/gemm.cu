@@ -264,7 +264,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGE * PSTAGES);
     uint64_t* empty = full_bar + PSTAGES;
 
-    const int tj = blockIdx.x, ti = blockIdx.y;
+    // Launch order = longest tiles first.  CTAs are dispatched in linear block order (x fastest); with a triangular operand the
+    // contraction length of a tile depends on its row or column, and the default order (tile rows ascending) can put the longest
+    // tiles LAST.  p.order: bit 0 = the tile COLUMN is the slow index, bit 1 = the slow index runs backwards (host: tile_order()).
+    int tj = blockIdx.x, ti = blockIdx.y;
+    if (p.order & 1) { const int lin = blockIdx.y * gridDim.x + blockIdx.x; tj = lin / (int)gridDim.y; ti = lin % (int)gridDim.y; }
+    if (p.order & 2) { if (p.order & 1) tj = (int)gridDim.x - 1 - tj; else ti = (int)gridDim.y - 1 - ti; }
     if (p.lower_out && tj > ti) return;
     if (p.row_mod > 1 && ti % p.row_mod != p.row_rem) return;
     const int zdiv = p.C2 != nullptr ? 2 : p.ksplit;
@@ -473,6 +478,18 @@ int g_variant = 1;   // 1 = mbarrier-decoupled pipeline (default), 0 = CTA-barri
 //    (64,64)+(0,32) — 32 / 32 / 36 / 36 per pipe — brings a diagonal tile to 0.78 x a full tile.
 unsigned g_wmap = 0x73625140u, g_wmap_diag = 0x17326054u;
 
+int g_tile_order = 1;   // TSVGP_TILE_ORDER=0: default launch order everywhere (A/B timing)
+// longest contraction first (see gemm_kernel_mb): which tile index bounds the k range, and in which direction it shrinks
+static int tile_order(const GemmP& p) {
+    if (p.tile_ctr) return 0;                               // the fused split-K reduction indexes its counters by grid position
+    if (p.a_tri && p.b_tri) return 0;                       // k range depends on both indices: keep the default
+    if (p.a_tri == 2) return 0;                             // k >= ti * 128: row 0 is longest and already first
+    if (p.a_tri == 1) return 2;                             // k <  (ti + 1) * 128: last row longest -> rows backwards
+    if (p.b_tri == 2) return 1;                             // k >= tj * 128: column 0 longest -> columns are the slow index
+    if (p.b_tri == 1) return 3;                             // k <  (tj + 1) * 128: last column longest
+    return 0;
+}
+
 template <bool A_KC, bool B_KC, bool SCALE>
 constexpr int mb_bytes() { return Smem<A_KC, B_KC, SCALE>::STAGE * PSTAGES * 8 + 2 * PSTAGES * 8; }
 
@@ -484,6 +501,7 @@ int launch_inst(const GemmP& p, cudaStream_t stream) {
         GemmP q = p;
         if (!q.wmap) q.wmap = g_wmap;
         if (!q.wmap_diag) q.wmap_diag = g_wmap_diag;
+        if (q.order < 0) q.order = g_tile_order ? tile_order(q) : 0;
         launch_k(p.pdl != 0, gemm_kernel_mb<A_KC, B_KC, SCALE, EPI>, grid, NTHREADS, mb_bytes<A_KC, B_KC, SCALE>(), stream, q);
     }
     else
@@ -504,6 +522,7 @@ int init_inst() {
 
 int gemm_init() {
     if (const char* v = getenv("TSVGP_GEMM_VARIANT")) g_variant = atoi(v);
+    if (const char* v = getenv("TSVGP_TILE_ORDER")) g_tile_order = atoi(v);
     if (const char* v = getenv("TSVGP_WMAP")) g_wmap = (unsigned)strtoul(v, nullptr, 16);
     if (const char* v = getenv("TSVGP_WMAP_DIAG")) g_wmap_diag = (unsigned)strtoul(v, nullptr, 16);
     int e = 0;

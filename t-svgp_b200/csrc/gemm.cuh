@@ -44,6 +44,7 @@ struct GemmP {
     int pdl = 0;   // launch with the programmatic-serialisation attribute (the kernels always run the PDL prologue)
     // warp -> sub-tile maps (one nibble per warp; 0 = the library default, see gemm.cu): general tiles / diagonal tiles of a symmetric product
     unsigned wmap = 0, wmap_diag = 0;
+    int order = -1;   // tile launch order (see gemm.cu::tile_order); -1 = chosen by the library
 };
 
 // Launch on `stream`. Returns cudaError_t as int (0 = ok), -1 for an unsupported combination.

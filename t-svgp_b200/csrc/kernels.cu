@@ -345,6 +345,124 @@ int point_stats_launch(const LikSpec& lik, const PointArgs& a, const GHTable& g_
     return count_launch();
 }
 
+// ---- Softmax (Monte Carlo) ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// two standard normals from one Philox block: 2 x 53-bit uniforms -> Box-Muller
+__device__ __forceinline__ void normal_pair(unsigned long long seed, unsigned long long draw, unsigned long long point, unsigned s, unsigned lp,
+                                            double& z0, double& z1) {
+    unsigned r[4];
+    philox4x32_10((unsigned)point, (unsigned)(point >> 32), s, lp ^ (unsigned)(draw << 8), (unsigned)seed ^ (unsigned)(draw >> 24),
+                  (unsigned)(seed >> 32), r);
+    const double u0 = ((double)(((unsigned long long)r[0] << 21) ^ (r[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+    const double u1 = ((double)(((unsigned long long)r[2] << 21) ^ (r[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+    const double rad = sqrt(-2.0 * log(u0));
+    double sn, cs;
+    sincospi(2.0 * u1, &sn, &cs);
+    z0 = rad * cs; z1 = rad * sn;
+}
+
+__global__ void __launch_bounds__(128) softmax_stats_kernel(SoftmaxArgs a) {
+    __shared__ double sred[4];
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    double ve = 0.0;
+    if (c < a.ncols) {
+        const bool valid = c < a.n_valid;
+        double mu[MAX_SOFTMAX_CLASSES], sd[MAX_SOFTMAX_CLASSES], gm[MAX_SOFTMAX_CLASSES], gs[MAX_SOFTMAX_CLASSES];
+        bool bad = false;
+        const double off = a.mean_off ? a.mean_off[c] : 0.0;
+        for (int l = 0; l < a.L; ++l) {
+            double m = 0.0, q = 0.0;
+            for (int p = 0; p < a.n_mu_part; ++p) m += a.mu_part[l * a.mu_lat + (long)p * a.ldmu + c];
+            for (int p = 0; p < a.n_q_part; ++p) q += a.q_part[l * a.q_lat + (long)p * a.ldq + c];
+            const double var = a.kdiag - q;
+            mu[l] = m + off;
+            bad = bad || !(var > 0.0);
+            sd[l] = sqrt(var);
+            gm[l] = 0.0; gs[l] = 0.0;
+            if (valid && a.mean_out) { a.mean_out[l * a.out_lat + c] = mu[l]; a.var_out[l * a.out_lat + c] = var; }
+        }
+        if (valid && bad) atomicOr(a.flags, 1);
+        if (valid && a.y && !bad) {
+            const int yc = (int)a.y[c];
+            const unsigned long long point = (unsigned long long)(a.n0 + c);
+            for (int s = 0; s < a.S; ++s) {
+                double f[MAX_SOFTMAX_CLASSES], e[MAX_SOFTMAX_CLASSES], fmax_ = -1e300;
+                for (int l = 0; l < a.L; l += 2) {
+                    double z0, z1;
+                    if (a.eps) {
+                        const double* ep = a.eps + ((long)s * a.n_total + (long)point) * a.L + l;
+                        z0 = ep[0]; z1 = l + 1 < a.L ? ep[1] : 0.0;
+                    } else {
+                        normal_pair(a.seed, a.draw, point, (unsigned)s, (unsigned)(l >> 1), z0, z1);
+                    }
+                    e[l] = z0; f[l] = fma(sd[l], z0, mu[l]); fmax_ = fmax(fmax_, f[l]);
+                    if (l + 1 < a.L) { e[l + 1] = z1; f[l + 1] = fma(sd[l + 1], z1, mu[l + 1]); fmax_ = fmax(fmax_, f[l + 1]); }
+                }
+                double den = 0.0;
+                for (int l = 0; l < a.L; ++l) { f[l] = exp(f[l] - fmax_); den += f[l]; }
+                // log softmax(f)[y] = (f_y - max) - log(den) ; d / d f_l = [l == y] - p_l
+                const double fy = (yc >= 0 && yc < a.L) ? log(f[yc]) : 0.0;
+                ve += fy - log(den);
+                const double inv = 1.0 / den;
+                for (int l = 0; l < a.L; ++l) {
+                    const double d = (l == yc ? 1.0 : 0.0) - f[l] * inv;
+                    gm[l] += d;
+                    gs[l] = fma(d, e[l], gs[l]);
+                }
+            }
+            const double invS = 1.0 / (double)a.S;
+            ve *= invS;
+            for (int l = 0; l < a.L; ++l) { gm[l] *= invS; gs[l] = fmin(gs[l] * invS / (2.0 * sd[l]), -1e-8); }
+        } else {
+            for (int l = 0; l < a.L; ++l) gs[l] = (valid && a.y) ? -1e-8 : 0.0;
+        }
+        if (a.g)
+            for (int l = 0; l < a.L; ++l) { a.g[l * a.gh_lat + c] = valid ? gm[l] : 0.0; a.h[l * a.gh_lat + c] = valid ? gs[l] : 0.0; }
+        if (!valid) ve = 0.0;
+    }
+    ve = warp_sum(ve);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = ve;
+    __syncthreads();
+    if (threadIdx.x == 0 && a.ve_blocks) {
+        const double s2 = (sred[0] + sred[1]) + (sred[2] + sred[3]);
+        // ve_blocks holds one slot per 256 points (point_stats_kernel's layout): two 128-thread blocks share one
+        atomicAdd(a.ve_blocks + (blockIdx.x >> 1), s2);
+    }
+}
+int softmax_stats_launch(const SoftmaxArgs& a, cudaStream_t s) {
+    if (a.L < 2 || a.L > MAX_SOFTMAX_CLASSES || a.S < 1) return -1;
+    softmax_stats_kernel<<<(a.ncols + 127) / 128, 128, 0, s>>>(a);
+    return count_launch();
+}
+
+__global__ void transpose_to_latent_major_kernel(const double* __restrict__ Y, long n, int L, double* __restrict__ Yt, long ld) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int l = 0; l < L; ++l) Yt[l * ld + i] = Y[i * L + l];
+}
+int transpose_to_latent_major_launch(const double* Y, long n, int L, double* Yt, long ld, cudaStream_t s) {
+    transpose_to_latent_major_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(Y, n, L, Yt, ld);
+    return count_launch();
+}
+__global__ void transpose_to_point_major_kernel(const double* __restrict__ src, long ld, long n, int L, double* __restrict__ dst) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int l = 0; l < L; ++l) dst[i * L + l] = src[l * ld + i];
+}
+int transpose_to_point_major_launch(const double* src, long ld, long n, int L, double* dst, cudaStream_t s) {
+    transpose_to_point_major_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, ld, n, L, dst);
+    return count_launch();
+}
+
 // =====================================================================================================================
 // M-vector products
 // =====================================================================================================================
@@ -1431,7 +1549,8 @@ int egrad_uf_launch(double* U, const double* Kp, long ld, int Mp, int ncols, con
     return count_launch();
 }
 // Xa[c][j] (row-major [ncols][128]) = xs_j | 1 | xs_j^2 | 0 ... of point n0 + c (zero rows for c >= nvalid)
-__global__ void xaug_kernel(const double* __restrict__ XsT, long ldx, long n0, long nvalid, int ncols, int D, double* __restrict__ Xa) {
+__global__ void xaug_kernel(const double* __restrict__ XsT, long ldx, long n0, long nvalid, int ncols, int D, double* __restrict__ Xa,
+                            const double* __restrict__ origin) {
     __shared__ double tile[32][33];
     // block: 32 points x 128 aug columns; transposes through shared memory so both sides stay coalesced
     const int c0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 256 threads = 8 rows of 32
@@ -1441,9 +1560,11 @@ __global__ void xaug_kernel(const double* __restrict__ XsT, long ldx, long n0, l
             const long c = c0 + tx;
             double v = 0.0;
             if (c < nvalid) {
-                if (j < D) v = XsT[(long)j * ldx + n0 + c];
+                // coordinates relative to a common origin (the centroid of the inducing inputs): the host expands
+                // sum E (z - x)^2 = z^2 S1 - 2 z EX + C2, which cancels catastrophically for inputs far from 0 (time stamps ...)
+                if (j < D) v = XsT[(long)j * ldx + n0 + c] - (origin ? origin[j] : 0.0);
                 else if (j == D) v = 1.0;
-                else if (j <= 2 * D) { const double x = XsT[(long)(j - D - 1) * ldx + n0 + c]; v = x * x; }
+                else if (j <= 2 * D) { const double x = XsT[(long)(j - D - 1) * ldx + n0 + c] - (origin ? origin[j - D - 1] : 0.0); v = x * x; }
             }
             tile[r][tx] = v;
         }
@@ -1454,8 +1575,8 @@ __global__ void xaug_kernel(const double* __restrict__ XsT, long ldx, long n0, l
         __syncthreads();
     }
 }
-int xaug_launch(const double* XsT, long ldx, long n0, long nvalid, int ncols, int D, double* Xa, cudaStream_t s) {
-    xaug_kernel<<<(ncols + 31) / 32, 256, 0, s>>>(XsT, ldx, n0, nvalid, ncols, D, Xa);
+int xaug_launch(const double* XsT, long ldx, long n0, long nvalid, int ncols, int D, double* Xa, cudaStream_t s, const double* origin) {
+    xaug_kernel<<<(ncols + 31) / 32, 256, 0, s>>>(XsT, ldx, n0, nvalid, ncols, D, Xa, origin);
     return count_launch();
 }
 // Gamma[i][j] = scale (QBQ_ij - (qb_i a_j + qb_j a_i)/2) - (a_i a_j - (qm_i a_j + qm_j a_i) + QKQ_ij)/2   (dELBO/dKuu, symmetric)

@@ -6,7 +6,8 @@
 namespace tsvgp {
 
 enum { KERN_SE = 0, KERN_MATERN52 = 1 };
-enum { LIK_GAUSSIAN = 0, LIK_BERNOULLI = 1, LIK_STUDENT_T = 2 };
+enum { LIK_GAUSSIAN = 0, LIK_BERNOULLI = 1, LIK_STUDENT_T = 2, LIK_SOFTMAX = 3 };
+constexpr int MAX_SOFTMAX_CLASSES = 16;
 constexpr int MAX_GH = 64;
 
 struct LikSpec {
@@ -44,6 +45,31 @@ struct PointArgs {
     int clip = 1;               // clip d ve / d var at -1e-8 (natgrad_step, tsvgp.py:262-263); the ELBO gradient does not
     int* flags;                 // flags[0] |= 1 if any var <= 0
 };
+// Softmax likelihood over L latents (gpflow.likelihoods.Softmax = MonteCarloLikelihood, S = num_monte_carlo_points): per point
+//   ve = mean_s log softmax(f_s)[y],  f_s = mu + sqrt(var) * eps_s ;  g_l = d ve / d mu_l ;  h_l = min(d ve / d var_l, -1e-8)
+// as called at reference tsvgp.py:256-263 (docs/notebooks/mnist.py:117-122).  Per-latent inputs / outputs are `*_lat` apart.
+// eps: explicit standard-normal draws [S][n_total][L] (GPflow's layout) or null = Philox4x32-10 + Box-Muller keyed by (seed, draw).
+struct SoftmaxArgs {
+    const double* mu_part; int n_mu_part; long ldmu, mu_lat;
+    const double* q_part; int n_q_part; long ldq, q_lat;
+    int L, S;
+    const double* y;            // class labels as doubles, chunk-local
+    const double* mean_off;
+    double kdiag;
+    long n_valid, n0, n_total;  // n0: global index of the chunk's first point (addresses eps / the random stream)
+    int ncols;
+    double* g; double* h; long gh_lat;
+    double* mean_out; double* var_out; long out_lat;
+    double* ve_blocks;
+    int* flags;
+    const double* eps;
+    unsigned long long seed, draw;
+};
+int softmax_stats_launch(const SoftmaxArgs& a, cudaStream_t s);
+// Y [n][L] row-major -> Yt [L][ld] ; and back for outputs: src [L][ld] -> dst [n][L]
+int transpose_to_latent_major_launch(const double* Y, long n, int L, double* Yt, long ld, cudaStream_t s);
+int transpose_to_point_major_launch(const double* src, long ld, long n, int L, double* dst, cudaStream_t s);
+
 struct GHTable { double z[MAX_GH]; double w[MAX_GH]; };   // nodes sqrt(2) x_k and weights w_k / sqrt(pi), passed by value
 int point_stats_launch(const LikSpec& lik, const PointArgs& a, const GHTable& gh, cudaStream_t s);
 
@@ -108,7 +134,8 @@ int stats_tail_launch(const double* ve_blocks, long nblocks, const int* flags, c
 // M-step gradient helpers (see tsvgp_elbo_grad)
 int egrad_uf_launch(double* U, const double* Kp, long ld, int Mp, int ncols, const double* alpha, const double* g, const double* h,
                     double scale, cudaStream_t s);
-int xaug_launch(const double* XsT, long ldx, long n0, long nvalid, int ncols, int D, double* Xa, cudaStream_t s);
+// Xa[c][0:128] = [xs - origin | 1 | (xs - origin)^2] of point n0 + c (origin [D] device vector or null)
+int xaug_launch(const double* XsT, long ldx, long n0, long nvalid, int ncols, int D, double* Xa, cudaStream_t s, const double* origin = nullptr);
 int gamma_uu_launch(const double* QBQ, const double* QKQ, const double* qb, const double* qm, const double* al, const double* Kp,
                     double* Gamma, double* E, long ld, int n, double scale, cudaStream_t s);
 

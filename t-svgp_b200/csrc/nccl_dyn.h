@@ -18,6 +18,8 @@ struct NcclApi {
     int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
     int (*CommDestroy)(NcclComm) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*ReduceScatter)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;   // recvcount per rank
+    int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;            // sendcount per rank
     const char* (*GetErrorString)(int) = nullptr;
     bool ok() const { return handle && GetUniqueId && CommInitRank && CommDestroy && AllReduce; }
 };
@@ -35,6 +37,8 @@ inline NcclApi& nccl_api() {
     api.CommInitRank = (int (*)(NcclComm*, int, NcclUniqueId, int))dlsym(api.handle, "ncclCommInitRank");
     api.CommDestroy = (int (*)(NcclComm))dlsym(api.handle, "ncclCommDestroy");
     api.AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
+    api.ReduceScatter = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(api.handle, "ncclReduceScatter");
+    api.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(api.handle, "ncclAllGather");
     api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
     return api;
 }

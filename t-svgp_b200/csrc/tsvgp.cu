@@ -16,6 +16,7 @@
 #include "gemm.cuh"
 #include "kernels.cuh"
 #include "nccl_dyn.h"
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges let ncu select the kernels of one phase (--nvtx --nvtx-include "tsvgp_stream/")
 
 #include <math.h>
 #include <stdio.h>
@@ -80,6 +81,8 @@ struct tsvgp_ctx {
     long chunk_opt = 0;        // 0 = automatic
     int n_streams = 2;
     int dist_min_m = 4096;     // distribute the dense M x M products over the ranks from this (padded) M upwards
+    int shard_min_m = 2048;    // from this (padded) M upwards the statistics are reduce-SCATTERED by tile rows and the two products of
+                               // G2 = K9^-1 B K9^-1 run on each rank's rows only, assembled by two all-gathers (sharded_update)
     int async_issue = 1;       // small M: enqueue the K9 chain from a helper host thread while this thread enqueues the posterior chain
     int fuse_b = 1;            // accumulate b += Kuf g inside the SYRK kernel instead of a separate mat-vec pass over the slab
     int balance = 1;           // split the SYRK's contraction in two pieces so that every SM gets equal work
@@ -119,6 +122,21 @@ struct tsvgp_ctx {
     GHTable gh;
     bool lik_set = false;
 
+    // Latent GPs sharing the kernel and the inducing inputs (num_latent_gps = L, reference tsvgp.py:276-281): one site pair, one set of
+    // posterior factors and one statistics accumulator per latent, stored as [L] contiguous copies.  The per-latent pointers below
+    // (lam1, L2, T, alpha, mZ, mq, scal, stats, stats2 and the per-slab mu_part / q_part / gbuf / hbuf / ve_blocks) always VIEW the
+    // latent selected by select_latent(); everything kernel-dependent (K, K6, the K9 chain, the Kuf slabs) exists once.
+    int L = 1, cur = 0;
+    double *lam1_all = nullptr, *L2_all = nullptr, *T_all = nullptr, *alpha_all = nullptr, *mZ_all = nullptr, *mq_all = nullptr, *scal_all = nullptr;
+    double *stats_all[MAXS] = {}, *stats2_all[MAXS] = {};
+    double *mu_part_all[MAXS] = {}, *q_part_all[MAXS] = {}, *gbuf_all[MAXS] = {}, *hbuf_all[MAXS] = {}, *ve_all = nullptr;
+    double* Yt = nullptr;      // Y [N, L] transposed to [L][n_pad] (L > 1)
+    long yt_cap = 0;
+    int y_cols = 1;            // columns of the resident Y: L for independent likelihood terms, 1 (class labels) for Softmax
+    Pool pyt, pmc;
+    double* mc_eps = nullptr;  // explicit Monte-Carlo draws [S][mc_eps_n][L] of the Softmax likelihood (tsvgp_set_mc_epsilon) or null
+    long mc_eps_n = 0;
+    unsigned long long mc_seed = 0x5eed5eedULL, mc_draw = 0;   // Philox key and per-call draw counter otherwise
     // inducing points and M x M state
     int M = 0, Mp = 0, D = 0;
     Pool pm;
@@ -138,7 +156,7 @@ struct tsvgp_ctx {
     int white = 0;             // 1: the whitened sibling t_SVGP_white (reference src/models/tsvgp_white.py): L2 holds the full Lambda_2
     double *C6 = nullptr, *C6inv = nullptr;   // chol(K6) and its inverse (whitened sibling)
     bool c6_valid = false, wpost_valid = false, wkl_valid = false;
-    double *zaug = nullptr, *fuu = nullptr;   // M-step: [zs | 1 | zs^2] and the Kuu counterpart of F
+    double *zaug = nullptr, *fuu = nullptr, *origin = nullptr;   // M-step: [zs | 1 | zs^2] and the Kuu counterpart of F
     double *tmp2 = nullptr, *dinv2 = nullptr, *pv1 = nullptr, *pv2 = nullptr, *gwork2 = nullptr, *scal2 = nullptr;   // side-stream workspace (K9 factor)
     bool k9inv_valid = false;  // K9inv = C9inv^T C9inv formed (on the main stream, on first use by the fused route)
     bool k9_pending = false;   // K9 work enqueued on the side stream, probe not read yet
@@ -163,6 +181,7 @@ struct tsvgp_ctx {
     cudaStream_t s_copy = nullptr;
     cudaEvent_t ev_copy = nullptr;
     long cap_x = 0, cap_n = 0;
+    int cap_yc = 1;
     double *XsT = nullptr, *x2 = nullptr;
     Pool pxs;
     long xs_cap = 0, xs_cap_n = 0;
@@ -232,6 +251,7 @@ namespace {
 
 int all_reduce(tsvgp_ctx* c, double* buf, size_t count);
 int ensure_posterior_white(tsvgp_ctx* c);
+int posterior_one(tsvgp_ctx* c);
 int ensure_kl_terms_white(tsvgp_ctx* c);
 int dense_update_white(tsvgp_ctx* c, double lr, double scale);
 int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale, bool only_G);
@@ -249,6 +269,28 @@ bool is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// ---- latent views ---------------------------------------------------------------------------------------------------
+void select_latent(tsvgp_ctx* c, int l) {
+    const size_t mm = (size_t)c->Mp * c->Mp, mp = c->Mp;
+    c->cur = l;
+    c->lam1 = c->lam1_all + l * mp; c->L2 = c->L2_all + l * mm; c->T = c->T_all + l * mm;
+    c->alpha = c->alpha_all + l * mp; c->mZ = c->mZ_all + l * mp; c->mq = c->mq_all + l * mp; c->scal = c->scal_all + (size_t)l * N_SCAL;
+    for (int s = 0; s < MAXS; ++s) {
+        c->stats[s] = c->stats_all[s] + l * (mm + mp + 4);
+        c->stats2[s] = c->stats2_all[s] + l * (mm + mp);
+    }
+    if (c->chunk > 0 && c->chunk_Mp == c->Mp) {
+        const size_t nc = c->chunk;
+        for (int s = 0; s < c->slab_streams; ++s) {
+            c->mu_part[s] = c->mu_part_all[s] + l * (size_t)(c->Mp / 64) * nc;
+            c->q_part[s] = c->q_part_all[s] + l * (size_t)(c->Mp / 128) * nc;
+            c->gbuf[s] = c->gbuf_all[s] + l * nc;
+            c->hbuf[s] = c->hbuf_all[s] + l * nc;
+        }
+        c->ve_blocks = c->ve_all + (size_t)l * c->ve_cap;
+    }
+}
+
 // ---- M-dependent state ----------------------------------------------------------------------------------------------
 int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     c->pm.release();
@@ -257,35 +299,40 @@ int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     Pool& p = c->pm;
     NEED(c->Zraw = p.get((size_t)M * D)); NEED(c->ZsT = p.get((size_t)D * mp)); NEED(c->Zs = p.get(mp * D));
     NEED(c->z2 = p.get(mp)); NEED(c->ls_dev = p.get(D)); NEED(c->meanZ_off = p.get(mp));
-    NEED(c->K = p.get(mm)); NEED(c->K6 = p.get(mm)); NEED(c->L2 = p.get(mm)); NEED(c->lam1 = p.get(mp));
-    NEED(c->Wm = p.get(mm)); NEED(c->Wf = p.get(mm)); NEED(c->V = p.get(mm)); NEED(c->T = p.get(mm));
+    const size_t nl = (size_t)c->L;
+    NEED(c->K = p.get(mm)); NEED(c->K6 = p.get(mm)); NEED(c->L2_all = p.get(nl * mm)); NEED(c->lam1_all = p.get(nl * mp));
+    NEED(c->Wm = p.get(mm)); NEED(c->Wf = p.get(mm)); NEED(c->V = p.get(mm)); NEED(c->T_all = p.get(nl * mm));
     NEED(c->X1 = p.get(mm)); NEED(c->X2 = p.get(mm)); NEED(c->C9 = p.get(mm)); NEED(c->C9inv = p.get(mm));
     NEED(c->G2 = p.get(mm)); NEED(c->P = p.get(mm)); NEED(c->K9inv = p.get(mm)); NEED(c->tmp = p.get((size_t)((c->Mp / 128 + 1) / 2) * 128 * mp));   // trtri_lower: ceil(nblk/2) block rows
     NEED(c->dinv = p.get((size_t)(c->Mp / 128) * 128 * 128));
-    CU(cudaMemset(c->dinv, 0, sizeof(double) * (size_t)(c->Mp / 128) * 128 * 128));   // contract of diag_potrf_inv_launch
-    for (int s = 0; s < MAXS; ++s) { NEED(c->stats[s] = p.get(mm + mp + 4)); NEED(c->stats2[s] = p.get(mm + mp)); }
-    NEED(c->alpha = p.get(mp)); NEED(c->mZ = p.get(mp)); NEED(c->mq = p.get(mp)); NEED(c->v1 = p.get(mp)); NEED(c->v2 = p.get(mp));
-    NEED(c->v3 = p.get(mp)); NEED(c->gwork = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal = p.get(N_SCAL)); NEED(c->red = p.get(128));
+    CU(cudaMemsetAsync(c->dinv, 0, sizeof(double) * (size_t)(c->Mp / 128) * 128 * 128, c->s_main));   // contract of diag_potrf_inv_launch
+    for (int s = 0; s < MAXS; ++s) { NEED(c->stats_all[s] = p.get(nl * (mm + mp + 4))); NEED(c->stats2_all[s] = p.get(nl * (mm + mp))); }
+    NEED(c->alpha_all = p.get(nl * mp)); NEED(c->mZ_all = p.get(nl * mp)); NEED(c->mq_all = p.get(nl * mp)); NEED(c->v1 = p.get(mp)); NEED(c->v2 = p.get(mp));
+    NEED(c->v3 = p.get(mp)); NEED(c->gwork = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal_all = p.get(nl * N_SCAL)); NEED(c->red = p.get(128));
     NEED(c->info = (int*)p.get(N_INFO)); NEED(c->flags = (int*)p.get(2));
     c->gws_doubles = (size_t)4 << 20;   // 32 MB per stream: up to 16 partial images of a 512 x 512 product, 4 of a 1024 x 1024 one
     NEED(c->gws = p.get(c->gws_doubles)); NEED(c->gws2 = p.get(c->gws_doubles));
-    CU(cudaMemset(c->gws + c->gws_doubles - GEMM_WS_COUNTER_DOUBLES, 0, sizeof(double) * GEMM_WS_COUNTER_DOUBLES));    // tile counters
-    CU(cudaMemset(c->gws2 + c->gws_doubles - GEMM_WS_COUNTER_DOUBLES, 0, sizeof(double) * GEMM_WS_COUNTER_DOUBLES));
-    NEED(c->zaug = p.get(mp * 128)); NEED(c->fuu = p.get(mp * 128));
+    // (on the context's own stream: it is non-blocking, a legacy-stream memset would not be ordered with it)
+    CU(cudaMemsetAsync(c->gws + c->gws_doubles - GEMM_WS_COUNTER_DOUBLES, 0, sizeof(double) * GEMM_WS_COUNTER_DOUBLES, c->s_main));    // tile counters
+    CU(cudaMemsetAsync(c->gws2 + c->gws_doubles - GEMM_WS_COUNTER_DOUBLES, 0, sizeof(double) * GEMM_WS_COUNTER_DOUBLES, c->s_main));
+    NEED(c->zaug = p.get(mp * 128)); NEED(c->fuu = p.get(mp * 128)); NEED(c->origin = p.get(D));
     NEED(c->C6 = p.get(mm)); NEED(c->C6inv = p.get(mm)); NEED(c->lam1_bak = p.get(mp));
     c->c6_valid = c->wpost_valid = c->wkl_valid = false;
     NEED(c->tmp2 = p.get((size_t)((c->Mp / 128 + 1) / 2) * 128 * mp)); NEED(c->dinv2 = p.get((size_t)(c->Mp / 128) * 128 * 128));
-    CU(cudaMemset(c->dinv2, 0, sizeof(double) * (size_t)(c->Mp / 128) * 128 * 128));
+    CU(cudaMemsetAsync(c->dinv2, 0, sizeof(double) * (size_t)(c->Mp / 128) * 128 * 128, c->s_main));
+    CU(cudaStreamSynchronize(c->s_main));   // the side and helper streams use these buffers too
     NEED(c->pv1 = p.get(mp)); NEED(c->pv2 = p.get(mp)); NEED(c->gwork2 = p.get((size_t)(c->Mp / 64 + 1) * mp)); NEED(c->scal2 = p.get(N_SCAL));
     c->sites_set = c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = c->c6_valid = c->wpost_valid = c->wkl_valid = false;
     c->chunk = 0;   // slab workspace depends on Mp
+    select_latent(c, 0);
     return TSVGP_OK;
 }
 
-int default_sites(tsvgp_ctx* c) {   // tsvgp.py:174-180 : lambda_1 = 0, lambda_2_sqrt = -1e-10 I
-    CU(cudaMemsetAsync(c->lam1, 0, sizeof(double) * c->Mp, c->s_main));
+int default_sites(tsvgp_ctx* c) {   // tsvgp.py:174-180 : lambda_1 = 0, lambda_2_sqrt = -1e-10 I  (every latent)
+    CU(cudaMemsetAsync(c->lam1_all, 0, sizeof(double) * c->Mp * c->L, c->s_main));
     // tsvgp.py:174-180 : lambda_2_sqrt = -1e-10 I ;  tsvgp_white.py:79-85 : lambda_2 = +1e-10 I
-    LA(set_scaled_identity_launch(c->L2, c->Mp, c->M, c->Mp, c->white ? 1e-10 : -1e-10, 0.0, c->s_main));
+    for (int l = 0; l < c->L; ++l)
+        LA(set_scaled_identity_launch(c->L2_all + (size_t)l * c->Mp * c->Mp, c->Mp, c->M, c->Mp, c->white ? 1e-10 : -1e-10, 0.0, c->s_main));
     c->sites_set = true;
     c->post_valid = c->kl_valid = c->wpost_valid = c->wkl_valid = false;
     return TSVGP_OK;
@@ -329,6 +376,18 @@ int ensure_posterior(tsvgp_ctx* c) {
     if (c->post_valid && c->cache_factors && !(dist_active(c) && !c->post_collective)) return TSVGP_OK;
     if (!c->sites_set) OK(default_sites(c));
     c->post_collective = dist_active(c);
+    for (int l = 0; l < c->L; ++l) {
+        select_latent(c, l);
+        OK(posterior_one(c));
+    }
+    select_latent(c, 0);
+    c->post_valid = true;
+    c->kl_valid = false;
+    return TSVGP_OK;
+}
+
+// the factors of ONE latent (the selected one): T, alpha, m_q, mZ, log det W
+int posterior_one(tsvgp_ctx* c) {
     cudaStream_t s = c->s_main;
     const int n = c->Mp;
     const long ld = c->Mp;
@@ -378,8 +437,6 @@ int ensure_posterior(tsvgp_ctx* c) {
     LA(gemv_n_launch(c->K6, ld, n, n, c->alpha, 1.0, 0.0, c->mq, s));
     LA(gemv_n_launch(c->K, ld, n, n, c->alpha, 1.0, 0.0, c->mZ, s));
     if (c->has_meanZ) LA(vadd_inplace_launch(c->mZ, c->meanZ_off, c->M, s));
-    c->post_valid = true;
-    c->kl_valid = false;
     return TSVGP_OK;
 }
 
@@ -391,22 +448,48 @@ int ensure_kl_terms(tsvgp_ctx* c) {
     cudaStream_t s = c->s_main;
     const int n = c->Mp;
     const long ld = c->Mp;
-    {   // X1 = K6 T
-        GemmP p;
-        p.A = c->K6; p.lda = ld; p.a_kc = 1;
-        p.B = c->T; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
-        p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
-        LA(mm_gemm(c, p, s));
+    for (int l = 0; l < c->L; ++l) {
+        select_latent(c, l);
+        {   // X1 = K6 T
+            GemmP p;
+            p.A = c->K6; p.lda = ld; p.a_kc = 1;
+            p.B = c->T; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
+            p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
+            LA(mm_gemm(c, p, s));
+        }
+        LA(matdot_launch(c->T, c->X1, ld, n, c->scal + SC_TR_QK, c->red, s));
+        LA(dot_launch(c->mq, c->alpha, n, c->scal + SC_M_ALPHA, s));
     }
-    LA(matdot_launch(c->T, c->X1, ld, n, c->scal + SC_TR_QK, c->red, s));
-    LA(dot_launch(c->mq, c->alpha, n, c->scal + SC_M_ALPHA, s));
+    select_latent(c, 0);
     c->kl_valid = true;
     return TSVGP_OK;
 }
 
+// sc: host copy of scal_all ([L][N_SCAL]); the KL of independent q(u_l) adds up (gauss_kl sums over the latent axis)
 double kl_value(const tsvgp_ctx* c, const double* sc) {
     if (c->white) return kl_white_from_scalars(c, sc);
-    return 0.5 * (sc[SC_M_ALPHA] - sc[SC_TR_QK] + 2.0 * sc[SC_LOGDIAG_W]);
+    double kl = 0.0;
+    for (int l = 0; l < c->L; ++l, sc += N_SCAL) kl += 0.5 * (sc[SC_M_ALPHA] - sc[SC_TR_QK] + 2.0 * sc[SC_LOGDIAG_W]);
+    return kl;
+}
+
+constexpr int MAX_LATENT = 64;
+// after a pass: [sum ve, variance flag, sum h, sum d ve / d lik] summed over the latents (the flag is the shared one)
+int read_tails(tsvgp_ctx* c, double* tail /*[4]*/, double* sc /*[MAX_LATENT * N_SCAL]*/, int* info_h) {
+    const size_t mm = (size_t)c->Mp * c->Mp, stride = mm + c->Mp + 4;
+    double t[MAX_LATENT][4];
+    cudaStream_t s = c->s_main;
+    CU(cudaMemcpy2DAsync(t, 4 * sizeof(double), c->stats_all[0] + mm + c->Mp, stride * sizeof(double), 4 * sizeof(double), c->L,
+                         cudaMemcpyDeviceToHost, s));
+    if (sc) CU(cudaMemcpyAsync(sc, c->scal_all, sizeof(double) * N_SCAL * c->L, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(info_h, c->info, sizeof(int) * N_INFO, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (int k = 0; k < 4; ++k) tail[k] = 0.0;
+    for (int l = 0; l < c->L; ++l) {
+        tail[0] += t[l][0]; tail[2] += t[l][2]; tail[3] += t[l][3];
+        if (t[l][1] != 0.0) tail[1] = t[l][1];
+    }
+    return TSVGP_OK;
 }
 
 
@@ -562,11 +645,11 @@ int ensure_slabs(tsvgp_ctx* c, long n_points, bool need_grad = false) {
     for (int s = 0; s < ns; ++s) {
         NEED(c->slab[s] = p.get((size_t)c->Mp * nc));
         if (need_w) NEED(c->wslab[s] = p.get((size_t)c->Mp * nc));
-        NEED(c->mu_part[s] = p.get((size_t)(c->Mp / 64) * nc));
-        NEED(c->q_part[s] = p.get((size_t)(c->Mp / 128) * nc));
+        NEED(c->mu_part_all[s] = p.get((size_t)c->L * (c->Mp / 64) * nc));
+        NEED(c->q_part_all[s] = p.get((size_t)c->L * (c->Mp / 128) * nc));
         NEED(c->q2_part[s] = p.get((size_t)(c->Mp / 128) * nc));
-        NEED(c->gbuf[s] = p.get(nc));
-        NEED(c->hbuf[s] = p.get(nc));
+        NEED(c->gbuf_all[s] = p.get((size_t)c->L * nc));
+        NEED(c->hbuf_all[s] = p.get((size_t)c->L * nc));
     }
     {   // few output tiles (small M): split the SYRK's contraction over the idle SMs, partials reduced by a second kernel
         const int nt = c->Mp / 128, tiles = nt * (nt + 1) / 2;
@@ -584,7 +667,7 @@ int ensure_slabs(tsvgp_ctx* c, long n_points, bool need_grad = false) {
             if (c->ksplit > 1) NEED(c->kpart[s] = p.get((size_t)c->ksplit * c->Mp * c->Mp));
         }
     }
-    NEED(c->ve_blocks = p.get(ve_need));
+    NEED(c->ve_all = p.get((size_t)c->L * ve_need));
     c->grad_ws = false;
     if (need_grad) {
         int sms = 148;
@@ -603,6 +686,7 @@ int ensure_slabs(tsvgp_ctx* c, long n_points, bool need_grad = false) {
     c->ve_cap = ve_need;
     c->chunk = nc;
     c->chunk_Mp = c->Mp;
+    select_latent(c, c->cur);   // the per-slab views of the selected latent
     return TSVGP_OK;
 }
 
@@ -612,15 +696,21 @@ int ensure_slabs(tsvgp_ctx* c, long n_points, bool need_grad = false) {
 // phase 1 has been enqueued: the early slabs only run their posterior-dependent part (means, variance product, point statistics,
 // b += Kuf g).
 enum { PASS_WHOLE = 0, PASS_EARLY = 1, PASS_REST = 2 };
+// y / mean_out / var_out of latent l live at + l * y_stride / + l * out_stride (Y transposed to [L][n_pad]; outputs [L][n_pad_out]).
+// lat_only >= 0 restricts the per-latent work to that latent (the M-step gradient pass runs latent by latent).
 int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, long N, const double* y, const double* mean_off,
-                int mode, double* mean_out, double* var_out, int phase = PASS_WHOLE) {
+                int mode, double* mean_out, double* var_out, int phase = PASS_WHOLE, long y_stride = 0, long out_stride = 0,
+                int lat_only = -1) {
     const bool grad = mode == MODE_GRAD;
     const bool stats = mode == MODE_STATS || grad;
     if (phase != PASS_REST) OK(ensure_slabs(c, N, grad));
     const long nc = c->chunk;
     const int Mp = c->Mp;
     const int nstr = c->profile ? 1 : (c->n_streams < 1 ? 1 : (c->n_streams > MAXS ? MAXS : c->n_streams));
-    const bool prof = c->profile && mode == MODE_STATS;
+    const bool prof = c->profile && mode == MODE_STATS && c->L == 1;
+    const int l_lo = lat_only >= 0 ? lat_only : 0, l_hi = lat_only >= 0 ? lat_only + 1 : c->L;
+    const bool multi = c->L > 1;
+    const bool joint = c->lik.kind == LIK_SOFTMAX;   // the likelihood couples the latents: one point kernel over all of them
     size_t pev_used = 0;
     auto mark = [&](cudaStream_t st) -> int {   // profile mode: one event between consecutive kernels
         if (!prof) return 0;
@@ -634,24 +724,25 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
     const long vstride = (nc + 255) / 256;
     const long ncu = used_chunk(c, N, nc, nstr);   // slab width of this pass (<= the allocated width nc, which stays the leading dimension)
     const long nchunks = (N + ncu - 1) / ncu;
+    const size_t mm = (size_t)Mp * Mp;
     cudaStream_t sm = c->s_main;
 
     if (phase != PASS_REST) {
         CU(cudaMemsetAsync(c->flags, 0, 2 * sizeof(int), sm));
-        CU(cudaMemsetAsync(c->ve_blocks, 0, sizeof(double) * (size_t)(nchunks * vstride), sm));
+        CU(cudaMemsetAsync(c->ve_all, 0, sizeof(double) * (size_t)c->L * c->ve_cap, sm));
         if (grad) CU(cudaMemsetAsync(c->aux_blocks, 0, sizeof(double) * (size_t)(2 * nchunks * vstride), sm));
         CU(cudaEventRecord(c->ev_fork, sm));
         for (int s = 0; s < nstr; ++s) {
             CU(cudaStreamWaitEvent(c->s_pp[s], c->ev_fork, 0));
             if (stats) {   // every slab stream zeroes its own accumulators (off the main stream, which runs the posterior chain)
-                CU(cudaMemsetAsync(c->stats[s], 0, sizeof(double) * ((size_t)Mp * Mp + Mp + 4), c->s_pp[s]));
-                CU(cudaMemsetAsync(c->stats2[s], 0, sizeof(double) * ((size_t)Mp * Mp + Mp), c->s_pp[s]));
+                CU(cudaMemsetAsync(c->stats_all[s], 0, sizeof(double) * c->L * (mm + Mp + 4), c->s_pp[s]));
+                CU(cudaMemsetAsync(c->stats2_all[s], 0, sizeof(double) * c->L * (mm + Mp), c->s_pp[s]));
                 if (grad) CU(cudaMemsetAsync(c->facc[s], 0, sizeof(double) * (size_t)Mp * 128, c->s_pp[s]));
             }
         }
         c->n_early = 0;
     }
-    // the weighted SYRK of one slab (and, fused into it, b += K g unless `with_b` is false)
+    // the weighted SYRK of one slab for the selected latent (and, fused into it, b += K g unless `with_b` is false)
     auto syrk = [&](int b, const double* stat_slab, int ncols, bool const_h, bool with_b, bool& fused_b) -> int {
         cudaStream_t s = c->s_pp[b];
         GemmP p;
@@ -661,7 +752,8 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
         p.beta = 1.0; p.lower_out = 1; p.kscale = c->hbuf[b];
         // Gaussian likelihood: h_n is the same constant -1/(2 s2) for every point (tsvgp.py:256-263 with the closed-form
         // variational expectation), so it multiplies the product once instead of every B fragment
-        if (const_h) { p.kscale = nullptr; p.alpha = fmin(-0.5 / c->lik.p0, -1e-8); }
+        // (the whitened sibling does not clip the variance gradient, tsvgp_white.py:183-212)
+        if (const_h) { p.kscale = nullptr; p.alpha = c->white ? -0.5 / c->lik.p0 : fmin(-0.5 / c->lik.p0, -1e-8); }
         const int nt = Mp / 128;
         const int ks_here = c->ksplit < ncols / 128 ? c->ksplit : ncols / 128;
         fused_b = false;
@@ -680,10 +772,10 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
         }
         return TSVGP_OK;
     };
-    const bool const_h_pass = c->lik.kind == LIK_GAUSSIAN && c->fuse_b && !grad;
+    const bool const_h_pass = c->lik.kind == LIK_GAUSSIAN && !grad;
     if (phase == PASS_EARLY) {
         const bool ok = mode == MODE_STATS && const_h_pass && c->route == ROUTE_FUSED && !c->white && !prof && c->ksplit <= 1 &&
-                        nchunks >= 2 * nstr;
+                        nchunks >= 2 * nstr && !multi;
         const int ne = ok ? (c->early_slabs < nstr ? c->early_slabs : nstr) : 0;
         for (int ci = 0; ci < ne; ++ci) {
             const long n0 = ci * ncu;
@@ -710,51 +802,74 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
         const long nvalid = N - n0 < ncu ? N - n0 : ncu;
         const int ncols = (int)round_up(nvalid, 128);
         const bool early = ci < n_early;   // Kuf slab and SYRK already enqueued by phase 1
+        select_latent(c, l_lo);
         if (mark(s)) FAIL(TSVGP_ERR_CUDA, "profile event");
-        // (a) covariance slab K[Mp x ncols] and the partial means sum_i alpha_i K[i][n]
+        // (a) covariance slab K[Mp x ncols] — ONE slab for all latents — and, for a single latent, the partial means
+        //     sum_i alpha_i K[i][n] in the same kernel
         if (!early)
-            LA(kuf_launch(c->kern_kind, c->kern_var, XsT, ldx, x2, n0, N, ncols, c->Zs, c->z2, c->M, Mp, c->D, c->alpha, c->slab[b],
-                          nc, c->mu_part[b], nc, 0, s, grad ? c->kpslab[b] : nullptr));
-        else   // the slab exists already: the same per-64-row partial means from a transposed mat-vec over it
-            LA(gemv_t_part_launch(c->slab[b], nc, Mp, ncols, c->alpha, c->mu_part[b], nc, s));
+            LA(kuf_launch(c->kern_kind, c->kern_var, XsT, ldx, x2, n0, N, ncols, c->Zs, c->z2, c->M, Mp, c->D, multi ? nullptr : c->alpha,
+                          c->slab[b], nc, multi ? nullptr : c->mu_part[b], nc, 0, s, grad ? c->kpslab[b] : nullptr));
         mark(s);
-        if (!c->white) {   // (b) |T^T k_n|^2 : upper-triangular T^T times the slab, reduced to column norms in the epilogue
-            GemmP p;
-            p.A = c->T; p.lda = Mp; p.a_kc = 0; p.a_tri = 2;
-            p.B = c->slab[b]; p.ldb = nc; p.b_kc = 0;
-            p.m = Mp; p.n = ncols; p.k = Mp;
-            p.epilogue = grad ? EPI_STORE_COLNORM : EPI_COLNORM; p.norm_out = c->q_part[b]; p.ldn = nc;
-            if (grad) { p.C = c->vslab[b]; p.ldc = nc; }   // the M-step also needs V = T^T K itself
-            LA(gemm_launch(p, s));
-        } else {           // (b') whitened sibling: |LA^-1 k_n|^2 and |LR^-1 k_n|^2, two lower-triangular products (util.py:78-85)
-            for (int which = 0; which < 2; ++which) {
+        for (int l = l_lo; l < l_hi; ++l) {
+            select_latent(c, l);
+            if (early || multi)   // the slab exists already: the same per-64-row partial means from a transposed mat-vec over it
+                LA(gemv_t_part_launch(c->slab[b], nc, Mp, ncols, c->alpha, c->mu_part[b], nc, s));
+            if (!c->white) {   // (b) |T^T k_n|^2 : upper-triangular T^T times the slab, reduced to column norms in the epilogue
                 GemmP p;
-                p.A = which == 0 ? c->C6inv : c->T; p.lda = Mp; p.a_kc = 1; p.a_tri = 1;
+                p.A = c->T; p.lda = Mp; p.a_kc = 0; p.a_tri = 2;
                 p.B = c->slab[b]; p.ldb = nc; p.b_kc = 0;
                 p.m = Mp; p.n = ncols; p.k = Mp;
-                p.epilogue = EPI_COLNORM; p.norm_out = which == 0 ? c->q_part[b] : c->q2_part[b]; p.ldn = nc;
+                p.epilogue = grad ? EPI_STORE_COLNORM : EPI_COLNORM; p.norm_out = c->q_part[b]; p.ldn = nc;
+                if (grad) { p.C = c->vslab[b]; p.ldc = nc; }   // the M-step also needs V = T^T K itself
                 LA(gemm_launch(p, s));
+            } else {           // (b') whitened sibling: |LA^-1 k_n|^2 and |LR^-1 k_n|^2, two lower-triangular products (util.py:78-85)
+                for (int which = 0; which < 2; ++which) {
+                    GemmP p;
+                    p.A = which == 0 ? c->C6inv : c->T; p.lda = Mp; p.a_kc = 1; p.a_tri = 1;
+                    p.B = c->slab[b]; p.ldb = nc; p.b_kc = 0;
+                    p.m = Mp; p.n = ncols; p.k = Mp;
+                    p.epilogue = EPI_COLNORM; p.norm_out = which == 0 ? c->q_part[b] : c->q2_part[b]; p.ldn = nc;
+                    LA(gemm_launch(p, s));
+                }
             }
+            mark(s);
+            if (!joint) {   // (c) marginals -> likelihood expectations and gradients, latent by latent (independent likelihood terms)
+                PointArgs a;
+                a.mu_part = c->mu_part[b]; a.n_mu_part = Mp / 64; a.ldmu = nc;
+                a.q_part = c->q_part[b]; a.n_q_part = Mp / 128; a.ldq = nc;
+                a.q2_part = c->white ? c->q2_part[b] : nullptr;
+                a.y = y ? y + l * y_stride + n0 : nullptr;
+                a.mean_off = mean_off ? mean_off + n0 : nullptr;
+                a.kdiag = c->kern_var;
+                a.n_valid = nvalid; a.ncols = ncols;
+                a.g = stats ? c->gbuf[b] : nullptr; a.h = stats ? c->hbuf[b] : nullptr;
+                a.clip = (grad || c->white) ? 0 : 1;   // tsvgp_white.py:183-212 does not clip the variance gradient
+                a.aux_blocks = grad ? c->aux_blocks + 2 * ci * vstride : nullptr;
+                a.mean_out = mean_out ? mean_out + l * out_stride + n0 : nullptr; a.var_out = var_out ? var_out + l * out_stride + n0 : nullptr;
+                a.ve_blocks = c->ve_blocks + ci * vstride;
+                a.flags = c->flags;
+                LA(point_stats_launch(c->lik, a, c->gh, s));
+            }
+            mark(s);
         }
-        mark(s);
-        {   // (c) marginals -> likelihood expectations and gradients
-            PointArgs a;
-            a.mu_part = c->mu_part[b]; a.n_mu_part = Mp / 64; a.ldmu = nc;
-            a.q_part = c->q_part[b]; a.n_q_part = Mp / 128; a.ldq = nc;
-            a.q2_part = c->white ? c->q2_part[b] : nullptr;
+        if (joint) {   // (c) Softmax: Monte-Carlo expectation over all latents of a point at once
+            select_latent(c, 0);
+            SoftmaxArgs a;
+            a.mu_part = c->mu_part[b]; a.n_mu_part = Mp / 64; a.ldmu = nc; a.mu_lat = (long)(Mp / 64) * nc;
+            a.q_part = c->q_part[b]; a.n_q_part = Mp / 128; a.ldq = nc; a.q_lat = (long)(Mp / 128) * nc;
+            a.L = c->L; a.S = c->lik.n_gh;
             a.y = y ? y + n0 : nullptr;
             a.mean_off = mean_off ? mean_off + n0 : nullptr;
             a.kdiag = c->kern_var;
-            a.n_valid = nvalid; a.ncols = ncols;
-            a.g = stats ? c->gbuf[b] : nullptr; a.h = stats ? c->hbuf[b] : nullptr;
-            a.clip = (grad || c->white) ? 0 : 1;   // tsvgp_white.py:183-212 does not clip the variance gradient
-            a.aux_blocks = grad ? c->aux_blocks + 2 * ci * vstride : nullptr;
-            a.mean_out = mean_out ? mean_out + n0 : nullptr; a.var_out = var_out ? var_out + n0 : nullptr;
+            a.n_valid = nvalid; a.ncols = ncols; a.n0 = n0; a.n_total = N;
+            a.g = stats ? c->gbuf[b] : nullptr; a.h = stats ? c->hbuf[b] : nullptr; a.gh_lat = nc;
+            a.mean_out = mean_out ? mean_out + n0 : nullptr; a.var_out = var_out ? var_out + n0 : nullptr; a.out_lat = out_stride;
             a.ve_blocks = c->ve_blocks + ci * vstride;
             a.flags = c->flags;
-            LA(point_stats_launch(c->lik, a, c->gh, s));
+            a.eps = (c->mc_eps && c->mc_eps_n == N) ? c->mc_eps : nullptr;
+            a.seed = c->mc_seed; a.draw = c->mc_draw;
+            LA(softmax_stats_launch(a, s));
         }
-        mark(s);
         if (stats) {
             const double* stat_slab = c->slab[b];
             if ((c->route == ROUTE_WHITENED || c->route == ROUTE_EXACT) && !grad) {   // (c') whitened slab  C9^-1 K  (reference order: A = K9^-1 Kuf first, tsvgp.py:271)
@@ -774,7 +889,8 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
                 }
             }
             mark(s);
-            {   // (d) B += K diag(h) K^T, lower tiles (already enqueued for an early slab)
+            for (int l = l_lo; l < l_hi; ++l) {   // (d) B_l += K diag(h_l) K^T, lower tiles (already enqueued for an early slab)
+                select_latent(c, l);
                 bool fused_b = false;
                 if (!early) OK(syrk(b, stat_slab, ncols, const_h_pass, true, fused_b));
                 mark(s);
@@ -784,6 +900,7 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
             mark(s);
         }
         if (grad) {
+            select_latent(c, l_lo);
             {   // U = T V = Q K  (lower-triangular T times the stored V)
                 GemmP p;
                 p.A = c->T; p.lda = Mp; p.a_kc = 1; p.a_tri = 1;
@@ -793,7 +910,7 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
             }
             // E = scale (alpha g^T - 2 U diag(h)) .* dK/dr2   (in place), then F += E [xs | 1 | xs^2]
             LA(egrad_uf_launch(c->uslab[b], c->kpslab[b], nc, Mp, ncols, c->alpha, c->gbuf[b], c->hbuf[b], c->grad_scale, s));
-            LA(xaug_launch(XsT, ldx, n0, nvalid, ncols, c->D, c->xaug[b], s));
+            LA(xaug_launch(XsT, ldx, n0, nvalid, ncols, c->D, c->xaug[b], s, c->origin));
             GemmP p;
             p.A = c->uslab[b]; p.lda = nc; p.a_kc = 1;
             p.B = c->xaug[b]; p.ldb = 128; p.b_kc = 0;
@@ -824,14 +941,30 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
         CU(cudaEventRecord(c->ev_join[s], c->s_pp[s]));
         CU(cudaStreamWaitEvent(sm, c->ev_join[s], 0));
     }
-    const size_t mm = (size_t)Mp * Mp;
-    if (stats) {
-        for (int s = 1; s < nstr; ++s) LA(vadd_inplace_launch(c->stats[0], c->stats[s], (long)(mm + Mp), sm));
+    if (stats) {   // the latents' accumulators are contiguous: one launch per pair of buffers sums all of them
+        const long cnt = (long)((l_hi - l_lo) * (mm + Mp + 4)), cnt2 = (long)((l_hi - l_lo) * (mm + Mp));
+        select_latent(c, l_lo);
+        for (int s = 1; s < nstr; ++s) LA(vadd_inplace_launch(c->stats[0], c->stats[s], cnt, sm));
         for (int s = 1; s < nstr && grad; ++s) LA(vadd_inplace_launch(c->facc[0], c->facc[s], (long)Mp * 128, sm));
-        for (int s = 0; s < nstr && c->balance; ++s) LA(vadd_inplace_launch(c->stats[0], c->stats2[s], (long)(mm + Mp), sm));
+        for (int l = l_lo; l < l_hi && c->balance; ++l) {
+            select_latent(c, l);
+            for (int s = 0; s < nstr; ++s) LA(vadd_inplace_launch(c->stats[0], c->stats2[s], (long)(mm + Mp), sm));
+        }
+        (void)cnt2;
     }
-    LA(stats_tail_launch(c->ve_blocks, nchunks * vstride, c->flags, grad ? c->aux_blocks : nullptr, c->stats[0] + mm + Mp, sm));
+    for (int l = l_lo; l < l_hi; ++l) {
+        select_latent(c, l);
+        LA(stats_tail_launch(c->ve_blocks, nchunks * vstride, c->flags, grad ? c->aux_blocks : nullptr, c->stats[0] + mm + Mp, sm));
+    }
+    select_latent(c, l_lo);
     return TSVGP_OK;
+}
+
+// the pass over the RESIDENT minibatch: Y is the transposed copy [L][n_pad] when the L latents have independent likelihood terms
+int data_pass(tsvgp_ctx* c, int mode, int phase = PASS_WHOLE, int lat_only = -1) {
+    const bool per_latent_y = c->L > 1 && c->lik.kind != LIK_SOFTMAX;
+    return stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, per_latent_y ? c->Yt : c->Y, c->meanX, mode, nullptr, nullptr, phase,
+                       per_latent_y ? c->n_pad : 0, 0, lat_only);
 }
 
 int all_reduce(tsvgp_ctx* c, double* buf, size_t count) {
@@ -990,7 +1123,77 @@ int choose_route(tsvgp_ctx* c, double jitter) {
 }
 
 // tsvgp.py:268-303 after the statistics are complete in stats[0]
+int dense_update_one(tsvgp_ctx* c, double lr, double jitter, double scale, bool only_G, bool G_ready = false);
 int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale, bool only_G) {
+    for (int l = 0; l < c->L; ++l) {   // the latents' site updates are independent (tsvgp.py:293-303 per latent)
+        select_latent(c, l);
+        OK(dense_update_one(c, lr, jitter, scale, only_G));
+    }
+    if (c->L > 1 && !only_G) {
+        // commit AFTER every latent has factored its -2 Lambda_2 + jitter I: the reference raises before any assign (tsvgp.py:300-303),
+        // so a failure in latent l must leave the latents before l untouched too (the guards read the shared device flags)
+        const size_t mm = (size_t)c->Mp * c->Mp;
+        for (int l = 0; l < c->L; ++l) {
+            select_latent(c, l);
+            const double* bad = c->stats[0] + mm + c->Mp + 1;
+            LA(update_lambda1_launch(c->lam1, c->stats2[0], c->stats2[0] + c->Mp, c->M, lr, scale, bad, c->info, c->s_main));
+            LA(finalize_sites_launch(c->stats[0], c->L2, c->Mp, c->M, c->Mp, bad, c->info, c->s_main));
+        }
+    }
+    select_latent(c, 0);
+    return TSVGP_OK;
+}
+
+// Multi-GPU, fused route: instead of all-reducing B and repeating G2 = K9^-1 B K9^-1 on every rank (3 M^3 flops each), the
+// statistics are reduce-scattered by tile rows, every rank forms its rows of Y = B K9^-1 and, after an all-gather of Y, its rows of
+// G2 = K9^-1 Y; a second all-gather leaves the same G2 bits on every rank, so the replicated factorisation that follows stays in
+// lock-step.  [b | sum ve | flag] goes through a small all-reduce.  (VERDICT r01 next #3c)
+bool sharded_update_active(const tsvgp_ctx* c) {
+    return c->world > 1 && c->route == ROUTE_FUSED && c->L == 1 && !c->white && c->Mp >= c->shard_min_m && (c->Mp / 128) % c->world == 0 &&
+           nccl_api().ReduceScatter && nccl_api().AllGather;
+}
+
+int sharded_reduce_and_form_G(tsvgp_ctx* c) {
+    cudaStream_t s = c->s_main;
+    NcclApi& api = nccl_api();
+    const int n = c->Mp;
+    const long ld = n;
+    const size_t mm = (size_t)n * n;
+    const int R = n / c->world;                  // rows per rank (whole 128-row tiles)
+    const size_t blk = (size_t)R * n;
+    double* B = c->stats[0];
+    double* bvec = c->stats[0] + mm;
+    auto chk = [&](int r, const char* what) -> int {
+        if (r != 0) FAIL(TSVGP_ERR_COMM, "%s: %s", what, api.GetErrorString ? api.GetErrorString(r) : "error");
+        return TSVGP_OK;
+    };
+    LA(mirror_lower_launch(B, ld, n, s));        // complete rows: the pass accumulated lower tiles only
+    double* Brows = c->X2 + (size_t)c->rank * blk;
+    OK(chk(api.ReduceScatter(B, Brows, blk, NCCL_FLOAT64, NCCL_SUM, c->comm, s), "ncclReduceScatter"));
+    OK(all_reduce(c, bvec, (size_t)n + 4));
+    CU(cudaEventRecord(c->ev[EV_REDUCE], s));
+    if (!c->k9inv_valid) FAIL(TSVGP_ERR_STATE, "sharded update needs K9^-1 (formed by the K9 chain)");
+    {   // Y[rows] = B[rows, :] K9^-1
+        GemmP p;
+        p.A = Brows; p.lda = ld; p.a_kc = 1;
+        p.B = c->K9inv; p.ldb = ld; p.b_kc = 0;
+        p.C = c->X1 + (size_t)c->rank * blk; p.ldc = ld; p.m = R; p.n = n; p.k = n;
+        LA(mm_gemm(c, p, s));
+    }
+    OK(chk(api.AllGather(c->X1 + (size_t)c->rank * blk, c->X1, blk, NCCL_FLOAT64, c->comm, s), "ncclAllGather"));
+    {   // G2[rows] = K9^-1[rows, :] Y
+        GemmP p;
+        p.A = c->K9inv + (size_t)c->rank * blk; p.lda = ld; p.a_kc = 1;
+        p.B = c->X1; p.ldb = ld; p.b_kc = 0;
+        p.C = c->G2 + (size_t)c->rank * blk; p.ldc = ld; p.m = R; p.n = n; p.k = n;
+        LA(mm_gemm(c, p, s));
+    }
+    OK(chk(api.AllGather(c->G2 + (size_t)c->rank * blk, c->G2, blk, NCCL_FLOAT64, c->comm, s), "ncclAllGather"));
+    LA(gemv_n_launch(c->K9inv, ld, n, n, bvec, 1.0, 0.0, c->v2, s));   // G1 = K9^-1 b
+    return TSVGP_OK;
+}
+
+int dense_update_one(tsvgp_ctx* c, double lr, double jitter, double scale, bool only_G, bool G_ready) {
     cudaStream_t s = c->s_main;
     const int n = c->Mp;
     const long ld = c->Mp;
@@ -998,8 +1201,10 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale, bool only
     double* B = c->stats[0];
     double* bvec = c->stats[0] + mm;
     const double* bad = c->stats[0] + mm + n + 1;
-    LA(mirror_lower_launch(B, ld, n, s));
-    if (c->route == ROUTE_FUSED) {
+    if (!G_ready) LA(mirror_lower_launch(B, ld, n, s));
+    if (G_ready) {
+        // G2 (all rows, gathered) and G1 are in place
+    } else if (c->route == ROUTE_FUSED) {
         if (!c->k9inv_valid) {   // K9^-1 = C9^-T C9^-1 (symmetric): two M^3 products per step instead of four; kept with chol(K9)
             GemmP p;
             p.A = c->C9inv; p.lda = ld; p.a_kc = 0; p.a_tri = 2;
@@ -1052,23 +1257,31 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale, bool only
     if (only_G) return TSVGP_OK;   // G2 (mirrored) in c->G2, G1 in c->v2, G2 mZ in c->v3
     if (c->white) return dense_update_white(c, lr, scale);
     // P = (1-lr) L2 L2^T - 2 lr scale G2 + jitter I                                     tsvgp.py:293-300
-    LA(init_update_launch(c->G2, c->P, ld, c->M, n, -2.0 * lr * scale, jitter, s));
+    // several latents: the factor and the two vectors of the lambda_1 update wait, per latent, in the (now dead) accumulators B_l and
+    // stats2_l until every latent has factored (dense_update commits them together)
+    double* Pl = c->L > 1 ? B : c->P;
+    LA(init_update_launch(c->G2, Pl, ld, c->M, n, -2.0 * lr * scale, jitter, s));
     if (lr != 1.0) {
         GemmP p;
         p.A = c->L2; p.lda = ld; p.a_kc = 1; p.a_tri = 1;
         p.B = c->L2; p.ldb = ld; p.b_kc = 1; p.b_tri = 1;
-        p.C = c->P; p.ldc = ld; p.m = p.n = p.k = n;
+        p.C = Pl; p.ldc = ld; p.m = p.n = p.k = n;
         p.alpha = 1.0 - lr; p.lower_out = 1;
         if (dist_active(c)) {   // (1 - lr) L2 L2^T assembled from the ranks' rows, then added
             p.C = c->X2;
             OK(dense_gemm(c, p, s));
-            LA(vadd_inplace_launch(c->P, c->X2, (long)n * ld, s));
+            LA(vadd_inplace_launch(Pl, c->X2, (long)n * ld, s));
         } else {
             p.beta = 1.0;
             LA(mm_gemm(c, p, s));
         }
     }
-    LA(chol_lower(c->P, ld, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles, &c->la_main));
+    LA(chol_lower(Pl, ld, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles, &c->la_main));
+    if (c->L > 1) {
+        CU(cudaMemcpyAsync(c->stats2[0], c->v2, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+        CU(cudaMemcpyAsync(c->stats2[0] + n, c->v3, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+        return TSVGP_OK;
+    }
     // commit (skipped on the device if any variance was non-positive or a factorisation failed)
     LA(update_lambda1_launch(c->lam1, c->v2, c->v3, c->M, lr, scale, bad, c->info, s));
     LA(finalize_sites_launch(c->P, c->L2, ld, c->M, n, bad, c->info, s));
@@ -1191,7 +1404,7 @@ void tsvgp_destroy(tsvgp_ctx* c) {
     cudaSetDevice(c->dev);
     cudaDeviceSynchronize();
     if (c->comm) nccl_api().CommDestroy(c->comm);
-    c->pm.release(); c->pd.release(); c->pc.release(); c->ps.release(); c->pxs.release();
+    c->pm.release(); c->pd.release(); c->pc.release(); c->ps.release(); c->pxs.release(); c->pyt.release(); c->pmc.release();
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     for (int s = 0; s < MAXS; ++s) {
@@ -1229,6 +1442,7 @@ int tsvgp_set_option(tsvgp_ctx* c, const char* name, double value) {
             FAIL(TSVGP_ERR_INVALID, "route must be 0 (auto), 1 (fused), 2 (whitened) or 3 (exact)");
         c->route_opt = (int)value; c->k9_valid = false; return TSVGP_OK;
     }
+    if (!strcmp(name, "mc_seed")) { c->mc_seed = (unsigned long long)value; c->mc_draw = 0; return TSVGP_OK; }
     if (!strcmp(name, "speculate")) { c->speculate = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "k9_defer")) { c->k9_defer = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "early_slabs")) { c->early_slabs = value < 0 ? 0 : (int)value; return TSVGP_OK; }
@@ -1241,6 +1455,7 @@ int tsvgp_set_option(tsvgp_ctx* c, const char* name, double value) {
         return TSVGP_OK;
     }
     if (!strcmp(name, "dist_min_m")) { c->dist_min_m = (int)value; return TSVGP_OK; }
+    if (!strcmp(name, "shard_min_m")) { c->shard_min_m = (int)value; return TSVGP_OK; }
     if (!strcmp(name, "async_issue")) { c->async_issue = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "fuse_b")) { c->fuse_b = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "balance")) { c->balance = value != 0.0; return TSVGP_OK; }
@@ -1249,6 +1464,44 @@ int tsvgp_set_option(tsvgp_ctx* c, const char* name, double value) {
     if (!strcmp(name, "invalidate")) { c->kuu_valid = c->post_valid = c->kl_valid = c->k9_valid = c->c6_valid = c->wpost_valid = c->wkl_valid = false; return TSVGP_OK; }
     FAIL(TSVGP_ERR_INVALID, "unknown option '%s'", name);
 }
+
+int tsvgp_set_num_latent(tsvgp_ctx* c, int L) {
+    if (!c) return TSVGP_ERR_INVALID;
+    if (L < 1 || L > MAX_LATENT) FAIL(TSVGP_ERR_INVALID, "num_latent_gps must be in [1, %d]", MAX_LATENT);
+    if (L == c->L) return TSVGP_OK;
+    CU(cudaSetDevice(c->dev));
+    CU(cudaDeviceSynchronize());
+    c->L = L;
+    c->k9_pending = false;
+    if (c->M > 0) {   // re-allocate the per-latent state; the inducing inputs survive on the host side of the caller: re-upload needed
+        std::vector<double> Z((size_t)c->M * c->D), mz(c->Mp);
+        CU(cudaMemcpy(Z.data(), c->Zraw, sizeof(double) * c->M * c->D, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(mz.data(), c->meanZ_off, sizeof(double) * c->Mp, cudaMemcpyDeviceToHost));
+        const int M = c->M, D = c->D;
+        OK(alloc_m_state(c, M, D));
+        CU(cudaMemcpy(c->Zraw, Z.data(), sizeof(double) * M * D, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->meanZ_off, mz.data(), sizeof(double) * c->Mp, cudaMemcpyHostToDevice));
+    }
+    c->X = nullptr;   // the resident Y layout depends on L: set the data again
+    c->y_cols = 1;
+    return TSVGP_OK;
+}
+
+int tsvgp_set_mc_epsilon(tsvgp_ctx* c, const double* eps, int S, int64_t N, int L) {
+    if (!c) return TSVGP_ERR_INVALID;
+    CU(cudaSetDevice(c->dev));
+    CU(cudaStreamSynchronize(c->s_main));
+    c->pmc.release();
+    c->mc_eps = nullptr; c->mc_eps_n = 0;
+    if (!eps) return TSVGP_OK;
+    if (S != c->lik.n_gh || L != c->L || N < 1) FAIL(TSVGP_ERR_INVALID, "epsilon must be [S = %d, N, L = %d]", c->lik.n_gh, c->L);
+    NEED(c->mc_eps = c->pmc.get((size_t)S * N * L));
+    CU(cudaMemcpy(c->mc_eps, eps, sizeof(double) * S * N * L, cudaMemcpyDefault));
+    c->mc_eps_n = N;
+    return TSVGP_OK;
+}
+
+int tsvgp_num_latent(const tsvgp_ctx* c) { return c ? c->L : 0; }
 
 int tsvgp_set_kernel(tsvgp_ctx* c, int kind, double variance, const double* lengthscales, int n_ls) {
     if (!c) return TSVGP_ERR_INVALID;
@@ -1265,7 +1518,13 @@ int tsvgp_set_kernel(tsvgp_ctx* c, int kind, double variance, const double* leng
 
 int tsvgp_set_likelihood(tsvgp_ctx* c, int kind, double p0, double p1, int n_gh, const double* gh_x, const double* gh_w) {
     if (!c) return TSVGP_ERR_INVALID;
-    if (kind < TSVGP_LIK_GAUSSIAN || kind > TSVGP_LIK_STUDENT_T) FAIL(TSVGP_ERR_INVALID, "unknown likelihood kind %d", kind);
+    if (kind < TSVGP_LIK_GAUSSIAN || kind > TSVGP_LIK_SOFTMAX) FAIL(TSVGP_ERR_INVALID, "unknown likelihood kind %d", kind);
+    if (kind == TSVGP_LIK_SOFTMAX) {   // p0 = number of classes (= latent GPs), n_gh = Monte-Carlo points per data point
+        if (p0 < 2 || p0 > MAX_SOFTMAX_CLASSES || n_gh < 1) FAIL(TSVGP_ERR_INVALID, "Softmax: 2..%d classes and >= 1 Monte-Carlo point", MAX_SOFTMAX_CLASSES);
+        c->lik.kind = kind; c->lik.p0 = p0; c->lik.p1 = 0.0; c->lik.n_gh = n_gh;
+        c->lik_set = true;
+        return TSVGP_OK;
+    }
     if (kind != TSVGP_LIK_BERNOULLI_PROBIT && !(p0 > 0.0)) FAIL(TSVGP_ERR_INVALID, "likelihood variance / scale must be positive");
     if (kind == TSVGP_LIK_STUDENT_T && !(p1 > 0.0)) FAIL(TSVGP_ERR_INVALID, "Student-t df must be positive");
     if (kind != TSVGP_LIK_GAUSSIAN && (n_gh < 1 || n_gh > MAX_GH)) FAIL(TSVGP_ERR_INVALID, "n_gh must be in [1, %d]", MAX_GH);
@@ -1311,15 +1570,22 @@ int tsvgp_set_sites(tsvgp_ctx* c, const double* lambda_1, const double* lambda_2
     CU(cudaSetDevice(c->dev));
     cudaStream_t s = c->s_main;
     if (!c->sites_set || (!lambda_1 && !lambda_2_sqrt)) OK(default_sites(c));
+    // layouts of the reference: lambda_1 [M, L] (sites.py:56), lambda_2_sqrt [L, M, M] (sites.py:63)
+    const size_t mm = (size_t)c->Mp * c->Mp;
     if (lambda_1) {
-        CU(cudaMemsetAsync(c->lam1, 0, sizeof(double) * c->Mp, s));
-        CU(cudaMemcpyAsync(c->lam1, lambda_1, sizeof(double) * c->M, cudaMemcpyDefault, s));
+        CU(cudaMemsetAsync(c->lam1_all, 0, sizeof(double) * c->Mp * c->L, s));
+        for (int l = 0; l < c->L; ++l)
+            CU(cudaMemcpy2DAsync(c->lam1_all + (size_t)l * c->Mp, sizeof(double), lambda_1 + l, sizeof(double) * c->L, sizeof(double), c->M,
+                                 cudaMemcpyDefault, s));
     }
     if (lambda_2_sqrt) {
-        CU(cudaMemsetAsync(c->L2, 0, sizeof(double) * (size_t)c->Mp * c->Mp, s));
-        CU(cudaMemcpy2DAsync(c->L2, sizeof(double) * c->Mp, lambda_2_sqrt, sizeof(double) * c->M, sizeof(double) * c->M, c->M,
-                             cudaMemcpyDefault, s));
-        if (!c->white) LA(zero_upper_launch(c->L2, c->Mp, c->Mp, s));   // sites.py:63 — the triangular() transform keeps the lower triangle
+        CU(cudaMemsetAsync(c->L2_all, 0, sizeof(double) * mm * c->L, s));
+        for (int l = 0; l < c->L; ++l) {
+            double* L2l = c->L2_all + l * mm;
+            CU(cudaMemcpy2DAsync(L2l, sizeof(double) * c->Mp, lambda_2_sqrt + (size_t)l * c->M * c->M, sizeof(double) * c->M,
+                                 sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
+            if (!c->white) LA(zero_upper_launch(L2l, c->Mp, c->Mp, s));   // sites.py:63 — the triangular() transform keeps the lower triangle
+        }
     }
     CU(cudaStreamSynchronize(s));
     c->sites_set = true;
@@ -1333,10 +1599,15 @@ int tsvgp_get_sites(tsvgp_ctx* c, double* lambda_1, double* lambda_2_sqrt) {
     CU(cudaSetDevice(c->dev));
     if (!c->sites_set) OK(default_sites(c));
     cudaStream_t s = c->s_main;
-    if (lambda_1) CU(cudaMemcpyAsync(lambda_1, c->lam1, sizeof(double) * c->M, cudaMemcpyDefault, s));
-    if (lambda_2_sqrt)
-        CU(cudaMemcpy2DAsync(lambda_2_sqrt, sizeof(double) * c->M, c->L2, sizeof(double) * c->Mp, sizeof(double) * c->M, c->M,
-                             cudaMemcpyDefault, s));
+    const size_t mm = (size_t)c->Mp * c->Mp;
+    for (int l = 0; l < c->L; ++l) {
+        if (lambda_1)
+            CU(cudaMemcpy2DAsync(lambda_1 + l, sizeof(double) * c->L, c->lam1_all + (size_t)l * c->Mp, sizeof(double), sizeof(double), c->M,
+                                 cudaMemcpyDefault, s));
+        if (lambda_2_sqrt)
+            CU(cudaMemcpy2DAsync(lambda_2_sqrt + (size_t)l * c->M * c->M, sizeof(double) * c->M, c->L2_all + l * mm, sizeof(double) * c->Mp,
+                                 sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
+    }
     CU(cudaStreamSynchronize(s));
     return TSVGP_OK;
 }
@@ -1353,13 +1624,17 @@ int tsvgp_get_lambda_2(tsvgp_ctx* c, double* lambda_2) {
         CU(cudaStreamSynchronize(s));
         return TSVGP_OK;
     }
-    GemmP p;   // L2 L2^T (tsvgp.py:197-200), lower tiles then mirrored
-    p.A = c->L2; p.lda = n; p.a_kc = 1; p.a_tri = 1;
-    p.B = c->L2; p.ldb = n; p.b_kc = 1; p.b_tri = 1;
-    p.C = c->X2; p.ldc = n; p.m = p.n = p.k = n; p.lower_out = 1;
-    LA(mm_gemm(c, p, s));
-    LA(mirror_lower_launch(c->X2, n, n, s));
-    CU(cudaMemcpy2DAsync(lambda_2, sizeof(double) * c->M, c->X2, sizeof(double) * n, sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
+    for (int l = 0; l < c->L; ++l) {   // [L, M, M]
+        const double* L2l = c->L2_all + (size_t)l * n * n;
+        GemmP p;   // L2 L2^T (tsvgp.py:197-200), lower tiles then mirrored
+        p.A = L2l; p.lda = n; p.a_kc = 1; p.a_tri = 1;
+        p.B = L2l; p.ldb = n; p.b_kc = 1; p.b_tri = 1;
+        p.C = c->X2; p.ldc = n; p.m = p.n = p.k = n; p.lower_out = 1;
+        LA(mm_gemm(c, p, s));
+        LA(mirror_lower_launch(c->X2, n, n, s));
+        CU(cudaMemcpy2DAsync(lambda_2 + (size_t)l * c->M * c->M, sizeof(double) * c->M, c->X2, sizeof(double) * n, sizeof(double) * c->M, c->M,
+                             cudaMemcpyDefault, s));
+    }
     CU(cudaStreamSynchronize(s));
     return TSVGP_OK;
 }
@@ -1371,11 +1646,14 @@ int tsvgp_set_data(tsvgp_ctx* c, const double* X, const double* Y, int64_t N, in
     CU(cudaSetDevice(c->dev));
     cudaStream_t s = c->s_main;
     const long npad = round_up(N, 128);
-    if (npad > c->cap_n || (long)N * D > c->cap_x) {   // (re)allocate the owned staging and scaled-coordinate buffers
+    // Y is [N, L] for L latents with independent likelihood terms (tsvgp.py:256-259 sums over the latent axis), [N, 1] class labels
+    // for the Softmax likelihood (set the likelihood before the data)
+    const int ycols = (c->L > 1 && c->lik.kind != LIK_SOFTMAX) ? c->L : 1;
+    if (npad > c->cap_n || (long)N * D > c->cap_x || ycols > c->cap_yc) {   // (re)allocate the owned staging and scaled-coordinate buffers
         CU(cudaStreamSynchronize(s));
         c->pd.release();
-        c->cap_n = npad; c->cap_x = (long)N * D;
-        NEED(c->Xown = c->pd.get((size_t)N * D)); NEED(c->Yown = c->pd.get(npad)); NEED(c->meanXown = c->pd.get(npad));
+        c->cap_n = npad; c->cap_x = (long)N * D; c->cap_yc = ycols;
+        NEED(c->Xown = c->pd.get((size_t)N * D)); NEED(c->Yown = c->pd.get((size_t)npad * ycols)); NEED(c->meanXown = c->pd.get(npad));
     }
     if (npad > c->xs_cap_n || (long)D * npad > c->xs_cap) {
         CU(cudaStreamSynchronize(s));
@@ -1386,7 +1664,17 @@ int tsvgp_set_data(tsvgp_ctx* c, const double* X, const double* Y, int64_t N, in
     if (is_device_ptr(X)) c->X = X;
     else { CU(cudaMemcpyAsync(c->Xown, X, sizeof(double) * (size_t)N * D, cudaMemcpyHostToDevice, s)); c->X = c->Xown; }
     if (is_device_ptr(Y)) c->Y = Y;
-    else { CU(cudaMemcpyAsync(c->Yown, Y, sizeof(double) * N, cudaMemcpyHostToDevice, s)); c->Y = c->Yown; }
+    else { CU(cudaMemcpyAsync(c->Yown, Y, sizeof(double) * N * ycols, cudaMemcpyHostToDevice, s)); c->Y = c->Yown; }
+    c->y_cols = ycols;
+    if (ycols > 1) {   // latent-major copy: every latent's point kernel reads its own contiguous column
+        if ((long)npad * ycols > c->yt_cap) {
+            CU(cudaStreamSynchronize(s));
+            c->pyt.release();
+            c->yt_cap = (long)npad * ycols;
+            NEED(c->Yt = c->pyt.get((size_t)c->yt_cap));
+        }
+        LA(transpose_to_latent_major_launch(c->Y, N, ycols, c->Yt, npad, s));
+    }
     if (!mean_X) c->meanX = nullptr;
     else if (is_device_ptr(mean_X)) c->meanX = mean_X;
     else { CU(cudaMemcpyAsync(c->meanXown, mean_X, sizeof(double) * N, cudaMemcpyHostToDevice, s)); c->meanX = c->meanXown; }
@@ -1398,6 +1686,7 @@ int tsvgp_set_data(tsvgp_ctx* c, const double* X, const double* Y, int64_t N, in
 
 int tsvgp_stage_data(tsvgp_ctx* c, const double* X, const double* Y, int64_t N, int D, const double* mean_X) {
     if (!c) return TSVGP_ERR_INVALID;
+    if (c->L > 1 && c->lik.kind != LIK_SOFTMAX) FAIL(TSVGP_ERR_INVALID, "stage_data with num_latent_gps > 1: use set_data");
     if (!X || !Y || N < 1) FAIL(TSVGP_ERR_INVALID, "X [N >= 1, D] and Y [N] are required");
     if (c->D > 0 && D != c->D) FAIL(TSVGP_ERR_INVALID, "X has D=%d but the inducing points have D=%d", D, c->D);
     CU(cudaSetDevice(c->dev));
@@ -1450,6 +1739,11 @@ static int require_model(tsvgp_ctx* c, bool need_data) {
     if (!c->lik_set) FAIL(TSVGP_ERR_STATE, "likelihood not set (tsvgp_set_likelihood)");
     if (c->M <= 0) FAIL(TSVGP_ERR_STATE, "inducing points not set (tsvgp_set_inducing)");
     if (need_data && !c->X) FAIL(TSVGP_ERR_STATE, "no data resident (tsvgp_set_data)");
+    if (c->lik.kind == LIK_SOFTMAX && (int)c->lik.p0 != c->L)
+        FAIL(TSVGP_ERR_INVALID, "Softmax with %d classes needs num_latent_gps = %d (tsvgp_set_num_latent), not %d", (int)c->lik.p0, (int)c->lik.p0, c->L);
+    if (c->white && c->L != 1) FAIL(TSVGP_ERR_INVALID, "the whitened sibling model is built for num_latent_gps = 1");
+    if (need_data && c->y_cols != ((c->L > 1 && c->lik.kind != LIK_SOFTMAX) ? c->L : 1))
+        FAIL(TSVGP_ERR_STATE, "the resident Y has %d column(s): set the likelihood and num_latent_gps before the data", c->y_cols);
     return TSVGP_OK;
 }
 
@@ -1488,7 +1782,7 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
         if (rc == TSVGP_OK && !k9_runs) rc = choose_route(c, jitter);   // cached factors: the route is known at once
         c->n_early = 0;
         const bool early = rc == TSVGP_OK && c->early_slabs && (!k9_runs || !join_before) && c->route == ROUTE_FUSED;
-        if (early) rc = stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_STATS, nullptr, nullptr, PASS_EARLY);
+        if (early) rc = data_pass(c, MODE_STATS, PASS_EARLY);
         if (rc == TSVGP_OK) rc = ensure_posterior(c);
         if (rc == TSVGP_OK && elbo_before) rc = ensure_kl_terms(c);
         if (rc == TSVGP_OK && defer_k9) rc = start_k9(c, jitter);   // forks from the main stream HERE: behind the posterior chain
@@ -1497,26 +1791,35 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
         if (side.rc != TSVGP_OK) return side.rc;
         if (k9_runs && join_before) OK(choose_route(c, jitter));
         CU(cudaEventRecord(c->ev[EV_PREP], s));
-        OK(stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_STATS, nullptr, nullptr, early ? PASS_REST : PASS_WHOLE));
+        nvtxRangePushA("tsvgp_stream");
+        const int rc_pass = data_pass(c, MODE_STATS, early ? PASS_REST : PASS_WHOLE);
+        nvtxRangePop();
+        OK(rc_pass);
         if (k9_runs && !join_before) {   // join the K9 chain, read the probe, repeat the pass if the guess was wrong
             const int guessed = c->route;
             OK(choose_route(c, jitter));
             if (c->route != guessed)
-                OK(stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_STATS, nullptr, nullptr));
+                OK(data_pass(c, MODE_STATS));
         }
     }
     CU(cudaEventRecord(c->ev[EV_STREAM], s));
-    OK(all_reduce(c, c->stats[0], mm + c->Mp + 4));
-    CU(cudaEventRecord(c->ev[EV_REDUCE], s));
-    OK(dense_update(c, lr, jitter, scale, false));
+    struct NvtxRange { NvtxRange(const char* n) { nvtxRangePushA(n); } ~NvtxRange() { nvtxRangePop(); } } nvtx_dense("tsvgp_dense");
+    if (sharded_update_active(c)) {
+        OK(sharded_reduce_and_form_G(c));   // records EV_REDUCE after the reduce-scatter
+        OK(dense_update_one(c, lr, jitter, scale, false, true));
+    } else {
+        OK(all_reduce(c, c->stats_all[0], c->L * (mm + c->Mp + 4)));
+        CU(cudaEventRecord(c->ev[EV_REDUCE], s));
+        OK(dense_update(c, lr, jitter, scale, false));
+    }
     CU(cudaEventRecord(c->ev[EV_DENSE], s));
 
-    double tail[4], sc[N_SCAL];
+    double tail[4];
+    std::vector<double> scv((size_t)c->L * N_SCAL);
+    double* sc = scv.data();
     int info_h[N_INFO];
-    CU(cudaMemcpyAsync(tail, c->stats[0] + mm + c->Mp, sizeof tail, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(sc, c->scal, sizeof sc, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(info_h, c->info, sizeof info_h, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    OK(read_tails(c, tail, sc, info_h));
+    ++c->mc_draw;
     // the step consumed the posterior factors of the old sites
     c->post_valid = c->kl_valid = c->wpost_valid = c->wkl_valid = false;
     float ms = 0;
@@ -1551,17 +1854,16 @@ int tsvgp_elbo(tsvgp_ctx* c, double scale, double* out) {
     OK(ensure_xs(c));
     OK(ensure_posterior(c));
     OK(ensure_kl_terms(c));
-    OK(stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_ELBO, nullptr, nullptr));
-    OK(all_reduce(c, c->stats[0] + mm + c->Mp, 4));
-    double tail[4], sc[N_SCAL];
+    OK(data_pass(c, MODE_ELBO));
+    for (int l = 0; l < c->L; ++l) OK(all_reduce(c, c->stats_all[0] + l * (mm + c->Mp + 4) + mm + c->Mp, 4));
+    double tail[4];
+    std::vector<double> scv((size_t)c->L * N_SCAL);
     int info_h[N_INFO];
-    CU(cudaMemcpyAsync(tail, c->stats[0] + mm + c->Mp, sizeof tail, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(sc, c->scal, sizeof sc, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(info_h, c->info, sizeof info_h, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    OK(read_tails(c, tail, scv.data(), info_h));
+    ++c->mc_draw;
     OK(check_info(c, info_h));
     if (tail[1] != 0.0) FAIL(TSVGP_ERR_NONPOSITIVE_VARIANCE, "predict_f: non-positive predictive variance");
-    *out = scale * tail[0] - kl_value(c, sc);
+    *out = scale * tail[0] - kl_value(c, scv.data());
     return TSVGP_OK;
 }
 
@@ -1574,33 +1876,26 @@ int tsvgp_prior_kl(tsvgp_ctx* c, double* out) {
     CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
     OK(ensure_posterior(c));
     OK(ensure_kl_terms(c));
-    double sc[N_SCAL];
+    std::vector<double> scv((size_t)c->L * N_SCAL);
     int info_h[N_INFO];
-    CU(cudaMemcpyAsync(sc, c->scal, sizeof sc, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(scv.data(), c->scal_all, sizeof(double) * N_SCAL * c->L, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(info_h, c->info, sizeof info_h, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     OK(check_info(c, info_h));
-    *out = kl_value(c, sc);
+    *out = kl_value(c, scv.data());
     return TSVGP_OK;
 }
 
-int tsvgp_elbo_grad(tsvgp_ctx* c, double scale, double* elbo, double* d_variance, double* d_lengthscales, double* d_Z, double* d_lik) {
-    if (!c || !elbo || !d_variance || !d_lengthscales || !d_Z || !d_lik) return TSVGP_ERR_INVALID;
-    OK(require_model(c, true));
-    if (2 * c->D + 1 > 128) FAIL(TSVGP_ERR_INVALID, "elbo_grad supports D <= 63 (D = %d)", c->D);
-    if (c->white) FAIL(TSVGP_ERR_INVALID, "elbo_grad is not available for the whitened sibling model");
-    CU(cudaSetDevice(c->dev));
-    c->collective_ok = true;
+// ELBO terms and gradients of ONE latent (the selected one): *elbo = scale * sum ve_l - KL_l; gradients written to HOST vectors
+static int elbo_grad_one(tsvgp_ctx* c, int lat, double scale, const std::vector<double>& origin, double* elbo, double* d_variance,
+                         std::vector<double>& dls_out, std::vector<double>& dZ, double* d_lik) {
     cudaStream_t s = c->s_main;
     const int n = c->Mp, M = c->M, D = c->D;
     const long ld = n;
     const size_t mm = (size_t)n * n;
-    CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
-    OK(ensure_xs(c));
-    OK(ensure_posterior(c));
-    OK(ensure_kl_terms(c));
     c->grad_scale = scale;
-    OK(stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_GRAD, nullptr, nullptr));
+    OK(data_pass(c, MODE_GRAD, PASS_WHOLE, lat));
+    select_latent(c, lat);
     OK(all_reduce(c, c->stats[0], mm + n + 4));
     OK(all_reduce(c, c->facc[0], (size_t)n * 128));
     double* B = c->stats[0];
@@ -1633,7 +1928,7 @@ int tsvgp_elbo_grad(tsvgp_ctx* c, double scale, double* elbo, double* d_variance
     LA(matdot_launch(c->X1, c->K, ld, n, c->scal + SC_G_K, c->red, s));
     LA(matdot_launch(c->Wm, B, ld, n, c->scal + SC_TR_QB, c->red, s));
     LA(dot_launch(c->alpha, bvec, n, c->scal + SC_A_B, s));
-    LA(xaug_launch(c->ZsT, n, 0, M, n, D, c->zaug, s));
+    LA(xaug_launch(c->ZsT, n, 0, M, n, D, c->zaug, s, c->origin));
     {   // F_uu = E_uu [zs | 1 | zs^2]
         GemmP p;
         p.A = c->G2; p.lda = ld; p.a_kc = 1;
@@ -1641,7 +1936,8 @@ int tsvgp_elbo_grad(tsvgp_ctx* c, double scale, double* elbo, double* d_variance
         p.C = c->fuu; p.ldc = 128; p.m = n; p.n = 128; p.k = n;
         LA(mm_gemm(c, p, s));
     }
-    std::vector<double> Fuf((size_t)n * 128), Fuu((size_t)n * 128), Zs((size_t)n * D), ls(D), dZ((size_t)M * D);
+    std::vector<double> Fuf((size_t)n * 128), Fuu((size_t)n * 128), Zs((size_t)n * D), ls(D);
+    dZ.assign((size_t)M * D, 0.0);
     double tail[4], sc[N_SCAL];
     int info_h[N_INFO];
     CU(cudaMemcpyAsync(Fuf.data(), c->facc[0], sizeof(double) * n * 128, cudaMemcpyDeviceToHost, s));
@@ -1655,7 +1951,7 @@ int tsvgp_elbo_grad(tsvgp_ctx* c, double scale, double* elbo, double* d_variance
     c->kl_valid = false;   // X1 was reused
     OK(check_info(c, info_h));
     if (tail[1] != 0.0) FAIL(TSVGP_ERR_NONPOSITIVE_VARIANCE, "predict_f: non-positive predictive variance");
-    *elbo = scale * tail[0] - kl_value(c, sc);
+    *elbo = scale * tail[0] - 0.5 * (sc[SC_M_ALPHA] - sc[SC_TR_QK] + 2.0 * sc[SC_LOGDIAG_W]);
     *d_variance = (scale * (sc[SC_A_B] - 2.0 * sc[SC_TR_QB]) + sc[SC_G_K]) / c->kern_var + scale * tail[2];
     *d_lik = scale * tail[3];
     // d r2 / d lengthscale_d = -2 delta_d^2 / l_d, d r2 / d z_id = 2 delta_d / l_d with delta = zs - xs (scaled coordinates);
@@ -1664,7 +1960,7 @@ int tsvgp_elbo_grad(tsvgp_ctx* c, double scale, double* elbo, double* d_variance
     for (int d = 0; d < D; ++d) {
         double acc = 0.0;
         for (int i = 0; i < M; ++i) {
-            const double z = Zs[(size_t)i * D + d];
+            const double z = Zs[(size_t)i * D + d] - origin[d];   // F was accumulated in the same shifted coordinates
             const double* fu = &Fuf[(size_t)i * 128];
             const double* fz = &Fuu[(size_t)i * 128];
             acc += z * z * fu[D] - 2.0 * z * fu[d] + fu[D + 1 + d];
@@ -1673,15 +1969,57 @@ int tsvgp_elbo_grad(tsvgp_ctx* c, double scale, double* elbo, double* d_variance
         }
         dls[d] = -(2.0 / ls[d]) * acc;
     }
+    dls_out = dls;
+    return TSVGP_OK;
+}
+
+int tsvgp_elbo_grad(tsvgp_ctx* c, double scale, double* elbo, double* d_variance, double* d_lengthscales, double* d_Z, double* d_lik) {
+    if (!c || !elbo || !d_variance || !d_lengthscales || !d_Z || !d_lik) return TSVGP_ERR_INVALID;
+    OK(require_model(c, true));
+    if (2 * c->D + 1 > 128) FAIL(TSVGP_ERR_INVALID, "elbo_grad supports D <= 63 (D = %d)", c->D);
+    if (c->white) FAIL(TSVGP_ERR_INVALID, "elbo_grad is not available for the whitened sibling model");
+    if (c->lik.kind == LIK_SOFTMAX) FAIL(TSVGP_ERR_INVALID, "elbo_grad is not available for the Softmax likelihood");
+    CU(cudaSetDevice(c->dev));
+    c->collective_ok = true;
+    cudaStream_t s = c->s_main;
+    const int M = c->M, D = c->D;
+    CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
+    OK(ensure_xs(c));
+    OK(ensure_posterior(c));
+    OK(ensure_kl_terms(c));
+    // common origin of the scaled coordinates: the centroid of the inducing inputs (see xaug_kernel)
+    std::vector<double> origin(D, 0.0);
+    {
+        std::vector<double> Zs((size_t)c->Mp * D);
+        CU(cudaMemcpyAsync(Zs.data(), c->Zs, sizeof(double) * c->Mp * D, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        for (int i = 0; i < M; ++i)
+            for (int d = 0; d < D; ++d) origin[d] += Zs[(size_t)i * D + d] / M;
+        CU(cudaMemcpyAsync(c->origin, origin.data(), sizeof(double) * D, cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    // the ELBO is additive over the latents (shared kernel: the expectations sum over the latent axis, the KL over the independent
+    // q(u_l); tsvgp.py:65-95), and so is every gradient
+    double e_sum = 0.0, dv_sum = 0.0, dl_sum = 0.0;
+    std::vector<double> dls_sum(D, 0.0), dZ_sum((size_t)M * D, 0.0), dls, dZ;
+    for (int l = 0; l < c->L; ++l) {
+        double e = 0.0, dv = 0.0, dl = 0.0;
+        const int rc = elbo_grad_one(c, l, scale, origin, &e, &dv, dls, dZ, &dl);
+        select_latent(c, 0);
+        if (rc != TSVGP_OK) return rc;
+        e_sum += e; dv_sum += dv; dl_sum += dl;
+        for (int d = 0; d < D; ++d) dls_sum[d] += dls[d];
+        for (size_t i = 0; i < dZ.size(); ++i) dZ_sum[i] += dZ[i];
+    }
+    *elbo = e_sum; *d_variance = dv_sum; *d_lik = dl_sum;
     if (c->ls_host.size() == 1) {
         double t = 0.0;
-        for (int d = 0; d < D; ++d) t += dls[d];
-        double one = t;
-        CU(cudaMemcpy(d_lengthscales, &one, sizeof(double), cudaMemcpyDefault));
+        for (int d = 0; d < D; ++d) t += dls_sum[d];
+        CU(cudaMemcpy(d_lengthscales, &t, sizeof(double), cudaMemcpyDefault));
     } else {
-        CU(cudaMemcpy(d_lengthscales, dls.data(), sizeof(double) * D, cudaMemcpyDefault));
+        CU(cudaMemcpy(d_lengthscales, dls_sum.data(), sizeof(double) * D, cudaMemcpyDefault));
     }
-    CU(cudaMemcpy(d_Z, dZ.data(), sizeof(double) * (size_t)M * D, cudaMemcpyDefault));
+    CU(cudaMemcpy(d_Z, dZ_sum.data(), sizeof(double) * (size_t)M * D, cudaMemcpyDefault));
     return TSVGP_OK;
 }
 
@@ -1705,21 +2043,28 @@ int tsvgp_predict_f(tsvgp_ctx* c, const double* Xnew, int64_t N, int D, const do
         CU(cudaMemcpyAsync(xd, Xnew, sizeof(double) * (size_t)N * D, cudaMemcpyHostToDevice, s));
         xsrc = xd;
     }
-    NEED(xsT = tp.get((size_t)D * npad)); NEED(x2 = tp.get(npad)); NEED(md = tp.get(npad)); NEED(vd = tp.get(npad));
+    const int L = c->L;
+    NEED(xsT = tp.get((size_t)D * npad)); NEED(x2 = tp.get(npad)); NEED(md = tp.get((size_t)L * npad)); NEED(vd = tp.get((size_t)L * npad));
     if (mean_X) {
         NEED(moff = tp.get(npad));
         CU(cudaMemcpyAsync(moff, mean_X, sizeof(double) * N, cudaMemcpyDefault, s));
     }
     LA(scale_points_launch(xsrc, N, D, c->ls_dev, xsT, npad, x2, npad, s));
-    OK(stream_pass(c, xsT, npad, x2, N, nullptr, moff, MODE_PREDICT, md, vd));
+    OK(stream_pass(c, xsT, npad, x2, N, nullptr, moff, MODE_PREDICT, md, vd, PASS_WHOLE, 0, npad));
     double tail[4];
     int info_h[N_INFO];
-    const size_t mm = (size_t)c->Mp * c->Mp;
-    CU(cudaMemcpyAsync(tail, c->stats[0] + mm + c->Mp, sizeof tail, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(info_h, c->info, sizeof info_h, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(mean_out, md, sizeof(double) * N, cudaMemcpyDefault, s));
-    CU(cudaMemcpyAsync(var_out, vd, sizeof(double) * N, cudaMemcpyDefault, s));
-    CU(cudaStreamSynchronize(s));
+    if (L == 1) {
+        CU(cudaMemcpyAsync(mean_out, md, sizeof(double) * N, cudaMemcpyDefault, s));
+        CU(cudaMemcpyAsync(var_out, vd, sizeof(double) * N, cudaMemcpyDefault, s));
+    } else {   // [L][npad] on the device -> the reference's [N, L]
+        double *mt, *vt;
+        NEED(mt = tp.get((size_t)N * L)); NEED(vt = tp.get((size_t)N * L));
+        LA(transpose_to_point_major_launch(md, npad, N, L, mt, s));
+        LA(transpose_to_point_major_launch(vd, npad, N, L, vt, s));
+        CU(cudaMemcpyAsync(mean_out, mt, sizeof(double) * N * L, cudaMemcpyDefault, s));
+        CU(cudaMemcpyAsync(var_out, vt, sizeof(double) * N * L, cudaMemcpyDefault, s));
+    }
+    OK(read_tails(c, tail, nullptr, info_h));
     OK(check_info(c, info_h));
     if (tail[1] != 0.0) FAIL(TSVGP_ERR_NONPOSITIVE_VARIANCE, "predict_f: non-positive predictive variance");
     return TSVGP_OK;
@@ -1743,7 +2088,7 @@ int tsvgp_predict_f_extra_data(tsvgp_ctx* c, const double* Xnew, int64_t N, int 
     OK(start_k9(c, 1e-9));
     OK(ensure_posterior(c));
     OK(choose_route(c, 1e-9));
-    OK(stream_pass(c, c->XsT, c->n_pad, c->x2, c->N, c->Y, c->meanX, MODE_STATS, nullptr, nullptr));
+    OK(data_pass(c, MODE_STATS));
     OK(all_reduce(c, c->stats[0], mm + n + 4));
     OK(dense_update(c, 1.0, 1e-9, 1.0, true));
     LA(lincomb_launch(c->v1, 1.0, c->v2, -2.0, c->v3, n, s));          // g0 = G1 - 2 G2 mZ
@@ -1803,7 +2148,10 @@ int tsvgp_posterior(tsvgp_ctx* c, double* m, double* chol_S) {
     const int n = c->Mp;
     CU(cudaMemsetAsync(c->info, 0, sizeof(int) * N_INFO, s));
     OK(ensure_posterior(c));
-    if (m) CU(cudaMemcpyAsync(m, c->mq, sizeof(double) * c->M, cudaMemcpyDefault, s));
+    if (m)   // m_q [M, L]
+        for (int l = 0; l < c->L; ++l)
+            CU(cudaMemcpy2DAsync(m + l, sizeof(double) * c->L, c->mq_all + (size_t)l * c->Mp, sizeof(double), sizeof(double), c->M,
+                                 cudaMemcpyDefault, s));
     if (chol_S && c->white) {   // S = (LR^-1 K6)^T (LR^-1 K6)   (util.py:421-424)
         GemmP p;
         p.A = c->T; p.lda = n; p.a_kc = 1; p.a_tri = 1;
@@ -1818,22 +2166,25 @@ int tsvgp_posterior(tsvgp_ctx* c, double* m, double* chol_S) {
         c->wkl_valid = false;
         LA(chol_lower(c->X2, n, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles, &c->la_main));
         CU(cudaMemcpy2DAsync(chol_S, sizeof(double) * c->M, c->X2, sizeof(double) * n, sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
-    } else if (chol_S) {   // S = K6 - (K6 T)(K6 T)^T   (util.py:387-388)
-        GemmP p;
-        p.A = c->K6; p.lda = n; p.a_kc = 1;
-        p.B = c->T; p.ldb = n; p.b_kc = 0; p.b_tri = 2;
-        p.C = c->X1; p.ldc = n; p.m = p.n = p.k = n;
-        LA(mm_gemm(c, p, s));
-        c->kl_valid = false;   // X1 is shared with the KL terms
-        CU(cudaMemcpyAsync(c->X2, c->K6, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, s));
-        GemmP q;
-        q.A = c->X1; q.lda = n; q.a_kc = 1;
-        q.B = c->X1; q.ldb = n; q.b_kc = 1;
-        q.C = c->X2; q.ldc = n; q.m = q.n = q.k = n;
-        q.alpha = -1.0; q.beta = 1.0; q.lower_out = 1;
-        LA(mm_gemm(c, q, s));
-        LA(chol_lower(c->X2, n, n, c->dinv, c->info + INFO_S, s, c->gws, c->gws_doubles, &c->la_main));
-        CU(cudaMemcpy2DAsync(chol_S, sizeof(double) * c->M, c->X2, sizeof(double) * n, sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
+    } else if (chol_S) {   // S_l = K6 - (K6 T_l)(K6 T_l)^T   (util.py:387-388), chol_S [L, M, M]
+        for (int l = 0; l < c->L; ++l) {
+            GemmP p;
+            p.A = c->K6; p.lda = n; p.a_kc = 1;
+            p.B = c->T_all + (size_t)l * n * n; p.ldb = n; p.b_kc = 0; p.b_tri = 2;
+            p.C = c->X1; p.ldc = n; p.m = p.n = p.k = n;
+            LA(mm_gemm(c, p, s));
+            c->kl_valid = false;   // X1 is shared with the KL terms
+            CU(cudaMemcpyAsync(c->X2, c->K6, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, s));
+            GemmP q;
+            q.A = c->X1; q.lda = n; q.a_kc = 1;
+            q.B = c->X1; q.ldb = n; q.b_kc = 1;
+            q.C = c->X2; q.ldc = n; q.m = q.n = q.k = n;
+            q.alpha = -1.0; q.beta = 1.0; q.lower_out = 1;
+            LA(mm_gemm(c, q, s));
+            LA(chol_lower(c->X2, n, n, c->dinv, c->info + INFO_S, s, c->gws, c->gws_doubles, &c->la_main));
+            CU(cudaMemcpy2DAsync(chol_S + (size_t)l * c->M * c->M, sizeof(double) * c->M, c->X2, sizeof(double) * n, sizeof(double) * c->M, c->M,
+                                 cudaMemcpyDefault, s));
+        }
     }
     int info_h[N_INFO];
     CU(cudaMemcpyAsync(info_h, c->info, sizeof info_h, cudaMemcpyDeviceToHost, s));
@@ -1865,6 +2216,8 @@ int tsvgp_comm_init(tsvgp_ctx* c, int world_size, int rank, const void* id_128_b
 }
 
 int tsvgp_comm_size(const tsvgp_ctx* c) { return c ? c->world : 0; }
+int tsvgp_device(const tsvgp_ctx* c) { return c ? c->dev : -1; }
+void* tsvgp_stream(const tsvgp_ctx* c) { return c ? (void*)c->s_main : nullptr; }
 
 int tsvgp_get_timings(tsvgp_ctx* c, double* out, int n) {
     if (!c || !out) return TSVGP_ERR_INVALID;

@@ -55,6 +55,8 @@ def _likelihood_spec(lik):
         return _lib.LIK_BERNOULLI_PROBIT, 0.0, 0.0, n_gh
     if name == "StudentT":
         return _lib.LIK_STUDENT_T, float(_value(lik.scale)), float(_value(lik.df)), n_gh
+    if name == "Softmax":   # gpflow.likelihoods.Softmax(num_classes): MonteCarloLikelihood, num_monte_carlo_points = 100
+        return _lib.LIK_SOFTMAX, float(lik.num_classes), 0.0, int(getattr(lik, "num_monte_carlo_points", 100))
     raise NotImplementedError(f"likelihood {name}: the B200 path implements Gaussian, Bernoulli (probit) and StudentT")
 
 
@@ -80,17 +82,11 @@ class DenseSites:
 class t_SVGP:
     """Drop-in for the reference `t_SVGP` on the natgrad / elbo / predict_f path.
 
-    `num_latent_gps = L > 1` (shared kernel and inducing points, one site pair per latent, `Y [N, L]`; reference
-    tsvgp.py:276-281 and its Bernoulli fixture with L = 2, tests/models/test_tsvgp.py:45-88) is served by L independent
-    device contexts — the latents do not interact in the reference either: every quantity is computed per latent and
-    `variational_expectations` sums over the latent axis.  It is functional coverage, not yet a fused multi-latent pass."""
-
-    def __new__(cls, kernel, likelihood, inducing_variable, *, num_latent_gps=1, lambda_2_sqrt=None, **kw):
-        if lambda_2_sqrt is not None:
-            num_latent_gps = np.asarray(lambda_2_sqrt).shape[0]
-        if num_latent_gps > 1 and cls is t_SVGP:
-            return object.__new__(MultiLatent_t_SVGP)
-        return object.__new__(cls)
+    `num_latent_gps = L > 1` (shared kernel and inducing points, one site pair per latent; reference tsvgp.py:276-281, its
+    Bernoulli fixture with L = 2 at tests/models/test_tsvgp.py:45-88, the Softmax classifier of docs/notebooks/mnist.py:117-122)
+    lives in ONE device context: one Kuu / Kuu + jitter I chain and one Kuf slab per launch serve all latents, the variance
+    product, the weighted SYRK and the site update run per latent.  `Y` is [N, L] for likelihoods whose terms are independent
+    over the latent axis (Gaussian, Bernoulli, StudentT) and [N, 1] class labels for `Softmax`."""
 
     def __init__(self, kernel, likelihood, inducing_variable, *, mean_function=None, num_latent_gps=1, lambda_1=None,
                  lambda_2_sqrt=None, num_data=None, force=False, device=0):
@@ -107,8 +103,9 @@ class t_SVGP:
             lambda_2_sqrt = np.asarray(lambda_2_sqrt, dtype=np.float64)
             assert lambda_2_sqrt.ndim == 3  # tsvgp.py:182
             num_latent_gps = lambda_2_sqrt.shape[0]
-        assert num_latent_gps == 1   # L > 1 is routed to MultiLatent_t_SVGP by __new__
-        self.num_latent_gps = 1
+        self.num_latent_gps = L = int(num_latent_gps)
+        if L > 1 and mean_function is not None and type(mean_function).__name__ != "Zero":
+            raise NotImplementedError("mean_function with num_latent_gps > 1")
         ctx = C.c_void_p()
         rc = self._lib.tsvgp_create(C.byref(ctx), int(device))
         if rc != _lib.OK:
@@ -118,9 +115,11 @@ class t_SVGP:
         self.world_size, self.rank = 1, 0
         self._kernel_key = self._lik_key = self._z_key = None
         self._resident = None  # (N_local, keepalive) of the data set by set_data
+        if L > 1:
+            self._check(self._lib.tsvgp_set_num_latent(self._ctx, L))
         self._sync_objects()
         if lambda_1 is not None or lambda_2_sqrt is not None:
-            self.assign_sites(lambda_1, None if lambda_2_sqrt is None else lambda_2_sqrt[0])
+            self.assign_sites(lambda_1, lambda_2_sqrt)
 
     # ---- lifetime ------------------------------------------------------------------------------------------------
     def close(self):
@@ -186,38 +185,41 @@ class t_SVGP:
 
     @property
     def lambda_1(self):
-        out = np.empty((self._M, 1))
+        out = np.empty((self._M, self.num_latent_gps))
         self._check(self._lib.tsvgp_get_sites(self._ctx, out.ctypes.data, None))
         return out
 
     @property
     def lambda_2_sqrt(self):
-        out = np.empty((1, self._M, self._M))
+        out = np.empty((self.num_latent_gps, self._M, self._M))
         self._check(self._lib.tsvgp_get_sites(self._ctx, None, out.ctypes.data))
         return out
 
     @property
     def lambda_2(self):
-        out = np.empty((1, self._M, self._M))
+        out = np.empty((self.num_latent_gps, self._M, self._M))
         self._check(self._lib.tsvgp_get_lambda_2(self._ctx, out.ctypes.data))
         return out
 
     def assign_sites(self, lambda_1=None, lambda_2_sqrt=None):
-        """`lambda_1.assign(...)` / `lambda_2_sqrt.assign(...)` of the reference (tsvgp.py:302-303)."""
+        """`lambda_1.assign(...)` / `lambda_2_sqrt.assign(...)` of the reference (tsvgp.py:302-303): [M, L] and [L, M, M]."""
+        L = self.num_latent_gps
         l1 = l2 = None
         if lambda_1 is not None:
-            l1 = np.ascontiguousarray(np.asarray(lambda_1, dtype=np.float64).reshape(-1))
-            if l1.size != self._M:
-                raise _lib.InvalidArgumentError(_lib.ERR_INVALID, f"lambda_1 must have {self._M} entries")
+            l1 = np.ascontiguousarray(np.asarray(lambda_1, dtype=np.float64).reshape(-1, L))
+            if l1.shape[0] != self._M:
+                raise _lib.InvalidArgumentError(_lib.ERR_INVALID, f"lambda_1 must be [{self._M}, {L}]")
         if lambda_2_sqrt is not None:
-            l2 = np.ascontiguousarray(np.asarray(lambda_2_sqrt, dtype=np.float64).reshape(-1, self._M, self._M)[0])
+            l2 = np.ascontiguousarray(np.asarray(lambda_2_sqrt, dtype=np.float64).reshape(-1, self._M, self._M))
+            if l2.shape[0] != L:
+                raise _lib.InvalidArgumentError(_lib.ERR_INVALID, f"lambda_2_sqrt must be [{L}, {self._M}, {self._M}]")
         self._check(self._lib.tsvgp_set_sites(self._ctx, None if l1 is None else l1.ctypes.data, None if l2 is None else l2.ctypes.data))
 
     def get_mean_chol_cov_inducing_posterior(self):
         """tsvgp.py:202-212 -> (m_q [M, 1], chol_S [1, M, M])."""
         self._sync_objects()
-        m = np.empty((self._M, 1))
-        cs = np.empty((1, self._M, self._M))
+        m = np.empty((self._M, self.num_latent_gps))
+        cs = np.empty((self.num_latent_gps, self._M, self._M))
         self._check(self._lib.tsvgp_posterior(self._ctx, m.ctypes.data, cs.ctypes.data))
         return m, cs
 
@@ -226,13 +228,14 @@ class t_SVGP:
         """Make (X [N, D], Y [N, 1]) — this rank's rows of the minibatch — resident on the GPU.  Host arrays are copied
         (H2D); device tensors (DLPack) are aliased and must stay alive and unchanged until the next set_data."""
         X, Y = data
-        tx, ty = as_tensor(X, "X"), as_tensor(Y, "Y")
+        tx, ty = as_tensor(X, "X", self), as_tensor(Y, "Y", self)
         if len(tx.shape) != 2:
             raise _lib.InvalidArgumentError(_lib.ERR_INVALID, "X must be [N, D]")
         N, D = tx.shape
         ny = int(np.prod(ty.shape))
-        if ny != N:
-            raise _lib.InvalidArgumentError(_lib.ERR_INVALID, f"Y must be [N, 1] with N = {N} (num_latent_gps = 1), got {ty.shape}")
+        ycols = 1 if type(self.likelihood).__name__ == "Softmax" else self.num_latent_gps
+        if ny != N * ycols:
+            raise _lib.InvalidArgumentError(_lib.ERR_INVALID, f"Y must be [N, {ycols}] with N = {N}, got {ty.shape}")
         mean_x = None
         if self._mean_fn(np.zeros((1, D))) is not None:
             if tx.on_device:
@@ -243,10 +246,12 @@ class t_SVGP:
         return N
 
     def stage_data(self, data):
+        if self.num_latent_gps > 1 and type(self.likelihood).__name__ != "Softmax":
+            raise NotImplementedError("stage_data with num_latent_gps > 1: use set_data")
         """Start copying the NEXT minibatch to the GPU on a copy stream while the current step computes (use pinned host
         arrays, `tsvgp_b200.pinned_empty`, for a truly asynchronous copy); `commit_staged()` makes it resident."""
         X, Y = data
-        tx, ty = as_tensor(X, "X"), as_tensor(Y, "Y")
+        tx, ty = as_tensor(X, "X", self), as_tensor(Y, "Y", self)
         N, D = tx.shape
         if int(np.prod(ty.shape)) != N:
             raise _lib.InvalidArgumentError(_lib.ERR_INVALID, "Y must be [N, 1]")
@@ -330,19 +335,31 @@ class t_SVGP:
         if full_cov or full_output_cov:
             raise NotImplementedError("full_cov / full_output_cov: never exercised on this path by the reference")
         self._sync_objects()
-        tx = as_tensor(Xnew, "Xnew")
+        tx = as_tensor(Xnew, "Xnew", self)
         if len(tx.shape) != 2:
             raise _lib.InvalidArgumentError(_lib.ERR_INVALID, "Xnew must be [N, D]")
         N, D = tx.shape
+        L = self.num_latent_gps
         if N == 0:   # an empty query returns empty moments, as the reference's conditional does
-            return np.empty((0, 1)), np.empty((0, 1))
+            return np.empty((0, L)), np.empty((0, L))
         mean_x = None
         if self._mean_fn(np.zeros((1, D))) is not None:
             mean_x = self._mean_fn(np.asarray(Xnew, dtype=np.float64))
-        mean, var = np.empty((N, 1)), np.empty((N, 1))
+        mean, var = np.empty((N, L)), np.empty((N, L))
         self._check(self._lib.tsvgp_predict_f(self._ctx, tx.ptr, N, D, None if mean_x is None else mean_x.ctypes.data,
                                               mean.ctypes.data, var.ctypes.data))
         return mean, var
+
+    def set_mc_epsilon(self, epsilon):
+        """Softmax likelihood: fix the Monte-Carlo draws to `epsilon [S, N, L]` (GPflow's `epsilon` argument of
+        MonteCarloLikelihood.variational_expectations) for every pass over exactly N points; None returns to the generator."""
+        if epsilon is None:
+            self._check(self._lib.tsvgp_set_mc_epsilon(self._ctx, None, 0, 0, 0))
+            return
+        self._sync_objects()
+        e = np.ascontiguousarray(epsilon, dtype=np.float64)
+        S, N, L = e.shape
+        self._check(self._lib.tsvgp_set_mc_epsilon(self._ctx, e.ctypes.data, S, N, L))
 
     # ---- inherited GPModel surface built on predict_f (used by the reference's callers: experiments/uci_regression.py:114,142,
     # 145,251).  O(N) host arithmetic on the GPU's predict_f output; GPflow 2.2.1 likelihood semantics [GPflow-recalled]:
@@ -427,111 +444,7 @@ class t_SVGP:
 
 
 class MultiLatent_t_SVGP(t_SVGP):
-    """`t_SVGP(..., num_latent_gps=L)` for L > 1: L single-latent models side by side (see t_SVGP)."""
-
-    def __init__(self, kernel, likelihood, inducing_variable, *, mean_function=None, num_latent_gps=1, lambda_1=None,
-                 lambda_2_sqrt=None, num_data=None, force=False, device=0):
-        if lambda_2_sqrt is not None:
-            lambda_2_sqrt = np.asarray(lambda_2_sqrt, dtype=np.float64)
-            assert lambda_2_sqrt.ndim == 3  # tsvgp.py:182
-            num_latent_gps = lambda_2_sqrt.shape[0]
-        if mean_function is not None and type(mean_function).__name__ != "Zero":
-            raise NotImplementedError("mean_function with num_latent_gps > 1")
-        L = self.num_latent_gps = int(num_latent_gps)
-        self.kernel, self.likelihood, self.inducing_variable = kernel, likelihood, inducing_variable
-        self.mean_function, self.whiten, self.force, self.name = mean_function, False, force, "t_svgp"
-        l1 = None if lambda_1 is None else np.asarray(lambda_1, dtype=np.float64).reshape(-1, L)
-        self._parts = [t_SVGP(kernel, likelihood, inducing_variable, num_data=num_data, force=force, device=device,
-                              lambda_1=None if l1 is None else l1[:, l:l + 1],
-                              lambda_2_sqrt=None if lambda_2_sqrt is None else lambda_2_sqrt[l:l + 1]) for l in range(L)]
-        self._M = self._parts[0]._M
-        self.world_size, self.rank = 1, 0
-
-    num_data = property(lambda self: self._parts[0].num_data, lambda self, v: [setattr(p, "num_data", v) for p in self._parts] and None)
-
-    def close(self):
-        for p in getattr(self, "_parts", []):
-            p.close()
-
-    def set_option(self, name, value):
-        for p in self._parts:
-            p.set_option(name, value)
-
-    @property
-    def lambda_1(self):
-        return np.concatenate([p.lambda_1 for p in self._parts], axis=1)
-
-    @property
-    def lambda_2_sqrt(self):
-        return np.concatenate([p.lambda_2_sqrt for p in self._parts], axis=0)
-
-    @property
-    def lambda_2(self):
-        return np.concatenate([p.lambda_2 for p in self._parts], axis=0)
-
-    def assign_sites(self, lambda_1=None, lambda_2_sqrt=None):
-        for l, p in enumerate(self._parts):
-            p.assign_sites(None if lambda_1 is None else np.asarray(lambda_1)[:, l], None if lambda_2_sqrt is None else np.asarray(lambda_2_sqrt)[l])
-
-    def get_mean_chol_cov_inducing_posterior(self):
-        out = [p.get_mean_chol_cov_inducing_posterior() for p in self._parts]
-        return np.concatenate([o[0] for o in out], axis=1), np.concatenate([o[1] for o in out], axis=0)
-
-    def _split(self, data):
-        X, Y = data
-        Y = np.asarray(Y, dtype=np.float64)
-        if Y.ndim != 2 or Y.shape[1] != self.num_latent_gps:
-            raise _lib.InvalidArgumentError(_lib.ERR_INVALID, f"Y must be [N, {self.num_latent_gps}]")
-        return [(X, np.ascontiguousarray(Y[:, l:l + 1])) for l in range(self.num_latent_gps)]
-
-    def set_data(self, data):
-        return [p.set_data(d) for p, d in zip(self._parts, self._split(data))][0]
-
-    def natgrad_step(self, data=None, lr=0.1, jitter=1e-9, *, global_minibatch_size=None, return_elbo=False):
-        parts = self._split(data) if data is not None else [None] * self.num_latent_gps
-        e = [p.natgrad_step(d, lr, jitter, global_minibatch_size=global_minibatch_size, return_elbo=return_elbo)
-             for p, d in zip(self._parts, parts)]
-        return sum(e) if return_elbo else None
-
-    def elbo(self, data=None, *, global_minibatch_size=None):   # sum over latents of (scaled expectations - KL_l)
-        parts = self._split(data) if data is not None else [None] * self.num_latent_gps
-        return sum(p.elbo(d, global_minibatch_size=global_minibatch_size) for p, d in zip(self._parts, parts))
-
-    def prior_kl(self):
-        return sum(p.prior_kl() for p in self._parts)
-
-    def predict_f(self, Xnew, full_cov=False, full_output_cov=False):
-        out = [p.predict_f(Xnew, full_cov, full_output_cov) for p in self._parts]
-        return np.concatenate([o[0] for o in out], axis=1), np.concatenate([o[1] for o in out], axis=1)
-
-    def init_comm(self, world_size, rank, unique_id):
-        raise NotImplementedError("sharding with num_latent_gps > 1")
-
-    def stage_data(self, data):
-        raise NotImplementedError("stage_data with num_latent_gps > 1")
-
-    def elbo_and_grad(self, data=None, *, global_minibatch_size=None):
-        """Sum over the latent GPs (shared kernel, inducing inputs and likelihood): the ELBO and every gradient add up."""
-        parts = self._split(data) if data is not None else [None] * self.num_latent_gps
-        total, grads = 0.0, None
-        for p, d in zip(self._parts, parts):
-            e, g = p.elbo_and_grad(d, global_minibatch_size=global_minibatch_size)
-            total += e
-            if grads is None:
-                grads = g
-            else:
-                for k in ("variance", "lengthscales", "Z"):
-                    grads[k] = grads[k] + g[k]
-                if g["likelihood"] is not None:
-                    grads["likelihood"] += g["likelihood"]
-        return total, grads
-
-    def timings(self):
-        return self._parts[-1].timings()
-
-    def sync(self):
-        for p in self._parts:
-            p.sync()
+    """Kept as a name for `t_SVGP(..., num_latent_gps = L > 1)`: since round 2 the L latents live in ONE device context (see t_SVGP)."""
 
 
 class t_SVGP_white(t_SVGP):
@@ -541,9 +454,6 @@ class t_SVGP_white(t_SVGP):
         lambda_1 <- (1-lr) lambda_1 + lr s K (G1 - 2 G2 mZ) ;  Lambda_2 <- (1-lr) Lambda_2 - 2 lr s K G2 K.
     Same constructor / natgrad_step / elbo / predict_f / prior_kl / get_mean_chol_cov_inducing_posterior surface
     (+ `predict_f_extra_data`; num_latent_gps = 1; `elbo_and_grad` is not built for this parameterisation)."""
-
-    def __new__(cls, *a, **k):
-        return object.__new__(cls)
 
     def __init__(self, kernel, likelihood, inducing_variable, *, mean_function=None, num_latent_gps=1, lambda_1=None,
                  lambda_2=None, num_data=None, device=0):
@@ -574,12 +484,17 @@ class t_SVGP_white(t_SVGP):
     def elbo_and_grad(self, data=None, *, global_minibatch_size=None):
         raise NotImplementedError("elbo_and_grad for t_SVGP_white")
 
+    def natgrad_step(self, data=None, lr=0.1, jitter=1e-9, *, global_minibatch_size=None, return_elbo=False):
+        """tsvgp_white.py:215-246.  The reference accepts `jitter` but never forwards it: compute_data_natural_params is called
+        without it (:228) and factors Kuu + 1e-9 I whatever the caller passed — reproduced here."""
+        return super().natgrad_step(data, lr, 1e-9, global_minibatch_size=global_minibatch_size, return_elbo=return_elbo)
+
     def predict_f_extra_data(self, Xnew, extra_data, jitter=1e-6):
         """tsvgp_white.py:134-158: predictions at Xnew after conditioning the current sites on `extra_data` (the sites themselves
         are left unchanged; `extra_data` becomes the resident minibatch)."""
         self._sync_objects()
         self.set_data(extra_data)
-        tx = as_tensor(Xnew, "Xnew")
+        tx = as_tensor(Xnew, "Xnew", self)
         N, D = tx.shape
         if self._mean_fn(np.zeros((1, D))) is not None:
             raise NotImplementedError("predict_f_extra_data with a non-zero mean_function")

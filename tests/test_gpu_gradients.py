@@ -101,3 +101,30 @@ def test_multi_latent_gradients_add_up():
     np.testing.assert_allclose(g["variance"], fd(lambda k, x: setattr(k, "variance", orc._param(x)), 1.2), rtol=2e-6)
     np.testing.assert_allclose(g["lengthscales"][1], fd(lambda k, x: setattr(k, "lengthscales", orc._param(np.array([1.1, x]))), 1.4), rtol=2e-6)
     dev.close()
+
+
+def test_gradients_for_inputs_far_from_the_origin():
+    # the host reduction expands sum E (z - x)^2 = z^2 S1 - 2 z EX + C2, which cancels catastrophically when |z| / l is
+    # large (time stamps, offsets); the coordinates are therefore taken relative to the centroid of the inducing inputs.  Same data
+    # as a centred problem, shifted by 1e3 lengthscales: the gradients must still match the oracle (which forms z - x per pair).
+    import tsvgp_b200 as tb
+    rng = np.random.default_rng(9)
+    N, M, D = 1500, 96, 3
+    ls = np.array([0.9, 1.3, 1.7])
+    shift = 1.0e3 * ls
+    X = rng.standard_normal((N, D)) + shift
+    Z = X[:M].copy()
+    Y = np.sin((X - shift).sum(1, keepdims=True)) + 0.2 * rng.standard_normal((N, 1))
+    kernel, lik = orc.Matern52(variance=1.1, lengthscales=ls), orc.Gaussian(variance=0.1)
+    ref = orc.OracleTSVGP(kernel, lik, orc.InducingPoints(Z.copy()))
+    ref.natgrad_step((X, Y), lr=0.6)
+    dev = tb.t_SVGP(kernel, lik, Z.copy(), lambda_1=ref.lambda_1, lambda_2_sqrt=ref.lambda_2_sqrt)
+    e_ref, g_ref = orc.elbo_gradients(ref, (X, Y))
+    e_dev, g_dev = dev.elbo_and_grad((X, Y))
+    # the kernel matrices themselves lose ~ eps * (|x| / l)^2 = 1e-10 relative in r^2 through the expansion form GPflow uses
+    # (square_distance), in the oracle and on the device alike: the bar here is 1e-6, far below the ~1 the uncentred sums gave
+    errs = {"elbo": abs(e_dev - e_ref) / abs(e_ref), "variance": abs(g_dev["variance"] - g_ref["variance"]) / abs(g_ref["variance"]),
+            "lengthscales": relerr(g_dev["lengthscales"], g_ref["lengthscales"]), "Z": relerr(g_dev["Z"], g_ref["Z"])}
+    bad = {k: v for k, v in errs.items() if not v <= 1e-6}
+    assert not bad, (bad, errs)
+    dev.close()

@@ -22,19 +22,19 @@ def _n_gpus():
         return 0
 
 
-def _case():
+def _case(M=300):
     import tsvgp_b200.synth as synth
     from tsvgp_b200 import standins as st
     cfg = synth.describe("cfg5")
-    X, Y, Z = synth.make_minibatch(cfg, n_rows=5001, M=300)
+    X, Y, Z = synth.make_minibatch(cfg, n_rows=5001, M=M)
     kernel, lik = synth.build_objects(cfg, st)
     return cfg, X, Y, Z, kernel, lik
 
 
-def _rank(rank, world, conn, out, opts):
+def _rank(rank, world, conn, out, opts, M):
     sys.path.insert(0, ROOT)
     import tsvgp_b200 as tb
-    cfg, X, Y, Z, kernel, lik = _case()
+    cfg, X, Y, Z, kernel, lik = _case(M)
     m = tb.t_SVGP(kernel, lik, Z, num_data=50_010, device=rank)
     for k, v in opts.items():
         m.set_option(k, v)
@@ -60,32 +60,38 @@ def _rank(rank, world, conn, out, opts):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("opts", [{}, {"dist_min_m": 128}], ids=["replicated_dense", "distributed_dense"])
-def test_two_gpu_sharded_step_matches_single_gpu(opts):
+@pytest.mark.parametrize("opts,M", [({"shard_min_m": 1 << 30}, 300), ({"dist_min_m": 128, "shard_min_m": 1 << 30}, 300), ({"shard_min_m": 128}, 500)],
+                         ids=["replicated_dense", "distributed_dense", "sharded_update"])
+def test_two_gpu_sharded_step_matches_single_gpu(opts, M):
     # distributed_dense: the M x M products of the dense phase are dealt out row-cyclically over the ranks and assembled by
     # all-reduce (forced here at small M; by default from M >= 4096)
+    # sharded_update: statistics reduce-scattered by tile rows, G2 = K9^-1 B K9^-1 formed on each rank's rows, two all-gathers
+    # (forced here at M = 500 = 4 tile rows; by default from M >= 2048 when the tile rows divide by the ranks)
     import tsvgp_b200 as tb
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     a, b = ctx.Pipe()
-    procs = [ctx.Process(target=_rank, args=(0, 2, [a], out, opts)), ctx.Process(target=_rank, args=(1, 2, b, out, opts))]
+    procs = [ctx.Process(target=_rank, args=(0, 2, [a], out, opts, M)), ctx.Process(target=_rank, args=(1, 2, b, out, opts, M))]
     for p in procs:
         p.start()
     res = sorted([out.get(timeout=300) for _ in procs], key=lambda r: r[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    cfg, X, Y, Z, kernel, lik = _case()
+    cfg, X, Y, Z, kernel, lik = _case(M)
     single = tb.t_SVGP(kernel, lik, Z, num_data=50_010)
     e = [single.natgrad_step((X, Y), lr=cfg["lr"], return_elbo=True) for _ in range(2)] + [None]
     e[2] = single.elbo((X, Y))
     mu, var = single.predict_f(X[:50])
     rel = lambda x, y: float(np.max(np.abs(np.asarray(x) - np.asarray(y))) / np.max(np.abs(y)))  # noqa: E731
+    # summation order only (1e-11); the sharded update forms G2 = K9^-1 (B K9^-1) instead of (K9^-1 B) K9^-1: the two orders differ
+    # by rounding amplified by cond(Kuu), so it is held to a tenth of the parity tolerance
+    tol = 1e-10 if "shard_min_m" in opts and opts["shard_min_m"] < 1 << 20 else 1e-11
     for rank, l1, l2, elbos, mu_r, var_r, mu_solo in res:
-        assert rel(l1, single.lambda_1) < 1e-11 and rel(l2, single.lambda_2) < 1e-11     # summation order only
-        assert rel(elbos, e) < 1e-11 and rel(mu_r, mu) < 1e-11 and rel(var_r, var) < 1e-11
+        assert rel(l1, single.lambda_1) < tol and rel(l2, single.lambda_2) < tol
+        assert rel(elbos, e) < tol and rel(mu_r, mu) < tol and rel(var_r, var) < tol
         if rank == 0:
-            assert rel(mu_solo, single.predict_f(X[50:100])[0]) < 1e-11
+            assert rel(mu_solo, single.predict_f(X[50:100])[0]) < tol
     np.testing.assert_array_equal(res[0][1], res[1][1])   # replicated dense phase: both ranks hold identical sites
     np.testing.assert_array_equal(res[0][2], res[1][2])
     single.close()
