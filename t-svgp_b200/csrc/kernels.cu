@@ -910,35 +910,71 @@ __device__ __forceinline__ void qblk_mma(double* C, const double* A, const doubl
 // d -= l^2: the next pivot never waits on shared memory.  The scaled column k and 1 / L[k][k] are published in colbuf[k][.] /
 // rsbuf[k] and signalled on mbarrier k, which is all warp 1 (below) needs to run the inverse one pivot behind on another scheduler.
 // Returns 0, or k + 1 for the first non-positive (or NaN) pivot k.
+// 1 / sqrt(m) for normal m > 0: hardware seed (MUFU.RSQ64H), two Newton steps — the pivot chain's longest link; CUDA's rsqrt()
+// adds special-case handling the positive, normal pivots of a Cholesky never need.  (A non-positive pivot is caught before.)
+__device__ __forceinline__ double rsqrt_pos(double m) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(m));
+    const double hm = 0.5 * m;
+    y = y * fma(-hm * y, y, 1.5);
+    y = y * fma(-hm * y, y, 1.5);
+    return y;
+}
+
+// PIPE = false: the round-1 loop.  PIPE = true [r02]: the next pivot's shuffle and reciprocal square root are issued BEFORE the
+// bulk of the current rank-1 update (a warp issues in order: behind 30 DFMAs the chain waited ~60 cycles per pivot for nothing),
+// and the reciprocal square root is the bare Newton form above.
+template <bool PIPE>
 __device__ __forceinline__ int warp_potrf_32(double* Ajj, double* colbuf, double* rsbuf, uint64_t* bars, int lane) {
     double a[QB];
 #pragma unroll
     for (int c = 0; c < QB; ++c) a[c] = c < lane ? Ajj[lane * QLD + c] : 0.0;
     double d = Ajj[lane * QLD + lane], dl = 0.0;
     int fail = 0;
+    if (!PIPE) {
 #pragma unroll
-    for (int k = 0; k < QB; ++k) {
-        const double piv = __shfl_sync(0xffffffffu, d, k);
-        if (!(piv > 0.0) && fail == 0) fail = k + 1;   // uniform across the warp
-        const double rs = rsqrt(piv);
-        const double lk = lane > k ? a[k] * rs : 0.0;
-        d = fma(-lk, lk, d);
-        a[k] = lk;
-        if (lane == k) dl = piv * rs;
-        colbuf[k * QB + lane] = lk;
-        if (lane == 0) rsbuf[k] = rs;
-        mbar_arrive(bars + k);   // release: the column and rs are visible to whoever observes the completed phase
-        __syncwarp();
+        for (int k = 0; k < QB; ++k) {
+            const double piv = __shfl_sync(0xffffffffu, d, k);
+            if (!(piv > 0.0) && fail == 0) fail = k + 1;   // uniform across the warp
+            const double rs = rsqrt(piv);
+            const double lk = lane > k ? a[k] * rs : 0.0;
+            d = fma(-lk, lk, d);
+            a[k] = lk;
+            if (lane == k) dl = piv * rs;
+            colbuf[k * QB + lane] = lk;
+            if (lane == 0) rsbuf[k] = rs;
+            mbar_arrive(bars + k);   // release: the column and rs are visible to whoever observes the completed phase
+            __syncwarp();
 #pragma unroll
-        for (int c = k + 1; c < QB; ++c) a[c] = fma(-lk, colbuf[k * QB + c], a[c]);
+            for (int c = k + 1; c < QB; ++c) a[c] = fma(-lk, colbuf[k * QB + c], a[c]);
+        }
+    } else {
+        double piv = __shfl_sync(0xffffffffu, d, 0);
+        if (!(piv > 0.0)) fail = 1;
+        double rs = rsqrt_pos(fail ? 1.0 : piv);
+#pragma unroll
+        for (int k = 0; k < QB; ++k) {
+            const double lk = lane > k ? a[k] * rs : 0.0;
+            d = fma(-lk, lk, d);
+            a[k] = lk;
+            if (lane == k) dl = piv * rs;
+            colbuf[k * QB + lane] = lk;
+            if (lane == 0) rsbuf[k] = rs;
+            mbar_arrive(bars + k);   // release: the column and rs are visible to whoever observes the completed phase
+            __syncwarp();
+            if (k + 1 < QB) {   // the chain first: next pivot and its reciprocal square root
+                piv = __shfl_sync(0xffffffffu, d, k + 1);
+                if (!(piv > 0.0) && fail == 0) fail = k + 2;   // uniform across the warp
+                rs = rsqrt_pos(fail ? 1.0 : piv);
+            }
+#pragma unroll
+            for (int c = k + 1; c < QB; ++c) a[c] = fma(-lk, colbuf[k * QB + c], a[c]);
+        }
     }
 #pragma unroll
     for (int c = 0; c < QB; ++c) Ajj[lane * QLD + c] = c < lane ? a[c] : (c == lane ? dl : 0.0);
     return fail;
 }
-
-// Warp 1: Xjj = Ljj^-1 by right-looking elimination of L X = I, lane c owning COLUMN c of X, consuming the columns of L as warp 0
-// publishes them:  X[k][c] *= 1 / L[k][k] ;  X[r][c] -= L[r][k] X[k][c]  (r > k).
 __device__ __forceinline__ void warp_trtri_32(double* Xjj, const double* colbuf, const double* rsbuf, uint64_t* bars, uint32_t parity,
                                               int lane) {
     double x[QB];
@@ -956,7 +992,7 @@ __device__ __forceinline__ void warp_trtri_32(double* Xjj, const double* colbuf,
     for (int c = 0; c < QB; ++c) Xjj[c * QLD + lane] = x[c];   // zero above the diagonal by construction
 }
 
-__global__ void __launch_bounds__(256) diag_potrf_inv_blocked_kernel(double* A, long lda, double* Dinv, int blk, int* info) {
+__global__ void __launch_bounds__(256) diag_potrf_inv_blocked_kernel(double* A, long lda, double* Dinv, int blk, int* info, int fast) {
     PDL_PROLOGUE();
     extern __shared__ __align__(16) double S[];
     double* As = S;                                       // 10 lower sub-blocks of A -> L
@@ -988,7 +1024,8 @@ __global__ void __launch_bounds__(256) diag_potrf_inv_blocked_kernel(double* A, 
 #pragma unroll 1
     for (int j = 0; j < QNB; ++j) {
         if (warp == 0) {
-            const int f = warp_potrf_32(As + qidx(j, j), colbuf, rsbuf, bars, lane);
+            const int f = fast ? warp_potrf_32<true>(As + qidx(j, j), colbuf, rsbuf, bars, lane)
+                               : warp_potrf_32<false>(As + qidx(j, j), colbuf, rsbuf, bars, lane);
             if (f && lane == 0) sfail = j * QB + f;
         } else if (warp == 1) {
             warp_trtri_32(Xs + qidx(j, j), colbuf, rsbuf, bars, (uint32_t)(j & 1), lane);
@@ -1110,7 +1147,7 @@ __device__ __forceinline__ void qwriteback(const double* As, const double* Xs, d
             if ((tsk++ % nw) + w0 == warp) qstore_rows(Xs + qidx(j, c), Dinv, DB, j, c, 16 * h, 16, lane);
 }
 
-__global__ void __launch_bounds__(256) diag_potrf_inv_lookahead_kernel(double* A, long lda, double* Dinv, int blk, int* info) {
+__global__ void __launch_bounds__(256) diag_potrf_inv_lookahead_kernel(double* A, long lda, double* Dinv, int blk, int* info, int fast) {
     PDL_PROLOGUE();
     extern __shared__ __align__(16) double S[];
     double* As = S;
@@ -1140,7 +1177,8 @@ __global__ void __launch_bounds__(256) diag_potrf_inv_lookahead_kernel(double* A
 #pragma unroll 1
     for (int j = 0; j < QNB; ++j) {
         if (warp == 0) {
-            const int f = warp_potrf_32(As + qidx(j, j), colbuf, rsbuf, bars, lane);
+            const int f = fast ? warp_potrf_32<true>(As + qidx(j, j), colbuf, rsbuf, bars, lane)
+                               : warp_potrf_32<false>(As + qidx(j, j), colbuf, rsbuf, bars, lane);
             if (f && lane == 0) sfail = j * QB + f;
         } else if (warp == 1) {
             warp_trtri_32(Xs + qidx(j, j), colbuf, rsbuf, bars, (uint32_t)(j & 1), lane);
@@ -1177,8 +1215,10 @@ __global__ void __launch_bounds__(256) diag_potrf_inv_lookahead_kernel(double* A
 #ifdef TSVGP_DIAG_TIMING
 int diag_read_stamps(long long* out32) { return (int)cudaMemcpyFromSymbol(out32, g_diag_clk, sizeof(long long) * 32); }
 #endif
+static int g_diag_fast = 1;      // 1 = pipelined pivot chain with the bare Newton rsqrt (TSVGP_DIAG_FAST=0: the round-1 loop, A/B timing)
 static int g_diag_variant = 1;   // 1 = blocked (DMMA) kernel, 2 = the same with look-ahead, 0 = per-pivot register kernel (A/B timing: tools/diag_bench)
 void diag_set_variant(int v) { g_diag_variant = v; }
+void diag_set_fast(int f) { g_diag_fast = f; }
 constexpr int DIAG_BLOCKED_SMEM = 2 * (QNB * (QNB + 1) / 2) * QBLK * 8;
 
 // opt in to the large dynamic shared memory of the diagonal-block kernels on the CURRENT device (call once per context)
@@ -1188,12 +1228,13 @@ int diag_init() {
     e |= (int)cudaFuncSetAttribute(diag_potrf_inv_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_BLOCKED_SMEM);
     e |= (int)cudaFuncSetAttribute(diag_potrf_inv_lookahead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_BLOCKED_SMEM);
     if (const char* v = getenv("TSVGP_DIAG_VARIANT")) g_diag_variant = atoi(v);
+    if (const char* v = getenv("TSVGP_DIAG_FAST")) g_diag_fast = atoi(v);
     return e;
 }
 
 int diag_potrf_inv_launch(double* A, long lda, double* Dinv, int blk_index, int* info, cudaStream_t s) {
-    if (g_diag_variant == 2) launch_k(true, diag_potrf_inv_lookahead_kernel, 1, 256, DIAG_BLOCKED_SMEM, s, A, lda, Dinv, blk_index, info);
-    else if (g_diag_variant == 1) launch_k(true, diag_potrf_inv_blocked_kernel, 1, 256, DIAG_BLOCKED_SMEM, s, A, lda, Dinv, blk_index, info);
+    if (g_diag_variant == 2) launch_k(true, diag_potrf_inv_lookahead_kernel, 1, 256, DIAG_BLOCKED_SMEM, s, A, lda, Dinv, blk_index, info, g_diag_fast);
+    else if (g_diag_variant == 1) launch_k(true, diag_potrf_inv_blocked_kernel, 1, 256, DIAG_BLOCKED_SMEM, s, A, lda, Dinv, blk_index, info, g_diag_fast);
     else diag_potrf_inv_kernel<<<1, 256, DB * DB_LD * 8, s>>>(A, lda, Dinv, blk_index, info);
     return count_launch();
 }

@@ -85,6 +85,7 @@ int gemv_t_part_launch(const double* A, long lda, int m, int n, const double* x,
 int unpack_rows_launch(const double* ZsT, long ldz, int Mp, int D, double* Zs, cudaStream_t s);
 
 int diag_init();   // once per device/context: opt in to the dynamic shared memory of the diagonal-block kernels
+void diag_set_fast(int f);      // 1 = pipelined pivot chain + bare Newton rsqrt (default), 0 = the round-1 loop (env TSVGP_DIAG_FAST)
 void diag_set_variant(int v);   // 1 = blocked DMMA kernel (default), 0 = per-pivot register kernel (A/B timing; env TSVGP_DIAG_VARIANT)
 // --- diagonal blocks --------------------------------------------------------------------------------------------
 // In-place lower Cholesky of the 128x128 block at A (lda) and its inverse into Dinv (ld 128, dense lower).

@@ -22,8 +22,11 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(dA, A.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
     double* ws; const size_t ws_doubles = (size_t)4 << 20; CK(cudaMalloc(&ws, sizeof(double) * ws_doubles)); CK(cudaMemset(ws, 0, sizeof(double) * ws_doubles));   // split-K workspace (gemm_launch_auto)
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); float ms;
-    for (int variant = 0; variant < 3; ++variant) {
+    for (int vv = 0; vv < 5; ++vv) {   // 0: per-pivot; 1, 2: blocked / blocked + look-ahead with the round-1 pivot loop; 3, 4: the same with the pipelined pivot chain
+        const int variant = vv < 3 ? vv : vv - 2;
         diag_set_variant(variant);
+        diag_set_fast(vv >= 3);
+        printf("-- pivot chain: %s\n", vv >= 3 ? "pipelined + Newton rsqrt [r02]" : "round-1 loop");
         for (int rep = 0; rep < 3; ++rep) {
             CK(cudaMemcpy(dW, dA, sizeof(double) * n * n, cudaMemcpyDeviceToDevice));
             cudaEventRecord(e0); diag_potrf_inv_launch(dW, n, dinv, 0, info, 0); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
@@ -78,6 +81,7 @@ int main(int argc, char** argv) {
         CK(cudaMemset(info, 0, 16));
     }
     diag_set_variant(argc > 2 ? atoi(argv[2]) : 1);
+    diag_set_fast(argc > 3 ? atoi(argv[3]) : 1);
     for (int rep = 0; rep < 2; ++rep) {
         cudaEventRecord(e0); diag_trtri_launch(dW, n, dinv, 1, 0); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
         cudaEventElapsedTime(&ms, e0, e1); printf("diag_trtri (1 block): %.1f us\n", ms * 1e3);
