@@ -75,6 +75,8 @@ TSVGP_API int tsvgp_set_option(tsvgp_ctx* ctx, const char* name, double value); 
  *          reduce-scattered by tile rows, G2 = K9^-1 B K9^-1 is formed on each rank's rows and assembled by two all-gathers,
  *          instead of an all-reduce followed by the full products on every rank; a huge value switches it off),
  * "streams" up to 4, "balance" / "fuse_b" (0 switches the balanced SYRK split / the fused b += Kuf g off, for A/B timing),
+ * "spread_b" (1 = the fused b += Kuf g is shared by all tiles of a SYRK tile row, each adding into a private slot; 0 (default) =
+ *          carried by the first tile column alone — measured equal or faster inside a step),
  * "route_cond_max" (automatic: fused while the power-iteration estimate of cond(Kuu + jitter I) is below this; default 1e4),
  * "route_exact_min" (automatic: exact above this estimate, whitened in between; default 1e8),
  * "async_issue" (1 = at M <= 1024 a helper host thread enqueues the Kuu + jitter I factorisation chain on the side stream while

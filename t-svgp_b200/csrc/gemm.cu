@@ -320,7 +320,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-    const bool matvec = SCALE && p.gvec != nullptr && tj == 0 && wn == 0;   // the two warps of the first tile column that cover all 128 rows
+    // Fused mat-vec b += A g: the two warps with wn == 0 cover all 128 rows of the tile.  With bstride == 0 only the first tile column
+    // carries it (round 1) — its 16 tiles then run 3 % longer than the rest and set the makespan of the launch.  With bstride > 0
+    // [r02] the tiles (ti, 0..ti) of a tile row share the work: tile (ti, tj) handles the k-tiles [KT tj/(ti+1), KT (tj+1)/(ti+1)) of
+    // its piece and adds into its PRIVATE slot bout[tj * bstride + row] (no atomics; the host sums the slots at the end of the pass).
+    const bool matvec = SCALE && p.gvec != nullptr && wn == 0 && (tj == 0 || p.bstride > 0);
+    int mv_lo = 0, mv_hi = KT;
+    if (matvec && p.bstride > 0) { mv_lo = (int)((long)KT * tj / (ti + 1)); mv_hi = (int)((long)KT * (tj + 1) / (ti + 1)); }
     const bool use_scale = SCALE && p.kscale != nullptr;
     double bacc[8];
 #pragma unroll
@@ -396,7 +402,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
         using Yes = std::true_type;
         using No = std::false_type;
         if (SCALE) {   // statistics products: optional per-k weights (absent when the weights are one constant, Gaussian likelihood)
-            if (matvec) {   // the two warps per row block that also carry b += A g (first tile column only)
+            if (matvec && kt >= mv_lo && kt < mv_hi) {   // the two warps per row block that also carry b += A g, on their share of k
                 if (use_scale) { if (dj_pat == 1) k_tile(I8{}, J0{}, Yes{}, Yes{}); else k_tile(I8{}, FULLJ{}, Yes{}, Yes{}); }
                 else { if (dj_pat == 1) k_tile(I8{}, J0{}, Yes{}, No{}); else k_tile(I8{}, FULLJ{}, Yes{}, No{}); }
             } else if (use_scale) {
@@ -424,7 +430,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel_mb(GemmP p) {
     __syncthreads();   // every global read of this CTA has landed and every warp is out of the pipeline buffers
 
     if (SCALE && matvec) {   // rows wm + 8 i + g : sum the 4 lanes that split k, then one lane adds into the (CTA-private) rows of b
-        double* bo = (p.C2 != nullptr && ks == 1) ? p.bout2 : p.bout;
+        double* bo = ((p.C2 != nullptr && ks == 1) ? p.bout2 : p.bout) + (long)tj * p.bstride;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             double v = bacc[i];

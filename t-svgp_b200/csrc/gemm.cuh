@@ -28,6 +28,7 @@ struct GemmP {
     // with kscale: optional fused mat-vec  bout[i] += sum_k A(i,k) gvec[k]  (b += Kuf g of the statistics pass), computed from the A
     // fragments the first tile column already holds in registers; the split-off k piece (C2) accumulates into bout2
     const double* gvec = nullptr; double* bout = nullptr; double* bout2 = nullptr;
+    long bstride = 0;   // > 0: the mat-vec is shared by the tiles of a tile row, tile column tj adds into bout[tj * bstride + row]
     int epilogue = EPI_STORE;
     double* norm_out = nullptr; long ldn = 0;   // EPI_COLNORM: norm_out[tile_i * ldn + j] = sum_{i in tile} C(i,j)^2
     int ksplit = 1; double* part = nullptr; long part_stride = 0;   // split-K partial slabs [ksplit][m*ldc]; caller reduces

@@ -1537,6 +1537,17 @@ __global__ void vadd_inplace_kernel(double* dst, const double* src, long n) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] += src[i];
 }
+__global__ void sum_rows_into_kernel(const double* __restrict__ src, int rows, int n, double* __restrict__ dst) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += src[(long)r * n + j];
+    dst[j] += s;
+}
+int sum_rows_into_launch(const double* src, int rows, int n, double* dst, cudaStream_t s) {
+    sum_rows_into_kernel<<<(n + 255) / 256, 256, 0, s>>>(src, rows, n, dst);
+    return count_launch();
+}
 int vadd_inplace_launch(double* dst, const double* src, long n, cudaStream_t s) {
     launch_k(true, vadd_inplace_kernel, (unsigned)((n + 255) / 256), 256, 0, s, dst, src, n);
     return count_launch();
