@@ -1191,7 +1191,15 @@ int sharded_reduce_and_form_G(tsvgp_ctx* c) {
     OK(chk(api.ReduceScatter(B, Brows, blk, NCCL_FLOAT64, NCCL_SUM, c->comm, s), "ncclReduceScatter"));
     OK(all_reduce(c, bvec, (size_t)n + 4));
     CU(cudaEventRecord(c->ev[EV_REDUCE], s));
-    if (!c->k9inv_valid) FAIL(TSVGP_ERR_STATE, "sharded update needs K9^-1 (formed by the K9 chain)");
+    if (!c->k9inv_valid) {   // large M with distributed products: the K9 chain left K9^-1 = C9^-T C9^-1 to a collective product
+        GemmP p;
+        p.A = c->C9inv; p.lda = ld; p.a_kc = 0; p.a_tri = 2;
+        p.B = c->C9inv; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
+        p.C = c->K9inv; p.ldc = ld; p.m = p.n = p.k = n; p.lower_out = 1;
+        OK(dense_gemm(c, p, s));
+        LA(mirror_lower_launch(c->K9inv, ld, n, s));
+        c->k9inv_valid = true;
+    }
     {   // Y[rows] = B[rows, :] K9^-1
         GemmP p;
         p.A = Brows; p.lda = ld; p.a_kc = 1;

@@ -60,8 +60,9 @@ def _rank(rank, world, conn, out, opts, M):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("opts,M", [({"shard_min_m": 1 << 30}, 300), ({"dist_min_m": 128, "shard_min_m": 1 << 30}, 300), ({"shard_min_m": 128}, 500)],
-                         ids=["replicated_dense", "distributed_dense", "sharded_update"])
+@pytest.mark.parametrize("opts,M", [({"shard_min_m": 1 << 30}, 300), ({"dist_min_m": 128, "shard_min_m": 1 << 30}, 300), ({"shard_min_m": 128}, 500),
+                                    ({"dist_min_m": 128, "shard_min_m": 128}, 500)],
+                         ids=["replicated_dense", "distributed_dense", "sharded_update", "sharded_update_with_distributed_products"])
 def test_two_gpu_sharded_step_matches_single_gpu(opts, M):
     # distributed_dense: the M x M products of the dense phase are dealt out row-cyclically over the ranks and assembled by
     # all-reduce (forced here at small M; by default from M >= 4096)
