@@ -1,11 +1,86 @@
 #include "dense.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "common.cuh"
 #include <stdlib.h>
 
 namespace tsvgp {
 
 #define TRY(x) do { int e_ = (x); if (e_) return e_; } while (0)
+
+// ---- 32-row strip product for the Cholesky's critical path [r02] ---------------------------------------------------------------
+//   C[r0 : r0+32, 0:128] = alpha * A[r0 : r0+32, 0:128] * B[0:128, 0:128]^T + beta * C          (B stored [j][k], k contiguous)
+// One CTA per 32 rows, the whole 128 x 128 B in shared memory.  It replaces, per block column of chol_lower, the panel solve
+// (A = C = the panel, B = the inverse of the diagonal block, lower triangular: b_lower skips its zero 8 x 8 blocks) and the update of
+// the next block column (A = the panel, B = its first 128 rows, alpha = -1, beta = 1): the generic 128 x 128-tile engine needed a
+// split-K launch plus a reduction kernel for each of them (4 launches, ~29 us per block column at M = 2048); these are 2 launches
+// of up to n/32 CTAs.  In-place use (C == A) is safe: a CTA stages its own 32 rows completely before it stores.
+constexpr int SG_LD = 132;   // 128 + 4: the 8 rows of a fragment read hit distinct banks
+constexpr int SG_SMEM = (32 + 128) * SG_LD * 8;
+__global__ void __launch_bounds__(256) strip_gemm_kernel(const double* __restrict__ A, long lda, const double* __restrict__ B, long ldb,
+                                                         double* C, long ldc, double alpha, double beta, int b_lower) {
+    PDL_PROLOGUE();
+    extern __shared__ __align__(16) double sg[];
+    double* sA = sg;                 // [32][SG_LD]
+    double* sB = sg + 32 * SG_LD;    // [128][SG_LD]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const long r0 = (long)blockIdx.x * 32;
+    for (int u = tid; u < 32 * 64; u += 256) {
+        const int r = u >> 6, c = (u & 63) * 2;
+        cp_async16(sA + r * SG_LD + c, A + (r0 + r) * lda + c);
+    }
+    for (int u = tid; u < 128 * 64; u += 256) {
+        const int r = u >> 6, c = (u & 63) * 2;
+        cp_async16(sB + r * SG_LD + c, B + (long)r * ldb + c);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    // warp w owns the column blocks w and 15 - w (8 columns each) of all four 8-row blocks: with a lower-triangular B the contraction
+    // of column block jb stops at k = 8 (jb + 1), and (w + 1) + (16 - w) = 17 k-blocks for every warp
+    const int jb0 = warp, jb1 = 15 - warp;
+    const int k0max = b_lower ? 8 * (jb0 + 1) : 128, k1max = b_lower ? 8 * (jb1 + 1) : 128;
+    double acc[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+#pragma unroll 4
+    for (int kk = 0; kk < k1max; kk += 4) {
+        double a[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = sA[(8 * i + g) * SG_LD + kk + t];
+        const double b1 = sB[(8 * jb1 + g) * SG_LD + kk + t];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dmma884(acc[i][1][0], acc[i][1][1], a[i], b1);
+        if (kk < k0max) {
+            const double b0 = sB[(8 * jb0 + g) * SG_LD + kk + t];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dmma884(acc[i][0][0], acc[i][0][1], a[i], b0);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int col = 8 * (j ? jb1 : jb0) + 2 * t;
+            double2* ptr = reinterpret_cast<double2*>(C + (r0 + 8 * i + g) * ldc + col);
+            double2 o = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+            if (beta != 0.0) { const double2 old = *ptr; o.x += beta * old.x; o.y += beta * old.y; }
+            *ptr = o;
+        }
+}
+
+static int g_chol_strip = 1;   // TSVGP_CHOL_STRIP=0: the generic engine (split-K + reduction) for the panel / next-column products
+int dense_init() {
+    if (const char* v = getenv("TSVGP_CHOL_STRIP")) g_chol_strip = atoi(v);
+    return (int)cudaFuncSetAttribute(strip_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM);
+}
+static int strip_gemm_launch(const double* A, long lda, const double* B, long ldb, double* C, long ldc, int rows, double alpha, double beta,
+                             int b_lower, cudaStream_t s) {
+    launch_k(true, strip_gemm_kernel, rows / 32, 256, SG_SMEM, s, A, lda, B, ldb, C, ldc, alpha, beta, b_lower);
+    return count_launch();
+}
 
 constexpr int NB = 128;
 static int g_chol_outer = 512;   // outer panel width of the two-level blocking (multiple of 128)
@@ -25,7 +100,9 @@ static int chol_lower_lookahead(double* A, long ld, int n, double* dinv, int* in
         const int below = n - (q + NB);
         if (below <= 0) break;
         double* panel = A + (long)(q + NB) * ld + q;
-        {   // panel <- panel * L_qq^-T
+        if (g_chol_strip) {   // panel <- panel * L_qq^-T, 32-row strips
+            TRY(strip_gemm_launch(panel, ld, Dq, NB, panel, ld, below, 1.0, 0.0, 1, s));
+        } else {
             GemmP p;
             p.A = panel; p.lda = ld; p.a_kc = 1;
             p.B = Dq; p.ldb = NB; p.b_kc = 1;
@@ -49,7 +126,9 @@ static int chol_lower_lookahead(double* A, long ld, int n, double* dinv, int* in
         }
         // block column q+1 on the critical stream; trailing(q-1), which also wrote this column, must be complete
         if (f_pending) CUQ(cudaStreamWaitEvent(s, aux.f, 0));
-        {
+        if (g_chol_strip) {
+            TRY(strip_gemm_launch(panel, ld, panel, ld, A + (long)(q + NB) * ld + (q + NB), ld, below, -1.0, 1.0, 0, s));
+        } else {
             GemmP p;
             p.A = panel; p.lda = ld; p.a_kc = 1;
             p.B = panel; p.ldb = ld; p.b_kc = 1;

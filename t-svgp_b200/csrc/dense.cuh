@@ -13,6 +13,8 @@ namespace tsvgp {
 // aux (optional): a helper stream and two events private to the caller's stream.  With it the factorisation runs with LOOK-AHEAD:
 // after panel q only block column q+1 is updated on `s` (so the next diagonal block can start at once); the rest of the trailing
 // update (columns >= q+2) runs on aux->s2 underneath the next diagonal-block kernel, which is one CTA and leaves 147 SMs idle.
+int dense_init();   // once per process: opt in to the strip kernel's dynamic shared memory
+
 struct CholAux { cudaStream_t s2 = nullptr; cudaEvent_t e = nullptr, f = nullptr; };
 int chol_lower(double* A, long ld, int n, double* dinv, int* info, cudaStream_t s, double* ws = nullptr, size_t ws_doubles = 0,
                const CholAux* aux = nullptr);

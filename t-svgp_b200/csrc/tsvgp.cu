@@ -1416,7 +1416,7 @@ int tsvgp_create(tsvgp_ctx** out, int device_id) {
     ok = ok && cudaEventCreateWithFlags(&c->ev_kuu, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < N_EV && ok; ++i) ok = ok && cudaEventCreate(&c->ev[i]) == cudaSuccess;
-    ok = ok && gemm_init() == 0 && diag_init() == 0;
+    ok = ok && gemm_init() == 0 && diag_init() == 0 && dense_init() == 0;
     if (!ok) {
         g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
         delete c;

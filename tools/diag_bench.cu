@@ -13,7 +13,7 @@ using namespace tsvgp;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1);} } while (0)
 int main(int argc, char** argv) {
     int n = argc > 1 ? atoi(argv[1]) : 2048;
-    gemm_init(); diag_init();
+    gemm_init(); diag_init(); dense_init();
     std::vector<double> A((size_t)n * n);
     for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) A[(size_t)i * n + j] = exp(-0.5 * (i - j) * (i - j) / 9.0) + (i == j ? 0.5 : 0.0);
     double *dA, *dW, *dinv, *dLinv, *tmp; int* info;
