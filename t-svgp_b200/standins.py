@@ -35,6 +35,14 @@ class StudentT:
         self.df = float(df)
 
 
+class Softmax:
+    """gpflow.likelihoods.Softmax(num_classes): a MonteCarloLikelihood with num_monte_carlo_points = 100."""
+
+    def __init__(self, num_classes, num_monte_carlo_points=100):
+        self.num_classes = int(num_classes)
+        self.num_monte_carlo_points = int(num_monte_carlo_points)
+
+
 class InducingPoints:
     def __init__(self, Z):
         self.Z = np.array(Z, dtype=np.float64)
