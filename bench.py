@@ -277,7 +277,7 @@ def workload_config(cfg, M, Nb, n_gpus):
             "parallelism": f"rows/{n_gpus} + 1 allreduce, dense phase replicated",
             "l2": (f"inputs larger than L2: {N_RESIDENT_MINIBATCHES} distinct resident minibatches of {Nb * (cfg['D'] + 1) * 8 / 1e6:.0f} MB "
                    f"rotate (plus {16 * Mp * Mp * 8 / 1e6:.0f} MB of M x M state touched every step); the Kuf slab of one launch "
-                   f"({Mp} x 8192 x 8 B = {Mp * 8192 * 8 / 1e6:.0f} MB per stream) is written and re-read through L2/HBM")
+                   f"({Mp} x 16384 x 8 B = {Mp * 16384 * 8 / 1e6:.0f} MB per stream) is written and re-read through L2/HBM")
                   if N_RESIDENT_MINIBATCHES * Nb * (cfg['D'] + 1) * 8 > 126e6 else
                   "inputs smaller than the 126 MB L2 and not flushed: this config is launch-latency-bound, not bandwidth-bound"}
 
@@ -480,6 +480,9 @@ def main():
         try:
             ent = json.load(open(summ)).get(args.config, {})
             traffic, traffic_source = ent.get("syrk_dram_bytes_per_launch"), ent.get("source")
+            if traffic is not None and ent.get("points_per_launch"):   # the capture's slab width may differ from this run's
+                traffic = traffic * rows_per_launch / ent["points_per_launch"]
+                traffic_source = f"{traffic_source}; scaled from {ent['points_per_launch']} to {rows_per_launch:.0f} points per launch"
         except Exception:
             traffic = None
     roofline = {"bound": "tensor", "kernel": "gemm_kernel_mb<kc,kc,scale> (weighted SYRK B += K diag(h) K^T, DMMA m8n8k4)",

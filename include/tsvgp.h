@@ -59,7 +59,7 @@ TSVGP_API const char* tsvgp_last_error(const tsvgp_ctx* ctx);        /* ctx may 
 TSVGP_API int tsvgp_last_info(const tsvgp_ctx* ctx);                 /* failing pivot of the last TSVGP_ERR_NOT_POSITIVE_DEFINITE   */
 TSVGP_API int tsvgp_set_option(tsvgp_ctx* ctx, const char* name, double value);   /* see below */
 
-/* options: "chunk" (points per Kuf slab; 0 = automatic = 8192 points, i.e. Mp x 8192 x 8 B per slab stream — 134 MB at M = 2048,
+/* options: "chunk" (points per Kuf slab; 0 = automatic = 16384 points, i.e. Mp x 16384 x 8 B per slab stream — 268 MB at M = 2048,
  *          larger than the 126 MB L2: the slab is written once and re-read Mp/128 times through L2/HBM by compute-bound DMMA
  *          products, measured at ~4 % of the HBM roof), "streams" (1|2 ping-pong streams),
  * "cache_factors" (1 = keep chol(Kuu+jitter I) and the posterior factors while kernel, Z and sites are unchanged),

@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include <math.h>
 #include <map>
+#include <queue>
+#include <functional>
 #include <mutex>
 #include <type_traits>
 #include <utility>
@@ -548,21 +550,21 @@ int gemm_init() {
 // also pays `ovh` k-tiles of prologue / epilogue (pipeline fill, C tile read-modify-write).
 constexpr double DIAG_COST = 0.78;   // measured: one diagonal tile / one full tile of the same k (tools/gemm_bench)
 static double dispatch_makespan(int nt, int sms, int kt1, int kt2, double ovh) {
-    std::vector<double> free_at(sms, 0.0);
+    std::priority_queue<double, std::vector<double>, std::greater<double>> free_at;   // earliest-free SM first
+    for (int s = 0; s < sms; ++s) free_at.push(0.0);
+    double last = 0.0;
     auto run = [&](double kt) {
         for (int ti = 0; ti < nt; ++ti)
             for (int tj = 0; tj <= ti; ++tj) {
-                int best = 0;
-                for (int s = 1; s < sms; ++s)
-                    if (free_at[s] < free_at[best]) best = s;
-                free_at[best] += (tj == ti ? DIAG_COST : 1.0) * kt + ovh;
+                const double t = free_at.top() + (tj == ti ? DIAG_COST : 1.0) * kt + ovh;
+                free_at.pop();
+                free_at.push(t);
+                last = t > last ? t : last;
             }
     };
     run(kt1);
     if (kt2 > 0) run(kt2);
-    double m = 0.0;
-    for (double f : free_at) m = f > m ? f : m;
-    return m;
+    return last;
 }
 
 int balanced_ksplit(int tiles, int k) {

@@ -142,6 +142,8 @@ class t_SVGP:
     # ---- model objects -> device (re-read on every call: GPflow parameters are mutable) ---------------------------
     def _Z(self):
         iv = self.inducing_variable
+        if hasattr(iv, "inducing_variables"):   # SharedIndependentInducingVariables: one Z shared by the L latents (tsvgp.py:249-254)
+            iv = iv.inducing_variables[0]
         return _value(iv.Z if hasattr(iv, "Z") else iv)
 
     def _mean_fn(self, X):

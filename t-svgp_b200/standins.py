@@ -50,3 +50,11 @@ class InducingPoints:
     @property
     def num_inducing(self):
         return self.Z.shape[0]
+
+
+class SharedIndependentInducingVariables:
+    """gpflow.inducing_variables.SharedIndependentInducingVariables(InducingPoints(Z)): `.inducing_variables[0].Z` is what
+    the reference reads (src/models/tsvgp.py:249-254)."""
+
+    def __init__(self, inducing_variable):
+        self.inducing_variables = [inducing_variable]

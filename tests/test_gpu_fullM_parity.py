@@ -2,7 +2,7 @@
 GPU oracle parity at the inducing-point counts that are BENCHMARKED (VERDICT r01 "what's weak" #2): the reduced-M cases of
 tests/test_gpu_parity.py never run the 16/32/64-block Cholesky recursion, the split-K thresholds at large M, the two-piece balanced
 SYRK or several slabs per stream.  Here:
-  cfg3  M = 2048 (full), 40 960 rows = 5 slabs of 8192 over 2 streams  -> reference-order oracle, tolerance 1e-9
+  cfg3  M = 2048 (full), 40 960 rows = 4 slabs of 10 240 over 2 streams -> reference-order oracle, tolerance 1e-9
   cfg5  M = 4096 (full), 8 192 rows, Student-t GH-20                    -> reference-order oracle, tolerance 1e-9
   cfg4  M = 8192 (full), 16 384 rows -> tests/algo_model.py (8 M^3 instead of the oracle's 37 M^3; pinned to the oracle at
         M <= 1024 by tests/test_algebra_model.py on the CPU and by test_algo_model_is_the_oracle_at_m1024 below), tolerance 1e-9
@@ -18,7 +18,7 @@ from tests.test_gpu_parity import check, relerr, run_pair
 pytestmark = pytest.mark.gpu
 
 
-def test_cfg3_full_m2048_five_slabs():
+def test_cfg3_full_m2048_several_slabs_per_stream():
     import tsvgp_b200.synth as synth
     cfg = synth.describe("cfg3")
     check(run_pair(cfg, n_rows=40_960, M=2048, steps=2, num_data=409_600, Xtest_rows=1024))

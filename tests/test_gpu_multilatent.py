@@ -126,3 +126,23 @@ def test_softmax_monte_carlo_with_fixed_draws_matches_the_oracle():
     e_fixed = ref.elbo((X, labels))
     assert e1 != e2 and abs(e1 - e_fixed) < 0.05 * abs(e_fixed) and abs(e2 - e_fixed) < 0.05 * abs(e_fixed)
     dev.close()
+
+
+def test_shared_independent_inducing_variables_are_the_shared_Z():
+    # reference tsvgp.py:249-254 ("hack to get heterokedastic demo to run"): SharedIndependentInducingVariables wraps ONE InducingPoints
+    # object shared by all latents; on this path that is exactly num_latent_gps = L over a shared Z
+    import tsvgp_b200 as tb
+    from tsvgp_b200 import standins as st
+    rng = np.random.default_rng(2)
+    N, M, D, L = 500, 48, 2, 2
+    X = rng.standard_normal((N, D))
+    Z = X[:M].copy()
+    Y = np.stack([np.sin(X[:, 0]), np.cos(X[:, 1])], 1) + 0.1 * rng.standard_normal((N, L))
+    kernel, lik = orc.SquaredExponential(variance=1.0, lengthscales=0.9), orc.Gaussian(variance=0.1)
+    a = tb.t_SVGP(kernel, lik, Z.copy(), num_latent_gps=L)
+    b = tb.t_SVGP(kernel, lik, st.SharedIndependentInducingVariables(st.InducingPoints(Z.copy())), num_latent_gps=L)
+    for m in (a, b):
+        m.natgrad_step((X, Y), lr=0.8)
+    np.testing.assert_array_equal(a.lambda_1, b.lambda_1)
+    np.testing.assert_array_equal(a.lambda_2_sqrt, b.lambda_2_sqrt)
+    a.close(); b.close()
