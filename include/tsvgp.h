@@ -106,7 +106,8 @@ TSVGP_API int tsvgp_set_inducing(tsvgp_ctx* ctx, const double* Z, int M, int D, 
  * its own site pair, in ONE context — one Kuu / Kuu + jitter I chain and one Kuf slab per launch serve all of them; the variance
  * product, the weighted SYRK and the site update run per latent.  Layouts follow the reference: lambda_1 [M, L], lambda_2_sqrt
  * [L, M, M], Y [N, L] (independent likelihood terms, summed over the latent axis) or [N, 1] class labels (Softmax), predictive
- * moments [N, L].  Resets the sites and drops the resident data.  Not available for the whitened sibling.                       */
+ * moments [N, L].  Resets the sites and drops the resident data.  The whitened sibling (option "white") takes any L too — Lambda_2
+ * [L, M, M], tsvgp_white.py:79-89 — except with the Softmax likelihood.                                                          */
 TSVGP_API int tsvgp_set_num_latent(tsvgp_ctx* ctx, int L);
 TSVGP_API int tsvgp_num_latent(const tsvgp_ctx* ctx);
 /* TSVGP_LIK_SOFTMAX (gpflow.likelihoods.Softmax, docs/notebooks/mnist.py:117-122): set_likelihood with p0 = number of classes
@@ -149,14 +150,14 @@ TSVGP_API int tsvgp_prior_kl(tsvgp_ctx* ctx, double* out);
  * Gradients are w.r.t. the constrained (natural) parameter values; Zero mean function; D <= 63.                         */
 TSVGP_API int tsvgp_elbo_grad(tsvgp_ctx* ctx, double scale, double* elbo, double* d_variance, double* d_lengthscales,
                               double* d_Z, double* d_lik);
-/* base_SVGP.predict_f, full_cov = False (tsvgp.py:97-114): mean_out, var_out [N]                                        */
+/* base_SVGP.predict_f, full_cov = False (tsvgp.py:97-114): mean_out, var_out [N, L]                                     */
 TSVGP_API int tsvgp_predict_f(tsvgp_ctx* ctx, const double* Xnew, int64_t N, int D, const double* mean_X, double* mean_out, double* var_out);
 /* t_SVGP_white.predict_f_extra_data (tsvgp_white.py:134-158; whitened sibling only): predictions at Xnew after conditioning the
  * current sites on the RESIDENT minibatch (the "extra data") without changing them; jitter is the reference's argument
- * (default gpflow default_jitter = 1e-6; its test passes 0).                                                              */
+ * (default gpflow default_jitter = 1e-6; its test passes 0).  mean_out, var_out [N, L].                                   */
 TSVGP_API int tsvgp_predict_f_extra_data(tsvgp_ctx* ctx, const double* Xnew, int64_t N, int D, const double* mean_X, double jitter,
                                          double* mean_out, double* var_out);
-/* t_SVGP.get_mean_chol_cov_inducing_posterior (tsvgp.py:202-212): m [M], chol_S [M, M]                                  */
+/* t_SVGP.get_mean_chol_cov_inducing_posterior (tsvgp.py:202-212): m [M, L], chol_S [L, M, M]                           */
 TSVGP_API int tsvgp_posterior(tsvgp_ctx* ctx, double* m, double* chol_S);
 
 /* ---- multi-GPU: one context per rank, rows of the minibatch sharded over ranks, one all-reduce of the statistics ---- */

@@ -517,18 +517,22 @@ int ensure_posterior_white(tsvgp_ctx* c) {
         c->c6_valid = true;
     }
     if (c->wpost_valid && c->cache_factors) return TSVGP_OK;
-    // R = P + K6 + 1e-9 I -> Wm = LR, T = LR^-1     (util.py:74-76, jitter default 1e-9)
-    CU(cudaMemcpyAsync(c->Wm, c->K6, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, s));
-    LA(vadd_inplace_launch(c->Wm, c->L2, (long)n * ld, s));
-    LA(add_diag_launch(c->Wm, ld, n, 1e-9, s));
-    LA(chol_lower(c->Wm, ld, n, c->dinv, c->info + INFO_S, s, c->gws, c->gws_doubles, &c->la_main));
-    LA(trtri_lower(c->Wm, ld, n, c->dinv, c->T, c->tmp, s, c->gws, c->gws_doubles));
-    // alpha = R^-1 lambda_1 ; mZ = K alpha (predict_f(Z), un-jittered Kuf) ; m_q = K6 alpha
-    LA(gemv_n_launch(c->T, ld, n, n, c->lam1, 1.0, 0.0, c->v1, s));
-    LA(gemv_t_launch(c->T, ld, n, n, c->v1, c->alpha, c->gwork, s));
-    LA(gemv_n_launch(c->K, ld, n, n, c->alpha, 1.0, 0.0, c->mZ, s));
-    if (c->has_meanZ) LA(vadd_inplace_launch(c->mZ, c->meanZ_off, c->M, s));
-    LA(gemv_n_launch(c->K6, ld, n, n, c->alpha, 1.0, 0.0, c->mq, s));
+    for (int l = 0; l < c->L; ++l) {   // util.py:60-88 loops over the latents the same way
+        select_latent(c, l);
+        // R = P + K6 + 1e-9 I -> Wm = LR, T = LR^-1     (util.py:74-76, jitter default 1e-9)
+        CU(cudaMemcpyAsync(c->Wm, c->K6, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, s));
+        LA(vadd_inplace_launch(c->Wm, c->L2, (long)n * ld, s));
+        LA(add_diag_launch(c->Wm, ld, n, 1e-9, s));
+        LA(chol_lower(c->Wm, ld, n, c->dinv, c->info + INFO_S, s, c->gws, c->gws_doubles, &c->la_main));
+        LA(trtri_lower(c->Wm, ld, n, c->dinv, c->T, c->tmp, s, c->gws, c->gws_doubles));
+        // alpha = R^-1 lambda_1 ; mZ = K alpha (predict_f(Z), un-jittered Kuf) ; m_q = K6 alpha
+        LA(gemv_n_launch(c->T, ld, n, n, c->lam1, 1.0, 0.0, c->v1, s));
+        LA(gemv_t_launch(c->T, ld, n, n, c->v1, c->alpha, c->gwork, s));
+        LA(gemv_n_launch(c->K, ld, n, n, c->alpha, 1.0, 0.0, c->mZ, s));
+        if (c->has_meanZ) LA(vadd_inplace_launch(c->mZ, c->meanZ_off, c->M, s));
+        LA(gemv_n_launch(c->K6, ld, n, n, c->alpha, 1.0, 0.0, c->mq, s));
+    }
+    select_latent(c, 0);
     c->wpost_valid = true;
     c->wkl_valid = false;
     return TSVGP_OK;
@@ -541,32 +545,39 @@ int ensure_kl_terms_white(tsvgp_ctx* c) {
     cudaStream_t s = c->s_main;
     const int n = c->Mp;
     const long ld = n;
-    CU(cudaMemcpyAsync(c->Wf, c->K6, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, s));
-    LA(vadd_inplace_launch(c->Wf, c->L2, (long)n * ld, s));
-    LA(chol_lower(c->Wf, ld, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles, &c->la_main));
-    LA(trtri_lower(c->Wf, ld, n, c->dinv, c->V, c->tmp, s, c->gws, c->gws_doubles));       // V = LR0^-1
-    LA(logdiag_launch(c->Wf, ld, n, c->scal + SC_LOGDIAG_W, s));
-    LA(logdiag_launch(c->C6, ld, n, c->scal + SC_PK0, s));
-    {   // X1 = LR0^-1 LA  (lower x lower)
-        GemmP p;
-        p.A = c->V; p.lda = ld; p.a_kc = 1; p.a_tri = 1;
-        p.B = c->C6; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
-        p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
-        CU(cudaMemsetAsync(c->X1, 0, sizeof(double) * (size_t)n * ld, s));
-        p.lower_out = 1;
-        LA(mm_gemm(c, p, s));
+    for (int l = 0; l < c->L; ++l) {   // util.py:264-291 sums the latents' terms
+        select_latent(c, l);
+        CU(cudaMemcpyAsync(c->Wf, c->K6, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, s));
+        LA(vadd_inplace_launch(c->Wf, c->L2, (long)n * ld, s));
+        LA(chol_lower(c->Wf, ld, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles, &c->la_main));
+        LA(trtri_lower(c->Wf, ld, n, c->dinv, c->V, c->tmp, s, c->gws, c->gws_doubles));       // V = LR0^-1
+        LA(logdiag_launch(c->Wf, ld, n, c->scal + SC_LOGDIAG_W, s));
+        LA(logdiag_launch(c->C6, ld, n, c->scal + SC_PK0, s));
+        {   // X1 = LR0^-1 LA  (lower x lower)
+            GemmP p;
+            p.A = c->V; p.lda = ld; p.a_kc = 1; p.a_tri = 1;
+            p.B = c->C6; p.ldb = ld; p.b_kc = 0; p.b_tri = 2;
+            p.C = c->X1; p.ldc = ld; p.m = p.n = p.k = n;
+            CU(cudaMemsetAsync(c->X1, 0, sizeof(double) * (size_t)n * ld, s));
+            p.lower_out = 1;
+            LA(mm_gemm(c, p, s));
+        }
+        LA(matdot_launch(c->X1, c->X1, ld, n, c->scal + SC_TR_QK, c->red, s));
+        LA(gemv_n_launch(c->V, ld, n, n, c->lam1, 1.0, 0.0, c->v1, s));
+        LA(gemv_t_launch(c->V, ld, n, n, c->v1, c->v2, c->gwork, s));   // R0^-1 lambda_1
+        LA(gemv_t_launch(c->C6, ld, n, n, c->v2, c->v3, c->gwork, s));  // LA^T (.)
+        LA(dot_launch(c->v3, c->v3, n, c->scal + SC_M_ALPHA, s));
     }
-    LA(matdot_launch(c->X1, c->X1, ld, n, c->scal + SC_TR_QK, c->red, s));
-    LA(gemv_n_launch(c->V, ld, n, n, c->lam1, 1.0, 0.0, c->v1, s));
-    LA(gemv_t_launch(c->V, ld, n, n, c->v1, c->v2, c->gwork, s));   // R0^-1 lambda_1
-    LA(gemv_t_launch(c->C6, ld, n, n, c->v2, c->v3, c->gwork, s));  // LA^T (.)
-    LA(dot_launch(c->v3, c->v3, n, c->scal + SC_M_ALPHA, s));
+    select_latent(c, 0);
     c->wkl_valid = true;
     return TSVGP_OK;
 }
 
 double kl_white_from_scalars(const tsvgp_ctx* c, const double* sc) {
-    return 0.5 * (2.0 * (sc[SC_LOGDIAG_W] - sc[SC_PK0]) + sc[SC_TR_QK] - (double)c->Mp + sc[SC_M_ALPHA]);
+    double kl = 0.0;
+    for (int l = 0; l < c->L; ++l, sc += N_SCAL)
+        kl += 0.5 * (2.0 * (sc[SC_LOGDIAG_W] - sc[SC_PK0]) + sc[SC_TR_QK] - (double)c->Mp + sc[SC_M_ALPHA]);
+    return kl;
 }
 
 // tsvgp_white.py:215-246 after the statistics are complete in stats[0]
@@ -834,13 +845,15 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
                 p.epilogue = grad ? EPI_STORE_COLNORM : EPI_COLNORM; p.norm_out = c->q_part[b]; p.ldn = nc;
                 if (grad) { p.C = c->vslab[b]; p.ldc = nc; }   // the M-step also needs V = T^T K itself
                 LA(gemm_launch(p, s));
-            } else {           // (b') whitened sibling: |LA^-1 k_n|^2 and |LR^-1 k_n|^2, two lower-triangular products (util.py:78-85)
-                for (int which = 0; which < 2; ++which) {
+            } else {           // (b') whitened sibling: |LA^-1 k_n|^2 and |LR^-1 k_n|^2, two lower-triangular products (util.py:78-85).
+                // The first does not depend on the latent: it is formed once per slab, into the buffer shared by the latents
+                // (`q2_part`); the per-latent one goes to the latent's own `q_part`.
+                for (int which = l == l_lo ? 0 : 1; which < 2; ++which) {
                     GemmP p;
                     p.A = which == 0 ? c->C6inv : c->T; p.lda = Mp; p.a_kc = 1; p.a_tri = 1;
                     p.B = c->slab[b]; p.ldb = nc; p.b_kc = 0;
                     p.m = Mp; p.n = ncols; p.k = Mp;
-                    p.epilogue = EPI_COLNORM; p.norm_out = which == 0 ? c->q_part[b] : c->q2_part[b]; p.ldn = nc;
+                    p.epilogue = EPI_COLNORM; p.norm_out = which == 0 ? c->q2_part[b] : c->q_part[b]; p.ldn = nc;
                     LA(gemm_launch(p, s));
                 }
             }
@@ -848,8 +861,8 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
             if (!joint) {   // (c) marginals -> likelihood expectations and gradients, latent by latent (independent likelihood terms)
                 PointArgs a;
                 a.mu_part = c->mu_part[b]; a.n_mu_part = Mp / 64; a.ldmu = nc;
-                a.q_part = c->q_part[b]; a.n_q_part = Mp / 128; a.ldq = nc;
-                a.q2_part = c->white ? c->q2_part[b] : nullptr;
+                a.q_part = c->white ? c->q2_part[b] : c->q_part[b]; a.n_q_part = Mp / 128; a.ldq = nc;   // subtracted: |LA^-1 k|^2 (white) / |T^T k|^2
+                a.q2_part = c->white ? c->q_part[b] : nullptr;                                           // added:      |LR_l^-1 k|^2 (white)
                 a.y = y ? y + l * y_stride + n0 : nullptr;
                 a.mean_off = mean_off ? mean_off + n0 : nullptr;
                 a.kdiag = c->kern_var;
@@ -1149,7 +1162,7 @@ int dense_update(tsvgp_ctx* c, double lr, double jitter, double scale, bool only
         select_latent(c, l);
         OK(dense_update_one(c, lr, jitter, scale, only_G));
     }
-    if (c->L > 1 && !only_G) {
+    if (c->L > 1 && !only_G && !c->white) {   // (the whitened sibling's update has no factorisation and commits latent by latent)
         // commit AFTER every latent has factored its -2 Lambda_2 + jitter I: the reference raises before any assign (tsvgp.py:300-303),
         // so a failure in latent l must leave the latents before l untouched too (the guards read the shared device flags)
         const size_t mm = (size_t)c->Mp * c->Mp;
@@ -1648,8 +1661,10 @@ int tsvgp_get_lambda_2(tsvgp_ctx* c, double* lambda_2) {
     if (!c->sites_set) OK(default_sites(c));
     cudaStream_t s = c->s_main;
     const int n = c->Mp;
-    if (c->white) {   // the whitened sibling stores Lambda_2 itself
-        CU(cudaMemcpy2DAsync(lambda_2, sizeof(double) * c->M, c->L2, sizeof(double) * n, sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
+    if (c->white) {   // the whitened sibling stores Lambda_2 itself, [L, M, M]
+        for (int l = 0; l < c->L; ++l)
+            CU(cudaMemcpy2DAsync(lambda_2 + (size_t)l * c->M * c->M, sizeof(double) * c->M, c->L2_all + (size_t)l * n * n, sizeof(double) * n,
+                                 sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
         CU(cudaStreamSynchronize(s));
         return TSVGP_OK;
     }
@@ -1770,7 +1785,7 @@ static int require_model(tsvgp_ctx* c, bool need_data) {
     if (need_data && !c->X) FAIL(TSVGP_ERR_STATE, "no data resident (tsvgp_set_data)");
     if (c->lik.kind == LIK_SOFTMAX && (int)c->lik.p0 != c->L)
         FAIL(TSVGP_ERR_INVALID, "Softmax with %d classes needs num_latent_gps = %d (tsvgp_set_num_latent), not %d", (int)c->lik.p0, (int)c->lik.p0, c->L);
-    if (c->white && c->L != 1) FAIL(TSVGP_ERR_INVALID, "the whitened sibling model is built for num_latent_gps = 1");
+    if (c->white && c->lik.kind == LIK_SOFTMAX) FAIL(TSVGP_ERR_INVALID, "the whitened sibling model is not built for the Softmax likelihood");
     if (need_data && c->y_cols != ((c->L > 1 && c->lik.kind != LIK_SOFTMAX) ? c->L : 1))
         FAIL(TSVGP_ERR_STATE, "the resident Y has %d column(s): set the likelihood and num_latent_gps before the data", c->y_cols);
     return TSVGP_OK;
@@ -2118,39 +2133,45 @@ int tsvgp_predict_f_extra_data(tsvgp_ctx* c, const double* Xnew, int64_t N, int 
     OK(ensure_posterior(c));
     OK(choose_route(c, 1e-9));
     OK(data_pass(c, MODE_STATS));
-    OK(all_reduce(c, c->stats[0], mm + n + 4));
-    OK(dense_update(c, 1.0, 1e-9, 1.0, true));
-    LA(lincomb_launch(c->v1, 1.0, c->v2, -2.0, c->v3, n, s));          // g0 = G1 - 2 G2 mZ
+    select_latent(c, 0);
+    OK(all_reduce(c, c->stats_all[0], (size_t)c->L * (mm + n + 4)));
     {   // the reference calls predict_f on the extra data here (assert_positive, failed Cholesky raise): check before going on,
         // the nested predict_f below clears the flags
         double tail[4];
         int info_h[N_INFO];
-        CU(cudaMemcpyAsync(tail, c->stats[0] + mm + n, sizeof tail, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(info_h, c->info, sizeof info_h, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+        OK(read_tails(c, tail, nullptr, info_h));
         OK(check_info(c, info_h));
         if (tail[1] != 0.0) FAIL(TSVGP_ERR_NONPOSITIVE_VARIANCE, "predict_f_extra_data: non-positive predictive variance at the extra data");
     }
-    // (2) K_j = Kuu + jitter I ; combined sites lambda_1 + K_j g0, Lambda_2 - 2 K_j G2 K_j     (tsvgp_white.py:144-150)
-    CU(cudaMemcpyAsync(c->lam1_bak, c->lam1, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
-    CU(cudaMemcpyAsync(c->P, c->L2, sizeof(double) * mm, cudaMemcpyDeviceToDevice, s));
+    // (2) K_j = Kuu + jitter I ; combined sites lambda_1 + K_j g0, Lambda_2 - 2 K_j G2 K_j, latent by latent (tsvgp_white.py:144-150).
+    // The current sites of latent l wait in its own accumulator B_l / b_l, dead once G2_l and G1_l are formed.
     struct Restore {   // every exit path puts the sites, K6 and its jitter back
-        tsvgp_ctx* c; double jit_saved; int n; size_t mm; cudaStream_t s;
+        tsvgp_ctx* c; double jit_saved; int n; size_t mm; cudaStream_t s; int saved;
         ~Restore() {
-            cudaMemcpyAsync(c->lam1, c->lam1_bak, sizeof(double) * n, cudaMemcpyDeviceToDevice, s);
-            cudaMemcpyAsync(c->L2, c->P, sizeof(double) * mm, cudaMemcpyDeviceToDevice, s);
+            for (int l = 0; l < saved; ++l) {
+                const double* bak = c->stats_all[0] + (size_t)l * (mm + n + 4);
+                cudaMemcpyAsync(c->L2_all + (size_t)l * mm, bak, sizeof(double) * mm, cudaMemcpyDeviceToDevice, s);
+                cudaMemcpyAsync(c->lam1_all + (size_t)l * n, bak + mm, sizeof(double) * n, cudaMemcpyDeviceToDevice, s);
+            }
             c->jit6 = jit_saved;
             copy_add_diag_launch(c->K, c->K6, n, n, c->jit6, s);
             c->c6_valid = c->wpost_valid = c->wkl_valid = false;
             cudaStreamSynchronize(s);
+            select_latent(c, 0);
         }
-    } restore{c, c->jit6, n, mm, s};
+    } restore{c, c->jit6, n, mm, s, 0};
     c->jit6 = jitter;
-    LA(copy_add_diag_launch(c->K, c->K6, n, n, jitter, s));
+    LA(copy_add_diag_launch(c->K, c->K6, n, n, jitter, s));   // (the statistics below use chol(K + 1e-9 I) and m_Z only)
     c->c6_valid = c->wpost_valid = c->wkl_valid = false;
-    LA(gemv_n_launch(c->K6, ld, n, c->M, c->v1, 1.0, 0.0, c->mq, s));
-    LA(axpby_vec_guarded_launch(c->lam1, c->mq, c->M, 1.0, 1.0, nullptr, nullptr, s));
-    {
+    for (int l = 0; l < c->L; ++l) {
+        select_latent(c, l);
+        OK(dense_update_one(c, 1.0, 1e-9, 1.0, true, false));
+        LA(lincomb_launch(c->v1, 1.0, c->v2, -2.0, c->v3, n, s));          // g0 = G1 - 2 G2 mZ
+        CU(cudaMemcpyAsync(c->stats[0], c->L2, sizeof(double) * mm, cudaMemcpyDeviceToDevice, s));
+        CU(cudaMemcpyAsync(c->stats[0] + mm, c->lam1, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+        restore.saved = l + 1;
+        LA(gemv_n_launch(c->K6, ld, n, c->M, c->v1, 1.0, 0.0, c->mq, s));
+        LA(axpby_vec_guarded_launch(c->lam1, c->mq, c->M, 1.0, 1.0, nullptr, nullptr, s));
         GemmP p;
         p.A = c->K6; p.lda = ld; p.a_kc = 1;
         p.B = c->G2; p.ldb = ld; p.b_kc = 0;
@@ -2162,8 +2183,9 @@ int tsvgp_predict_f_extra_data(tsvgp_ctx* c, const double* Xnew, int64_t N, int 
         q.C = c->X2; q.ldc = ld; q.m = q.n = q.k = n; q.lower_out = 1;
         LA(mm_gemm(c, q, s));
         LA(mirror_lower_launch(c->X2, ld, n, s));
+        LA(axpby_guarded_launch(c->L2, c->X2, ld, c->M, 1.0, -2.0, nullptr, nullptr, s));
     }
-    LA(axpby_guarded_launch(c->L2, c->X2, ld, c->M, 1.0, -2.0, nullptr, nullptr, s));
+    select_latent(c, 0);
     // (3) the conditional at Xnew with the combined sites; `restore` puts everything back as it was
     return tsvgp_predict_f(c, Xnew, N, D, mean_X, mean_out, var_out);
 }
@@ -2181,20 +2203,23 @@ int tsvgp_posterior(tsvgp_ctx* c, double* m, double* chol_S) {
         for (int l = 0; l < c->L; ++l)
             CU(cudaMemcpy2DAsync(m + l, sizeof(double) * c->L, c->mq_all + (size_t)l * c->Mp, sizeof(double), sizeof(double), c->M,
                                  cudaMemcpyDefault, s));
-    if (chol_S && c->white) {   // S = (LR^-1 K6)^T (LR^-1 K6)   (util.py:421-424)
-        GemmP p;
-        p.A = c->T; p.lda = n; p.a_kc = 1; p.a_tri = 1;
-        p.B = c->K6; p.ldb = n; p.b_kc = 0;
-        p.C = c->X1; p.ldc = n; p.m = p.n = p.k = n;
-        LA(mm_gemm(c, p, s));
-        GemmP q;
-        q.A = c->X1; q.lda = n; q.a_kc = 0;
-        q.B = c->X1; q.ldb = n; q.b_kc = 0;
-        q.C = c->X2; q.ldc = n; q.m = q.n = q.k = n; q.lower_out = 1;
-        LA(mm_gemm(c, q, s));
-        c->wkl_valid = false;
-        LA(chol_lower(c->X2, n, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles, &c->la_main));
-        CU(cudaMemcpy2DAsync(chol_S, sizeof(double) * c->M, c->X2, sizeof(double) * n, sizeof(double) * c->M, c->M, cudaMemcpyDefault, s));
+    if (chol_S && c->white) {   // S_l = (LR_l^-1 K6)^T (LR_l^-1 K6)   (util.py:421-424), chol_S [L, M, M]
+        for (int l = 0; l < c->L; ++l) {
+            GemmP p;
+            p.A = c->T_all + (size_t)l * n * n; p.lda = n; p.a_kc = 1; p.a_tri = 1;
+            p.B = c->K6; p.ldb = n; p.b_kc = 0;
+            p.C = c->X1; p.ldc = n; p.m = p.n = p.k = n;
+            LA(mm_gemm(c, p, s));
+            GemmP q;
+            q.A = c->X1; q.lda = n; q.a_kc = 0;
+            q.B = c->X1; q.ldb = n; q.b_kc = 0;
+            q.C = c->X2; q.ldc = n; q.m = q.n = q.k = n; q.lower_out = 1;
+            LA(mm_gemm(c, q, s));
+            c->wkl_valid = false;
+            LA(chol_lower(c->X2, n, n, c->dinv, c->info + INFO_P, s, c->gws, c->gws_doubles, &c->la_main));
+            CU(cudaMemcpy2DAsync(chol_S + (size_t)l * c->M * c->M, sizeof(double) * c->M, c->X2, sizeof(double) * n, sizeof(double) * c->M, c->M,
+                                 cudaMemcpyDefault, s));
+        }
     } else if (chol_S) {   // S_l = K6 - (K6 T_l)(K6 T_l)^T   (util.py:387-388), chol_S [L, M, M]
         for (int l = 0; l < c->L; ++l) {
             GemmP p;

@@ -455,7 +455,8 @@ class t_SVGP_white(t_SVGP):
     (`lambda_2 [1, M, M]`, default 1e-10 I), updated without any factorisation:
         lambda_1 <- (1-lr) lambda_1 + lr s K (G1 - 2 G2 mZ) ;  Lambda_2 <- (1-lr) Lambda_2 - 2 lr s K G2 K.
     Same constructor / natgrad_step / elbo / predict_f / prior_kl / get_mean_chol_cov_inducing_posterior surface
-    (+ `predict_f_extra_data`; num_latent_gps = 1; `elbo_and_grad` is not built for this parameterisation)."""
+    (+ `predict_f_extra_data`; any num_latent_gps with Gaussian / Bernoulli / StudentT; `elbo_and_grad` is not built for this
+    parameterisation)."""
 
     def __init__(self, kernel, likelihood, inducing_variable, *, mean_function=None, num_latent_gps=1, lambda_1=None,
                  lambda_2=None, num_data=None, device=0):
@@ -463,25 +464,22 @@ class t_SVGP_white(t_SVGP):
             lambda_2 = np.asarray(lambda_2, dtype=np.float64)
             assert lambda_2.ndim == 3  # tsvgp_white.py:87
             num_latent_gps = lambda_2.shape[0]
-        if num_latent_gps != 1:
-            raise NotImplementedError("t_SVGP_white with num_latent_gps > 1")
-        super().__init__(kernel, likelihood, inducing_variable, mean_function=mean_function, num_data=num_data, device=device)
+        if type(likelihood).__name__ == "Softmax":
+            raise NotImplementedError("t_SVGP_white with the Softmax likelihood")
+        super().__init__(kernel, likelihood, inducing_variable, mean_function=mean_function, num_latent_gps=num_latent_gps,
+                         num_data=num_data, device=device)
         self.name = "t_svgp_white"
         self.set_option("white", 1)
         if lambda_1 is not None or lambda_2 is not None:
-            self.assign_sites(lambda_1, None if lambda_2 is None else lambda_2[0])
+            self.assign_sites(lambda_1, lambda_2)
 
     @property
     def lambda_2_sqrt(self):
         raise AttributeError("t_SVGP_white stores lambda_2 itself (src/models/tsvgp_white.py:91-97)")
 
     def assign_sites(self, lambda_1=None, lambda_2=None):
-        l1 = l2 = None
-        if lambda_1 is not None:
-            l1 = np.ascontiguousarray(np.asarray(lambda_1, dtype=np.float64).reshape(-1))
-        if lambda_2 is not None:
-            l2 = np.ascontiguousarray(np.asarray(lambda_2, dtype=np.float64).reshape(-1, self._M, self._M)[0])
-        self._check(self._lib.tsvgp_set_sites(self._ctx, None if l1 is None else l1.ctypes.data, None if l2 is None else l2.ctypes.data))
+        """`lambda_1 [M, L]`, `lambda_2 [L, M, M]` (full symmetric matrices, tsvgp_white.py:79-89)."""
+        super().assign_sites(lambda_1, lambda_2)
 
     def elbo_and_grad(self, data=None, *, global_minibatch_size=None):
         raise NotImplementedError("elbo_and_grad for t_SVGP_white")
@@ -500,7 +498,7 @@ class t_SVGP_white(t_SVGP):
         N, D = tx.shape
         if self._mean_fn(np.zeros((1, D))) is not None:
             raise NotImplementedError("predict_f_extra_data with a non-zero mean_function")
-        mean, var = np.empty((N, 1)), np.empty((N, 1))
+        mean, var = np.empty((N, self.num_latent_gps)), np.empty((N, self.num_latent_gps))
         self._check(self._lib.tsvgp_predict_f_extra_data(self._ctx, tx.ptr, N, D, None, float(jitter), mean.ctypes.data, var.ctypes.data))
         return mean, var
 

@@ -114,3 +114,55 @@ def test_predict_f_extra_data(jitter):
     mu0_r, var0_r = ref.predict_f(X[:300] + 0.1)
     assert relerr(mu0_d, mu0_r) < 1e-9 and relerr(var0_d, var0_r) < 1e-9
     dev.close()
+
+
+@pytest.mark.parametrize("lik_name,L,M", [("gaussian", 3, 200), ("bernoulli", 2, 130)])
+def test_white_model_with_several_latents(lik_name, L, M):
+    # tsvgp_white.py:79-89 builds one Lambda_2 per latent, util.py:60-88 / :264-291 / :411-426 loop over them and the update
+    # (:240-246) broadcasts K_uu over the latent axis: L sets of sites in ONE context, one Kuf slab and one |LA^-1 k|^2 pass for all
+    import tsvgp_b200 as tb
+    import tsvgp_b200.synth as synth
+    rng = np.random.default_rng(11)
+    n = 1500
+    cfg = synth.describe("cfg3" if lik_name == "gaussian" else "cfg2")      # inputs with cond(Kuu) ~ 1e3, as in the L = 1 cases above
+    X, _, Z = synth.make_minibatch(cfg, n_rows=n, M=M)
+    kernel, lik = synth.build_objects(cfg, orc)
+    F = np.stack([np.sin(X @ rng.standard_normal(X.shape[1])) for _ in range(L)], 1)
+    Y = F + 0.3 * rng.standard_normal((n, L)) if lik_name == "gaussian" else (F + 0.3 * rng.standard_normal((n, L)) > 0).astype(float)
+    ref = orc.OracleTSVGPWhite(kernel, lik, orc.InducingPoints(Z.copy()), num_latent_gps=L, num_data=4 * n)
+    dev = tb.t_SVGP_white(kernel, lik, Z.copy(), num_latent_gps=L, num_data=4 * n)
+    dev.set_option("chunk", 512)                     # several slabs per stream
+    errs = {}
+    for s in range(2):
+        e_ref = ref.elbo((X, Y))
+        e_dev = dev.natgrad_step((X, Y), lr=0.5, return_elbo=True)
+        ref.natgrad_step((X, Y), lr=0.5)
+        errs[f"elbo_before{s}"] = abs(e_dev - e_ref) / abs(e_ref)
+        errs[f"lambda_1_{s}"] = relerr(dev.lambda_1, ref.lambda_1)
+        errs[f"lambda_2_{s}"] = relerr(dev.lambda_2, ref.lambda_2)
+    assert dev.lambda_1.shape == (M, L) and dev.lambda_2.shape == (L, M, M)
+    mu_d, var_d = dev.predict_f(X[:200] + 0.05)
+    mu_r, var_r = ref.predict_f(X[:200] + 0.05)
+    assert mu_d.shape == (200, L)
+    errs["mean"], errs["var"] = relerr(mu_d, mu_r), relerr(var_d, var_r)
+    errs["prior_kl"] = abs(dev.prior_kl() - ref.prior_kl()) / abs(ref.prior_kl())
+    m_d, cs_d = dev.get_mean_chol_cov_inducing_posterior()
+    m_r, cs_r = ref.get_mean_chol_cov_inducing_posterior()
+    errs["m_q"] = relerr(m_d, m_r)
+    errs["S_q"] = max(relerr(cs_d[l] @ cs_d[l].T, cs_r[l] @ cs_r[l].T) for l in range(L))
+    # conditioning on extra data, latent by latent, leaves every latent's sites as they were
+    l1, l2 = dev.lambda_1, dev.lambda_2
+    Xe, Ye = X[:600] * 0.9 + 0.1, Y[:600]
+    mu_r, var_r = ref.predict_f_extra_data(X[:100] + 0.1, (Xe, Ye))
+    mu_d, var_d = dev.predict_f_extra_data(X[:100] + 0.1, (Xe, Ye))
+    errs["extra_mean"], errs["extra_var"] = relerr(mu_d, mu_r), relerr(var_d, var_r)
+    np.testing.assert_array_equal(dev.lambda_1, l1)
+    np.testing.assert_array_equal(dev.lambda_2, l2)
+    # assigned sites round-trip in the reference's layouts
+    ref2 = orc.OracleTSVGPWhite(kernel, lik, orc.InducingPoints(Z.copy()), lambda_1=l1, lambda_2=l2)
+    dev2 = tb.t_SVGP_white(kernel, lik, Z.copy(), lambda_1=l1, lambda_2=l2)
+    assert dev2.num_latent_gps == L
+    errs["elbo_assigned"] = abs(dev2.elbo((X, Y)) - ref2.elbo((X, Y))) / abs(ref2.elbo((X, Y)))
+    bad = {k: v for k, v in errs.items() if not v <= 1e-9}
+    assert not bad, (bad, errs)
+    dev.close(); dev2.close()

@@ -60,6 +60,10 @@ w = tb.t_SVGP_white(st.SquaredExponential(variance=1.0, lengthscales=1.3), st.Ga
 w.natgrad_step((X, Y), lr=0.7)
 print("white", w.elbo((X, Y)), w.predict_f_extra_data(X[:9], (X[100:300], Y[100:300]))[0].shape)
 w.close()
+w = tb.t_SVGP_white(st.SquaredExponential(variance=1.0, lengthscales=1.3), st.Gaussian(variance=0.2), Z, num_latent_gps=2)
+w.natgrad_step((X, np.hstack([Y, -Y])), lr=0.7)
+print("white L=2", w.elbo(), w.predict_f_extra_data(X[:9], (X[100:300], np.hstack([Y, -Y])[100:300]))[0].shape, w.lambda_2.shape)
+w.close()
 s = tb.t_SVGP(st.SquaredExponential(variance=1.0, lengthscales=1.3), st.StudentT(scale=0.3, df=3.0), Z, num_data=9000)
 s.natgrad_step((X, Y), lr=0.3)
 print("student-t", s.elbo((X, Y)))
