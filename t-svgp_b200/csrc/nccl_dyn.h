@@ -10,7 +10,7 @@ namespace tsvgp {
 
 struct NcclUniqueId { char internal[128]; };
 typedef struct ncclComm* NcclComm;
-enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0 };   // ncclDouble / ncclSum in nccl.h (stable since NCCL 2.0)
+enum { NCCL_INT32 = 2, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };   // ncclInt / ncclDouble / ncclSum in nccl.h (stable since NCCL 2.0)
 
 struct NcclApi {
     void* handle = nullptr;
@@ -20,7 +20,12 @@ struct NcclApi {
     int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*ReduceScatter)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;   // recvcount per rank
     int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;            // sendcount per rank
+    int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;   // buf, count, type, peer
+    int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
+    bool p2p() const { return Send && Recv && GroupStart && GroupEnd; }
     bool ok() const { return handle && GetUniqueId && CommInitRank && CommDestroy && AllReduce; }
 };
 
@@ -39,6 +44,10 @@ inline NcclApi& nccl_api() {
     api.AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
     api.ReduceScatter = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(api.handle, "ncclReduceScatter");
     api.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(api.handle, "ncclAllGather");
+    api.Send = (int (*)(const void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(api.handle, "ncclSend");
+    api.Recv = (int (*)(void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(api.handle, "ncclRecv");
+    api.GroupStart = (int (*)())dlsym(api.handle, "ncclGroupStart");
+    api.GroupEnd = (int (*)())dlsym(api.handle, "ncclGroupEnd");
     api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
     return api;
 }

@@ -82,6 +82,7 @@ struct tsvgp_ctx {
     int n_streams = 2;
     int dist_min_m = 4096;     // distribute the dense M x M products over the ranks from this (padded) M upwards
     int shard_min_m = 2048;    // from this (padded) M upwards the statistics are reduce-SCATTERED by tile rows and the two products of
+    int split_chains = 0;      // 1: even ranks build the posterior factors, odd ranks the K9 chain; the results are exchanged pairwise (see chain_split_active)
                                // G2 = K9^-1 B K9^-1 run on each rank's rows only, assembled by two all-gathers (sharded_update)
     int async_issue = 1;       // small M: enqueue the K9 chain from a helper host thread while this thread enqueues the posterior chain
     int fuse_b = 1;            // accumulate b += Kuf g inside the SYRK kernel instead of a separate mat-vec pass over the slab
@@ -1234,6 +1235,96 @@ int sharded_reduce_and_form_G(tsvgp_ctx* c) {
     return TSVGP_OK;
 }
 
+// Two ranks, two chains [r02].  The prepare phase of a step whose kernel matrix changed is two independent latency-bound chains:
+// the posterior factors of the sites (T, alpha, m_Z) and the chain of K9 = Kuu + jitter I (C9^-1, K9^-1, conditioning probe).  Every
+// rank used to run both, side by side (3.4 ms at M = 2048 where either alone takes 2.6 / 2.0 ms).  With an even number of ranks the
+// ranks of a pair (2k, 2k + 1) split them: the even rank builds the posterior factors, the odd one the K9 chain, and each SENDS its
+// result to the other (ncclSend / ncclRecv, copies: every rank ends with the same bits as before).  The K9 results travel on the side
+// stream (on the even rank the "K9 chain" is just a receive) and are joined after the pass like the chain itself; the posterior
+// factors travel on the main stream in front of the pass.  Used when the K9 chain is joined AFTER the pass anyway (fused route forced
+// or speculated) and the dense products are replicated (below dist_min_m; above, the chains' products are themselves collective).
+// MEASURED (2 x B200, cfg3, ms per step): with the early slabs (default) 135.8 split / 135.4 side by side — the chain that is left
+// alone on a GPU is slowed by the early slabs' 2 ms DMMA tiles just as it was by the other chain; without early slabs 135.45 split
+// (prepare 2.45) / 135.95 side by side (prepare 2.90).  The two ways of filling the prepare phase do not add up, so the option is OFF
+// by default and kept for A/B.
+bool chain_split_active(const tsvgp_ctx* c) {
+    return c->split_chains && c->world > 1 && c->world % 2 == 0 && c->L == 1 && !c->white && c->Mp >= c->shard_min_m && !dist_active(c) &&
+           nccl_api().p2p();
+}
+
+int nccl_chk(tsvgp_ctx* c, int r, const char* what) {
+    NcclApi& api = nccl_api();
+    if (r != 0) FAIL(TSVGP_ERR_COMM, "%s: %s", what, api.GetErrorString ? api.GetErrorString(r) : "error");
+    return TSVGP_OK;
+}
+
+// K9 results of the pair's odd rank -> even rank, on the side stream (odd: behind its chain; even: in place of the chain)
+int exchange_k9(tsvgp_ctx* c, double jitter) {
+    NcclApi& api = nccl_api();
+    cudaStream_t s = c->s_side;
+    const size_t mm = (size_t)c->Mp * c->Mp;
+    const int peer = c->rank ^ 1;
+    const bool recv = c->rank % 2 == 0;
+    if (recv) OK(k9_fork(c));
+    OK(nccl_chk(c, api.GroupStart(), "ncclGroupStart"));
+    int r = 0;
+    if (recv) {
+        r |= api.Recv(c->C9inv, mm, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Recv(c->K9inv, mm, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Recv(c->scal2, N_SCAL, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Recv(c->info + INFO_K9, 1, NCCL_INT32, peer, c->comm, s);
+    } else {
+        r |= api.Send(c->C9inv, mm, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Send(c->K9inv, mm, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Send(c->scal2, N_SCAL, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Send(c->info + INFO_K9, 1, NCCL_INT32, peer, c->comm, s);
+    }
+    const int rg = api.GroupEnd();
+    OK(nccl_chk(c, r ? r : rg, "ncclSend / ncclRecv (K9 chain)"));
+    if (recv) {   // the state the chain would have left
+        c->k9_valid = true; c->k9_jitter = jitter; c->k9inv_valid = true;
+        c->cond_est = 0.0;
+        c->k9_pending = true;
+    }
+    CU(cudaEventRecord(c->ev_side, s));   // (re-recorded on the odd rank: the join after the pass also covers its send)
+    return TSVGP_OK;
+}
+
+// posterior factors of the pair's even rank -> odd rank, on the main stream in front of the pass
+int exchange_posterior(tsvgp_ctx* c, bool with_kl) {
+    NcclApi& api = nccl_api();
+    cudaStream_t s = c->s_main;
+    const size_t mm = (size_t)c->Mp * c->Mp, mp = c->Mp;
+    const int peer = c->rank ^ 1;
+    const bool recv = c->rank % 2 == 1;
+    CU(cudaStreamWaitEvent(s, c->ev_side, 0));   // one exchange at a time on the communicator: behind the K9 one (which is ready first)
+    OK(nccl_chk(c, api.GroupStart(), "ncclGroupStart"));
+    int r = 0;
+    if (recv) {
+        r |= api.Recv(c->T, mm, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Recv(c->alpha, mp, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Recv(c->mZ, mp, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Recv(c->mq, mp, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Recv(c->scal, N_SCAL, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Recv(c->info + INFO_W, 1, NCCL_INT32, peer, c->comm, s);
+    } else {
+        r |= api.Send(c->T, mm, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Send(c->alpha, mp, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Send(c->mZ, mp, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Send(c->mq, mp, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Send(c->scal, N_SCAL, NCCL_FLOAT64, peer, c->comm, s);
+        r |= api.Send(c->info + INFO_W, 1, NCCL_INT32, peer, c->comm, s);
+    }
+    const int rg = api.GroupEnd();
+    OK(nccl_chk(c, r ? r : rg, "ncclSend / ncclRecv (posterior factors)"));
+    if (recv) {
+        c->post_valid = true;
+        c->post_collective = false;
+        c->kl_valid = with_kl;
+    }
+    return TSVGP_OK;
+}
+
 int dense_update_one(tsvgp_ctx* c, double lr, double jitter, double scale, bool only_G, bool G_ready) {
     cudaStream_t s = c->s_main;
     const int n = c->Mp;
@@ -1497,6 +1588,7 @@ int tsvgp_set_option(tsvgp_ctx* c, const char* name, double value) {
     }
     if (!strcmp(name, "dist_min_m")) { c->dist_min_m = (int)value; return TSVGP_OK; }
     if (!strcmp(name, "shard_min_m")) { c->shard_min_m = (int)value; return TSVGP_OK; }
+    if (!strcmp(name, "split_chains")) { c->split_chains = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "async_issue")) { c->async_issue = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "fuse_b")) { c->fuse_b = value != 0.0; return TSVGP_OK; }
     if (!strcmp(name, "spread_b")) { c->spread_b = value != 0.0; return TSVGP_OK; }
@@ -1803,6 +1895,7 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
     c->collective_ok = true;
     OK(ensure_xs(c));
     OK(ensure_kuu(c));
+    int chain_role = 0;   // 0: both chains here; 1 / 2: this rank built the posterior factors / the K9 chain and received the other
     {
         SideIssue side;
         struct PdlGuard { ~PdlGuard() { g_pdl_suspended = 0; } } pdl_guard;
@@ -1820,15 +1913,21 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
         // ... and when does it start?  Side by side with the posterior chain the two latency-bound chains slow each other down
         // (measured at M = 2048: posterior chain 2.6 ms alone, 3.4 ms beside the K9 chain, programmatic launch suspended).  When the
         // chain is only needed after the pass it therefore starts once the posterior chain is complete and runs under the pass.
-        const bool defer_k9 = k9_runs && !join_before && c->k9_defer && c->Mp >= 2048;
-        if (c->Mp >= 2048 && k9_runs && !defer_k9) g_pdl_suspended = 1;   // two concurrent chains of large kernels: see common.cuh
-        if (!defer_k9) rc = start_k9_async(c, jitter, side);
+        // several ranks: the two chains are split over the ranks of a pair and exchanged (chain_split_active)
+        const bool split = k9_runs && !join_before && c->sites_set && chain_split_active(c);
+        const bool k9_here = !split || c->rank % 2 == 1, post_here = !split || c->rank % 2 == 0;
+        chain_role = split ? 1 + c->rank % 2 : 0;
+        const bool defer_k9 = k9_runs && !join_before && c->k9_defer && c->Mp >= 2048 && !split;
+        if (c->Mp >= 2048 && k9_runs && !defer_k9 && !split) g_pdl_suspended = 1;   // two concurrent chains of large kernels: see common.cuh
+        if (!defer_k9 && k9_here) rc = start_k9_async(c, jitter, side);
+        if (rc == TSVGP_OK && split) rc = exchange_k9(c, jitter);
         if (rc == TSVGP_OK && !k9_runs) rc = choose_route(c, jitter);   // cached factors: the route is known at once
         c->n_early = 0;
         const bool early = rc == TSVGP_OK && c->early_slabs && (!k9_runs || !join_before) && c->route == ROUTE_FUSED;
         if (early) rc = data_pass(c, MODE_STATS, PASS_EARLY);
-        if (rc == TSVGP_OK) rc = ensure_posterior(c);
-        if (rc == TSVGP_OK && elbo_before) rc = ensure_kl_terms(c);
+        if (rc == TSVGP_OK && post_here) rc = ensure_posterior(c);
+        if (rc == TSVGP_OK && post_here && elbo_before) rc = ensure_kl_terms(c);
+        if (rc == TSVGP_OK && split) rc = exchange_posterior(c, elbo_before != nullptr);
         if (rc == TSVGP_OK && defer_k9) rc = start_k9(c, jitter);   // forks from the main stream HERE: behind the posterior chain
         side.join_into(g_launches);
         if (rc != TSVGP_OK) return rc;
@@ -1878,6 +1977,7 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
     c->timings[6] = (double)(g_launches - launches0);
     c->timings[7] = (double)c->route;
     c->timings[8] = c->cond_est;
+    c->timings[9] = (double)chain_role;
     OK(check_info(c, info_h));
     if (tail[1] != 0.0) {
         c->post_valid = c->kl_valid = c->wpost_valid = c->wkl_valid = false;

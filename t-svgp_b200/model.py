@@ -417,9 +417,9 @@ class t_SVGP:
 
     def timings(self):
         """CUDA-event milliseconds of the last natgrad_step (see tsvgp_get_timings)."""
-        buf = (C.c_double * 9)()
-        self._check(self._lib.tsvgp_get_timings(self._ctx, buf, 9))
-        keys = ["total", "prepare", "stream", "allreduce", "dense", "slabs", "launches", "route", "cond_est"]
+        buf = (C.c_double * 10)()
+        self._check(self._lib.tsvgp_get_timings(self._ctx, buf, 10))
+        keys = ["total", "prepare", "stream", "allreduce", "dense", "slabs", "launches", "route", "cond_est", "chain_role"]
         return {k: buf[i] for i, k in enumerate(keys)}
 
     def kernel_profile(self):
