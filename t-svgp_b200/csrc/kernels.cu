@@ -1216,7 +1216,7 @@ __global__ void __launch_bounds__(256) diag_potrf_inv_lookahead_kernel(double* A
 int diag_read_stamps(long long* out32) { return (int)cudaMemcpyFromSymbol(out32, g_diag_clk, sizeof(long long) * 32); }
 #endif
 static int g_diag_fast = 1;      // 1 = pipelined pivot chain with the bare Newton rsqrt (TSVGP_DIAG_FAST=0: the round-1 loop, A/B timing)
-static int g_diag_variant = 1;   // 1 = blocked (DMMA) kernel, 2 = the same with look-ahead, 0 = per-pivot register kernel (A/B timing: tools/diag_bench)
+static int g_diag_variant = 2;   // 2 = blocked (DMMA) kernel with look-ahead (36.9 us per block), 1 = without (38.9 us), 0 = per-pivot register kernel (A/B timing: tools/diag_bench, TSVGP_DIAG_VARIANT)
 void diag_set_variant(int v) { g_diag_variant = v; }
 void diag_set_fast(int f) { g_diag_fast = f; }
 constexpr int DIAG_BLOCKED_SMEM = 2 * (QNB * (QNB + 1) / 2) * QBLK * 8;
