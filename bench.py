@@ -75,6 +75,7 @@ def parse():
     ap.add_argument("--no-grad", action="store_true", help="skip the (reported, untimed-in-the-metric) M-step gradient measurement")
     ap.add_argument("--keep-cache", action="store_true", help="do not invalidate the kernel-matrix factors every step")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (tsvgp_set_option), repeatable")
+    ap.add_argument("--no-balance", action="store_true", help="several GPUs: equal row shares and both preparation chains on every rank")
     return ap.parse_args()
 
 
@@ -329,16 +330,23 @@ class Ranks:
             self.dist.destroy_process_group()
 
 
-def build_model(tb, st, synth, rk, cfg, M, Nb, opts=()):
-    """The rank's model, its rows of N_RESIDENT_MINIBATCHES synthetic minibatches (host), the row range."""
-    kernel, lik = synth.build_objects(cfg, st)
-    lo, hi = tb.shard_rows(Nb, rk.world, rk.rank)
+def host_minibatches(tb, synth, rk, cfg, M, Nb, weights=None):
+    """This rank's rows [lo, hi) of N_RESIDENT_MINIBATCHES synthetic minibatches (host) and the inducing inputs: the same seeds on
+    every rank, so the minibatch does not depend on how it is sharded."""
+    lo, hi = tb.shard_rows(Nb, rk.world, rk.rank, weights)
     mbs_host, Z = [], None
-    for i in range(N_RESIDENT_MINIBATCHES):   # same seeds on every rank; each rank keeps its rows
+    for i in range(N_RESIDENT_MINIBATCHES):
         X, Y, Zi = synth.make_minibatch(cfg, n_rows=Nb, M=M, seed_offset=100 * i)
         Z = Zi if Z is None else Z
         mbs_host.append((np.ascontiguousarray(X[lo:hi]), np.ascontiguousarray(Y[lo:hi])))
         del X, Y
+    return mbs_host, Z, hi - lo
+
+
+def build_model(tb, st, synth, rk, cfg, M, Nb, opts=()):
+    """The rank's model, its rows of N_RESIDENT_MINIBATCHES synthetic minibatches (host), the row count."""
+    kernel, lik = synth.build_objects(cfg, st)
+    mbs_host, Z, n_local = host_minibatches(tb, synth, rk, cfg, M, Nb)
     model = tb.t_SVGP(kernel, lik, Z, num_data=cfg["N"], device=rk.local_rank)
     for kv in opts:
         k, v = kv.split("=")
@@ -346,7 +354,36 @@ def build_model(tb, st, synth, rk, cfg, M, Nb, opts=()):
     if rk.world > 1:
         uid = rk.bcast_bytes(tb.comm_unique_id() if rk.rank == 0 else b"", 128)
         model.init_comm(rk.world, rk.rank, uid)
-    return model, mbs_host, hi - lo
+    return model, mbs_host, n_local
+
+
+def balance_rows(tb, synth, rk, model, cfg, M, Nb, mbs_dev, invalidate, cal_steps=5):
+    """Several ranks with option "split_chains": the ranks do different things in front of the pass, so equal row shares
+    leave rank 0 the straggler.  A few untimed calibration steps with equal shares measure every rank's prepare
+    and stream phases; tsvgp_b200.balance_weights turns them into row shares that equalise the finish times, the rank's rows are
+    cut again from the SAME minibatches, and the sites are reset so that the steps that follow start where a run without
+    calibration starts (the `check` object stays comparable across N).  Returns (shares, host minibatches, rows, table) or None when the
+    library did not split the chains (M above dist_min_m, another route, ...)."""
+    prep = stream = 0.0
+    role = 0.0
+    for i in range(cal_steps):
+        if invalidate:
+            model.set_option("invalidate", 1)
+        model.set_data(mbs_dev[i % N_RESIDENT_MINIBATCHES])
+        model.natgrad_step(lr=cfg["lr"], global_minibatch_size=Nb)
+        tm = model.timings()
+        if i >= cal_steps - 3:
+            prep += tm["prepare"] / 3
+            stream += tm["stream"] / 3
+            role = tm["chain_role"]
+    n_local = mbs_dev[0][0].shape[0]
+    table = rk.gather_rows(np.array([prep, stream, float(n_local), role]))
+    model.assign_sites(None, None)          # back to the default sites
+    if not np.any(table[:, 3] != 0):
+        return None
+    w = tb.balance_weights(table[:, 0], table[:, 1], table[:, 2], table[:, 3])
+    mbs_host, _, n_new = host_minibatches(tb, synth, rk, cfg, M, Nb, w)
+    return [float(x) for x in w], mbs_host, n_new, [[round(float(v), 3) for v in row] for row in table]
 
 
 def result_check(model, rk, mb, lr, Nb):
@@ -408,9 +445,20 @@ def main():
     import tsvgp_b200 as tb
     from tsvgp_b200 import standins as st
 
-    model, mbs_host, n_local = build_model(tb, st, synth, rk, cfg, M, Nb, args.opt)
+    opts = list(args.opt)
+    balance = world > 1 and not args.no_balance and not any(o.startswith("split_chains=") for o in opts)
+    if balance:
+        opts.append("split_chains=1")
+    model, mbs_host, n_local = build_model(tb, st, synth, rk, cfg, M, Nb, opts)
     mbs_dev = [(model.device_array(X), model.device_array(Y)) for X, Y in mbs_host]
     invalidate = not args.keep_cache
+    row_shares = cal_table = None
+    if balance:
+        got = balance_rows(tb, synth, rk, model, cfg, M, Nb, mbs_dev, invalidate)
+        if got is not None:
+            row_shares, mbs_host, n_local, cal_table = got
+            del mbs_dev
+            mbs_dev = [(model.device_array(X), model.device_array(Y)) for X, Y in mbs_host]
 
     # ---------- value: device-resident inputs ----------
     res = timed_steps(model, rk, mbs_dev, cfg["lr"], Nb, args.warmup, args.steps, invalidate)
@@ -514,6 +562,13 @@ def main():
         "dtype": "f64", "data": "synthetic", "config": workload_config(cfg, M, Nb, world), "clocks": clocks, "e2e": e2e,
         "gpu_launches": launches, "roofline": roofline, "check": check, "detail": extra,
     }
+    if row_shares is not None:
+        line["config"]["row_shares"] = row_shares
+        line["config"]["calibration"] = cal_table
+        line["config"]["parallelism"] += ("; option split_chains: rank 0 builds the posterior factors, rank 1 the Kuu + jitter I chain underneath "
+                                          "early slabs, the others only early slabs, results by ncclBroadcast; row shares from "
+                                          "tsvgp_b200.balance_weights after 5 untimed calibration steps with equal shares (sites reset afterwards); "
+                                          "calibration = per rank [prepare ms, stream ms, rows, role]")
     model.close()
     del mbs_dev, model
     default_run = args.config == "cfg3" and args.minibatch is None and args.M is None and not args.no_e2e

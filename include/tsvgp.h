@@ -74,10 +74,10 @@ TSVGP_API int tsvgp_set_option(tsvgp_ctx* ctx, const char* name, double value); 
  * "shard_min_m" (multi-GPU, fused route: from this padded M upwards (default 2048; needs (M/128) % ranks == 0) the statistics are
  *          reduce-scattered by tile rows, G2 = K9^-1 B K9^-1 is formed on each rank's rows and assembled by two all-gathers,
  *          instead of an all-reduce followed by the full products on every rank; a huge value switches it off),
- * "split_chains" (multi-GPU, even number of ranks, same size gate and below dist_min_m; default 0; 1: when the Kuu + jitter I chain
- *          is joined after the pass (fused route forced or speculated) the even rank of each pair (2k, 2k + 1) builds the posterior
- *          factors, the odd one the Kuu + jitter I chain, and each sends its result to the other (ncclSend / ncclRecv) — every
- *          rank holds the same bits as without the split; measured equal to the default schedule with early slabs),
+ * "split_chains" (multi-GPU, same size gate and below dist_min_m; default 0; 1: when the Kuu + jitter I chain is joined after the
+ *          pass (fused route forced or speculated) rank 0 builds the posterior factors, rank 1 the Kuu + jitter I chain, each
+ *          broadcasts its result (ncclBroadcast) — every rank holds the same bits as without the split — and every rank but 0
+ *          fills the wait with early slabs; pays off with row shares from tsvgp_b200.balance_weights),
  * "streams" up to 4, "balance" / "fuse_b" (0 switches the balanced SYRK split / the fused b += Kuf g off, for A/B timing),
  * "spread_b" (1 = the fused b += Kuf g is shared by all tiles of a SYRK tile row, each adding into a private slot; 0 (default) =
  *          carried by the first tile column alone — measured equal or faster inside a step),
@@ -178,7 +178,7 @@ TSVGP_API void* tsvgp_stream(const tsvgp_ctx* ctx);
  *  0 total, 1 prepare (posterior factors), 2 streaming pass, 3 all-reduce, 4 dense update, 5 number of slabs,
  *  6 kernels launched by the step, 7 route used (1 fused, 2 whitened, 3 exact), 8 estimated cond(Kuu + jitter I) (0 if not probed),
  *  9 chain split ("split_chains"): 0 = both preparation chains ran here, 1 / 2 = this rank built the posterior factors / the
- *    Kuu + jitter I chain and received the other from its pair rank                                                              */
+ *    Kuu + jitter I chain and received the other, 3 = it received both                                                           */
 TSVGP_API int tsvgp_get_timings(tsvgp_ctx* ctx, double* out, int n);
 TSVGP_API int tsvgp_sync(tsvgp_ctx* ctx);
 /* With option "profile" = 1 the streaming pass runs on one stream and brackets every kernel with CUDA events.  After a

@@ -20,12 +20,11 @@ struct NcclApi {
     int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*ReduceScatter)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;   // recvcount per rank
     int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;            // sendcount per rank
-    int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;   // buf, count, type, peer
-    int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;   // send, recv, count, type, root
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
-    bool p2p() const { return Send && Recv && GroupStart && GroupEnd; }
+    bool bcast() const { return Broadcast && GroupStart && GroupEnd; }
     bool ok() const { return handle && GetUniqueId && CommInitRank && CommDestroy && AllReduce; }
 };
 
@@ -44,8 +43,7 @@ inline NcclApi& nccl_api() {
     api.AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
     api.ReduceScatter = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(api.handle, "ncclReduceScatter");
     api.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(api.handle, "ncclAllGather");
-    api.Send = (int (*)(const void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(api.handle, "ncclSend");
-    api.Recv = (int (*)(void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(api.handle, "ncclRecv");
+    api.Broadcast = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(api.handle, "ncclBroadcast");
     api.GroupStart = (int (*)())dlsym(api.handle, "ncclGroupStart");
     api.GroupEnd = (int (*)())dlsym(api.handle, "ncclGroupEnd");
     api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");

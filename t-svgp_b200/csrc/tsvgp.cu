@@ -112,6 +112,10 @@ struct tsvgp_ctx {
     int early_slabs = 1;
     int n_early = 0;
     cudaEvent_t ev_post = nullptr;
+    cudaEvent_t ev_xpost = nullptr;   // posterior exchange of the chain split complete (main stream)
+    cudaEvent_t ev_early0 = nullptr;  // first early slab of slab stream 0 complete
+    cudaEvent_t ev_mid = nullptr;     // second slab of slab stream 0 complete (or the last one of a short pass)
+    bool mark_mid = false;            // stream_pass records ev_mid
     CholAux la_main, la_side;   // look-ahead helper streams of the Cholesky factorisations on the main / side stream (dense.cuh)
     // Entry points that every rank calls together (natgrad_step, elbo, elbo_grad, predict_f_extra_data) may distribute the dense
     // M x M products over the ranks; predict_f / prior_kl / posterior may be called by one rank alone and must not hide a collective.
@@ -809,6 +813,7 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
                           nc, nullptr, 0, 0, c->s_pp[ci], nullptr));
             bool fb;
             OK(syrk(ci, c->slab[ci], ncols, true, false, fb));
+            if (ci == 0) CU(cudaEventRecord(c->ev_early0, c->s_pp[0]));
         }
         c->n_early = ne;
         return TSVGP_OK;
@@ -950,6 +955,7 @@ int stream_pass(tsvgp_ctx* c, const double* XsT, long ldx, const double* x2, lon
                 LA(gemm_launch(p, s));
             }
         }
+        if (c->mark_mid && ci == (nstr < nchunks - 1 ? nstr : nchunks - 1)) CU(cudaEventRecord(c->ev_mid, s));
     }
     if (prof) {   // 7 events per slab: [start, kuf, var, point, whiten, syrk, gemv]
         CU(cudaStreamSynchronize(c->s_pp[0]));
@@ -1235,22 +1241,25 @@ int sharded_reduce_and_form_G(tsvgp_ctx* c) {
     return TSVGP_OK;
 }
 
-// Two ranks, two chains [r02].  The prepare phase of a step whose kernel matrix changed is two independent latency-bound chains:
-// the posterior factors of the sites (T, alpha, m_Z) and the chain of K9 = Kuu + jitter I (C9^-1, K9^-1, conditioning probe).  Every
-// rank used to run both, side by side (3.4 ms at M = 2048 where either alone takes 2.6 / 2.0 ms).  With an even number of ranks the
-// ranks of a pair (2k, 2k + 1) split them: the even rank builds the posterior factors, the odd one the K9 chain, and each SENDS its
-// result to the other (ncclSend / ncclRecv, copies: every rank ends with the same bits as before).  The K9 results travel on the side
-// stream (on the even rank the "K9 chain" is just a receive) and are joined after the pass like the chain itself; the posterior
-// factors travel on the main stream in front of the pass.  Used when the K9 chain is joined AFTER the pass anyway (fused route forced
-// or speculated) and the dense products are replicated (below dist_min_m; above, the chains' products are themselves collective).
-// MEASURED (2 x B200, cfg3, ms per step): with the early slabs (default) 135.8 split / 135.4 side by side — the chain that is left
-// alone on a GPU is slowed by the early slabs' 2 ms DMMA tiles just as it was by the other chain; without early slabs 135.45 split
-// (prepare 2.45) / 135.95 side by side (prepare 2.90).  The two ways of filling the prepare phase do not add up, so the option is OFF
-// by default and kept for A/B.
+// One rank per chain [r02].  The prepare phase of a step whose kernel matrix changed is two independent latency-bound chains: the
+// posterior factors of the sites (T, alpha, m_Z) and the chain of K9 = Kuu + jitter I (C9^-1, K9^-1, conditioning probe).  Every
+// rank used to run both, side by side.  With several ranks (option "split_chains") rank 0 builds the posterior factors, with its GPU
+// to itself, rank 1 the K9 chain, and each BROADCASTS its result (ncclBroadcast: copies, every rank ends with the same bits as
+// before); ranks 2.. build nothing.  The posterior factors travel on the main stream in front of the pass; the K9 results, which the
+// fused route needs only after the pass, travel second, on the side stream, and are joined after the pass like the chain itself.
+// Every rank but 0 fills the wait for the posterior factors with early slabs (posterior-independent Kuf + constant-weight SYRK):
+// they may slow rank 1's K9 chain down, which is off the critical path.  Rank 0 is then the straggler by its chain time unless it gets
+// fewer rows: tsvgp_b200.balance_weights (host) turns measured phase times into row shares.
+// Used when the K9 chain is joined AFTER the pass anyway (fused route forced or speculated) and the dense products are replicated
+// (below dist_min_m; above, the chains' products are themselves collective).
+// MEASURED (2 x B200, cfg3, ms per step), pairwise version of the same split with equal rows: 135.8 split / 135.4 side by side with
+// early slabs on both ranks; 135.45 / 135.95 without early slabs; with early slabs on the odd rank only and balanced rows 135.05.
+// OFF by default in the library (it needs the caller's cooperation for the row shares); bench.py switches it on for N > 1.
+enum { ROLE_BOTH = 0, ROLE_POSTERIOR = 1, ROLE_K9 = 2, ROLE_NONE = 3 };
 bool chain_split_active(const tsvgp_ctx* c) {
-    return c->split_chains && c->world > 1 && c->world % 2 == 0 && c->L == 1 && !c->white && c->Mp >= c->shard_min_m && !dist_active(c) &&
-           nccl_api().p2p();
+    return c->split_chains && c->world > 1 && c->L == 1 && !c->white && c->Mp >= c->shard_min_m && !dist_active(c) && nccl_api().bcast();
 }
+int chain_role_of(const tsvgp_ctx* c) { return c->rank == 0 ? ROLE_POSTERIOR : (c->rank == 1 ? ROLE_K9 : ROLE_NONE); }
 
 int nccl_chk(tsvgp_ctx* c, int r, const char* what) {
     NcclApi& api = nccl_api();
@@ -1258,70 +1267,55 @@ int nccl_chk(tsvgp_ctx* c, int r, const char* what) {
     return TSVGP_OK;
 }
 
-// K9 results of the pair's odd rank -> even rank, on the side stream (odd: behind its chain; even: in place of the chain)
-int exchange_k9(tsvgp_ctx* c, double jitter) {
-    NcclApi& api = nccl_api();
-    cudaStream_t s = c->s_side;
-    const size_t mm = (size_t)c->Mp * c->Mp;
-    const int peer = c->rank ^ 1;
-    const bool recv = c->rank % 2 == 0;
-    if (recv) OK(k9_fork(c));
-    OK(nccl_chk(c, api.GroupStart(), "ncclGroupStart"));
-    int r = 0;
-    if (recv) {
-        r |= api.Recv(c->C9inv, mm, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Recv(c->K9inv, mm, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Recv(c->scal2, N_SCAL, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Recv(c->info + INFO_K9, 1, NCCL_INT32, peer, c->comm, s);
-    } else {
-        r |= api.Send(c->C9inv, mm, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Send(c->K9inv, mm, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Send(c->scal2, N_SCAL, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Send(c->info + INFO_K9, 1, NCCL_INT32, peer, c->comm, s);
-    }
-    const int rg = api.GroupEnd();
-    OK(nccl_chk(c, r ? r : rg, "ncclSend / ncclRecv (K9 chain)"));
-    if (recv) {   // the state the chain would have left
-        c->k9_valid = true; c->k9_jitter = jitter; c->k9inv_valid = true;
-        c->cond_est = 0.0;
-        c->k9_pending = true;
-    }
-    CU(cudaEventRecord(c->ev_side, s));   // (re-recorded on the odd rank: the join after the pass also covers its send)
-    return TSVGP_OK;
-}
-
-// posterior factors of the pair's even rank -> odd rank, on the main stream in front of the pass
+// posterior factors of rank 0 -> every rank, on the main stream in front of the pass
 int exchange_posterior(tsvgp_ctx* c, bool with_kl) {
     NcclApi& api = nccl_api();
     cudaStream_t s = c->s_main;
     const size_t mm = (size_t)c->Mp * c->Mp, mp = c->Mp;
-    const int peer = c->rank ^ 1;
-    const bool recv = c->rank % 2 == 1;
-    CU(cudaStreamWaitEvent(s, c->ev_side, 0));   // one exchange at a time on the communicator: behind the K9 one (which is ready first)
+    const int root = 0;
     OK(nccl_chk(c, api.GroupStart(), "ncclGroupStart"));
     int r = 0;
-    if (recv) {
-        r |= api.Recv(c->T, mm, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Recv(c->alpha, mp, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Recv(c->mZ, mp, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Recv(c->mq, mp, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Recv(c->scal, N_SCAL, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Recv(c->info + INFO_W, 1, NCCL_INT32, peer, c->comm, s);
-    } else {
-        r |= api.Send(c->T, mm, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Send(c->alpha, mp, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Send(c->mZ, mp, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Send(c->mq, mp, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Send(c->scal, N_SCAL, NCCL_FLOAT64, peer, c->comm, s);
-        r |= api.Send(c->info + INFO_W, 1, NCCL_INT32, peer, c->comm, s);
-    }
+    r |= api.Broadcast(c->T, c->T, mm, NCCL_FLOAT64, root, c->comm, s);
+    r |= api.Broadcast(c->alpha, c->alpha, mp, NCCL_FLOAT64, root, c->comm, s);
+    r |= api.Broadcast(c->mZ, c->mZ, mp, NCCL_FLOAT64, root, c->comm, s);
+    r |= api.Broadcast(c->mq, c->mq, mp, NCCL_FLOAT64, root, c->comm, s);
+    r |= api.Broadcast(c->scal, c->scal, N_SCAL, NCCL_FLOAT64, root, c->comm, s);
+    r |= api.Broadcast(c->info + INFO_W, c->info + INFO_W, 1, NCCL_INT32, root, c->comm, s);
     const int rg = api.GroupEnd();
-    OK(nccl_chk(c, r ? r : rg, "ncclSend / ncclRecv (posterior factors)"));
-    if (recv) {
+    OK(nccl_chk(c, r ? r : rg, "ncclBroadcast (posterior factors)"));
+    CU(cudaEventRecord(c->ev_xpost, s));
+    if (c->rank != root) {
         c->post_valid = true;
         c->post_collective = false;
         c->kl_valid = with_kl;
     }
+    return TSVGP_OK;
+}
+
+// K9 results of rank 1 -> every rank, on the side stream (rank 1: behind its chain; the others: in place of the chain)
+int exchange_k9(tsvgp_ctx* c, double jitter) {
+    NcclApi& api = nccl_api();
+    cudaStream_t s = c->s_side;
+    const size_t mm = (size_t)c->Mp * c->Mp;
+    const int root = 1;
+    CU(cudaStreamWaitEvent(s, c->ev_xpost, 0));   // one exchange at a time on the communicator: behind the posterior one (the urgent one)
+    // ... and not before the pass is a few slabs in: an NCCL kernel that waits for its root polls on a dozen SMs, which the DMMA tiles
+    // of the pass (one CTA per SM, sized for all 148) cannot share; by then rank 1's chain is complete and the transfer is immediate
+    CU(cudaStreamWaitEvent(s, c->ev_mid, 0));
+    OK(nccl_chk(c, api.GroupStart(), "ncclGroupStart"));
+    int r = 0;
+    r |= api.Broadcast(c->C9inv, c->C9inv, mm, NCCL_FLOAT64, root, c->comm, s);
+    r |= api.Broadcast(c->K9inv, c->K9inv, mm, NCCL_FLOAT64, root, c->comm, s);
+    r |= api.Broadcast(c->scal2, c->scal2, N_SCAL, NCCL_FLOAT64, root, c->comm, s);
+    r |= api.Broadcast(c->info + INFO_K9, c->info + INFO_K9, 1, NCCL_INT32, root, c->comm, s);
+    const int rg = api.GroupEnd();
+    OK(nccl_chk(c, r ? r : rg, "ncclBroadcast (K9 chain)"));
+    if (c->rank != root) {   // the state the chain would have left
+        c->k9_valid = true; c->k9_jitter = jitter; c->k9inv_valid = true;
+        c->cond_est = 0.0;
+        c->k9_pending = true;
+    }
+    CU(cudaEventRecord(c->ev_side, s));   // (re-recorded on rank 1: the join after the pass also covers its broadcast)
     return TSVGP_OK;
 }
 
@@ -1510,6 +1504,9 @@ int tsvgp_create(tsvgp_ctx** out, int device_id) {
     }
     ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_post, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_xpost, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_early0, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_mid, cudaEventDisableTiming) == cudaSuccess;
     // the side chain (Kuu + jitter I) yields to the main chain (posterior, site update) where they meet, and both outrank the slabs
     const int prio_mid = prio_high < prio_low - 1 ? prio_high + 1 : prio_high;
     ok = ok && cudaStreamCreateWithPriority(&c->s_side, cudaStreamNonBlocking, prio_mid) == cudaSuccess;
@@ -1545,6 +1542,9 @@ void tsvgp_destroy(tsvgp_ctx* c) {
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_post) cudaEventDestroy(c->ev_post);
+    if (c->ev_xpost) cudaEventDestroy(c->ev_xpost);
+    if (c->ev_early0) cudaEventDestroy(c->ev_early0);
+    if (c->ev_mid) cudaEventDestroy(c->ev_mid);
     if (c->ev_kuu) cudaEventDestroy(c->ev_kuu);
     if (c->ev_side) cudaEventDestroy(c->ev_side);
     if (c->s_side) cudaStreamDestroy(c->s_side);
@@ -1895,7 +1895,7 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
     c->collective_ok = true;
     OK(ensure_xs(c));
     OK(ensure_kuu(c));
-    int chain_role = 0;   // 0: both chains here; 1 / 2: this rank built the posterior factors / the K9 chain and received the other
+    int chain_role = 0;   // ROLE_*: 0 both chains here; 1 / 2: this rank built the posterior factors / the K9 chain; 3: neither (received both)
     {
         SideIssue side;
         struct PdlGuard { ~PdlGuard() { g_pdl_suspended = 0; } } pdl_guard;
@@ -1915,19 +1915,24 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
         // chain is only needed after the pass it therefore starts once the posterior chain is complete and runs under the pass.
         // several ranks: the two chains are split over the ranks of a pair and exchanged (chain_split_active)
         const bool split = k9_runs && !join_before && c->sites_set && chain_split_active(c);
-        const bool k9_here = !split || c->rank % 2 == 1, post_here = !split || c->rank % 2 == 0;
-        chain_role = split ? 1 + c->rank % 2 : 0;
+        chain_role = split ? chain_role_of(c) : ROLE_BOTH;
+        const bool k9_here = chain_role == ROLE_BOTH || chain_role == ROLE_K9, post_here = chain_role == ROLE_BOTH || chain_role == ROLE_POSTERIOR;
         const bool defer_k9 = k9_runs && !join_before && c->k9_defer && c->Mp >= 2048 && !split;
         if (c->Mp >= 2048 && k9_runs && !defer_k9 && !split) g_pdl_suspended = 1;   // two concurrent chains of large kernels: see common.cuh
         if (!defer_k9 && k9_here) rc = start_k9_async(c, jitter, side);
-        if (rc == TSVGP_OK && split) rc = exchange_k9(c, jitter);
         if (rc == TSVGP_OK && !k9_runs) rc = choose_route(c, jitter);   // cached factors: the route is known at once
         c->n_early = 0;
-        const bool early = rc == TSVGP_OK && c->early_slabs && (!k9_runs || !join_before) && c->route == ROUTE_FUSED;
+        // split chains: no early slabs on the rank that builds the posterior factors — every rank waits for that chain
+        const bool early = rc == TSVGP_OK && c->early_slabs && (!k9_runs || !join_before) && c->route == ROUTE_FUSED && (!split || !post_here);
         if (early) rc = data_pass(c, MODE_STATS, PASS_EARLY);
         if (rc == TSVGP_OK && post_here) rc = ensure_posterior(c);
         if (rc == TSVGP_OK && post_here && elbo_before) rc = ensure_kl_terms(c);
-        if (rc == TSVGP_OK && split) rc = exchange_posterior(c, elbo_before != nullptr);
+        if (rc == TSVGP_OK && split) {
+            // a receiver's broadcast kernel polls on SMs until rank 0 delivers: it is launched when the first early slab is done
+            // (one slab's Kuf + SYRK is about as long as the posterior chain), not underneath it
+            if (!post_here && c->n_early > 0) CU(cudaStreamWaitEvent(s, c->ev_early0, 0));
+            rc = exchange_posterior(c, elbo_before != nullptr);   // rank 0: behind its chain; the others receive
+        }
         if (rc == TSVGP_OK && defer_k9) rc = start_k9(c, jitter);   // forks from the main stream HERE: behind the posterior chain
         side.join_into(g_launches);
         if (rc != TSVGP_OK) return rc;
@@ -1935,9 +1940,12 @@ int tsvgp_natgrad_step(tsvgp_ctx* c, double lr, double jitter, double scale, dou
         if (k9_runs && join_before) OK(choose_route(c, jitter));
         CU(cudaEventRecord(c->ev[EV_PREP], s));
         nvtxRangePushA("tsvgp_stream");
+        c->mark_mid = split;
         const int rc_pass = data_pass(c, MODE_STATS, early ? PASS_REST : PASS_WHOLE);
+        c->mark_mid = false;
         nvtxRangePop();
         OK(rc_pass);
+        if (split) OK(exchange_k9(c, jitter));   // second on the communicator, on the side stream, once the pass is a few slabs in
         if (k9_runs && !join_before) {   // join the K9 chain, read the probe, repeat the pass if the guess was wrong
             const int guessed = c->route;
             OK(choose_route(c, jitter));

@@ -537,8 +537,48 @@ def comm_unique_id() -> bytes:
     return buf.raw
 
 
-def shard_rows(n_rows, world_size, rank):
-    """Contiguous, near-equal row ranges of the minibatch: rank r owns rows [lo, hi)."""
-    base, rem = divmod(int(n_rows), int(world_size))
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+def shard_rows(n_rows, world_size, rank, weights=None):
+    """Contiguous row ranges of the minibatch: rank r owns rows [lo, hi).  Near-equal by default; with `weights`
+    (one relative share per rank, e.g. from `balance_weights`) the inner boundaries fall on multiples of 128 rows at the
+    cumulative shares."""
+    n_rows, world_size = int(n_rows), int(world_size)
+    if weights is None:
+        base, rem = divmod(n_rows, world_size)
+        lo = rank * base + min(rank, rem)
+        return lo, lo + base + (1 if rank < rem else 0)
+    w = np.asarray(weights, dtype=np.float64)
+    if w.shape != (world_size,) or not np.all(w > 0):
+        raise ValueError("weights must be one positive share per rank")
+    cum = np.concatenate([[0.0], np.cumsum(w / w.sum())])
+    bounds = [min(n_rows, int(round(c * n_rows / 128.0)) * 128) for c in cum]
+    bounds[0], bounds[-1] = 0, n_rows
+    for r in range(1, world_size + 1):          # every rank keeps at least one row
+        bounds[r] = max(bounds[r], bounds[r - 1] + 1)
+    if bounds[-1] != n_rows:
+        raise ValueError("too few rows for this many ranks")
+    return bounds[rank], bounds[rank + 1]
+
+
+def balance_weights(prepare_ms, stream_ms, rows, roles, max_skew=0.1):
+    """Row shares that let every rank finish its streaming pass at the same time when the ranks do different things in front of
+    it (option "split_chains": rank 0 builds the posterior factors alone, rank 1 runs the K9 chain underneath early slabs, the
+    others only early slabs).  Inputs, one entry per rank, from the last step(s) with the current shares:
+    timings()["prepare"], timings()["stream"], the rank's row count, timings()["chain_role"].
+    Model: prepare_r + stream_r = o_r + rows_r / rate, with ONE streaming rate (rows per ms, measured on the ranks whose stream
+    phase is streaming only: role 1, no early slabs) and a per-rank offset o_r (the chain in front of the pass on rank 0, next to
+    nothing on the others, whose early slabs fill the wait).  The shares solve  o_r + rows_r / rate = T  for all r  with
+    sum rows_r = N, and are clipped to 1 +- max_skew of the mean.  All roles 0 (no split): equal shares."""
+    prep, stream, rows, roles = (np.asarray(a, dtype=np.float64) for a in (prepare_ms, stream_ms, rows, roles))
+    W = rows.size
+    if not np.any(roles != 0):
+        return np.full(W, 1.0 / W)
+    pure = roles == 1
+    if not np.any(pure):
+        pure = np.ones(W, dtype=bool)
+    rate = np.sum(rows[pure]) / np.sum(stream[pure])
+    off = prep + stream - rows / rate
+    T = (np.sum(rows) / rate + np.sum(off)) / W
+    new_rows = np.maximum(rate * (T - off), 1.0)
+    w = new_rows / np.sum(new_rows)
+    w = np.clip(w, (1.0 - max_skew) / W, (1.0 + max_skew) / W)
+    return w / np.sum(w)

@@ -155,3 +155,33 @@ def test_every_library_option_is_documented_in_the_header():
     assert accepted, "no options found in tsvgp_set_option"
     internal = {"profile"}   # measurement switch behind tsvgp_get_kernel_profile, described there
     assert accepted - internal <= documented, sorted(accepted - internal - documented)
+
+
+def test_weighted_shards_and_balance_weights():
+    # host side of option "split_chains" (DESIGN 5): weighted contiguous shards on 128-row boundaries, and the shares that equalise
+    # the ranks' finish times under the model  busy_r = offset_r + rows_r / rate
+    from tsvgp_b200 import balance_weights, shard_rows
+    N, W = 1_000_000, 8
+    equal = [shard_rows(N, W, r) for r in range(W)]
+    assert equal == [shard_rows(N, W, r, None) for r in range(W)]
+    rows = np.array([hi - lo for lo, hi in equal], dtype=float)
+    roles = np.array([1.0, 2.0] + [3.0] * (W - 2))      # rank 0 builds the posterior factors, rank 1 the K9 chain, the rest receive
+    rate = N / W / 32.9                                    # rows per ms
+
+    def phases(rows):                                      # rank 0: chain 2.5 ms in front; the others do part of the pass while they wait
+        done = np.array([0.0, 1.2] + [2.2] * (W - 2))
+        return np.where(np.arange(W) == 0, 2.5, 2.7), rows / rate - done
+
+    prep, stream = phases(rows)
+    assert np.ptp(prep + stream) > 1.9
+    w = balance_weights(prep, stream, rows, roles)
+    assert abs(w.sum() - 1.0) < 1e-12 and w[0] < w[1] < w[2] and np.allclose(w[2:], w[2])
+    spans = [shard_rows(N, W, r, w) for r in range(W)]
+    assert spans[0][0] == 0 and spans[-1][1] == N
+    assert all(spans[r][1] == spans[r + 1][0] for r in range(W - 1)) and all(s[0] % 128 == 0 for s in spans)
+    prep2, stream2 = phases(np.array([hi - lo for lo, hi in spans], dtype=float))
+    assert np.ptp(prep2 + stream2) < 0.05                  # finish times equalised (128-row granularity)
+    assert np.allclose(balance_weights(prep, stream, rows, np.zeros(W)), 1 / W)   # no split: equal shares
+    with pytest.raises(ValueError):
+        shard_rows(N, W, 0, [1.0] * (W - 1))
+    assert [shard_rows(10, 3, r, [1, 1, 1]) for r in range(3)][-1][1] == 10

@@ -77,7 +77,7 @@ def test_two_gpu_sharded_step_matches_single_gpu(opts, M):
     # sharded_update: statistics reduce-scattered by tile rows, G2 = K9^-1 B K9^-1 formed on each rank's rows, two all-gathers
     # (forced here at M = 500 = 4 tile rows; by default from M >= 2048 when the tile rows divide by the ranks)
     # chains_split_over_the_pair: from the second step on (kernel matrix invalidated before every step, route speculated) rank 0
-    # builds the posterior factors, rank 1 the Kuu + jitter I chain, and they exchange the results — same bits as side by side
+    # builds the posterior factors, rank 1 the Kuu + jitter I chain, and each broadcasts its result — same bits as side by side
     import tsvgp_b200 as tb
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
