@@ -12,6 +12,9 @@ under `other_configs`; `--config cfgK` selects any config as the main line.
 
 A "step" is one `t_SVGP.natgrad_step` (posterior factors + streaming statistics pass + all-reduce + dense site update) over
 one minibatch of the named config, sharded by rows over the N ranks (strong scaling: the minibatch is fixed).
+For N > 1 the library option "split_chains" is switched on (rank 0 builds the posterior factors, rank 1 the Kuu + jitter I chain, both
+broadcast) and the row shares are balanced from 5 untimed calibration steps (`balance_rows`; `--no-balance`: equal shares, both chains on
+every rank); the shares and the calibration table are reported under `config`.
   value : minibatch rows / step time with the minibatch resident in HBM when the clock starts (4 distinct minibatches rotate)
   e2e   : the same through the public API with HOST (pinned) buffers: H2D of the rank's rows every step, and the pre-step
           ELBO and lambda_1 read back, inside the timed region
