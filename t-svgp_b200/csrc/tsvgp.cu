@@ -82,7 +82,7 @@ struct tsvgp_ctx {
     int n_streams = 2;
     int dist_min_m = 4096;     // distribute the dense M x M products over the ranks from this (padded) M upwards
     int shard_min_m = 2048;    // from this (padded) M upwards the statistics are reduce-SCATTERED by tile rows and the two products of
-    int split_chains = 0;      // 1: even ranks build the posterior factors, odd ranks the K9 chain; the results are exchanged pairwise (see chain_split_active)
+    int split_chains = 0;      // 1: rank 0 builds the posterior factors, rank 1 the K9 chain, both broadcast their results (see chain_split_active)
                                // G2 = K9^-1 B K9^-1 run on each rank's rows only, assembled by two all-gathers (sharded_update)
     int async_issue = 1;       // small M: enqueue the K9 chain from a helper host thread while this thread enqueues the posterior chain
     int fuse_b = 1;            // accumulate b += Kuf g inside the SYRK kernel instead of a separate mat-vec pass over the slab
@@ -160,7 +160,6 @@ struct tsvgp_ctx {
     size_t gws_doubles = 0;
     double *scal = nullptr, *red = nullptr;   // device scalars; [128] scratch of the two-stage reductions (per context)
     double jit6 = GPFLOW_DEFAULT_JITTER;   // jitter of K6 (gpflow default_jitter; predict_f_extra_data passes its own)
-    double* lam1_bak = nullptr;
     int white = 0;             // 1: the whitened sibling t_SVGP_white (reference src/models/tsvgp_white.py): L2 holds the full Lambda_2
     double *C6 = nullptr, *C6inv = nullptr;   // chol(K6) and its inverse (whitened sibling)
     bool c6_valid = false, wpost_valid = false, wkl_valid = false;
@@ -325,7 +324,7 @@ int alloc_m_state(tsvgp_ctx* c, int M, int D) {
     CU(cudaMemsetAsync(c->gws + c->gws_doubles - GEMM_WS_COUNTER_DOUBLES, 0, sizeof(double) * GEMM_WS_COUNTER_DOUBLES, c->s_main));    // tile counters
     CU(cudaMemsetAsync(c->gws2 + c->gws_doubles - GEMM_WS_COUNTER_DOUBLES, 0, sizeof(double) * GEMM_WS_COUNTER_DOUBLES, c->s_main));
     NEED(c->zaug = p.get(mp * 128)); NEED(c->fuu = p.get(mp * 128)); NEED(c->origin = p.get(D));
-    NEED(c->C6 = p.get(mm)); NEED(c->C6inv = p.get(mm)); NEED(c->lam1_bak = p.get(mp));
+    NEED(c->C6 = p.get(mm)); NEED(c->C6inv = p.get(mm));
     c->c6_valid = c->wpost_valid = c->wkl_valid = false;
     NEED(c->tmp2 = p.get((size_t)((c->Mp / 128 + 1) / 2) * 128 * mp)); NEED(c->dinv2 = p.get((size_t)(c->Mp / 128) * 128 * 128));
     CU(cudaMemsetAsync(c->dinv2, 0, sizeof(double) * (size_t)(c->Mp / 128) * 128 * 128, c->s_main));
@@ -1252,8 +1251,10 @@ int sharded_reduce_and_form_G(tsvgp_ctx* c) {
 // fewer rows: tsvgp_b200.balance_weights (host) turns measured phase times into row shares.
 // Used when the K9 chain is joined AFTER the pass anyway (fused route forced or speculated) and the dense products are replicated
 // (below dist_min_m; above, the chains' products are themselves collective).
-// MEASURED (2 x B200, cfg3, ms per step), pairwise version of the same split with equal rows: 135.8 split / 135.4 side by side with
-// early slabs on both ranks; 135.45 / 135.95 without early slabs; with early slabs on the odd rank only and balanced rows 135.05.
+// MEASURED (cfg3, ms per step; profiles/scale_r02_n2_chains.txt, scale_r02_n8_ab.txt): 8 x B200 37.26 with both chains on every
+// rank and equal rows, 36.44 with this split and balanced rows; 2 x B200 135.4-135.65 against 135.05-135.24 (both ranks have a chain).
+// With equal rows the split and the early slabs do not add up (a first version with ncclSend/ncclRecv inside rank pairs: 135.8 / 135.45
+// with / without early slabs against 135.4 / 135.95).
 // OFF by default in the library (it needs the caller's cooperation for the row shares); bench.py switches it on for N > 1.
 enum { ROLE_BOTH = 0, ROLE_POSTERIOR = 1, ROLE_K9 = 2, ROLE_NONE = 3 };
 bool chain_split_active(const tsvgp_ctx* c) {
