@@ -185,3 +185,31 @@ def test_weighted_shards_and_balance_weights():
     with pytest.raises(ValueError):
         shard_rows(N, W, 0, [1.0] * (W - 1))
     assert [shard_rows(10, 3, r, [1, 1, 1]) for r in range(3)][-1][1] == 10
+
+
+def test_bench_reference_arm_contract():
+    # bench.py --impl reference (the driver's reference arm): ONE JSON line on stdout with the contract's keys, the oracle timed on
+    # the host cores; under torchrun only rank 0 runs and prints, the other ranks exit 0 without work
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "cfg1", "--steps", "2", "--warmup", "1"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["steps"] == 2 and d["warmup"] == 1 and d["higher_is_better"] is True
+    assert d["metric"] == "natgrad_step datapoints/sec" and d["unit"] == "datapoints/s" and d["dtype"] == "f64" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+    # a non-zero rank of a torchrun launch: no output, exit 0, no rendezvous attempted
+    env1 = dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1", MASTER_ADDR="127.0.0.1", MASTER_PORT="29999")
+    out1 = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=120, env=env1)
+    assert out1.returncode == 0 and out1.stdout.strip() == ""
